@@ -1,0 +1,197 @@
+/*
+ * speedyml_engine.h -- C ABI of the B200-native SPEEDY-ML local-reservoir engine.
+ *
+ * The reference has no FFI: its hot path is reached through Fortran module procedures on derived
+ * types (mod_reservoir / mod_linalg / mpires / resdomain).  Each entry point below names the
+ * reference procedure it replaces (paths relative to the reference tree); the thin ISO_C_BINDING
+ * layer that keeps those Fortran names and forwards here is speedy-ml_b200/fortran/speedyml_gpu.f90,
+ * and INTEGRATION.md shows where the reference calls change.
+ *
+ * Conventions (kept from the reference):
+ *   - all floating point data is FP64, column-major, caller-owned; the engine copies;
+ *   - COO indices are 1-based int32 exactly as mklsparse receives them; region ids are 0-based
+ *     (reservoir%assigned_region); every other index this API returns is 1-based like res_domain.f90;
+ *   - one host thread calls in program order (as each MPI rank does); calls block until results the
+ *     caller can read are in its arrays;
+ *   - return value: 0 ok, <0 engine error (sml_last_error), >0 LAPACK-style info where stated.
+ *     The library never aborts and has NO CPU fallback: without a usable CUDA device sml_create fails.
+ *
+ * Scope: num_vert_levels == 1 (the reference's configuration, src/mod_reservoir.f90:57).
+ */
+#ifndef SPEEDYML_ENGINE_H
+#define SPEEDYML_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SML_XGRID 96
+#define SML_YGRID 48
+#define SML_ZGRID 8
+
+/* reservoir kinds: res%reservoir(i,1) and res%reservoir_special(i,1) (src/parallelmain.f90:56-61) */
+#define SML_ATMO 0
+#define SML_OCEAN 1
+
+#define SML_ALL_REGIONS (-1)
+
+/* model_parameters_type subset (src/mod_utilities.f90:371-509; values src/mod_reservoir.f90:12-77) */
+typedef struct sml_params {
+    int32_t number_of_regions;     /* 1152 */
+    int32_t overlap;               /* 1 */
+    int32_t precip_bool;           /* 1 */
+    int32_t slab_ocean_model_bool; /* 1: SST grid is exchanged and fed back */
+    int32_t ml_only;               /* 0: hybrid (chunk_size_speedy > 0) */
+    int32_t irank, numprocs;       /* region sharding: processor_decomposition(irank, numprocs) */
+    int32_t device;                /* CUDA device ordinal for this rank */
+    int32_t timestep, timestep_slab; /* hours: 6, 168 */
+    int32_t sst_prescribed;        /* 1: wholegrid_sst comes from the host every step (no ocean reservoirs) */
+    int32_t reserved[5];
+} sml_params;
+
+/* what read_trained_res / allocate_res_new hold for one reservoir (src/mod_io.f90:2938-2983,
+ * src/mod_reservoir.f90:80-180).  Exactly one of win_dense / win_compact must be non-NULL. */
+typedef struct sml_region_weights {
+    int32_t region;          /* reservoir%assigned_region, 0-based */
+    int32_t kind;            /* SML_ATMO / SML_OCEAN */
+    int32_t n, k;            /* reservoir%n, reservoir%k */
+    int32_t D, P, S;         /* reservoir_numinputs, chunk_size_prediction, chunk_size_speedy */
+    int32_t L;               /* length of mean/std */
+    int32_t sst_bool_input;  /* atmosphere: SST slot present in the input vector */
+    int32_t reserved0;
+    double leakage;          /* reservoir%leakage */
+    double sst_mean, sst_std;/* grid_special%mean/std(sst_mean_std_idx) used for the SST feedback slot */
+    const int32_t *rows;     /* [k] 1-based */
+    const int32_t *cols;     /* [k] 1-based */
+    const double *vals;      /* [k] */
+    const double *win_dense; /* [n*D] column-major win(n,D), or NULL */
+    const double *win_compact; /* [n]: the single non-zero of each row, or NULL */
+    const int32_t *win_col;  /* [n] 0-based column of that non-zero (with win_compact) */
+    const double *wout;      /* [P*(n+S)] column-major wout(P,n+S); NULL = zeros (to be trained) */
+    const double *mean;      /* [L] */
+    const double *std;       /* [L] */
+} sml_region_weights;
+
+typedef struct sml_engine sml_engine;
+
+/* ---- life cycle ---- */
+int sml_create(sml_engine **h, const sml_params *p);
+int sml_destroy(sml_engine *h);
+const char *sml_last_error(const sml_engine *h); /* also valid with h == NULL for sml_create failures */
+int sml_set_stream(sml_engine *h, void *cuda_stream); /* run on the caller's stream (NULL: engine's own) */
+int sml_synchronize_stream(sml_engine *h);
+int sml_num_local_regions(const sml_engine *h);
+int sml_local_region_ids(const sml_engine *h, int32_t *ids); /* processor_decomposition, src/res_domain.f90:31-62 */
+
+/* ---- res_domain.f90 index arithmetic (host, integers; bit-exact contract) ---- */
+int sml_domaindecomposition(int numregions, int *factorx, int *factory);           /* :258-280 */
+int sml_getxyresextent(int num_regions, int region, int *xs, int *xe, int *ys, int *ye,
+                       int *xchunk, int *ychunk);                                  /* :123-141 */
+int sml_getoverlapindices(int num_regions, int region, int overlap, int *ixs, int *ixe, int *iys,
+                          int *iye, int *ixc, int *iyc, int *pole, int *periodic);  /* :155-204 */
+int sml_get_trainingdataindices(int num_regions, int region, int overlap, int *xs, int *xe,
+                                int *ys, int *ye);                                 /* :547-574 */
+int sml_processor_decomposition(int irank, int numprocs, int number_of_regions,
+                                int32_t *region_indices, int *count);              /* :31-62 */
+/* sizes of allocate_res_new (src/mod_reservoir.f90:155-173) for an atmosphere reservoir */
+int sml_region_dims(int num_regions, int region, int overlap, int m, double deg, int precip_bool,
+                    int sst_bool, int sst_bool_input, int ml_only, int *n, int *k, int *D, int *P,
+                    int *S, int *L);
+/* flattened 0-based gather/scatter maps into the global buffers (layout: sml_global_layout):
+ *   input_map[D]  : feedback element -> offset in G  (tile_4d_and_logp_to_local_state_input :1081-1125,
+ *                   tileoverlapgrid2d for sst/tisr)         input_ms[D] : 0-based mean/std slot, L = sst
+ *   output_map[P] : outvec element   -> offset in G  (tile_full_grid_with_local_state_vec_res1d :791-826)
+ *   model_map[S]  : local_model elem -> offset in F  (tile_4d_and_logp_full_grid_to_local_res_vec :1022-1053)
+ *   target_map[P] : target row -> input-vector row   (tile_full_input_to_target_data2d :602-651) */
+int sml_region_maps(int num_regions, int region, int overlap, int precip_bool, int sst_bool_input,
+                    int32_t *input_map, int32_t *input_ms, int32_t *output_map, int32_t *output_ms,
+                    int32_t *model_map, int32_t *model_ms, int32_t *target_map);
+/* offsets (in doubles) of wholegrid4d, wholegrid2d, wholegrid_precip, wholegrid_sst, tisr in G and the
+ * total; F = [forecast_4d | forecast_2d] */
+int sml_global_layout(int64_t off[5], int64_t *g_total, int64_t *f_total);
+
+/* ---- weights: mklsparse (src/mod_linalg.f90:10-25) + trained_reservoir_prediction
+ *      (src/mod_reservoir.f90:1783-1886); slab twin src/mod_slab_ocean_reservoir.f90:1561-1652 ---- */
+int sml_region_upload(sml_engine *h, const sml_region_weights *w);
+int sml_finalize(sml_engine *h); /* after the last upload: builds the batched step plan */
+
+/* ---- per-region state (reservoir%current_state / saved_state / feedback / local_model / outvec) ---- */
+int sml_state_set(sml_engine *h, int kind, int region, const double *x);
+int sml_state_get(sml_engine *h, int kind, int region, double *x);
+int sml_feedback_set(sml_engine *h, int kind, int region, const double *feedback);
+int sml_feedback_get(sml_engine *h, int kind, int region, double *feedback);
+int sml_local_model_set(sml_engine *h, int kind, int region, const double *local_model);
+int sml_local_model_get(sml_engine *h, int kind, int region, double *local_model);
+int sml_outvec_get(sml_engine *h, int kind, int region, double *outvec);
+int sml_wout_get(sml_engine *h, int kind, int region, double *wout);
+int sml_wout_set(sml_engine *h, int kind, int region, const double *wout);
+
+/* ---- synchronize (src/mod_reservoir.f90:1354-1381, synchronize_print :1383-1416; slab :1237-1266)
+ * input(ld, length) column-major for ONE region, or with region == SML_ALL_REGIONS the local regions'
+ * series back to back (region i's block starts at inputs + offsets[i], leading dimension D_i). ---- */
+int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, int ld, int length,
+                    const int64_t *offsets);
+
+/* ---- predict / predict_ml (src/mod_reservoir.f90:1418-1535; slab :1268-1363) for every local
+ * region of the kind: state update + readout + un-standardise; outvec stays on the device ---- */
+int sml_predict(sml_engine *h, int kind);
+
+/* ---- sendrecievegrid (src/mpires.f90:218-804), split where the root calls run_model (:565-569).
+ * begin: gathers the outvecs into the global grids, applies the clamps (:456-490) and returns them
+ *        (rank 0 arrays may be NULL to skip the copy-out): wholegrid4d[4*96*48*8], wholegrid2d[96*48],
+ *        wholegrid_precip[96*48], wholegrid_sst[96*48].
+ * end:   takes run_model's forecast (forecast_4d, forecast_2d), the date's global TISR field
+ *        (get_tisr_by_date :1676-1708) and rebuilds every local region's feedback and local_model
+ *        (:581-604, :749-791). ---- */
+int sml_step_exchange_begin(sml_engine *h, int timestep, double *wholegrid4d, double *wholegrid2d,
+                            double *wholegrid_precip, double *wholegrid_sst);
+int sml_step_exchange_end(sml_engine *h, int timestep, const double *forecast_4d,
+                          const double *forecast_2d, const double *tisr_grid);
+/* static fields of the exchange: base_sst_grid and sea_mask (src/mod_reservoir.f90:847-887) */
+int sml_set_sst_static(sml_engine *h, const double *base_sst_grid, const double *sea_mask);
+/* sst_prescribed == 1: the SST field (96x48) the next exchanges start from instead of ocean-reservoir
+ * output; the land mask and the 272 K floor still apply (the role full_sst plays in get_sst_by_date,
+ * src/mpires.f90:1710-1757) */
+int sml_set_sst_prescribed(sml_engine *h, const double *sst_grid);
+
+/* multi-rank plumbing (one process per GPU): device pointers of the exchange buffers so the host
+ * can run the collective (NCCL all-gather of the outvec slabs; broadcast of F) on them. */
+int sml_exchange_buffers(sml_engine *h, void **outvec_slab, int64_t *slab_count, void **gathered,
+                         int64_t *gathered_count, void **gbuf, int64_t *g_count, void **fbuf,
+                         int64_t *f_count);
+/* device-only halves of begin/end for callers that keep the grids on the device */
+int sml_step_pack_device(sml_engine *h, int timestep);                 /* gathered -> G (+clamps) */
+int sml_step_unpack_device(sml_engine *h, int timestep);               /* G,F -> feedback, local_model */
+
+/* ---- training: reservoir_layer_chunking_hybrid/_ml + chunking_matmul(_ml)
+ *      (src/mod_reservoir.f90:963-1175,1594-1701), fit_chunk_hybrid/_ml (:1177-1334) ---- */
+int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregions, int batch_size);
+/* one phase (trainingdata(:, i::timestep)) for the regions of sml_train_begin, series back to back:
+ * trainingdata block of region i at td + td_off[i] (ld D_i), imperfect at im + im_off[i] (ld S_i);
+ * inputs are pre-noised. */
+int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const double *im,
+                   const int64_t *im_off, int ncols, int discard_cols);
+int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using_prior,
+                    double prior_val, int32_t *info_per_region);
+int sml_train_gram_get(sml_engine *h, int region, double *states_x_states_aug,
+                       double *states_x_trainingdata_aug);
+int sml_train_end(sml_engine *h);
+
+/* mldivide (src/mod_linalg.f90:109-151): solves A X = B in place of B; A(n,n) lda, B(n,nrhs) ldb.
+ * returns dgesv's info (>0: singular, B is not the solution) */
+int sml_mldivide(sml_engine *h, double *A, int lda, double *B, int ldb, int n, int nrhs);
+
+/* ---- measurement hooks (bench.py): with profiling on, every sml_predict brackets its step kernel and
+ * its finish kernel with CUDA events on the launching stream; sml_kernel_times sums and resets them ---- */
+int sml_profile(sml_engine *h, int on);
+int sml_kernel_times(sml_engine *h, double *step_ms_sum, double *finish_ms_sum, int *count);
+int64_t sml_kernel_launch_count(const sml_engine *h);
+/* algorithmic bytes one sml_predict(kind) moves */
+int64_t sml_predict_algorithmic_bytes(const sml_engine *h, int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

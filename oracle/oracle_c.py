@@ -65,6 +65,7 @@ def lib():
         L.orc_region_ptr.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_region_set_weights.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int]
         L.orc_region_set_leakage.argtypes = [C.c_void_p, C.c_double]
+        L.orc_region_set_win_compact.argtypes = [C.c_void_p, _dp, _ip]
         L.orc_synchronize.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int]
         L.orc_predict.argtypes = [C.c_void_p, _dp]
         L.orc_predict_ml.argtypes = [C.c_void_p, _dp]
@@ -222,6 +223,13 @@ class Region:
                                           _d(wout) if wout is not None else None, _d(mean), _d(std), mean.size)
         if rc:
             raise ValueError(f"orc_region_set_weights rc={rc}")
+
+    def set_win_compact(self, winc, wcol):
+        winc = np.ascontiguousarray(winc, dtype=np.float64)
+        wcol = np.ascontiguousarray(wcol, dtype=np.int32)
+        assert winc.size == self.n and wcol.size == self.n
+        if lib().orc_region_set_win_compact(self.h, _d(winc), _i(wcol)):
+            raise ValueError("win_col out of range")
 
     def set_leakage(self, leak):
         lib().orc_region_set_leakage(self.h, float(leak))

@@ -716,6 +716,10 @@ struct orc_region {
     int *rows, *cols;
     double *vals, *win, *wout, *mean, *std;
     double *x, *feedback, *local_model, *outvec;
+    /* optional one-non-zero-per-row form of win (test scaffolding for full-model runs; bit-identical to
+     * the dense GEMV because every other term of matmul(win,u) is an exact zero -- tests/test_oracle_predict.py) */
+    double *winc;
+    int *wcol;
     /* training */
     int batch_size;
     double *states, *augmented_states, *saved_state, *sxs, *sxt; /* states_x_states_aug, states_x_trainingdata_aug */
@@ -730,7 +734,7 @@ orc_region *orc_region_new(const orc_grid *g, const orc_dims *d)
     r->rows = (int *)calloc((size_t)d->k + 1, sizeof(int));
     r->cols = (int *)calloc((size_t)d->k + 1, sizeof(int));
     r->vals = (double *)calloc((size_t)d->k + 1, sizeof(double));
-    r->win = (double *)calloc((size_t)n * D, sizeof(double));
+    r->win = NULL; /* allocated by orc_region_set_weights when a dense win is given */
     r->wout = (double *)calloc((size_t)P * (n + S), sizeof(double));
     r->mean = (double *)calloc((size_t)g->mean_std_length + 1, sizeof(double));
     r->std = (double *)calloc((size_t)g->mean_std_length + 1, sizeof(double));
@@ -753,6 +757,7 @@ void orc_region_free(orc_region *r)
     orc_train_free(r);
     free(r->rows); free(r->cols); free(r->vals); free(r->win); free(r->wout); free(r->mean); free(r->std);
     free(r->x); free(r->feedback); free(r->local_model); free(r->outvec);
+    free(r->winc); free(r->wcol);
     free(r);
 }
 
@@ -770,7 +775,12 @@ int orc_region_set_weights(orc_region *r, const int *rows, const int *cols, cons
     memcpy(r->rows, rows, sizeof(int) * (size_t)d->k);
     memcpy(r->cols, cols, sizeof(int) * (size_t)d->k);
     memcpy(r->vals, vals, sizeof(double) * (size_t)d->k);
-    if (win) memcpy(r->win, win, sizeof(double) * (size_t)n * D);
+    if (win) {
+        if (!r->win) r->win = (double *)malloc(sizeof(double) * (size_t)n * D);
+        memcpy(r->win, win, sizeof(double) * (size_t)n * D);
+        free(r->winc); free(r->wcol);
+        r->winc = NULL; r->wcol = NULL;
+    }
     if (wout) memcpy(r->wout, wout, sizeof(double) * (size_t)P * (n + S));
     memcpy(r->mean, mean, sizeof(double) * (size_t)mean_std_length);
     memcpy(r->std, std, sizeof(double) * (size_t)mean_std_length);
@@ -778,6 +788,23 @@ int orc_region_set_weights(orc_region *r, const int *rows, const int *cols, cons
 }
 
 void orc_region_set_leakage(orc_region *r, double leakage) { r->d.leakage = leakage; }
+
+/* compact W_in: value and 0-based column of the single non-zero of each row (src/mod_reservoir.f90:270-280).
+ * Frees the dense copy. */
+int orc_region_set_win_compact(orc_region *r, const double *winc, const int *wcol)
+{
+    const int n = r->d.n, D = r->d.reservoir_numinputs;
+    for (int j = 0; j < n; ++j)
+        if (wcol[j] < 0 || wcol[j] >= D) return -1;
+    free(r->winc); free(r->wcol);
+    r->winc = (double *)malloc(sizeof(double) * (size_t)n);
+    r->wcol = (int *)malloc(sizeof(int) * (size_t)n);
+    memcpy(r->winc, winc, sizeof(double) * (size_t)n);
+    memcpy(r->wcol, wcol, sizeof(int) * (size_t)n);
+    free(r->win);
+    r->win = NULL;
+    return 0;
+}
 const orc_grid *orc_region_grid(const orc_region *r) { return &r->g; }
 const orc_dims *orc_region_dims(const orc_region *r) { return &r->d; }
 
@@ -802,6 +829,10 @@ double *orc_region_ptr(orc_region *r, const char *f)
 static void dense_win_gemv(const orc_region *r, const double *u, double *temp)
 {
     const int n = r->d.n, D = r->d.reservoir_numinputs;
+    if (r->winc) {
+        for (int j = 0; j < n; ++j) temp[j] = r->winc[j] * u[r->wcol[j]];
+        return;
+    }
     for (int j = 0; j < n; ++j) temp[j] = 0.0;
     for (int i = 0; i < D; ++i) {
         const double ui = u[i];

@@ -1,0 +1,888 @@
+// engine.cu -- host side of the B200 reservoir engine behind include/speedyml_engine.h.
+//
+// Data layout in HBM (per rank = per GPU):
+//   per region, allocated at upload (256 B aligned by cudaMalloc):
+//     ELL adjacency  ell_col[W][n] int32 + ell_val[W][n] f64, slot-major (thread-per-row loads coalesce)
+//     W_in compact   winc[n] f64 + wcol[n] int32   (dense n*D copy only when the one-per-row test fails)
+//     W_out          ldw*(S+n) f64 column-major, ldw = P rounded up to even (TMA tiles stay 16 B aligned)
+//     mean/std       L+1 f64 each (slot L: SST feedback constants)
+//     gather maps    fb_src/fb_ms[D], lm_src/lm_ms[S], out_ms[P] int32
+//   pooled at finalize: x ping/pong, feedback, local_model, outvec slab [nloc][P], readout partials,
+//     the global buffers G = [w4d|w2d|precip|sst|tisr], F = [f4d|f2d] and the scatter table out_dst[R][P].
+// No CPU fallback anywhere: every entry point that computes launches the kernels in kernels.cuh.
+#include "../../include/speedyml_engine.h"
+#include "kernels.cuh"
+#include "resdomain.hpp"
+#include "train.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace sml;
+
+namespace {
+
+std::string g_create_err;
+
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES_TARGET = 20 * 1088;  // 20 columns of a 136-row W_out
+constexpr int PROFILE_RING = 4096;
+
+struct HostRegion {
+    bool uploaded = false;
+    int region = -1;
+    RegionDev dev{};
+    std::vector<void *> allocs;
+    RegionSizes sizes{};
+    bool sst_in = false;
+};
+
+struct KindState {
+    bool any = false;
+    int P = -1, ldw = 0;
+    std::vector<HostRegion> regs;
+    RegionDev *d_regs = nullptr;
+    StepItem *d_items = nullptr;
+    std::vector<StepItem> items;
+    int nitems = 0;
+    double *d_x[2] = {nullptr, nullptr};
+    int cur = 0;
+    double *d_fb = nullptr, *d_lm = nullptr, *d_out = nullptr, *d_partials = nullptr, *d_temp = nullptr;
+    long long *d_fb_offs = nullptr;
+    long long x_total = 0, fb_total = 0, lm_total = 0;
+    int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0;
+    size_t smem_bytes = 0;
+    bool any_dense = false;
+    int64_t alg_bytes = 0;
+    // synchronize input staging
+    double *d_in = nullptr;
+    size_t d_in_cap = 0;
+    long long *d_in_offs = nullptr;
+};
+
+}  // namespace
+
+struct sml_engine {
+    sml_params p{};
+    std::string err;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    Tiling tiling;
+    std::vector<int32_t> local_ids;
+    std::unordered_map<int, int> local_index;
+    KindState kinds[2];
+    bool finalized = false;
+    int P_atmo = 0;
+    // exchange
+    double *d_G = nullptr, *d_F = nullptr, *d_gathered = nullptr;
+    double *d_base_sst = nullptr, *d_mask = nullptr, *d_prescribed = nullptr;
+    int *d_out_dst = nullptr;
+    int *d_cell_region = nullptr, *d_cell_slot = nullptr, *d_region_ocean_slab = nullptr;
+    double *d_ocean_gathered = nullptr;
+    double *h_pin_G = nullptr, *h_pin_F = nullptr;
+    bool sst_static_set = false, sst_prescribed_set = false;
+    // profiling
+    std::vector<cudaEvent_t> ev;  // ring of (start, step done, finish done) triples
+    int ev_used = 0;              // triples recorded since the last read
+    bool profile = false;
+    int64_t launches = 0;
+    TrainState train;
+};
+
+#define FAIL(h, ...)                                      \
+    do {                                                  \
+        char _b[512];                                     \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);            \
+        (h)->err = _b;                                    \
+        return -1;                                        \
+    } while (0)
+
+#define CK(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) FAIL(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+template <typename T>
+int dev_upload(sml_engine *h, HostRegion *hr, const T *src, size_t count, const T **out)
+{
+    T *d = nullptr;
+    CK(h, cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+    if (hr) hr->allocs.push_back(d);
+    if (count) CK(h, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    *out = d;
+    return 0;
+}
+
+int check_ready(sml_engine *h, int kind)
+{
+    if (!h) return -1;
+    if (kind != SML_ATMO && kind != SML_OCEAN) FAIL(h, "bad kind %d", kind);
+    if (!h->finalized) FAIL(h, "sml_finalize has not been called");
+    if (!h->kinds[kind].any) FAIL(h, "no reservoirs of kind %d uploaded", kind);
+    return 0;
+}
+
+int local_of(sml_engine *h, int kind, int region, int *li)
+{
+    auto it = h->local_index.find(region);
+    if (it == h->local_index.end()) FAIL(h, "region %d is not owned by rank %d", region, h->p.irank);
+    if (!h->kinds[kind].regs[it->second].uploaded) FAIL(h, "region %d kind %d has no reservoir", region, kind);
+    *li = it->second;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sml_last_error(const sml_engine *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int sml_create(sml_engine **out, const sml_params *p)
+{
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU fallback)";
+        return -1;
+    }
+    if (p->device < 0 || p->device >= ndev) {
+        g_create_err = "device ordinal out of range";
+        return -1;
+    }
+    if (p->numprocs < 1 || p->irank < 0 || p->irank >= p->numprocs) {
+        g_create_err = "bad irank/numprocs";
+        return -1;
+    }
+    Tiling t = make_tiling(p->number_of_regions);
+    if (!t.ok || t.ntx * t.nty != p->number_of_regions) {
+        g_create_err = "number_of_regions does not tile the 96x48 grid (domaindecomposition would not exit)";
+        return -1;
+    }
+    if (t.fx + 2 * p->overlap > XG || p->overlap < 0) {
+        g_create_err = "overlap too large for the tiling";
+        return -1;
+    }
+    if (p->numprocs > 1 && p->number_of_regions % p->numprocs != 0) {
+        g_create_err = "multi-rank runs need number_of_regions divisible by numprocs (contiguous slabs)";
+        return -1;
+    }
+    if ((e = cudaSetDevice(p->device)) != cudaSuccess) {
+        g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return -1;
+    }
+    sml_engine *h = new sml_engine();
+    h->p = *p;
+    h->tiling = t;
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete h;
+        return -1;
+    }
+    h->stream = h->own_stream;
+    h->local_ids = regions_of_rank(p->irank, p->numprocs, p->number_of_regions);
+    for (size_t i = 0; i < h->local_ids.size(); ++i) h->local_index[h->local_ids[i]] = (int)i;
+    for (int k = 0; k < 2; ++k) h->kinds[k].regs.resize(h->local_ids.size());
+    *out = h;
+    return 0;
+}
+
+static void free_kind(KindState &K)
+{
+    for (auto &r : K.regs)
+        for (void *p : r.allocs) cudaFree(p);
+    cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
+    cudaFree(K.d_lm); cudaFree(K.d_out); cudaFree(K.d_partials); cudaFree(K.d_temp); cudaFree(K.d_fb_offs);
+    cudaFree(K.d_in); cudaFree(K.d_in_offs);
+}
+
+int sml_destroy(sml_engine *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->p.device);
+    cudaDeviceSynchronize();
+    train_release(h->train);
+    for (int k = 0; k < 2; ++k) free_kind(h->kinds[k]);
+    cudaFree(h->d_G); cudaFree(h->d_F); cudaFree(h->d_gathered); cudaFree(h->d_base_sst); cudaFree(h->d_mask);
+    cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);
+    cudaFree(h->d_region_ocean_slab); cudaFree(h->d_ocean_gathered);
+    cudaFreeHost(h->h_pin_G); cudaFreeHost(h->h_pin_F);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+int sml_set_stream(sml_engine *h, void *s)
+{
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return 0;
+}
+int sml_synchronize_stream(sml_engine *h)
+{
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int sml_num_local_regions(const sml_engine *h) { return (int)h->local_ids.size(); }
+int sml_local_region_ids(const sml_engine *h, int32_t *ids)
+{
+    std::copy(h->local_ids.begin(), h->local_ids.end(), ids);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ index arithmetic */
+int sml_domaindecomposition(int numregions, int *fx, int *fy)
+{
+    Tiling t = make_tiling(numregions);
+    if (!t.ok) return -1;
+    *fx = t.fx; *fy = t.fy;
+    return 0;
+}
+int sml_getxyresextent(int R, int region, int *xs, int *xe, int *ys, int *ye, int *xc, int *yc)
+{
+    Tiling t = make_tiling(R);
+    if (!t.ok) return -1;
+    RegionGeom g = make_geom(t, region, 0);
+    *xs = g.xs; *xe = g.xe; *ys = g.ys; *ye = g.ye; *xc = t.fx; *yc = t.fy;
+    return 0;
+}
+int sml_getoverlapindices(int R, int region, int ov, int *ixs, int *ixe, int *iys, int *iye, int *ixc, int *iyc,
+                          int *pole, int *periodic)
+{
+    Tiling t = make_tiling(R);
+    if (!t.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    *ixs = g.ixs; *ixe = g.ixe; *iys = g.iys; *iye = g.iye; *ixc = g.ixc; *iyc = g.iyc;
+    *pole = g.pole; *periodic = g.periodic;
+    return 0;
+}
+int sml_get_trainingdataindices(int R, int region, int ov, int *xs, int *xe, int *ys, int *ye)
+{
+    Tiling t = make_tiling(R);
+    if (!t.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    *xs = g.tdx0 + 1; *xe = g.tdx0 + t.fx; *ys = g.tdy0 + 1; *ye = g.tdy0 + t.fy;
+    return 0;
+}
+int sml_processor_decomposition(int irank, int numprocs, int nregions, int32_t *idx, int *count)
+{
+    if (numprocs < 1 || irank < 0 || irank >= numprocs) return -1;
+    auto v = regions_of_rank(irank, numprocs, nregions);
+    std::copy(v.begin(), v.end(), idx);
+    *count = (int)v.size();
+    return 0;
+}
+int sml_region_dims(int R, int region, int ov, int m, double deg, int precip, int sst_bool, int sst_in, int ml_only,
+                    int *n, int *k, int *D, int *P, int *S, int *L)
+{
+    Tiling t = make_tiling(R);
+    if (!t.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    RegionSizes s = make_sizes(t, g, m, deg, precip, sst_bool, sst_in, ml_only);
+    *n = s.n; *k = s.k; *D = s.D; *P = s.P; *S = s.S; *L = s.L;
+    return 0;
+}
+int sml_region_maps(int R, int region, int ov, int precip, int sst_in, int32_t *input_map, int32_t *input_ms,
+                    int32_t *output_map, int32_t *output_ms, int32_t *model_map, int32_t *model_ms,
+                    int32_t *target_map)
+{
+    Tiling t = make_tiling(R);
+    if (!t.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    RegionSizes s = make_sizes(t, g, 6000, 6.0, precip, true, sst_in, false);
+    RegionMaps m = make_maps(t, g, s, precip, sst_in);
+    if (input_map) std::copy(m.input_map.begin(), m.input_map.end(), input_map);
+    if (input_ms) std::copy(m.input_ms.begin(), m.input_ms.end(), input_ms);
+    if (output_map) std::copy(m.output_map.begin(), m.output_map.end(), output_map);
+    if (output_ms) std::copy(m.output_ms.begin(), m.output_ms.end(), output_ms);
+    if (model_map) std::copy(m.model_map.begin(), m.model_map.end(), model_map);
+    if (model_ms) std::copy(m.model_ms.begin(), m.model_ms.end(), model_ms);
+    if (target_map) std::copy(m.target_map.begin(), m.target_map.end(), target_map);
+    return 0;
+}
+int sml_global_layout(int64_t off[5], int64_t *g_total, int64_t *f_total)
+{
+    off[0] = G_W4D; off[1] = G_W2D; off[2] = G_PRECIP; off[3] = G_SST; off[4] = G_TISR;
+    *g_total = G_TOTAL;
+    *f_total = F_TOTAL;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ upload */
+int sml_region_upload(sml_engine *h, const sml_region_weights *w)
+{
+    if (!h || !w) return -1;
+    if (h->finalized) FAIL(h, "upload after sml_finalize");
+    if (w->kind != SML_ATMO && w->kind != SML_OCEAN) FAIL(h, "bad kind %d", w->kind);
+    CK(h, cudaSetDevice(h->p.device));
+    auto it = h->local_index.find(w->region);
+    if (it == h->local_index.end()) FAIL(h, "region %d is not owned by rank %d", w->region, h->p.irank);
+    KindState &K = h->kinds[w->kind];
+    HostRegion &hr = K.regs[it->second];
+    if (hr.uploaded) FAIL(h, "region %d kind %d uploaded twice", w->region, w->kind);
+    const int n = w->n, k = w->k, D = w->D, P = w->P, S = w->S, L = w->L;
+    if (n <= 0 || k < 0 || D <= 0 || P <= 0 || S < 0 || L <= 0) FAIL(h, "bad dimensions for region %d", w->region);
+    if (!w->rows || !w->cols || !w->vals || !w->mean || !w->std) FAIL(h, "null weight array for region %d", w->region);
+    if ((w->win_dense != nullptr) == (w->win_compact != nullptr))
+        FAIL(h, "exactly one of win_dense / win_compact must be given (region %d)", w->region);
+    if (w->win_compact && !w->win_col) FAIL(h, "win_compact needs win_col (region %d)", w->region);
+
+    RegionGeom g = make_geom(h->tiling, w->region, h->p.overlap);
+    RegionMaps maps;
+    if (w->kind == SML_ATMO) {
+        // the vector layouts are fixed by the tiling: D, P, S, L must be what allocate_res_new derives
+        RegionSizes s = make_sizes(h->tiling, g, 6000, 6.0, h->p.precip_bool, h->p.slab_ocean_model_bool,
+                                   w->sst_bool_input, h->p.ml_only);
+        if (s.D != D || s.P != P || s.S != S || s.L != L)
+            FAIL(h, "region %d: D/P/S/L = %d/%d/%d/%d but the tiling gives %d/%d/%d/%d", w->region, D, P, S, L, s.D,
+                 s.P, s.S, s.L);
+        hr.sizes = s;
+        hr.sst_in = w->sst_bool_input && h->p.slab_ocean_model_bool;
+        maps = make_maps(h->tiling, g, s, h->p.precip_bool, hr.sst_in);
+    } else {
+        FAIL(h, "ocean reservoirs are not supported in this build");
+    }
+    const int ldw = P + (P & 1);
+    if (ldw / 2 > NCONS) FAIL(h, "chunk_size_prediction %d too large for the readout kernel", P);
+    if (K.P >= 0 && K.P != P) FAIL(h, "all reservoirs of a kind must share chunk_size_prediction");
+    K.P = P;
+    K.ldw = ldw;
+
+    // --- adjacency: COO (1-based, duplicates kept, entry order preserved per row) -> ELL, slot-major
+    std::vector<int> cnt(n, 0);
+    for (int e = 0; e < k; ++e) {
+        const int r = w->rows[e], c = w->cols[e];
+        if (r < 1 || r > n || c < 1 || c > n)  // mkl_sparse_d_create_coo would fail and mklsparse stop
+            FAIL(h, "region %d: COO entry %d (%d,%d) outside 1..%d", w->region, e, r, c, n);
+        cnt[r - 1]++;
+    }
+    int W = 1;
+    for (int r = 0; r < n; ++r) W = std::max(W, cnt[r]);
+    std::vector<int> ecol((size_t)W * n, 0);
+    std::vector<double> eval((size_t)W * n, 0.0);
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int e = 0; e < k; ++e) {
+        const int r = w->rows[e] - 1;
+        const int s = cnt[r]++;
+        ecol[(size_t)s * n + r] = w->cols[e] - 1;
+        eval[(size_t)s * n + r] = w->vals[e];
+    }
+    RegionDev &d = hr.dev;
+    d = RegionDev{};
+    d.n = n; d.D = D; d.P = P; d.S = S; d.ldw = ldw; d.ell_w = W; d.L = L; d.leak = w->leakage;
+    if (dev_upload(h, &hr, ecol.data(), ecol.size(), &d.ell_col)) return -1;
+    if (dev_upload(h, &hr, eval.data(), eval.size(), &d.ell_val)) return -1;
+
+    // --- W_in: accept the dense n x D matrix, verify the one-non-zero-per-row structure, compress
+    std::vector<double> winc(n, 0.0);
+    std::vector<int> wcol(n, 0);
+    d.win_mode = 0;
+    if (w->win_compact) {
+        for (int j = 0; j < n; ++j) {
+            if (w->win_col[j] < 0 || w->win_col[j] >= D) FAIL(h, "region %d: win_col[%d] out of range", w->region, j);
+            winc[j] = w->win_compact[j];
+            wcol[j] = w->win_col[j];
+        }
+    } else {
+        std::vector<int> nnz(n, 0);
+        for (int i = 0; i < D; ++i) {
+            const double *col = w->win_dense + (size_t)i * n;
+            for (int j = 0; j < n; ++j)
+                if (col[j] != 0.0) {
+                    nnz[j]++;
+                    winc[j] = col[j];
+                    wcol[j] = i;
+                }
+        }
+        for (int j = 0; j < n; ++j)
+            if (nnz[j] > 1) { d.win_mode = 1; break; }
+        if (d.win_mode == 1) {
+            if (dev_upload(h, &hr, w->win_dense, (size_t)n * D, &d.win_dense)) return -1;
+            K.any_dense = true;
+        }
+    }
+    if (dev_upload(h, &hr, winc.data(), winc.size(), &d.winc)) return -1;
+    if (dev_upload(h, &hr, wcol.data(), wcol.size(), &d.wcol)) return -1;
+
+    // --- W_out, padded to an even leading dimension
+    const size_t N = (size_t)n + S;
+    if (ldw == P && w->wout) {
+        if (dev_upload(h, &hr, w->wout, (size_t)P * N, &d.wout)) return -1;
+    } else {
+        std::vector<double> wp((size_t)ldw * N, 0.0);
+        if (w->wout)
+            for (size_t j = 0; j < N; ++j) std::memcpy(&wp[j * ldw], w->wout + j * P, sizeof(double) * P);
+        if (dev_upload(h, &hr, wp.data(), wp.size(), &d.wout)) return -1;
+    }
+
+    // --- mean/std (+ slot L for the SST feedback)
+    std::vector<double> mean(w->mean, w->mean + L), sd(w->std, w->std + L);
+    mean.push_back(w->sst_mean);
+    sd.push_back(w->sst_std != 0.0 ? w->sst_std : 1.0);
+    if (dev_upload(h, &hr, mean.data(), mean.size(), &d.mean)) return -1;
+    if (dev_upload(h, &hr, sd.data(), sd.size(), &d.std)) return -1;
+
+    // --- maps
+    if (dev_upload(h, &hr, maps.input_map.data(), maps.input_map.size(), &d.fb_src)) return -1;
+    if (dev_upload(h, &hr, maps.input_ms.data(), maps.input_ms.size(), &d.fb_ms)) return -1;
+    if (dev_upload(h, &hr, maps.model_map.data(), maps.model_map.size(), &d.lm_src)) return -1;
+    if (dev_upload(h, &hr, maps.model_ms.data(), maps.model_ms.size(), &d.lm_ms)) return -1;
+    if (dev_upload(h, &hr, maps.output_ms.data(), maps.output_ms.size(), &d.out_ms)) return -1;
+
+    hr.region = w->region;
+    hr.uploaded = true;
+    K.any = true;
+    return 0;
+}
+
+static int finalize_kind(sml_engine *h, int kind)
+{
+    KindState &K = h->kinds[kind];
+    if (!K.any) return 0;
+    const int nloc = (int)K.regs.size();
+    int chunk_rows = 720;
+    if (const char *s = getenv("SML_CHUNK_ROWS")) chunk_rows = std::max(64, atoi(s));
+    long long xo = 0, fo = 0, lo = 0;
+    int S_max = 0, max_rows = 0;
+    K.items.clear();
+    K.alg_bytes = 0;
+    std::vector<long long> fb_offs(nloc, 0);
+    for (int i = 0; i < nloc; ++i) {
+        HostRegion &hr = K.regs[i];
+        if (!hr.uploaded) {
+            if (kind == SML_ATMO) FAIL(h, "atmosphere reservoir of region %d was never uploaded", h->local_ids[i]);
+            hr.dev = RegionDev{};  // region without an ocean reservoir
+            continue;
+        }
+        RegionDev &d = hr.dev;
+        d.x_off = xo; d.fb_off = fo; d.lm_off = lo; d.out_off = (long long)i * K.P;
+        fb_offs[i] = fo;
+        xo += (d.n + 31) / 32 * 32;
+        fo += (d.D + 31) / 32 * 32;
+        lo += (d.S + 31) / 32 * 32;
+        S_max = std::max(S_max, d.S);
+        K.n_max = std::max(K.n_max, d.n);
+        const int nch = (d.n + chunk_rows - 1) / chunk_rows;
+        const int rows_per = (d.n + nch - 1) / nch;
+        d.item0 = (int)K.items.size();
+        for (int c = 0, r0 = 0; r0 < d.n; ++c, r0 += rows_per) {
+            StepItem it;
+            it.reg = i;
+            it.row0 = r0;
+            it.nrows = std::min(rows_per, d.n - r0);
+            it.col0 = (c == 0) ? 0 : d.S + r0;
+            it.ncols = (c == 0) ? d.S + it.nrows : it.nrows;
+            it.xs_off = (c == 0) ? d.S : 0;
+            max_rows = std::max(max_rows, it.nrows);
+            K.items.push_back(it);
+        }
+        d.nitems = (int)K.items.size() - d.item0;
+        // algorithmic bytes per region-step: ELL adjacency + x read + x write +
+        // compact W_in + feedback + W_out + local_model + outvec + mean/std
+        K.alg_bytes += (int64_t)d.ell_w * d.n * 12 + 8LL * d.n * 2 + 12LL * d.n + 8LL * d.D +
+                       8LL * d.P * ((int64_t)d.n + d.S) + 8LL * d.S + 8LL * d.P + 16LL * d.L;
+    }
+    K.x_total = xo; K.fb_total = fo; K.lm_total = lo;
+    K.nitems = (int)K.items.size();
+    K.stage_cols = std::max(1, STAGE_BYTES_TARGET / (K.ldw * 8));
+    if (const char *s = getenv("SML_STAGE_COLS")) K.stage_cols = std::max(1, atoi(s));
+    K.stage_bytes = K.stage_cols * K.ldw * 8;
+    K.xs_cap = (S_max + max_rows + 1) & ~1;
+    K.smem_bytes = (size_t)STAGES * K.stage_bytes + ((size_t)K.xs_cap + 2 * NCONS) * 8 + 2 * STAGES * 8;
+    if (K.smem_bytes > 227 * 1024) FAIL(h, "step kernel needs %zu B of shared memory", K.smem_bytes);
+    CK(h, cudaFuncSetAttribute(k_step<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.smem_bytes));
+
+    std::vector<RegionDev> regs(nloc);
+    for (int i = 0; i < nloc; ++i) regs[i] = K.regs[i].dev;
+    CK(h, cudaMalloc(&K.d_regs, sizeof(RegionDev) * nloc));
+    CK(h, cudaMemcpy(K.d_regs, regs.data(), sizeof(RegionDev) * nloc, cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&K.d_items, sizeof(StepItem) * std::max(1, K.nitems)));
+    CK(h, cudaMemcpy(K.d_items, K.items.data(), sizeof(StepItem) * K.nitems, cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&K.d_fb_offs, sizeof(long long) * nloc));
+    CK(h, cudaMemcpy(K.d_fb_offs, fb_offs.data(), sizeof(long long) * nloc, cudaMemcpyHostToDevice));
+    for (int b = 0; b < 2; ++b) {
+        CK(h, cudaMalloc(&K.d_x[b], sizeof(double) * std::max<long long>(1, xo)));
+        CK(h, cudaMemset(K.d_x[b], 0, sizeof(double) * std::max<long long>(1, xo)));
+    }
+    CK(h, cudaMalloc(&K.d_fb, sizeof(double) * std::max<long long>(1, fo)));
+    CK(h, cudaMemset(K.d_fb, 0, sizeof(double) * std::max<long long>(1, fo)));
+    CK(h, cudaMalloc(&K.d_lm, sizeof(double) * std::max<long long>(1, lo)));
+    CK(h, cudaMemset(K.d_lm, 0, sizeof(double) * std::max<long long>(1, lo)));
+    CK(h, cudaMalloc(&K.d_out, sizeof(double) * (size_t)nloc * K.P));
+    CK(h, cudaMemset(K.d_out, 0, sizeof(double) * (size_t)nloc * K.P));
+    CK(h, cudaMalloc(&K.d_partials, sizeof(double) * (size_t)std::max(1, K.nitems) * K.ldw));
+    if (K.any_dense) {
+        CK(h, cudaMalloc(&K.d_temp, sizeof(double) * std::max<long long>(1, xo)));
+        CK(h, cudaMemset(K.d_temp, 0, sizeof(double) * std::max<long long>(1, xo)));
+    }
+    return 0;
+}
+
+int sml_finalize(sml_engine *h)
+{
+    if (!h) return -1;
+    if (h->finalized) FAIL(h, "sml_finalize called twice");
+    CK(h, cudaSetDevice(h->p.device));
+    for (int k = 0; k < 2; ++k)
+        if (finalize_kind(h, k)) return -1;
+    if (!h->kinds[SML_ATMO].any) FAIL(h, "no atmosphere reservoirs uploaded");
+    const int R = h->p.number_of_regions, P = h->kinds[SML_ATMO].P;
+    h->P_atmo = P;
+    // scatter table for ALL regions of the model (every rank rebuilds the whole grid after the all-gather)
+    std::vector<int> out_dst((size_t)R * P);
+    std::vector<int> cell_region(XG * YG), cell_slot(XG * YG);
+    for (int r = 0; r < R; ++r) {
+        RegionGeom g = make_geom(h->tiling, r, h->p.overlap);
+        RegionSizes s = make_sizes(h->tiling, g, 6000, 6.0, h->p.precip_bool, h->p.slab_ocean_model_bool, false,
+                                   h->p.ml_only);
+        RegionMaps m = make_maps(h->tiling, g, s, h->p.precip_bool, false);
+        if (s.P != P) FAIL(h, "internal: P mismatch");
+        std::copy(m.output_map.begin(), m.output_map.end(), out_dst.begin() + (size_t)r * P);
+        for (int ry = 0; ry < h->tiling.fy; ++ry)
+            for (int rx = 0; rx < h->tiling.fx; ++rx) {
+                const int e = (int)off2(g.xs - 1 + rx, g.ys - 1 + ry);
+                cell_region[e] = r;
+                cell_slot[e] = rx + h->tiling.fx * ry;
+            }
+    }
+    CK(h, cudaMalloc(&h->d_out_dst, sizeof(int) * out_dst.size()));
+    CK(h, cudaMemcpy(h->d_out_dst, out_dst.data(), sizeof(int) * out_dst.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&h->d_cell_region, sizeof(int) * XG * YG));
+    CK(h, cudaMemcpy(h->d_cell_region, cell_region.data(), sizeof(int) * XG * YG, cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&h->d_cell_slot, sizeof(int) * XG * YG));
+    CK(h, cudaMemcpy(h->d_cell_slot, cell_slot.data(), sizeof(int) * XG * YG, cudaMemcpyHostToDevice));
+    std::vector<int> ocean_slab(R, -1);
+    CK(h, cudaMalloc(&h->d_region_ocean_slab, sizeof(int) * R));
+    CK(h, cudaMemcpy(h->d_region_ocean_slab, ocean_slab.data(), sizeof(int) * R, cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&h->d_G, sizeof(double) * G_TOTAL));
+    CK(h, cudaMemset(h->d_G, 0, sizeof(double) * G_TOTAL));
+    CK(h, cudaMalloc(&h->d_F, sizeof(double) * F_TOTAL));
+    CK(h, cudaMemset(h->d_F, 0, sizeof(double) * F_TOTAL));
+    CK(h, cudaMalloc(&h->d_gathered, sizeof(double) * (size_t)R * P));
+    CK(h, cudaMemset(h->d_gathered, 0, sizeof(double) * (size_t)R * P));
+    CK(h, cudaMalloc(&h->d_base_sst, sizeof(double) * XG * YG));
+    CK(h, cudaMemset(h->d_base_sst, 0, sizeof(double) * XG * YG));
+    CK(h, cudaMalloc(&h->d_mask, sizeof(double) * XG * YG));
+    CK(h, cudaMemset(h->d_mask, 0, sizeof(double) * XG * YG));
+    CK(h, cudaMalloc(&h->d_prescribed, sizeof(double) * XG * YG));
+    CK(h, cudaMemset(h->d_prescribed, 0, sizeof(double) * XG * YG));
+    CK(h, cudaMalloc(&h->d_ocean_gathered, sizeof(double) * (size_t)R * 8));
+    CK(h, cudaMemset(h->d_ocean_gathered, 0, sizeof(double) * (size_t)R * 8));
+    CK(h, cudaMallocHost(&h->h_pin_G, sizeof(double) * G_TOTAL));
+    CK(h, cudaMallocHost(&h->h_pin_F, sizeof(double) * (F_TOTAL + XG * YG)));
+    h->finalized = true;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ state access */
+static int copy_vec(sml_engine *h, int kind, int region, double *host, const double *chost, int which)
+{
+    if (check_ready(h, kind)) return -1;
+    int li;
+    if (local_of(h, kind, region, &li)) return -1;
+    KindState &K = h->kinds[kind];
+    const RegionDev &d = K.regs[li].dev;
+    double *dp = nullptr;
+    size_t cnt = 0;
+    switch (which) {
+    case 0: dp = K.d_x[K.cur] + d.x_off; cnt = d.n; break;
+    case 1: dp = K.d_fb + d.fb_off; cnt = d.D; break;
+    case 2: dp = K.d_lm + d.lm_off; cnt = d.S; break;
+    case 3: dp = K.d_out + d.out_off; cnt = d.P; break;
+    }
+    CK(h, cudaSetDevice(h->p.device));
+    if (cnt == 0) return 0;
+    if (chost) CK(h, cudaMemcpyAsync(dp, chost, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    else CK(h, cudaMemcpyAsync(host, dp, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int sml_state_set(sml_engine *h, int kind, int region, const double *x) { return copy_vec(h, kind, region, nullptr, x, 0); }
+int sml_state_get(sml_engine *h, int kind, int region, double *x) { return copy_vec(h, kind, region, x, nullptr, 0); }
+int sml_feedback_set(sml_engine *h, int kind, int region, const double *v) { return copy_vec(h, kind, region, nullptr, v, 1); }
+int sml_feedback_get(sml_engine *h, int kind, int region, double *v) { return copy_vec(h, kind, region, v, nullptr, 1); }
+int sml_local_model_set(sml_engine *h, int kind, int region, const double *v) { return copy_vec(h, kind, region, nullptr, v, 2); }
+int sml_local_model_get(sml_engine *h, int kind, int region, double *v) { return copy_vec(h, kind, region, v, nullptr, 2); }
+int sml_outvec_get(sml_engine *h, int kind, int region, double *v) { return copy_vec(h, kind, region, v, nullptr, 3); }
+
+int sml_wout_get(sml_engine *h, int kind, int region, double *wout)
+{
+    if (check_ready(h, kind)) return -1;
+    int li;
+    if (local_of(h, kind, region, &li)) return -1;
+    const RegionDev &d = h->kinds[kind].regs[li].dev;
+    CK(h, cudaMemcpy2DAsync(wout, (size_t)d.P * 8, d.wout, (size_t)d.ldw * 8, (size_t)d.P * 8, (size_t)d.n + d.S,
+                            cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int sml_wout_set(sml_engine *h, int kind, int region, const double *wout)
+{
+    if (check_ready(h, kind)) return -1;
+    int li;
+    if (local_of(h, kind, region, &li)) return -1;
+    const RegionDev &d = h->kinds[kind].regs[li].dev;
+    CK(h, cudaMemcpy2DAsync(const_cast<double *>(d.wout), (size_t)d.ldw * 8, wout, (size_t)d.P * 8, (size_t)d.P * 8,
+                            (size_t)d.n + d.S, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------ step launches */
+static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int nitems, const double *u_pool,
+                       const long long *u_offs, int u_t, int do_readout)
+{
+    if (nitems == 0) return 0;
+    if (K.any_dense) {
+        dim3 grid((K.n_max + 255) / 256, (unsigned)K.regs.size());
+        k_win_dense<<<grid, 256, 0, h->stream>>>(K.d_regs, u_pool, u_offs, u_t, K.d_temp);
+        h->launches++;
+    }
+    const size_t smem = do_readout ? K.smem_bytes : 0;
+    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool,
+                                                          u_offs, u_t, K.d_lm, K.d_temp, K.d_partials, K.ldw,
+                                                          K.stage_cols, K.stage_bytes, K.xs_cap, do_readout);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int sml_predict(sml_engine *h, int kind)
+{
+    if (check_ready(h, kind)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[kind];
+    cudaEvent_t *ev = nullptr;
+    if (h->profile && h->ev_used < PROFILE_RING) {
+        while ((int)h->ev.size() < 3 * (h->ev_used + 1)) {
+            cudaEvent_t e;
+            CK(h, cudaEventCreate(&e));
+            h->ev.push_back(e);
+        }
+        ev = &h->ev[3 * h->ev_used++];
+    }
+    if (ev) CK(h, cudaEventRecord(ev[0], h->stream));
+    if (launch_step(h, K, K.d_items, K.nitems, K.d_fb, K.d_fb_offs, 0, 1)) return -1;
+    K.cur ^= 1;
+    if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
+    k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
+    return 0;
+}
+
+int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, int ld, int length,
+                    const int64_t *offsets)
+{
+    if (check_ready(h, kind)) return -1;
+    if (length <= 0) return 0;
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[kind];
+    const int nloc = (int)K.regs.size();
+    std::vector<long long> offs(nloc, 0);
+    size_t total = 0;
+    int first = 0, last = nloc;
+    if (region != SML_ALL_REGIONS) {
+        int li;
+        if (local_of(h, kind, region, &li)) return -1;
+        first = li;
+        last = li + 1;
+        if (ld < K.regs[li].dev.D) FAIL(h, "synchronize: ld %d < reservoir_numinputs %d", ld, K.regs[li].dev.D);
+    } else if (!offsets) {
+        FAIL(h, "synchronize(ALL) needs the per-region offsets");
+    }
+    for (int i = first; i < last; ++i) {
+        if (!K.regs[i].uploaded) continue;
+        offs[i] = (long long)total;
+        total += (size_t)K.regs[i].dev.D * length;
+    }
+    if (total > K.d_in_cap) {
+        cudaFree(K.d_in);
+        K.d_in = nullptr;
+        CK(h, cudaMalloc(&K.d_in, total * 8));
+        K.d_in_cap = total;
+    }
+    if (!K.d_in_offs) CK(h, cudaMalloc(&K.d_in_offs, sizeof(long long) * nloc));
+    for (int i = first; i < last; ++i) {
+        if (!K.regs[i].uploaded) continue;
+        const int D = K.regs[i].dev.D;
+        if (region != SML_ALL_REGIONS)
+            CK(h, cudaMemcpy2DAsync(K.d_in + offs[i], (size_t)D * 8, inputs, (size_t)ld * 8, (size_t)D * 8, length,
+                                    cudaMemcpyHostToDevice, h->stream));
+        else
+            CK(h, cudaMemcpyAsync(K.d_in + offs[i], inputs + offsets[i], (size_t)D * length * 8,
+                                  cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(h, cudaMemcpyAsync(K.d_in_offs, offs.data(), sizeof(long long) * nloc, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const StepItem *items = K.d_items;
+    int nitems = K.nitems;
+    if (region != SML_ALL_REGIONS) {
+        items = K.d_items + K.regs[first].dev.item0;
+        nitems = K.regs[first].dev.nitems;
+    }
+    for (int t = 0; t < length; ++t) {
+        if (region != SML_ALL_REGIONS) {
+            // the untouched regions keep their state: copy theirs forward is avoided by updating only
+            // this region's slice of the ping-pong pair
+            if (launch_step(h, K, items, nitems, K.d_in, K.d_in_offs, t, 0)) return -1;
+            const RegionDev &d = K.regs[first].dev;
+            CK(h, cudaMemcpyAsync(K.d_x[K.cur] + d.x_off, K.d_x[K.cur ^ 1] + d.x_off, (size_t)d.n * 8,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            if (launch_step(h, K, items, nitems, K.d_in, K.d_in_offs, t, 0)) return -1;
+            K.cur ^= 1;
+        }
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------ exchange */
+int sml_set_sst_static(sml_engine *h, const double *base, const double *mask)
+{
+    if (!h || !h->finalized) return -1;
+    CK(h, cudaMemcpy(h->d_base_sst, base, sizeof(double) * XG * YG, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->d_mask, mask, sizeof(double) * XG * YG, cudaMemcpyHostToDevice));
+    h->sst_static_set = true;
+    return 0;
+}
+int sml_set_sst_prescribed(sml_engine *h, const double *sst)
+{
+    if (!h || !h->finalized) return -1;
+    CK(h, cudaMemcpy(h->d_prescribed, sst, sizeof(double) * XG * YG, cudaMemcpyHostToDevice));
+    h->sst_prescribed_set = true;
+    return 0;
+}
+
+int sml_exchange_buffers(sml_engine *h, void **slab, int64_t *slab_count, void **gathered, int64_t *gathered_count,
+                         void **gbuf, int64_t *g_count, void **fbuf, int64_t *f_count)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    KindState &K = h->kinds[SML_ATMO];
+    *slab = K.d_out;
+    *slab_count = (int64_t)K.regs.size() * K.P;
+    *gathered = h->d_gathered;
+    *gathered_count = (int64_t)h->p.number_of_regions * K.P;
+    *gbuf = h->d_G;
+    *g_count = G_TOTAL;
+    *fbuf = h->d_F;
+    *f_count = F_TOTAL;
+    return 0;
+}
+
+int sml_step_pack_device(sml_engine *h, int timestep)
+{
+    (void)timestep;
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[SML_ATMO];
+    const int total = h->p.number_of_regions * K.P;
+    const double *gathered = (h->p.numprocs == 1) ? K.d_out : h->d_gathered;
+    k_scatter_grid<<<(total + 255) / 256, 256, 0, h->stream>>>(gathered, h->d_out_dst, total, h->d_G, G_PRECIP,
+                                                                G_SST, G_W2D);
+    h->launches++;
+    if (h->p.slab_ocean_model_bool) {
+        if (!h->sst_static_set) FAIL(h, "sml_set_sst_static (base_sst_grid, sea_mask) has not been called");
+        const int mode = h->p.sst_prescribed ? 1 : 0;
+        if (mode == 1 && !h->sst_prescribed_set) FAIL(h, "sst_prescribed is on but sml_set_sst_prescribed was never called");
+        k_sst_grid<<<(XG * YG + 255) / 256, 256, 0, h->stream>>>(h->d_G + G_SST, h->d_base_sst, h->d_mask,
+                                                                 h->d_prescribed, h->d_cell_region, h->d_cell_slot,
+                                                                 h->d_region_ocean_slab, h->d_ocean_gathered, 8, mode);
+        h->launches++;
+    }
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int sml_step_exchange_begin(sml_engine *h, int timestep, double *w4d, double *w2d, double *wprecip, double *wsst)
+{
+    if (sml_step_pack_device(h, timestep)) return -1;
+    if (w4d || w2d || wprecip || wsst) {
+        CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (w4d) std::memcpy(w4d, h->h_pin_G + G_W4D, sizeof(double) * G_W2D);
+        if (w2d) std::memcpy(w2d, h->h_pin_G + G_W2D, sizeof(double) * XG * YG);
+        if (wprecip) std::memcpy(wprecip, h->h_pin_G + G_PRECIP, sizeof(double) * XG * YG);
+        if (wsst) std::memcpy(wsst, h->h_pin_G + G_SST, sizeof(double) * XG * YG);
+    }
+    return 0;
+}
+
+int sml_step_unpack_device(sml_engine *h, int timestep)
+{
+    (void)timestep;
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[SML_ATMO];
+    k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
+                                                                   h->p.ml_only ? 0 : 1);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const double *f2d, const double *tisr)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    if (!tisr) FAIL(h, "tisr_grid is required");
+    if (!h->p.ml_only) {
+        if (!f4d || !f2d) FAIL(h, "hybrid mode needs forecast_4d and forecast_2d");
+        std::memcpy(h->h_pin_F + F_F4D, f4d, sizeof(double) * G_W2D);
+        std::memcpy(h->h_pin_F + F_F2D, f2d, sizeof(double) * XG * YG);
+        CK(h, cudaMemcpyAsync(h->d_F, h->h_pin_F, sizeof(double) * F_TOTAL, cudaMemcpyHostToDevice, h->stream));
+    }
+    std::memcpy(h->h_pin_F + F_TOTAL, tisr, sizeof(double) * XG * YG);
+    CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_F + F_TOTAL, sizeof(double) * XG * YG, cudaMemcpyHostToDevice,
+                          h->stream));
+    if (sml_step_unpack_device(h, timestep)) return -1;
+    CK(h, cudaStreamSynchronize(h->stream));  // pinned staging is reused by the next call
+    return 0;
+}
+
+/* ------------------------------------------------------------------ measurement */
+int sml_profile(sml_engine *h, int on)
+{
+    if (!h) return -1;
+    h->profile = on != 0;
+    h->ev_used = 0;
+    return 0;
+}
+int sml_kernel_times(sml_engine *h, double *step_ms_sum, double *finish_ms_sum, int *count)
+{
+    if (!h) return -1;
+    *step_ms_sum = 0.0;
+    *finish_ms_sum = 0.0;
+    *count = h->ev_used;
+    if (h->ev_used == 0) return 0;
+    CK(h, cudaEventSynchronize(h->ev[3 * (h->ev_used - 1) + 2]));
+    for (int i = 0; i < h->ev_used; ++i) {
+        float a = 0.f, b = 0.f;
+        CK(h, cudaEventElapsedTime(&a, h->ev[3 * i], h->ev[3 * i + 1]));
+        CK(h, cudaEventElapsedTime(&b, h->ev[3 * i + 1], h->ev[3 * i + 2]));
+        *step_ms_sum += a;
+        *finish_ms_sum += b;
+    }
+    h->ev_used = 0;
+    return 0;
+}
+int64_t sml_kernel_launch_count(const sml_engine *h) { return h ? h->launches : 0; }
+int64_t sml_predict_algorithmic_bytes(const sml_engine *h, int kind)
+{
+    if (!h || kind < 0 || kind > 1) return 0;
+    return h->kinds[kind].alg_bytes;
+}
+
+}  // extern "C"
+
+#include "train_api.inl"

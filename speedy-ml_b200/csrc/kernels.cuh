@@ -1,0 +1,353 @@
+// kernels.cuh -- sm_100a kernels of the forecast hot path.
+//
+//  k_step            fused state update (ELL SpMV + compact W_in + tanh + leak + even-square) and
+//                    W_out readout partials; W_out tiles arrive by TMA bulk copies (cp.async.bulk,
+//                    mbarrier complete_tx) through a multi-stage shared-memory ring.
+//  k_win_dense       fallback W_in*u for regions whose W_in is not one-non-zero-per-row.
+//  k_readout_finish  fixed-order reduction of the partials + un-standardise -> outvec slab.
+//  k_scatter_grid    outvec slabs of all regions -> global grids, with the exchange clamps.
+//  k_sst_grid        wholegrid_sst assembly (ocean tiles / 272 K / land mask / floor).
+//  k_build_inputs    global grids -> every region's feedback and local_model (gather + standardise).
+//
+// Reference statements each kernel reproduces are cited at the kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sml {
+
+struct RegionDev {
+    int n, D, P, S;
+    int ldw;        // leading dimension of the device W_out copy: P rounded up to even
+    int ell_w;      // ELL width (max entries per row; every row padded with (col 0, val 0.0))
+    int win_mode;   // 0: compact one-per-row W_in, 1: dense fallback (temp pool)
+    int item0, nitems;
+    int L;          // mean/std length; slot L holds the SST feedback mean/std
+    double leak;
+    const int *ell_col;      // [ell_w][n] slot-major, 0-based
+    const double *ell_val;   // [ell_w][n]
+    const double *winc;      // [n]
+    const int *wcol;         // [n]
+    const double *win_dense; // [n*D] or null
+    const double *wout;      // [ldw*(S+n)]
+    const double *mean;      // [L+1]
+    const double *std;       // [L+1]
+    long long x_off, fb_off, lm_off, out_off;
+    const int *fb_src, *fb_ms;   // [D]
+    const int *lm_src, *lm_ms;   // [S]
+    const int *out_ms;           // [P]
+};
+
+struct StepItem {
+    int reg;     // local region index
+    int row0;    // first state row of the chunk
+    int nrows;
+    int col0;    // first W_out column (0 for the chunk that also carries the S model columns)
+    int ncols;
+    int xs_off;  // where the chunk's x~ starts in the feature tile (S for the first chunk, else 0)
+};
+
+constexpr int NCONS = 544;            // consumer threads (17 warps); 2*NCONS = 1088 = 8 * 136
+constexpr int NTHREADS = NCONS + 32;  // + one TMA producer warp
+constexpr int NCONS_WARPS = NCONS / 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// state update of one row:  y = A x (ELL, entries in COO order so duplicates sum in entry order),
+// temp = W_in u (one product), x <- (1-leak) x + leak tanh(y + temp)
+// src/mod_reservoir.f90:1444-1448 (predict), :1373-1377 (synchronize)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double update_row(const RegionDev &R, int row, const double *__restrict__ xo,
+                                             const double *__restrict__ u, const double *__restrict__ temp_pool)
+{
+    const int n = R.n;
+    const int *__restrict__ ec = R.ell_col + row;
+    const double *__restrict__ ev = R.ell_val + row;
+    double acc = 0.0;
+    int s = 0;
+    const int W = R.ell_w;
+    for (; s + 6 <= W; s += 6) {
+        int c[6];
+        double v[6], xv[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            c[i] = __ldg(ec + (size_t)(s + i) * n);
+            v[i] = __ldg(ev + (size_t)(s + i) * n);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xv[i] = xo[c[i]];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc = fma(v[i], xv[i], acc);
+    }
+    for (; s < W; ++s) {
+        const int c = __ldg(ec + (size_t)s * n);
+        const double v = __ldg(ev + (size_t)s * n);
+        acc = fma(v, xo[c], acc);
+    }
+    double t;
+    if (R.win_mode == 0) t = __dmul_rn(__ldg(R.winc + row), u[__ldg(R.wcol + row)]);
+    else t = temp_pool[R.x_off + row];
+    const double xt = tanh(__dadd_rn(acc, t));
+    return __dadd_rn(__dmul_rn(1.0 - R.leak, xo[row]), __dmul_rn(R.leak, xt));
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_step: one CTA per (region, row chunk).
+//   warps 0..16 : state update of the chunk's rows -> x_new (global) and x~ (shared), then consume
+//                 W_out column tiles from the shared-memory ring: thread (rp, cs) owns rows 2rp,2rp+1
+//                 and columns cs, cs+cpi, ... of every tile.
+//   warp 17     : lane 0 streams W_out[:, col0 : col0+ncols] with TMA bulk copies, STAGES deep.
+// do_readout == 0 gives the update-only step used by synchronize.
+// Readout statement: outvec = matmul(wout, [local_model ; x~])   src/mod_reservoir.f90:1450-1456
+// ---------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, const double *__restrict__ x_old,
+       double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
+       const double *__restrict__ lm_pool, const double *__restrict__ temp_pool, double *__restrict__ partials,
+       int ldw_max, int stage_cols, int stage_bytes, int xs_cap, int do_readout)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *xs = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * stage_bytes);
+    double *red = xs + xs_cap;
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * NCONS);
+    uint64_t *empty = full + STAGES;
+
+    const StepItem it = items[blockIdx.x];
+    const RegionDev R = regs[it.reg];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ldw = R.ldw;
+    const int nst = do_readout ? (it.ncols + stage_cols - 1) / stage_cols : 0;
+
+    if (do_readout) {
+        if (tid == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], NCONS_WARPS);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncthreads();
+    }
+
+    if (warp == NCONS_WARPS) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            const double *src = R.wout + (size_t)it.col0 * ldw;
+            for (int k = 0; k < nst; ++k) {
+                const int s = k % STAGES;
+                const uint32_t par = ((k / STAGES) & 1) ^ 1;
+                mbar_wait(&empty[s], par);  // passes at once on the first lap
+                const int nc = min(stage_cols, it.ncols - k * stage_cols);
+                const uint32_t bytes = (uint32_t)nc * ldw * 8u;
+                mbar_expect_tx(&full[s], bytes);
+                tma_load_1d(smem_raw + (size_t)s * stage_bytes, src + (size_t)k * stage_cols * ldw, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: state update of this chunk ----------------
+    const double *xo = x_old + R.x_off;
+    double *xn = x_new + R.x_off;
+    const double *u = u_pool + u_offs[it.reg] + (long long)u_t * R.D;
+    if (do_readout && it.xs_off > 0) {
+        const double *lm = lm_pool + R.lm_off;
+        for (int i = tid; i < it.xs_off; i += NCONS) xs[i] = lm[i];
+    }
+    for (int j = tid; j < it.nrows; j += NCONS) {
+        const int row = it.row0 + j;
+        const double xv = update_row(R, row, xo, u, temp_pool);
+        xn[row] = xv;
+        if (do_readout) xs[it.xs_off + j] = (row & 1) ? __dmul_rn(xv, xv) : xv;  // even 1-based index squared
+    }
+    if (!do_readout) return;
+    consumer_bar();
+
+    // ---------------- consumers: W_out tiles ----------------
+    const int HP = ldw >> 1;            // row pairs
+    const int cpi = NCONS / HP;         // columns processed per sweep of the consumer threads
+    const bool active = tid < cpi * HP;
+    const int rp = tid % HP, cs = tid / HP;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    for (int k = 0; k < nst; ++k) {
+        const int s = k % STAGES;
+        mbar_wait(&full[s], (k / STAGES) & 1);
+        const int nc = min(stage_cols, it.ncols - k * stage_cols);
+        const double *sb = reinterpret_cast<const double *>(smem_raw + (size_t)s * stage_bytes) + 2 * rp;
+        const double *xk = xs + k * stage_cols;
+        if (active) {
+            int c = cs;
+            for (; c + cpi < nc; c += 2 * cpi) {
+                const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldw);
+                const double2 w1 = *reinterpret_cast<const double2 *>(sb + (size_t)(c + cpi) * ldw);
+                const double x0 = xk[c], x1 = xk[c + cpi];
+                a0 = fma(w0.x, x0, a0);
+                a1 = fma(w0.y, x0, a1);
+                b0 = fma(w1.x, x1, b0);
+                b1 = fma(w1.y, x1, b1);
+            }
+            if (c < nc) {
+                const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldw);
+                const double x0 = xk[c];
+                a0 = fma(w0.x, x0, a0);
+                a1 = fma(w0.y, x0, a1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    if (active) {
+        red[cs * ldw + 2 * rp] = a0 + b0;
+        red[cs * ldw + 2 * rp + 1] = a1 + b1;
+    }
+    consumer_bar();
+    for (int p = tid; p < ldw; p += NCONS) {
+        double sum = 0.0;
+        for (int g = 0; g < cpi; ++g) sum += red[g * ldw + p];
+        partials[(size_t)blockIdx.x * ldw_max + p] = sum;
+    }
+}
+
+// dense W_in fallback: temp = matmul(win, u) for regions with win_mode == 1 (src/mod_reservoir.f90:1445).
+// grid: (ceil(n_max/256), nregions)
+__global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__restrict__ u_pool,
+                            const long long *__restrict__ u_offs, int u_t, double *__restrict__ temp_pool)
+{
+    const RegionDev R = regs[blockIdx.y];
+    if (R.win_mode != 1) return;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R.n) return;
+    const double *u = u_pool + u_offs[blockIdx.y] + (long long)u_t * R.D;
+    double acc = 0.0;
+    for (int i = 0; i < R.D; ++i) acc = fma(R.win_dense[(size_t)i * R.n + row], u[i], acc);
+    temp_pool[R.x_off + row] = acc;
+}
+
+// partials of a region summed in item order, then unstandardize_state_vec_res (src/res_domain.f90:1424-1475):
+// v*std then +mean, two roundings (src/mod_utilities.f90:799-829).  One block per region.
+__global__ void k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ partials, int ldw_max,
+                                 double *__restrict__ out_pool, int unstandardize)
+{
+    const RegionDev R = regs[blockIdx.x];
+    for (int p = threadIdx.x; p < R.P; p += blockDim.x) {
+        double v = 0.0;
+        for (int c = 0; c < R.nitems; ++c) v += partials[(size_t)(R.item0 + c) * ldw_max + p];
+        if (unstandardize) {
+            const int ms = R.out_ms[p];
+            if (ms >= 0) v = __dadd_rn(__dmul_rn(v, R.std[ms]), R.mean[ms]);
+        }
+        out_pool[R.out_off + p] = v;
+    }
+}
+
+// tile_full_grid_with_local_state_vec_res1d for every region of the model (src/res_domain.f90:791-826) +
+// the root's clamps: q < 1e-6 -> 1e-6 (src/mpires.f90:460-462), precip < 1e-5 -> 0 (:486-490).
+__global__ void k_scatter_grid(const double *__restrict__ gathered, const int *__restrict__ out_dst, int total,
+                               double *__restrict__ G, long long precip_lo, long long precip_hi, long long w4d_hi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int dst = out_dst[i];
+    double v = gathered[i];
+    if (dst < w4d_hi) {
+        if ((dst & 3) == 3 && v < 0.000001) v = 0.000001;
+    } else if (dst >= precip_lo && dst < precip_hi) {
+        if (v < 0.00001) v = 0.0;
+    }
+    G[dst] = v;
+}
+
+// wholegrid_sst (src/mpires.f90:288-290, 315-328, 470-484).  mode 0: reference -- base grid, ocean tiles
+// (first fx*fy outputs of each ocean reservoir) or 272.0 for regions without one; mode 1: prescribed field.
+__global__ void k_sst_grid(double *__restrict__ sst, const double *__restrict__ base, const double *__restrict__ mask,
+                           const double *__restrict__ prescribed, const int *__restrict__ cell_region,
+                           const int *__restrict__ cell_slot, const int *__restrict__ region_ocean_slab,
+                           const double *__restrict__ ocean_gathered, int ocean_P, int mode)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 96 * 48) return;
+    double v;
+    if (mode == 1) {
+        v = prescribed[e];
+    } else {
+        const int r = cell_region[e];
+        const int slab = region_ocean_slab[r];
+        v = (slab >= 0) ? ocean_gathered[(size_t)slab * ocean_P + cell_slot[e]] : 272.0;
+    }
+    if (mask[e] > 0.0) v = base[e];
+    if (v < 272.0) v = 272.0;
+    sst[e] = v;
+}
+
+// feedback / local_model from the global buffers (src/mpires.f90:581-604, 749-775):
+// gather by precomputed maps, then (x - mean) / std with the slot's constants (two roundings,
+// src/mod_utilities.f90:1307-1329).  grid: (nregions), threads stride over D then S.
+__global__ void k_build_inputs(const RegionDev *__restrict__ regs, const double *__restrict__ G,
+                               const double *__restrict__ F, double *__restrict__ fb_pool,
+                               double *__restrict__ lm_pool, int do_model)
+{
+    const RegionDev R = regs[blockIdx.x];
+    for (int d = threadIdx.x; d < R.D; d += blockDim.x) {
+        double v = G[R.fb_src[d]];
+        const int ms = R.fb_ms[d];
+        if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
+        fb_pool[R.fb_off + d] = v;
+    }
+    if (do_model)
+        for (int s = threadIdx.x; s < R.S; s += blockDim.x) {
+            double v = F[R.lm_src[s]];
+            const int ms = R.lm_ms[s];
+            if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
+            lm_pool[R.lm_off + s] = v;
+        }
+}
+
+}  // namespace sml

@@ -1,0 +1,483 @@
+"""Host-side mirror of the reference call surface over the C ABI (include/speedyml_engine.h).
+
+Method names follow the reference procedures they stand for (mod_reservoir.f90 / mpires.f90 /
+mod_linalg.f90 / res_domain.f90); arguments keep their meaning.  Everything that computes goes
+through libspeedyml_b200.so -- there is no NumPy/torch fallback here: if the library cannot be
+loaded or no CUDA device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+ATMO, OCEAN, ALL_REGIONS = 0, 1, -1
+XGRID, YGRID, ZGRID = 96, 48, 8
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+class SmlParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "number_of_regions", "overlap", "precip_bool", "slab_ocean_model_bool", "ml_only", "irank", "numprocs",
+        "device", "timestep", "timestep_slab", "sst_prescribed")] + [("reserved", C.c_int32 * 5)]
+
+
+class SmlRegionWeights(C.Structure):
+    _fields_ = [("region", C.c_int32), ("kind", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("D", C.c_int32),
+                ("P", C.c_int32), ("S", C.c_int32), ("L", C.c_int32), ("sst_bool_input", C.c_int32),
+                ("reserved0", C.c_int32), ("leakage", C.c_double), ("sst_mean", C.c_double), ("sst_std", C.c_double),
+                ("rows", _ip), ("cols", _ip), ("vals", _dp), ("win_dense", _dp), ("win_compact", _dp),
+                ("win_col", _ip), ("wout", _dp), ("mean", _dp), ("std", _dp)]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+_SIGNATURES = {
+    "sml_create": ([C.POINTER(C.c_void_p), C.POINTER(SmlParams)], C.c_int),
+    "sml_destroy": ([C.c_void_p], C.c_int),
+    "sml_last_error": ([C.c_void_p], C.c_char_p),
+    "sml_set_stream": ([C.c_void_p, C.c_void_p], C.c_int),
+    "sml_synchronize_stream": ([C.c_void_p], C.c_int),
+    "sml_num_local_regions": ([C.c_void_p], C.c_int),
+    "sml_local_region_ids": ([C.c_void_p, _ip], C.c_int),
+    "sml_domaindecomposition": ([C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    "sml_getxyresextent": ([C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 6, C.c_int),
+    "sml_getoverlapindices": ([C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 8, C.c_int),
+    "sml_get_trainingdataindices": ([C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4, C.c_int),
+    "sml_processor_decomposition": ([C.c_int, C.c_int, C.c_int, _ip, C.POINTER(C.c_int)], C.c_int),
+    "sml_region_dims": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+                        + [C.POINTER(C.c_int)] * 6, C.c_int),
+    "sml_region_maps": ([C.c_int] * 5 + [_ip] * 7, C.c_int),
+    "sml_global_layout": ([_lp, _lp, _lp], C.c_int),
+    "sml_region_upload": ([C.c_void_p, C.POINTER(SmlRegionWeights)], C.c_int),
+    "sml_finalize": ([C.c_void_p], C.c_int),
+    "sml_state_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_state_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_feedback_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_feedback_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_local_model_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_local_model_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_outvec_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_wout_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_wout_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_synchronize": ([C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _lp], C.c_int),
+    "sml_predict": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_step_exchange_begin": ([C.c_void_p, C.c_int, _dp, _dp, _dp, _dp], C.c_int),
+    "sml_step_exchange_end": ([C.c_void_p, C.c_int, _dp, _dp, _dp], C.c_int),
+    "sml_set_sst_static": ([C.c_void_p, _dp, _dp], C.c_int),
+    "sml_set_sst_prescribed": ([C.c_void_p, _dp], C.c_int),
+    "sml_exchange_buffers": ([C.c_void_p] + [C.POINTER(C.c_void_p), _lp] * 4, C.c_int),
+    "sml_step_pack_device": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_step_unpack_device": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_train_begin": ([C.c_void_p, C.c_int, _ip, C.c_int, C.c_int], C.c_int),
+    "sml_train_feed": ([C.c_void_p, _dp, _lp, _dp, _lp, C.c_int, C.c_int], C.c_int),
+    "sml_train_solve": ([C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, _ip], C.c_int),
+    "sml_train_gram_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
+    "sml_train_end": ([C.c_void_p], C.c_int),
+    "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
+    "sml_profile": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_kernel_times": ([C.c_void_p, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
+    "sml_kernel_launch_count": ([C.c_void_p], C.c_int64),
+    "sml_predict_algorithmic_bytes": ([C.c_void_p, C.c_int], C.c_int64),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library(path: str | None = None):
+    """dlopen the C-ABI library (building it in-tree first if the sources are newer)."""
+    global _LIB
+    if _LIB is None:
+        path = path or _build.build()
+        if not os.path.exists(path):
+            raise EngineError(f"{path} is missing: build it with python speedy-ml_b200/build.py")
+        lib = C.CDLL(path)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library ever diverge
+            fn.argtypes, fn.restype = argtypes, restype
+        _LIB = lib
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _farr(a, shape=None):
+    a = np.asfortranarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class DeviceArray:
+    """zero-copy view of an engine-owned device buffer (__cuda_array_interface__), so the host can run
+    torch.distributed collectives on it: torch.as_tensor(DeviceArray, device='cuda')."""
+
+    def __init__(self, ptr: int, count: int, owner):
+        self.ptr, self.count, self._owner = ptr, count, owner
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2,
+                                         "strides": None}
+
+
+# ------------------------------------------------------------------------------------------ index arithmetic
+def domaindecomposition(numregions):
+    """res_domain.f90:258-280"""
+    fx, fy = C.c_int(), C.c_int()
+    if load_library().sml_domaindecomposition(numregions, C.byref(fx), C.byref(fy)):
+        raise ValueError(f"{numregions} regions do not tile the grid")
+    return fx.value, fy.value
+
+
+def getxyresextent(num_regions, region):
+    """res_domain.f90:123-141 -> (xstart, xend, ystart, yend, xchunk, ychunk), 1-based"""
+    v = [C.c_int() for _ in range(6)]
+    if load_library().sml_getxyresextent(num_regions, region, *[C.byref(a) for a in v]):
+        raise ValueError("unsupported region count")
+    return tuple(a.value for a in v)
+
+
+def getoverlapindices(num_regions, region, overlap):
+    """res_domain.f90:155-204"""
+    v = [C.c_int() for _ in range(8)]
+    if load_library().sml_getoverlapindices(num_regions, region, overlap, *[C.byref(a) for a in v]):
+        raise ValueError("unsupported region count")
+    t = tuple(a.value for a in v)
+    return t[:6] + (bool(t[6]), bool(t[7]))
+
+
+def get_trainingdataindices(num_regions, region, overlap):
+    """res_domain.f90:547-574"""
+    v = [C.c_int() for _ in range(4)]
+    if load_library().sml_get_trainingdataindices(num_regions, region, overlap, *[C.byref(a) for a in v]):
+        raise ValueError("unsupported region count")
+    return tuple(a.value for a in v)
+
+
+def processor_decomposition(irank, numprocs, number_of_regions):
+    """res_domain.f90:31-62"""
+    buf = np.zeros(number_of_regions // numprocs + 2, dtype=np.int32)
+    cnt = C.c_int()
+    if load_library().sml_processor_decomposition(irank, numprocs, number_of_regions, _i(buf), C.byref(cnt)):
+        raise ValueError("bad rank")
+    return buf[:cnt.value].tolist()
+
+
+def region_dims(num_regions, region, overlap=1, m=6000, deg=6.0, precip_bool=True, sst_bool=True,
+                sst_bool_input=True, ml_only=False):
+    """allocate_res_new sizes -> dict(n, k, D, P, S, L)"""
+    v = [C.c_int() for _ in range(6)]
+    if load_library().sml_region_dims(num_regions, region, overlap, m, float(deg), int(precip_bool), int(sst_bool),
+                                      int(sst_bool_input), int(ml_only), *[C.byref(a) for a in v]):
+        raise ValueError("unsupported region count")
+    return dict(zip(("n", "k", "D", "P", "S", "L"), (a.value for a in v)))
+
+
+def region_maps(num_regions, region, overlap=1, precip_bool=True, sst_bool_input=True):
+    """flattened 0-based gather/scatter maps (see sml_region_maps)"""
+    d = region_dims(num_regions, region, overlap, precip_bool=precip_bool, sst_bool_input=sst_bool_input)
+    D, P, S = d["D"], d["P"], d["S"]
+    arrs = [np.zeros(D, np.int32), np.zeros(D, np.int32), np.zeros(P, np.int32), np.zeros(P, np.int32),
+            np.zeros(S, np.int32), np.zeros(S, np.int32), np.zeros(P, np.int32)]
+    if load_library().sml_region_maps(num_regions, region, overlap, int(precip_bool), int(sst_bool_input),
+                                      *[_i(a) for a in arrs]):
+        raise ValueError("unsupported region count")
+    return dict(zip(("input_map", "input_ms", "output_map", "output_ms", "model_map", "model_ms", "target_map"), arrs))
+
+
+def global_layout():
+    off = (C.c_int64 * 5)()
+    g, f = C.c_int64(), C.c_int64()
+    load_library().sml_global_layout(off, C.byref(g), C.byref(f))
+    return dict(w4d=off[0], w2d=off[1], precip=off[2], sst=off[3], tisr=off[4], g_total=g.value, f_total=f.value)
+
+
+# ------------------------------------------------------------------------------------------ engine
+class Engine:
+    """one rank's shard of the reservoir model on one B200"""
+
+    def __init__(self, number_of_regions=1152, overlap=1, precip_bool=True, slab_ocean_model_bool=True,
+                 ml_only=False, irank=0, numprocs=1, device=0, timestep=6, timestep_slab=168,
+                 sst_prescribed=False, stream=None):
+        self.lib = load_library()
+        self.p = SmlParams(number_of_regions, overlap, int(precip_bool), int(slab_ocean_model_bool), int(ml_only),
+                           irank, numprocs, device, timestep, timestep_slab, int(sst_prescribed))
+        self.h = C.c_void_p()
+        if self.lib.sml_create(C.byref(self.h), C.byref(self.p)):
+            raise EngineError(self.lib.sml_last_error(None).decode())
+        if stream is not None:
+            self.set_stream(stream)
+        n = self.lib.sml_num_local_regions(self.h)
+        ids = np.zeros(n, dtype=np.int32)
+        self.lib.sml_local_region_ids(self.h, _i(ids))
+        self.region_indices = ids.tolist()        # model_parameters%region_indices
+        self.num_of_regions_on_proc = n
+        self.dims = {}                             # (kind, region) -> dict(n, D, P, S, L)
+
+    # -- plumbing
+    def _ck(self, rc, allow_positive=False):
+        if rc < 0 or (rc > 0 and not allow_positive):
+            raise EngineError(self.lib.sml_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sml_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        """stream: int cudaStream_t or an object with .cuda_stream (torch.cuda.Stream)"""
+        ptr = getattr(stream, "cuda_stream", stream)
+        self._ck(self.lib.sml_set_stream(self.h, C.c_void_p(ptr)))
+
+    def synchronize_stream(self):
+        self._ck(self.lib.sml_synchronize_stream(self.h))
+
+    # -- mklsparse + trained_reservoir_prediction
+    def region_upload(self, region, rows, cols, vals, wout, mean, std, win=None, win_compact=None, win_col=None,
+                      kind=ATMO, leakage=1.0, sst_bool_input=True, sst_mean=None, sst_std=None, S=None, P=None, D=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        std = np.ascontiguousarray(std, dtype=np.float64)
+        keep = [rows, cols, vals, mean, std]
+        w = SmlRegionWeights()
+        if win is not None:
+            win = _farr(win)
+            n, Dw = win.shape
+            w.win_dense = _d(win)
+            keep.append(win)
+        else:
+            win_compact = np.ascontiguousarray(win_compact, dtype=np.float64)
+            win_col = np.ascontiguousarray(win_col, dtype=np.int32)
+            n, Dw = win_compact.size, D
+            w.win_compact, w.win_col = _d(win_compact), _i(win_col)
+            keep += [win_compact, win_col]
+        if wout is not None:
+            wout = _farr(wout)
+            Pw, N = wout.shape
+            w.wout = _d(wout)
+            keep.append(wout)
+            Sw = N - n
+        else:
+            Pw, Sw = P, S
+        if D is not None and Dw is None:
+            Dw = D
+        if Dw is None:
+            raise ValueError("D is needed with win_compact")
+        w.region, w.kind, w.n, w.k, w.D, w.P, w.S, w.L = region, kind, n, rows.size, Dw, Pw, Sw, mean.size
+        w.sst_bool_input = int(sst_bool_input)
+        w.leakage = float(leakage)
+        w.sst_mean = float(mean[-1] if sst_mean is None else sst_mean)
+        w.sst_std = float(std[-1] if sst_std is None else sst_std)
+        w.rows, w.cols, w.vals, w.mean, w.std = _i(rows), _i(cols), _d(vals), _d(mean), _d(std)
+        self._ck(self.lib.sml_region_upload(self.h, C.byref(w)))
+        self.dims[(kind, region)] = dict(n=n, D=Dw, P=Pw, S=Sw, L=mean.size)
+
+    def finalize(self):
+        self._ck(self.lib.sml_finalize(self.h))
+
+    # -- reservoir%current_state / feedback / local_model / outvec
+    def _get(self, fn, kind, region, size):
+        out = np.zeros(size)
+        self._ck(fn(self.h, kind, region, _d(out)))
+        return out
+
+    def state_get(self, region, kind=ATMO):
+        return self._get(self.lib.sml_state_get, kind, region, self.dims[(kind, region)]["n"])
+
+    def state_set(self, region, x, kind=ATMO):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.dims[(kind, region)]["n"]
+        self._ck(self.lib.sml_state_set(self.h, kind, region, _d(x)))
+
+    def feedback_get(self, region, kind=ATMO):
+        return self._get(self.lib.sml_feedback_get, kind, region, self.dims[(kind, region)]["D"])
+
+    def feedback_set(self, region, v, kind=ATMO):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.size == self.dims[(kind, region)]["D"]
+        self._ck(self.lib.sml_feedback_set(self.h, kind, region, _d(v)))
+
+    def local_model_get(self, region, kind=ATMO):
+        return self._get(self.lib.sml_local_model_get, kind, region, self.dims[(kind, region)]["S"])
+
+    def local_model_set(self, region, v, kind=ATMO):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.size == self.dims[(kind, region)]["S"]
+        self._ck(self.lib.sml_local_model_set(self.h, kind, region, _d(v)))
+
+    def outvec_get(self, region, kind=ATMO):
+        return self._get(self.lib.sml_outvec_get, kind, region, self.dims[(kind, region)]["P"])
+
+    def wout_get(self, region, kind=ATMO):
+        d = self.dims[(kind, region)]
+        out = np.zeros((d["P"], d["n"] + d["S"]), order="F")
+        self._ck(self.lib.sml_wout_get(self.h, kind, region, _d(out)))
+        return out
+
+    def wout_set(self, region, wout, kind=ATMO):
+        d = self.dims[(kind, region)]
+        wout = _farr(wout, (d["P"], d["n"] + d["S"]))
+        self._ck(self.lib.sml_wout_set(self.h, kind, region, _d(wout)))
+
+    # -- synchronize(reservoir, input, x, length)   mod_reservoir.f90:1354
+    def synchronize(self, region, inputs, length=None, kind=ATMO):
+        inputs = _farr(inputs)
+        length = inputs.shape[1] if length is None else length
+        self._ck(self.lib.sml_synchronize(self.h, kind, region, _d(inputs), inputs.shape[0], length, None))
+
+    def synchronize_all(self, inputs_by_region, length, kind=ATMO):
+        """inputs_by_region: list (local order) of (D_i, >=length) arrays"""
+        blocks, offs, pos = [], [], 0
+        for a in inputs_by_region:
+            a = _farr(a)[:, :length]
+            blocks.append(np.asfortranarray(a).ravel(order="F"))
+            offs.append(pos)
+            pos += blocks[-1].size
+        flat = np.concatenate(blocks)
+        offs = np.asarray(offs, dtype=np.int64)
+        self._ck(self.lib.sml_synchronize(self.h, kind, ALL_REGIONS, _d(flat), 0, length, offs.ctypes.data_as(_lp)))
+
+    # -- predict / predict_ml for every local region   mod_reservoir.f90:1418,1491
+    def predict(self, kind=ATMO):
+        self._ck(self.lib.sml_predict(self.h, kind))
+
+    # -- sendrecievegrid   mpires.f90:218
+    def set_sst_static(self, base_sst_grid, sea_mask):
+        b, m = _farr(base_sst_grid, (XGRID, YGRID)), _farr(sea_mask, (XGRID, YGRID))
+        self._ck(self.lib.sml_set_sst_static(self.h, _d(b), _d(m)))
+
+    def set_sst_prescribed(self, sst_grid):
+        s = _farr(sst_grid, (XGRID, YGRID))
+        self._ck(self.lib.sml_set_sst_prescribed(self.h, _d(s)))
+
+    def step_exchange_begin(self, timestep, copy_out=True):
+        if not copy_out:
+            self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, None, None, None, None))
+            return None
+        w4d = np.zeros((4, XGRID, YGRID, ZGRID), order="F")
+        w2d = np.zeros((XGRID, YGRID), order="F")
+        wp = np.zeros((XGRID, YGRID), order="F")
+        wsst = np.zeros((XGRID, YGRID), order="F")
+        self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, _d(w4d), _d(w2d), _d(wp), _d(wsst)))
+        return w4d, w2d, wp, wsst
+
+    def step_exchange_end(self, timestep, forecast_4d, forecast_2d, tisr_grid):
+        f4 = _farr(forecast_4d, (4, XGRID, YGRID, ZGRID)) if forecast_4d is not None else None
+        f2 = _farr(forecast_2d, (XGRID, YGRID)) if forecast_2d is not None else None
+        ti = _farr(tisr_grid, (XGRID, YGRID))
+        self._ck(self.lib.sml_step_exchange_end(self.h, timestep, _d(f4), _d(f2), _d(ti)))
+
+    def step_pack_device(self, timestep=0):
+        self._ck(self.lib.sml_step_pack_device(self.h, timestep))
+
+    def step_unpack_device(self, timestep=0):
+        self._ck(self.lib.sml_step_unpack_device(self.h, timestep))
+
+    def exchange_buffers(self):
+        """-> dict of DeviceArray: outvec_slab, gathered, G, F"""
+        ptrs = [C.c_void_p() for _ in range(4)]
+        cnts = [C.c_int64() for _ in range(4)]
+        args = []
+        for p, c in zip(ptrs, cnts):
+            args += [C.byref(p), C.byref(c)]
+        self._ck(self.lib.sml_exchange_buffers(self.h, *args))
+        names = ("outvec_slab", "gathered", "G", "F")
+        return {n: DeviceArray(p.value, c.value, self) for n, p, c in zip(names, ptrs, cnts)}
+
+    # -- training: chunking_matmul / fit_chunk_hybrid   mod_reservoir.f90:1645,1235
+    def train_begin(self, regions, batch_size, kind=ATMO):
+        regions = np.ascontiguousarray(regions, dtype=np.int32)
+        self._train_regions = regions.tolist()
+        self._train_kind = kind
+        self._ck(self.lib.sml_train_begin(self.h, kind, _i(regions), regions.size, batch_size))
+
+    def train_feed(self, trainingdata_by_region, imperfect_by_region, discard_cols):
+        tds, tdo, ims, imo, pt, pi = [], [], [], [], 0, 0
+        ncols = None
+        for r, td in zip(self._train_regions, trainingdata_by_region):
+            td = _farr(td)
+            ncols = td.shape[1] if ncols is None else ncols
+            assert td.shape == (self.dims[(self._train_kind, r)]["D"], ncols)
+            tds.append(td.ravel(order="F"))
+            tdo.append(pt)
+            pt += td.size
+        if imperfect_by_region is not None:
+            for r, im in zip(self._train_regions, imperfect_by_region):
+                im = _farr(im)
+                assert im.shape == (self.dims[(self._train_kind, r)]["S"], ncols)
+                ims.append(im.ravel(order="F"))
+                imo.append(pi)
+                pi += im.size
+        td = np.concatenate(tds)
+        tdo = np.asarray(tdo, dtype=np.int64)
+        im = np.concatenate(ims) if ims else None
+        imo = np.asarray(imo, dtype=np.int64) if ims else None
+        self._ck(self.lib.sml_train_feed(self.h, _d(td), tdo.ctypes.data_as(_lp), _d(im),
+                                         imo.ctypes.data_as(_lp) if imo is not None else None, ncols, discard_cols))
+
+    def train_solve(self, beta_res, beta_model=1.0, using_prior=True, prior_val=0.0):
+        info = np.zeros(len(self._train_regions), dtype=np.int32)
+        self._ck(self.lib.sml_train_solve(self.h, beta_res, beta_model, int(using_prior), prior_val, _i(info)))
+        return info
+
+    def train_gram_get(self, region):
+        d = self.dims[(self._train_kind, region)]
+        N = d["n"] + d["S"]
+        sxs = np.zeros((N, N), order="F")
+        sxt = np.zeros((d["P"], N), order="F")
+        self._ck(self.lib.sml_train_gram_get(self.h, region, _d(sxs), _d(sxt)))
+        return sxs, sxt
+
+    def train_end(self):
+        self._ck(self.lib.sml_train_end(self.h))
+
+    # -- mldivide(A, B)   mod_linalg.f90:109
+    def mldivide(self, A, B):
+        """returns (X, info) like dgesv; A and B are not modified"""
+        A = np.array(A, dtype=np.float64, order="F", copy=True)
+        B = np.array(B, dtype=np.float64, order="F", copy=True)
+        if A.shape[0] != B.shape[0]:
+            return B, -1  # 'Cant compute solution returning A and B unchanged' (mod_linalg.f90:134-137)
+        info = self.lib.sml_mldivide(self.h, _d(A), A.shape[0], _d(B), B.shape[0], A.shape[0], B.shape[1])
+        if info < 0:
+            raise EngineError(self.lib.sml_last_error(self.h).decode())
+        return B, info
+
+    # -- measurement
+    def profile(self, on=True):
+        self._ck(self.lib.sml_profile(self.h, int(on)))
+
+    def kernel_times(self):
+        """-> (sum of step-kernel ms, sum of finish-kernel ms, launches) since the last call"""
+        a, b, c = C.c_double(), C.c_double(), C.c_int()
+        self._ck(self.lib.sml_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def kernel_launch_count(self):
+        return int(self.lib.sml_kernel_launch_count(self.h))
+
+    def predict_algorithmic_bytes(self, kind=ATMO):
+        return int(self.lib.sml_predict_algorithmic_bytes(self.h, kind))

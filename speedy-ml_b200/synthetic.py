@@ -36,8 +36,7 @@ def make_adjacency(n: int, k: int, rng: np.random.Generator, radius: float = 0.7
     v = np.full(n, 1.0 / np.sqrt(n))
     lam = 1.0
     for _ in range(power_iters):
-        w = np.zeros(n)
-        np.add.at(w, rows - 1, vals * v[cols - 1])
+        w = np.bincount(rows - 1, weights=vals * v[cols - 1], minlength=n)
         lam = np.linalg.norm(w)
         if lam == 0.0:
             break

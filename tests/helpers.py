@@ -50,7 +50,9 @@ def region_weights(num_regions, region, m, precip_bool=True, sst_bool=True, sst_
 def c_region(w) -> "oc.Region":
     r = oc.Region(w["num_regions"], w["region"], m=w["m"], deg=w["deg"], precip_bool=w["precip_bool"],
                   sst_bool=w["sst_bool"], sst_bool_input=w["sst_bool_input"], ml_only=w["ml_only"])
-    r.set_weights(w["rows"], w["cols"], w["vals"], w["win"], w["wout"], w["mean"], w["std"])
+    r.set_weights(w["rows"], w["cols"], w["vals"], w.get("win"), w["wout"], w["mean"], w["std"])
+    if w.get("win") is None:
+        r.set_win_compact(w["winc"], w["wcol"])
     return r
 
 

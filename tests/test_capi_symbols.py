@@ -1,0 +1,48 @@
+"""The C-ABI library loads and exports every symbol include/speedyml_engine.h declares (no GPU needed)."""
+import ctypes
+import importlib
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "speedyml_engine.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sml_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported():
+    eng = importlib.import_module("speedy-ml_b200.engine")
+    build = importlib.import_module("speedy-ml_b200.build")
+    lib = ctypes.CDLL(build.build())
+    names = _declared()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    # and the Python mirror binds exactly the declared set
+    assert sorted(eng.EXPORTED_SYMBOLS) == names
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    eng = importlib.import_module("speedy-ml_b200.engine")
+    try:
+        eng.Engine(number_of_regions=1152)
+    except eng.EngineError as e:
+        assert "no CUDA device" in str(e) or "CPU fallback" in str(e)
+    else:
+        raise AssertionError("engine creation must fail without a CUDA device (no CPU fallback)")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "speedy-ml_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".inl", ".cpp", ".h", ".f90")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                for needle in ("import oracle", "from oracle", "oracle_c", "oracle_np", "speedyml_oracle", "orc_"):
+                    assert needle not in src, f"{f} uses the oracle ({needle})"

@@ -1,0 +1,325 @@
+"""CUDA engine vs the CPU oracle, through the C ABI (ctypes).  All tests here need a B200: -m gpu.
+
+Tolerances: single predict step <= 1e-13 relative (inf-norm, scaled by the vector's
+inf-norm); open/closed loop over N steps <= 1e-10; index work exact.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+from helpers import c_region, initial_grids, oc, region_weights, rel_inf, sst_input_mask, syn
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-13
+TOL_LOOP = 1e-10
+
+
+@pytest.fixture(scope="module")
+def E():
+    return importlib.import_module("speedy-ml_b200.engine")
+
+
+def upload(eng, w, dense=True, **kw):
+    if dense and w.get("win") is not None:
+        eng.region_upload(w["region"], w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"], win=w["win"],
+                          sst_bool_input=w["sst_bool_input"], **kw)
+    else:
+        eng.region_upload(w["region"], w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"],
+                          win_compact=w["winc"], win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"], **kw)
+
+
+def single_region_engine(E, w, **kw):
+    """numprocs = number_of_regions makes rank r own exactly region r"""
+    eng = E.Engine(number_of_regions=w["num_regions"], irank=w["region"], numprocs=w["num_regions"],
+                   precip_bool=w["precip_bool"], slab_ocean_model_bool=w["sst_bool"], ml_only=w["ml_only"])
+    assert eng.region_indices == [w["region"]]
+    upload(eng, w, **kw)
+    eng.finalize()
+    return eng
+
+
+REGIONS = [0, 23, 555, 556, 557, 24 * 47 + 3, 1151, 24 * 20]
+
+
+@pytest.mark.parametrize("region", REGIONS)
+@pytest.mark.parametrize("m", [600, 2000])
+def test_predict_single_step(E, region, m):
+    w = region_weights(1152, region, m=m)
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    rng = np.random.default_rng(100 + region)
+    x0 = 0.3 * rng.standard_normal(w["n"])
+    fb = rng.standard_normal(w["D"])
+    lm = rng.standard_normal(w["S"])
+    rc.x[:] = x0
+    rc.feedback[:] = fb
+    rc.local_model[:] = lm
+    eng.state_set(region, x0)
+    eng.feedback_set(region, fb)
+    eng.local_model_set(region, lm)
+    rc.predict()
+    eng.predict()
+    assert rel_inf(eng.state_get(region), rc.x) < TOL_STEP
+    assert rel_inf(eng.outvec_get(region), rc.outvec) < TOL_STEP
+    eng.close()
+
+
+def test_predict_full_size_region_open_loop(E):
+    # config 1: region 555, m=6000 (n=5760, D=576, P=136, S=132, k=33177); sync 55 then 100 open-loop steps
+    w = region_weights(1152, 555, m=6000, with_dense_win=True)
+    assert (w["n"], w["D"], w["P"], w["S"], w["k"]) == (5760, 576, 136, 132, 33177)
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    rng = np.random.default_rng(555)
+    T = 55 + 100
+    series = syn.ar1_series(w["D"], T, rng)
+    model = np.asfortranarray(rng.standard_normal((w["S"], T)))
+    rc.synchronize(series[:, :55], 55)
+    eng.synchronize(555, series[:, :55])
+    assert rel_inf(eng.state_get(555), rc.x) < TOL_LOOP
+    worst = 0.0
+    for t in range(55, T):
+        rc.feedback[:] = series[:, t]
+        rc.local_model[:] = model[:, t]
+        eng.feedback_set(555, series[:, t])
+        eng.local_model_set(555, model[:, t])
+        rc.predict()
+        eng.predict()
+        worst = max(worst, rel_inf(eng.outvec_get(555), rc.outvec))
+    assert worst < TOL_LOOP
+    assert rel_inf(eng.state_get(555), rc.x) < TOL_LOOP
+    eng.close()
+
+
+def test_synchronize_leakage_and_ld(E):
+    w = region_weights(1152, 24 * 5 + 7, m=900)
+    rc = c_region(w)
+    rc.set_leakage(0.35)
+    eng = single_region_engine(E, w, leakage=0.35)
+    rng = np.random.default_rng(3)
+    padded = np.asfortranarray(rng.standard_normal((w["D"] + 5, 9)))   # ld > D
+    rc.synchronize(np.asfortranarray(padded[:w["D"], :]), 9)
+    eng.synchronize(w["region"], padded, 9)
+    assert rel_inf(eng.state_get(w["region"]), rc.x) < TOL_STEP * 10
+    eng.close()
+
+
+def test_coo_duplicates_sum_and_wide_rows(E):
+    # duplicate (row,col) pairs must sum (COO semantics, src/mod_linalg.f90:17); rows may exceed 6 entries
+    w = region_weights(1152, 555, m=600)
+    rows, cols, vals = w["rows"].copy(), w["cols"].copy(), w["vals"].copy()
+    rows[10:20] = rows[0]
+    cols[10:20] = cols[0]
+    w["rows"], w["cols"], w["vals"] = rows, cols, vals
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    rng = np.random.default_rng(4)
+    x0 = rng.standard_normal(w["n"])
+    fb = rng.standard_normal(w["D"])
+    rc.x[:] = x0
+    rc.feedback[:] = fb
+    eng.state_set(555, x0)
+    eng.feedback_set(555, fb)
+    rc.predict()
+    eng.predict()
+    assert rel_inf(eng.state_get(555), rc.x) < TOL_STEP
+    eng.close()
+
+
+def test_dense_win_fallback(E):
+    # a W_in that is NOT one-non-zero-per-row must still be honoured (dense path)
+    w = region_weights(1152, 555, m=600)
+    rng = np.random.default_rng(6)
+    win = w["win"].copy(order="F")
+    win[::7, 3] += rng.standard_normal(win[::7, 3].shape)
+    win[5, :] = rng.standard_normal(w["D"])
+    w["win"] = win
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    x0 = rng.standard_normal(w["n"]) * 0.2
+    fb = rng.standard_normal(w["D"])
+    lm = rng.standard_normal(w["S"])
+    rc.x[:] = x0
+    rc.feedback[:] = fb
+    rc.local_model[:] = lm
+    eng.state_set(555, x0)
+    eng.feedback_set(555, fb)
+    eng.local_model_set(555, lm)
+    for _ in range(3):
+        rc.predict()
+        eng.predict()
+    assert rel_inf(eng.state_get(555), rc.x) < 1e-12
+    assert rel_inf(eng.outvec_get(555), rc.outvec) < 1e-12
+    eng.close()
+
+
+def test_dense_and_compact_upload_agree_bitwise(E):
+    w = region_weights(1152, 777, m=600)
+    outs = []
+    for dense in (True, False):
+        eng = E.Engine(number_of_regions=1152, irank=777, numprocs=1152)
+        upload(eng, w, dense=dense)
+        eng.finalize()
+        eng.feedback_set(777, np.linspace(-1, 1, w["D"]))
+        eng.local_model_set(777, np.linspace(1, -1, w["S"]))
+        eng.predict()
+        eng.predict()
+        outs.append((eng.state_get(777), eng.outvec_get(777)))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_ml_only_predict(E):
+    w = region_weights(1152, 555, m=600, ml_only=True)
+    assert w["S"] == 0
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    rng = np.random.default_rng(12)
+    fb = rng.standard_normal(w["D"])
+    rc.feedback[:] = fb
+    eng.feedback_set(555, fb)
+    for _ in range(2):
+        rc.predict()
+        eng.predict()
+    assert rel_inf(eng.outvec_get(555), rc.outvec) < TOL_STEP * 10
+    eng.close()
+
+
+def test_upload_errors_are_reported_not_fatal(E):
+    w = region_weights(1152, 555, m=600)
+    eng = E.Engine(number_of_regions=1152, irank=555, numprocs=1152)
+    with pytest.raises(E.EngineError):      # predict before finalize
+        eng.predict()
+    bad = dict(w)
+    bad["rows"] = w["rows"].copy()
+    bad["rows"][3] = w["n"] + 1              # mklsparse would stop (src/mod_linalg.f90:18-22)
+    with pytest.raises(E.EngineError):
+        upload(eng, bad)
+    other = region_weights(1152, 556, m=600)
+    with pytest.raises(E.EngineError):      # region not owned by this rank
+        upload(eng, other)
+    wrong = dict(w)
+    wrong["mean"], wrong["std"] = w["mean"][:-1], w["std"][:-1]
+    with pytest.raises(E.EngineError):      # L does not match the tiling
+        upload(eng, wrong)
+    upload(eng, w)
+    eng.finalize()
+    eng.predict()
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def small_model(E):
+    """full 1152-region tiling with minimal reservoirs (n = D): engine + oracle twins"""
+    ws = [region_weights(1152, r, m=300, with_dense_win=False) for r in range(1152)]
+    eng = E.Engine(number_of_regions=1152, sst_prescribed=True)
+    for w in ws:
+        upload(eng, w, dense=False)
+    eng.finalize()
+    rcs = [c_region(w) for w in ws]
+    return ws, eng, rcs
+
+
+def test_closed_hybrid_loop_full_tiling(E, small_model):
+    ws, eng, rcs = small_model
+    G = initial_grids()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    eng.set_sst_prescribed(G["base_sst"])
+    sst_mean = np.array([w["mean"][-1] for w in ws])
+    sst_std = np.array([w["std"][-1] for w in ws])
+    rng = np.random.default_rng(21)
+    for w, rc in zip(ws, rcs):
+        fb = rng.standard_normal(w["D"])
+        lm = rng.standard_normal(w["S"])
+        rc.feedback[:] = fb
+        rc.local_model[:] = lm
+        rc.x[:] = 0.0
+        eng.feedback_set(w["region"], fb)
+        eng.local_model_set(w["region"], lm)
+        eng.state_set(w["region"], np.zeros(w["n"]))
+    nthreads = 8
+    for step in range(1, 6):
+        oc.predict_all(rcs, nthreads=nthreads)
+        eng.predict()
+        # prescribed-SST mode: every region "has an ocean reservoir" whose output is the prescribed field
+        has = np.ones(len(rcs), dtype=np.int32)
+        oo = np.zeros((len(rcs), 4))
+        for i, w in enumerate(ws):
+            xs, xe, ys, ye, *_ = oc.getxyresextent(1152, w["region"])
+            oo[i] = G["base_sst"][xs - 1:xe, ys - 1:ye].ravel(order="F")
+        gc = oc.step_gather(rcs, True, True, G["base_sst"], G["sea_mask"], ocean_out=oo, has_ocean=has)
+        ge = eng.step_exchange_begin(step)
+        tol = TOL_STEP * 10 if step == 1 else TOL_LOOP
+        for a, b in zip(ge, gc):
+            assert rel_inf(a, b) < tol
+        assert ge[0][3].min() >= 0.000001 and ge[3].min() >= 272.0
+        f4c, f2c = oc.host_stub(gc[0], gc[1], G["clim4d"], G["clim2d"])
+        f4e, f2e = oc.host_stub(ge[0], ge[1], G["clim4d"], G["clim2d"])
+        oc.step_scatter(rcs, True, True, False, *gc, f4c, f2c, G["tisr"], sst_mean, sst_std, nthreads=nthreads)
+        eng.step_exchange_end(step, f4e, f2e, G["tisr"])
+        for r in (0, 23, 555, 556, 1151, 1128, 700):
+            assert rel_inf(eng.feedback_get(r), rcs[r].feedback) < tol
+            assert rel_inf(eng.local_model_get(r), rcs[r].local_model) < tol
+            assert rel_inf(eng.outvec_get(r), rcs[r].outvec) < tol
+
+
+def test_exchange_is_exact_given_identical_outvecs(E, small_model):
+    # scatter -> clamp -> gather -> standardise is pure index work + two roundings per element: feed the
+    # engine's own outvecs to the oracle and require BIT equality of grids, feedback and local_model.
+    ws, eng, rcs = small_model
+    G = initial_grids()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    eng.set_sst_prescribed(G["base_sst"])
+    eng.predict()
+    for w, rc in zip(ws, rcs):
+        rc.outvec[:] = eng.outvec_get(w["region"])
+    has = np.ones(len(rcs), dtype=np.int32)
+    oo = np.zeros((len(rcs), 4))
+    for i, w in enumerate(ws):
+        xs, xe, ys, ye, *_ = oc.getxyresextent(1152, w["region"])
+        oo[i] = G["base_sst"][xs - 1:xe, ys - 1:ye].ravel(order="F")
+    gc = oc.step_gather(rcs, True, True, G["base_sst"], G["sea_mask"], ocean_out=oo, has_ocean=has)
+    ge = eng.step_exchange_begin(1)
+    for a, b in zip(ge, gc):
+        assert np.array_equal(a, b)
+    f4, f2 = oc.host_stub(gc[0], gc[1], G["clim4d"], G["clim2d"])
+    sst_mean = np.array([w["mean"][-1] for w in ws])
+    sst_std = np.array([w["std"][-1] for w in ws])
+    oc.step_scatter(rcs, True, True, False, *gc, f4, f2, G["tisr"], sst_mean, sst_std, nthreads=8)
+    eng.step_exchange_end(1, f4, f2, G["tisr"])
+    for w, rc in zip(ws, rcs):
+        assert np.array_equal(eng.feedback_get(w["region"]), rc.feedback)
+        assert np.array_equal(eng.local_model_get(w["region"]), rc.local_model)
+
+
+def test_readout_properties_full_tiling(E, small_model):
+    """size-independent properties: W_out = 0 -> outvec is the mean vector; readout is linear in W_out"""
+    ws, eng, rcs = small_model
+    r = 600
+    w = ws[r]
+    saved = eng.wout_get(r)
+    assert np.array_equal(saved, w["wout"])
+    x = eng.state_get(r)
+    fb = eng.feedback_get(r)
+    lm = eng.local_model_get(r)
+
+    def run(wout):
+        eng.wout_set(r, wout)
+        eng.state_set(r, x)
+        eng.feedback_set(r, fb)
+        eng.local_model_set(r, lm)
+        eng.predict()
+        return eng.outvec_get(r)
+
+    m = E.region_maps(1152, r, 1, True, w["sst_bool_input"])
+    mean_vec = w["mean"][m["output_ms"]]
+    std_vec = w["std"][m["output_ms"]]
+    o0 = run(np.zeros_like(saved))
+    assert np.array_equal(o0, mean_vec)
+    o1 = run(saved)
+    o2 = run(2.0 * saved)
+    # (o - mean)/std is linear in W_out
+    assert rel_inf((o2 - mean_vec) / std_vec, 2.0 * (o1 - mean_vec) / std_vec) < 1e-12
+    eng.wout_set(r, saved)

@@ -111,3 +111,22 @@ def test_gather_clamps():
     assert np.all(tile[~mask] == 272.0)
     assert np.all(tile[mask] == np.maximum(G["base_sst"][xs - 1:xe, ys - 1:ye][mask], 272.0))
     assert wsst.min() >= 272.0
+
+
+def test_compact_win_is_bit_identical_to_dense():
+    # matmul(win,u)(j) == win(j,c_j)*u(c_j) exactly when every other entry of the row is zero
+    w = region_weights(1152, 555, m=1100)
+    rd = c_region(w)
+    w2 = dict(w)
+    w2["win"] = None
+    rk = c_region(w2)
+    rng = np.random.default_rng(8)
+    inputs = syn.ar1_series(w["D"], 9, rng)
+    rd.synchronize(inputs, 9)
+    rk.synchronize(inputs, 9)
+    assert np.array_equal(rd.x, rk.x)
+    for r in (rd, rk):
+        r.feedback[:] = inputs[:, 3]
+        r.local_model[:] = 0.5
+        r.predict()
+    assert np.array_equal(rd.outvec, rk.outvec)
