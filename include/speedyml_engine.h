@@ -178,6 +178,10 @@ int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using
 int sml_train_gram_get(sml_engine *h, int region, double *states_x_states_aug,
                        double *states_x_trainingdata_aug);
 int sml_train_end(sml_engine *h);
+/* measurement: useful Gram flops N(N+1)K + 2PNK accumulated by sml_train_feed and the CUDA-event time (ms) of
+ * the Gram kernels, the state generation and the solves of the current wave */
+int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms,
+                    double *solve_ms);
 
 /* mldivide (src/mod_linalg.f90:109-151): solves A X = B in place of B; A(n,n) lda, B(n,nrhs) ldb.
  * returns dgesv's info (>0: singular, B is not the solution) */

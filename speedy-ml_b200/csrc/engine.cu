@@ -210,6 +210,7 @@ int sml_destroy(sml_engine *h)
     cudaSetDevice(h->p.device);
     cudaDeviceSynchronize();
     train_release(h->train);
+    if (h->train.solver) cusolverDnDestroy(h->train.solver);
     for (int k = 0; k < 2; ++k) free_kind(h->kinds[k]);
     cudaFree(h->d_G); cudaFree(h->d_F); cudaFree(h->d_gathered); cudaFree(h->d_base_sst); cudaFree(h->d_mask);
     cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);

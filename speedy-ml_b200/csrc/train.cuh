@@ -1,14 +1,293 @@
-// train.cuh -- training-path state and kernels (Gram accumulation, ridge solve).
+// train.cuh -- training path: state generation, FP64 tensor-core (DMMA) Gram accumulation, ridge terms.
+//
+// One augmented slab per region holds, column by column (one column per kept reservoir state):
+//     rows [0, S)        imperfect-model (SPEEDY) forecast valid at the target time
+//     rows [S, S+n)      x~ : the state with even 1-based entries squared
+//     rows [N, N+P)      the target (truth at t+1, region interior rows of the input series), N = S+n
+// and ONE symmetric accumulation  Gaug += slab * slab^T  on the lower triangle gives both reference
+// accumulators at once:  states_x_states_aug = Gaug[0:N,0:N]  and  states_x_trainingdata_aug = Gaug[N:N+P,0:N]
+// (chunking_matmul, src/mod_reservoir.f90:1645-1701: R*R^T via DGEMM and target*aug^T via matmul).
 #pragma once
+#include "kernels.cuh"
 #include <cuda_runtime.h>
+#include <cusolverDn.h>
 #include <vector>
 
 namespace sml {
 
-struct TrainState {
-    bool active = false;
+struct TrainRegionDev {
+    RegionDev R;              // the reservoir's weights (ELL adjacency, W_in, ...)
+    double *slab;             // [ld][KS] column-major
+    double *gram;             // [ld][ld] column-major, lower triangle accumulated
+    double *xa, *xb;          // training state ping-pong [n]
+    const double *td;         // [D][ncols] this phase's (pre-noised) input series
+    const double *im;         // [S][ncols] imperfect-model series (hybrid) or null
+    const int *target_map;    // [P] rows of the input vector that form the target
+    int ld;                   // padded N+P (multiple of 16)
+    int pad0;
 };
 
-inline void train_release(TrainState &t) { t.active = false; }
+// one reservoir step for every region of the wave: reads input column in_col, writes the new state to the
+// other ping-pong buffer and (out_col >= 0) x~ into slab column out_col.  gather_col >= 0 takes the SpMV
+// operand from slab column gather_col instead of the state -- the ML-only restart of the reference, which
+// feeds the squared copy states(:,batch_size) back (src/mod_reservoir.f90:1034; slab ocean :933).
+// reservoir_layer_chunking_hybrid/_ml, src/mod_reservoir.f90:963-1175.   grid (ceil(n_max/256), nwave)
+__global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity, int in_col, int out_col, int gather_col)
+{
+    const TrainRegionDev &t = T[blockIdx.y];
+    const RegionDev &R = t.R;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R.n) return;
+    const double *xo = parity ? t.xb : t.xa;
+    double *xn = parity ? t.xa : t.xb;
+    const double *gsrc = (gather_col >= 0) ? t.slab + (size_t)t.ld * gather_col + R.S : xo;
+    const double *u = t.td + (size_t)R.D * in_col;
+    const int n = R.n;
+    const int *__restrict__ ec = R.ell_col + row;
+    const double *__restrict__ ev = R.ell_val + row;
+    double acc = 0.0;
+    for (int s = 0; s < R.ell_w; ++s) acc = fma(__ldg(ev + (size_t)s * n), gsrc[__ldg(ec + (size_t)s * n)], acc);
+    double tw;
+    if (R.win_mode == 0) {
+        tw = __dmul_rn(__ldg(R.winc + row), u[__ldg(R.wcol + row)]);
+    } else {
+        tw = 0.0;
+        for (int i = 0; i < R.D; ++i) tw = fma(R.win_dense[(size_t)i * n + row], u[i], tw);
+    }
+    const double xt = tanh(__dadd_rn(acc, tw));
+    const double xv = __dadd_rn(__dmul_rn(1.0 - R.leak, xo[row]), __dmul_rn(R.leak, xt));
+    xn[row] = xv;
+    if (out_col >= 0) t.slab[(size_t)t.ld * out_col + R.S + row] = (row & 1) ? __dmul_rn(xv, xv) : xv;
+}
+
+// copy the current state (no update) into slab column out_col: states(:,1) = x after the discard loop
+__global__ void k_train_store_state(const TrainRegionDev *__restrict__ T, int parity, int out_col)
+{
+    const TrainRegionDev &t = T[blockIdx.y];
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= t.R.n) return;
+    const double xv = (parity ? t.xb : t.xa)[row];
+    t.slab[(size_t)t.ld * out_col + t.R.S + row] = (row & 1) ? __dmul_rn(xv, xv) : xv;
+}
+
+// imperfect-model rows and target rows of slab columns [0, ncols): series column = first_series_col + c.
+// chunking_matmul :1668 (imperfect), tile_full_input_to_target_data2d src/res_domain.f90:602-651 (target).
+// Columns [ncols, kpad) are zeroed entirely (K padding of the tensor-core kernel).  grid (kpad, nwave)
+__global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_series_col, int ncols, int kpad)
+{
+    const TrainRegionDev &t = T[blockIdx.y];
+    const RegionDev &R = t.R;
+    const int c = blockIdx.x;
+    double *col = t.slab + (size_t)t.ld * c;
+    const int N = R.S + R.n;
+    if (c >= ncols) {
+        for (int i = threadIdx.x; i < t.ld; i += blockDim.x) col[i] = 0.0;
+        return;
+    }
+    const int sc = first_series_col + c;
+    for (int i = threadIdx.x; i < R.S; i += blockDim.x) col[i] = t.im[(size_t)R.S * sc + i];
+    for (int p = threadIdx.x; p < R.P; p += blockDim.x) col[N + p] = t.td[(size_t)R.D * sc + t.target_map[p]];
+    for (int i = N + R.P + threadIdx.x; i < t.ld; i += blockDim.x) col[i] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_syrk_dmma: Gaug(lower) += slab * slab^T with FP64 tensor-core MMA (mma.sync m8n8k4 f64 -> DMMA).
+//   CTA = one 128x128 tile (ti >= tj) of one region; K is walked in chunks of 16 columns.
+//   warp 8 (producer): TMA bulk copies -- each slab column restricted to the tile's rows is one
+//     contiguous run (column-major), so a chunk is 16 (+16) cp.async.bulk of <= 1 KB into padded rows.
+//   warps 0..7 (2 x 4): each owns a 64x32 sub-tile = 8 x 4 DMMA tiles, 64 FP64 accumulators per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int SY_BM = 128, SY_BK = 16, SY_LDS = 132, SY_STAGES = 4;
+constexpr int SY_CONS_WARPS = 8;
+constexpr int SY_THREADS = (SY_CONS_WARPS + 1) * 32;
+constexpr int SY_STAGE_DOUBLES = 2 * SY_BK * SY_LDS;
+constexpr size_t SY_SMEM = (size_t)SY_STAGES * SY_STAGE_DOUBLES * 8 + 2 * SY_STAGES * 8;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(SY_THREADS, 1)
+k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles, int kpad)
+{
+    extern __shared__ __align__(128) unsigned char sy_smem[];
+    double *stage0 = reinterpret_cast<double *>(sy_smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sy_smem + (size_t)SY_STAGES * SY_STAGE_DOUBLES * 8);
+    uint64_t *empty = full + SY_STAGES;
+
+    const TrainRegionDev &t = T[blockIdx.y];
+    const int2 tile = tiles[blockIdx.x];
+    const int ld = t.ld;
+    const int i0 = tile.x * SY_BM, j0 = tile.y * SY_BM;
+    if (i0 >= ld) return;  // tile list is built for the widest region of the wave
+    const bool diag = tile.x == tile.y;
+    const int rowsA = min(SY_BM, ld - i0), rowsB = min(SY_BM, ld - j0);
+    const int nchunks = kpad / SY_BK;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < SY_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], SY_CONS_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == SY_CONS_WARPS) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)SY_BK * (rowsA + (diag ? 0 : rowsB)) * 8u;
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const int s = kc % SY_STAGES;
+                mbar_wait(&empty[s], ((kc / SY_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[s], bytes);
+                double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
+                double *sB = sA + SY_BK * SY_LDS;
+                const double *src = t.slab + (size_t)ld * (kc * SY_BK);
+                for (int kk = 0; kk < SY_BK; ++kk) {
+                    tma_load_1d(sA + kk * SY_LDS, src + (size_t)ld * kk + i0, rowsA * 8u, &full[s]);
+                    if (!diag) tma_load_1d(sB + kk * SY_LDS, src + (size_t)ld * kk + j0, rowsB * 8u, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps
+    const int g = lane >> 2, q = lane & 3;         // DMMA group / thread-in-group
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    for (int kc = 0; kc < nchunks; ++kc) {
+        const int s = kc % SY_STAGES;
+        mbar_wait(&full[s], (kc / SY_STAGES) & 1);
+        const double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
+        const double *sB = diag ? sA : sA + SY_BK * SY_LDS;
+#pragma unroll
+        for (int k4 = 0; k4 < SY_BK; k4 += 4) {
+            double af[8], bf[4];
+            const double *pa = sA + (k4 + q) * SY_LDS + wm * 64 + g;
+            const double *pb = sB + (k4 + q) * SY_LDS + wn * 32 + g;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) af[a] = pa[a * 8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // epilogue: Gaug[i, j] += acc ; thread holds C[g][2q], C[g][2q+1] of every 8x8 tile
+    const int rows_total = ld;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int i = i0 + wm * 64 + a * 8 + g;
+        if (i >= rows_total) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + wn * 32 + b * 8 + 2 * q;
+            if (j < rows_total) t.gram[(size_t)ld * j + i] += acc[a][b][0];
+            if (j + 1 < rows_total) t.gram[(size_t)ld * (j + 1) + i] += acc[a][b][1];
+        }
+    }
+}
+
+// ridge terms on the diagonal and the prior on the right-hand side (fit_chunk_hybrid
+// src/mod_reservoir.f90:1261-1291,1308-1310; fit_chunk_ml :1203-1205), then mirror the lower triangle
+// (incl. the target block) into the upper one so that A = Gaug[0:N,0:N] is a full matrix and
+// B = Gaug[0:N, N:N+P] = states_x_trainingdata_aug^T.   grid: (ceil(ld/32), ceil(ld/32))
+__global__ void k_train_ridge_mirror(double *__restrict__ G, int ld, int N, int S, int P, double add_model,
+                                     double add_res, double prior_add, int ml_first_n)
+{
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (bi < bj) return;  // lower-triangle blocks only
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int i = bi * 32 + tx, j = bj * 32 + r;
+        double v = 0.0;
+        if (i < ld && j < ld) {
+            v = G[(size_t)ld * j + i];
+            if (i == j && i < N) {
+                const double add = (ml_first_n >= 0) ? (i < ml_first_n ? add_res : 0.0) : (i < S ? add_model : add_res);
+                v += add;
+                G[(size_t)ld * j + i] = v;
+            }
+            // prior(i,i) on states_x_trainingdata_aug(p = i, column i), i < S: element Gaug[N+i, i]
+            if (i >= N && i - N == j && j < S && j < P && prior_add != 0.0) {
+                v += prior_add;
+                G[(size_t)ld * j + i] = v;
+            }
+        }
+        tile[r][tx] = v;  // tile[j_local][i_local]
+    }
+    __syncthreads();
+    if (bi == bj) {
+        for (int r = ty; r < 32; r += blockDim.y) {
+            const int i = bi * 32 + r, j = bj * 32 + tx;  // upper element (i < j) <- lower (j, i)
+            if (i < j && j < ld) G[(size_t)ld * j + i] = tile[r][tx];
+        }
+    } else {
+        for (int r = ty; r < 32; r += blockDim.y) {
+            const int i = bj * 32 + tx, j = bi * 32 + r;  // transposed block
+            if (i < ld && j < ld) G[(size_t)ld * j + i] = tile[tx][r];
+        }
+    }
+}
+
+// W_out(P, N) <- X^T where X (N x P, ld) is the solution sitting in Gaug[0:N, N:N+P]; wout has leading dim ldw
+__global__ void k_train_store_wout(const double *__restrict__ X, int ldx, int N, int P, double *__restrict__ wout, int ldw)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;  // feature index
+    if (j >= N) return;
+    for (int p = 0; p < P; ++p) wout[(size_t)ldw * j + p] = X[(size_t)ldx * p + j];
+}
+
+struct TrainRegionHost {
+    int local = -1, region = -1;
+    TrainRegionDev dev{};
+    std::vector<void *> allocs;
+};
+
+struct TrainState {
+    bool active = false;
+    int kind = 0, batch_size = 0;
+    bool hybrid = true;
+    std::vector<TrainRegionHost> regs;
+    TrainRegionDev *d_regs = nullptr;
+    int2 *d_tiles = nullptr;
+    int ntiles = 0;
+    int ld_max = 0, n_max = 0, ks = 512;
+    double *d_series_td = nullptr, *d_series_im = nullptr;
+    size_t series_td_cap = 0, series_im_cap = 0;
+    cusolverDnHandle_t solver = nullptr;
+    double gram_flops_useful = 0.0;   // N(N+1)K + 2PNK summed over feeds
+    double gram_ms = 0.0;             // CUDA-event time of the Gram kernels
+    double stategen_ms = 0.0;
+    double solve_ms = 0.0;
+};
+
+inline void train_release(TrainState &t)
+{
+    for (auto &r : t.regs)
+        for (void *p : r.allocs) cudaFree(p);
+    t.regs.clear();
+    cudaFree(t.d_regs); t.d_regs = nullptr;
+    cudaFree(t.d_tiles); t.d_tiles = nullptr;
+    cudaFree(t.d_series_td); t.d_series_td = nullptr; t.series_td_cap = 0;
+    cudaFree(t.d_series_im); t.d_series_im = nullptr; t.series_im_cap = 0;
+    t.active = false;
+}
 
 }  // namespace sml

@@ -1,11 +1,354 @@
 // train_api.inl -- C entry points of the training path (included at the end of engine.cu).
+//
+// sml_train_begin / sml_train_feed / sml_train_solve / sml_train_end replace, for a wave of regions,
+// train_reservoir's inner sequence (src/mod_reservoir.f90:287-316):
+//   initialize_chunk_training -> reservoir_layer_chunking_hybrid|_ml per phase (state generation,
+//   chunking_matmul per batch) -> fit_chunk_hybrid|_ml (ridge terms, mldivide).
+// Batches only decide which states are kept (floor(TL/batch_size)*batch_size) and, on the ML-only path,
+// where the squared copy is fed back; the Gram itself is accumulated over larger K slabs (summation
+// order is the only difference).
+
+namespace {
+
+int solver_handle(sml_engine *h)
+{
+    if (!h->train.solver) {
+        if (cusolverDnCreate(&h->train.solver) != CUSOLVER_STATUS_SUCCESS) FAIL(h, "cusolverDnCreate failed");
+    }
+    if (cusolverDnSetStream(h->train.solver, h->stream) != CUSOLVER_STATUS_SUCCESS) FAIL(h, "cusolverDnSetStream failed");
+    return 0;
+}
+
+// LU with partial pivoting + solve, the dgesv the reference calls (src/mod_linalg.f90:145); A, B on device
+int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n, int nrhs, int *info_out)
+{
+    if (solver_handle(h)) return -1;
+    int lwork = 0;
+    if (cusolverDnDgetrf_bufferSize(h->train.solver, n, n, dA, lda, &lwork) != CUSOLVER_STATUS_SUCCESS)
+        FAIL(h, "cusolverDnDgetrf_bufferSize failed");
+    double *work = nullptr;
+    int *ipiv = nullptr, *dinfo = nullptr;
+    CK(h, cudaMalloc(&work, sizeof(double) * (size_t)std::max(lwork, 1)));
+    CK(h, cudaMalloc(&ipiv, sizeof(int) * (size_t)std::max(n, 1)));
+    CK(h, cudaMalloc(&dinfo, sizeof(int)));
+    int info = 0;
+    cusolverStatus_t st = cusolverDnDgetrf(h->train.solver, n, n, dA, lda, work, ipiv, dinfo);
+    if (st == CUSOLVER_STATUS_SUCCESS) {
+        cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        if (info == 0) {
+            st = cusolverDnDgetrs(h->train.solver, CUBLAS_OP_N, n, nrhs, dA, lda, ipiv, dB, ldb, dinfo);
+            cudaStreamSynchronize(h->stream);
+        }
+    }
+    cudaFree(work); cudaFree(ipiv); cudaFree(dinfo);
+    if (st != CUSOLVER_STATUS_SUCCESS) FAIL(h, "cusolver getrf/getrs failed (status %d)", (int)st);
+    *info_out = info;
+    return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
-int sml_train_begin(sml_engine *h, int, const int32_t *, int, int) { FAIL(h, "training path not built yet"); }
-int sml_train_feed(sml_engine *h, const double *, const int64_t *, const double *, const int64_t *, int, int) { FAIL(h, "training path not built yet"); }
-int sml_train_solve(sml_engine *h, double, double, int, double, int32_t *) { FAIL(h, "training path not built yet"); }
-int sml_train_gram_get(sml_engine *h, int, double *, double *) { FAIL(h, "training path not built yet"); }
-int sml_train_end(sml_engine *h) { FAIL(h, "training path not built yet"); }
-int sml_mldivide(sml_engine *h, double *, int, double *, int, int, int) { FAIL(h, "training path not built yet"); }
+int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregions, int batch_size)
+{
+    if (check_ready(h, kind)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    TrainState &T = h->train;
+    if (T.active) FAIL(h, "sml_train_begin while a training wave is active (call sml_train_end)");
+    if (nregions <= 0 || batch_size < 2) FAIL(h, "bad training wave (nregions %d, batch_size %d)", nregions, batch_size);
+    KindState &K = h->kinds[kind];
+    cusolverDnHandle_t keep_solver = T.solver;
+    T = TrainState{};
+    T.solver = keep_solver;
+    T.kind = kind;
+    T.batch_size = batch_size;
+    if (const char *s = getenv("SML_TRAIN_SLAB")) T.ks = std::max(16, atoi(s) / 16 * 16);
+    std::vector<TrainRegionDev> devs;
+    for (int i = 0; i < nregions; ++i) {
+        int li;
+        if (local_of(h, kind, regions[i], &li)) { train_release(T); return -1; }
+        TrainRegionHost tr;
+        tr.local = li;
+        tr.region = regions[i];
+        TrainRegionDev &d = tr.dev;
+        d.R = K.regs[li].dev;
+        const int N = d.R.n + d.R.S;
+        d.ld = (N + d.R.P + 15) / 16 * 16;
+        T.ld_max = std::max(T.ld_max, d.ld);
+        T.n_max = std::max(T.n_max, d.R.n);
+        T.hybrid = d.R.S > 0;
+        auto alloc = [&](size_t bytes, void **p) -> int {
+            cudaError_t e = cudaMalloc(p, bytes);
+            if (e != cudaSuccess) {
+                h->err = std::string("training wave does not fit in HBM (cudaMalloc: ") + cudaGetErrorString(e) + "); use fewer regions per wave";
+                return -1;
+            }
+            tr.allocs.push_back(*p);
+            return 0;
+        };
+        void *p = nullptr;
+        bool bad = false;
+        bad = bad || alloc((size_t)d.ld * d.ld * 8, &p); d.gram = (double *)p;
+        if (!bad) cudaMemsetAsync(d.gram, 0, (size_t)d.ld * d.ld * 8, h->stream);
+        bad = bad || alloc((size_t)d.ld * T.ks * 8, &p); d.slab = (double *)p;
+        bad = bad || alloc((size_t)d.R.n * 8, &p); d.xa = (double *)p;
+        bad = bad || alloc((size_t)d.R.n * 8, &p); d.xb = (double *)p;
+        // target rows (tile_full_input_to_target_data2d) from the tiling
+        std::vector<int32_t> tmap(d.R.P, 0);
+        if (kind == SML_ATMO) {
+            RegionGeom g = make_geom(h->tiling, regions[i], h->p.overlap);
+            RegionMaps m = make_maps(h->tiling, g, K.regs[li].sizes, h->p.precip_bool, K.regs[li].sst_in);
+            tmap = m.target_map;
+        }
+        bad = bad || alloc(sizeof(int) * d.R.P, &p);
+        if (!bad) {
+            cudaMemcpyAsync(p, tmap.data(), sizeof(int) * d.R.P, cudaMemcpyHostToDevice, h->stream);
+            cudaStreamSynchronize(h->stream);
+        }
+        d.target_map = (const int *)p;
+        T.regs.push_back(tr);
+        if (bad) { train_release(T); return -1; }
+        devs.push_back(d);
+    }
+    CK(h, cudaMalloc(&T.d_regs, sizeof(TrainRegionDev) * devs.size()));
+    // lower-triangle tile list, row-major so that neighbouring CTAs share slab row blocks in L2
+    std::vector<int2> tiles;
+    const int nt = (T.ld_max + SY_BM - 1) / SY_BM;
+    for (int ti = 0; ti < nt; ++ti)
+        for (int tj = 0; tj <= ti; ++tj) tiles.push_back(make_int2(ti, tj));
+    T.ntiles = (int)tiles.size();
+    CK(h, cudaMalloc(&T.d_tiles, sizeof(int2) * tiles.size()));
+    CK(h, cudaMemcpy(T.d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    CK(h, cudaStreamSynchronize(h->stream));
+    T.active = true;
+    return 0;
+}
+
+int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const double *im, const int64_t *im_off,
+                   int ncols, int discard_cols)
+{
+    if (!h) return -1;
+    TrainState &T = h->train;
+    if (!T.active) FAIL(h, "sml_train_feed without sml_train_begin");
+    CK(h, cudaSetDevice(h->p.device));
+    if (!td || !td_off) FAIL(h, "trainingdata is required");
+    if (T.hybrid && (!im || !im_off)) FAIL(h, "hybrid training needs the imperfect-model series");
+    if (discard_cols < 0 || ncols - discard_cols < T.batch_size) FAIL(h, "phase too short: %d columns, discard %d, batch %d", ncols, discard_cols, T.batch_size);
+    const int nw = (int)T.regs.size();
+    // upload this phase's series
+    size_t td_total = 0, im_total = 0;
+    for (auto &r : T.regs) {
+        td_total += (size_t)r.dev.R.D * ncols;
+        im_total += (size_t)r.dev.R.S * ncols;
+    }
+    if (td_total > T.series_td_cap) {
+        cudaFree(T.d_series_td);
+        T.d_series_td = nullptr;
+        CK(h, cudaMalloc(&T.d_series_td, td_total * 8));
+        T.series_td_cap = td_total;
+    }
+    if (im_total > T.series_im_cap) {
+        cudaFree(T.d_series_im);
+        T.d_series_im = nullptr;
+        CK(h, cudaMalloc(&T.d_series_im, im_total * 8));
+        T.series_im_cap = im_total;
+    }
+    size_t pt = 0, pi = 0;
+    std::vector<TrainRegionDev> devs(nw);
+    for (int i = 0; i < nw; ++i) {
+        TrainRegionDev &d = T.regs[i].dev;
+        const size_t tsz = (size_t)d.R.D * ncols, isz = (size_t)d.R.S * ncols;
+        CK(h, cudaMemcpyAsync(T.d_series_td + pt, td + td_off[i], tsz * 8, cudaMemcpyHostToDevice, h->stream));
+        d.td = T.d_series_td + pt;
+        pt += tsz;
+        if (isz) {
+            CK(h, cudaMemcpyAsync(T.d_series_im + pi, im + im_off[i], isz * 8, cudaMemcpyHostToDevice, h->stream));
+            d.im = T.d_series_im + pi;
+            pi += isz;
+        } else {
+            d.im = nullptr;
+        }
+        CK(h, cudaMemsetAsync(d.xa, 0, (size_t)d.R.n * 8, h->stream));  // x = 0 at the start of every phase (:1091)
+        devs[i] = d;
+    }
+    CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * nw, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    const dim3 ugrid((T.n_max + 255) / 256, nw);
+    int parity = 0;
+    // discard loop (:1093-1106)
+    for (int i = 0; i < discard_cols; ++i) {
+        k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, i, -1, -1);
+        parity ^= 1;
+        h->launches++;
+    }
+    const int TL = ncols - discard_cols;
+    const int bs = T.batch_size;
+    const int kept = (TL / bs) * bs;  // states 1..kept enter the Gram
+    // state s (1-based) pairs with series column discard+s (1-based) = discard+s-1 (0-based); it is produced
+    // from state s-1 with input column discard+s-1 (1-based) = discard+s-2 (0-based)
+    for (int s0 = 0; s0 < kept; s0 += T.ks) {
+        const int nc = std::min(T.ks, kept - s0);
+        const int kpad = (nc + SY_BK - 1) / SY_BK * SY_BK;
+        CK(h, cudaEventRecord(e0, h->stream));
+        for (int c = 0; c < nc; ++c) {
+            const int s = s0 + c;  // 0-based state index
+            if (s == 0) {
+                k_train_store_state<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, 0);
+            } else {
+                // ML-only paths restart every batch from the squared copy (SpMV operand only)
+                // (at a slab boundary the previous slab was full, its last column is still intact)
+                int gather = -1;
+                if (!T.hybrid && (s % bs) == 0) gather = (c > 0) ? c - 1 : T.ks - 1;
+                k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, discard_cols + s - 1, c, gather);
+                parity ^= 1;
+            }
+            h->launches++;
+        }
+        k_train_fill<<<dim3(kpad, nw), 128, 0, h->stream>>>(T.d_regs, discard_cols + s0, nc, kpad);
+        h->launches++;
+        CK(h, cudaEventRecord(e1, h->stream));
+        k_syrk_dmma<<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
+        h->launches++;
+        CK(h, cudaEventRecord(e2, h->stream));
+        CK(h, cudaGetLastError());
+        CK(h, cudaEventSynchronize(e2));
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        T.stategen_ms += a;
+        T.gram_ms += b;
+        for (auto &r : T.regs) {
+            const double N = r.dev.R.n + r.dev.R.S, P = r.dev.R.P;
+            T.gram_flops_useful += (N * (N + 1.0) + 2.0 * P * N) * nc;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return 0;
+}
+
+int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using_prior, double prior_val,
+                    int32_t *info_per_region)
+{
+    if (!h) return -1;
+    TrainState &T = h->train;
+    if (!T.active) FAIL(h, "sml_train_solve without sml_train_begin");
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[T.kind];
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    CK(h, cudaEventRecord(e0, h->stream));
+    for (size_t i = 0; i < T.regs.size(); ++i) {
+        TrainRegionDev &d = T.regs[i].dev;
+        const int N = d.R.n + d.R.S, S = d.R.S, P = d.R.P, ld = d.ld;
+        double add_model, add_res, prior_add = 0.0;
+        int ml_first_n = -1;
+        if (T.hybrid) {
+            // fit_chunk_hybrid :1275-1291: beta**2 with a prior, plain beta without
+            add_model = using_prior ? beta_model * beta_model : beta_model;
+            add_res = using_prior ? beta_res * beta_res : beta_res;
+            if (using_prior) prior_add = prior_val * beta_model * beta_model;
+        } else {
+            // fit_chunk_ml :1203-1205: + beta_res on the first n diagonals only
+            add_model = 0.0;
+            add_res = beta_res;
+            ml_first_n = d.R.n;
+        }
+        const dim3 mg((ld + 31) / 32, (ld + 31) / 32);
+        k_train_ridge_mirror<<<mg, dim3(32, 8), 0, h->stream>>>(d.gram, ld, N, S, P, add_model, add_res, prior_add, ml_first_n);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        int info = 0;
+        if (device_dgesv(h, d.gram, ld, d.gram + (size_t)ld * N, ld, N, P, &info)) return -1;
+        if (info_per_region) info_per_region[i] = info;
+        if (info == 0) {
+            // reservoir%wout = transpose(b_trans) (:1313)
+            double *wout = const_cast<double *>(K.regs[T.regs[i].local].dev.wout);
+            k_train_store_wout<<<(N + 127) / 128, 128, 0, h->stream>>>(d.gram + (size_t)ld * N, ld, N, P, wout, d.R.ldw);
+            h->launches++;
+        }
+        // 'something went wrong with dgesv' is print-and-continue in the reference (src/mod_linalg.f90:147-150):
+        // W_out is left untouched and info is reported
+    }
+    CK(h, cudaEventRecord(e1, h->stream));
+    CK(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    T.solve_ms += ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+int sml_train_gram_get(sml_engine *h, int region, double *sxs, double *sxt)
+{
+    if (!h) return -1;
+    TrainState &T = h->train;
+    if (!T.active) FAIL(h, "no active training wave");
+    for (auto &r : T.regs) {
+        if (r.region != region) continue;
+        const TrainRegionDev &d = r.dev;
+        const int N = d.R.n + d.R.S, P = d.R.P, ld = d.ld;
+        std::vector<double> g((size_t)ld * ld);
+        CK(h, cudaMemcpyAsync(g.data(), d.gram, g.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (sxs)
+            for (int j = 0; j < N; ++j)
+                for (int i = 0; i < N; ++i) sxs[(size_t)N * j + i] = (i >= j) ? g[(size_t)ld * j + i] : g[(size_t)ld * i + j];
+        if (sxt)
+            for (int j = 0; j < N; ++j)
+                for (int p = 0; p < P; ++p) sxt[(size_t)P * j + p] = g[(size_t)ld * j + N + p];
+        return 0;
+    }
+    FAIL(h, "region %d is not in the training wave", region);
+}
+
+int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms, double *solve_ms)
+{
+    if (!h) return -1;
+    *gram_flops_useful = h->train.gram_flops_useful;
+    *gram_ms = h->train.gram_ms;
+    *stategen_ms = h->train.stategen_ms;
+    *solve_ms = h->train.solve_ms;
+    return 0;
+}
+
+int sml_train_end(sml_engine *h)
+{
+    if (!h) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    cudaStreamSynchronize(h->stream);
+    cusolverDnHandle_t keep = h->train.solver;
+    train_release(h->train);
+    h->train.solver = keep;
+    return 0;
+}
+
+int sml_mldivide(sml_engine *h, double *A, int lda, double *B, int ldb, int n, int nrhs)
+{
+    if (!h) return -1;
+    if (n <= 0 || nrhs <= 0 || lda < n || ldb < n) FAIL(h, "mldivide: bad dimensions");
+    CK(h, cudaSetDevice(h->p.device));
+    double *dA = nullptr, *dB = nullptr;
+    CK(h, cudaMalloc(&dA, (size_t)n * n * 8));
+    CK(h, cudaMalloc(&dB, (size_t)n * nrhs * 8));
+    CK(h, cudaMemcpy2DAsync(dA, (size_t)n * 8, A, (size_t)lda * 8, (size_t)n * 8, n, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpy2DAsync(dB, (size_t)n * 8, B, (size_t)ldb * 8, (size_t)n * 8, nrhs, cudaMemcpyHostToDevice, h->stream));
+    int info = 0;
+    int rc = device_dgesv(h, dA, n, dB, n, n, nrhs, &info);
+    if (rc == 0) {
+        // like dgesv, A returns its LU factors and B the solution (only meaningful when info == 0)
+        cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, (size_t)n * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost, h->stream);
+        if (info == 0)
+            cudaMemcpy2DAsync(B, (size_t)ldb * 8, dB, (size_t)n * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(dA); cudaFree(dB);
+    return rc ? -1 : info;
+}
 
 }  // extern "C"

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "sml_train_solve": ([C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, _ip], C.c_int),
     "sml_train_gram_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
     "sml_train_end": ([C.c_void_p], C.c_int),
+    "sml_train_stats": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
     "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_profile": ([C.c_void_p, C.c_int], C.c_int),
     "sml_kernel_times": ([C.c_void_p, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
@@ -450,6 +451,12 @@ class Engine:
         sxt = np.zeros((d["P"], N), order="F")
         self._ck(self.lib.sml_train_gram_get(self.h, region, _d(sxs), _d(sxt)))
         return sxs, sxt
+
+    def train_stats(self):
+        """-> dict(gram_flops_useful, gram_ms, stategen_ms, solve_ms) of the current wave"""
+        v = [C.c_double() for _ in range(4)]
+        self._ck(self.lib.sml_train_stats(self.h, *[C.byref(a) for a in v]))
+        return dict(zip(("gram_flops_useful", "gram_ms", "stategen_ms", "solve_ms"), (a.value for a in v)))
 
     def train_end(self):
         self._ck(self.lib.sml_train_end(self.h))

@@ -1,0 +1,175 @@
+"""Training path on the GPU (state generation + DMMA Gram + ridge solve) vs the CPU oracle.  -m gpu."""
+import importlib
+
+import numpy as np
+import pytest
+from scipy.linalg import lapack
+
+from helpers import c_region, oc, region_weights, rel_inf, syn
+from test_engine_gpu import single_region_engine, upload
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    return importlib.import_module("speedy-ml_b200.engine")
+
+
+def _series(w, T, seed):
+    rng = np.random.default_rng(seed)
+    td = syn.ar1_series(w["D"], T, rng)
+    im = np.asfortranarray(rng.standard_normal((w["S"], T))) if w["S"] else None
+    return td, im
+
+
+def _residual(A, X, B):
+    return np.linalg.norm(A @ X - B) / (np.linalg.norm(A) * np.linalg.norm(X) + np.linalg.norm(B))
+
+
+@pytest.mark.parametrize("region,m,bs,nb,discard", [(555, 450, 7, 4, 5), (24 * 3, 450, 16, 3, 2), (556, 1300, 98, 2, 40)])
+def test_hybrid_training_parity(E, region, m, bs, nb, discard):
+    w = region_weights(1152, region, m=m)
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    phases = [_series(w, discard + nb * bs + 3, 50 + p) for p in range(2)]   # +3: trailing states are dropped
+    rc.train_init(bs)
+    eng.train_begin([region], bs)
+    for td, im in phases:
+        rc.train_phase(td, im, discard)
+        eng.train_feed([td], [im], discard)
+    sxs_e, sxt_e = eng.train_gram_get(region)
+    assert rel_inf(sxs_e, rc.sxs) < 1e-12
+    assert rel_inf(sxt_e, rc.sxt) < 1e-12
+    assert np.array_equal(sxs_e, sxs_e.T)
+    sxs0, sxt0 = rc.sxs.copy(), rc.sxt.copy()
+    assert rc.fit(beta_res=1e-3, beta_model=1.0, using_prior=True, prior_val=0.0) == 0
+    info = eng.train_solve(1e-3, 1.0, True, 0.0)
+    assert info[0] == 0
+    wout_e = eng.wout_get(region)
+    # ridge system: (sxs + diag)^T X = sxt^T ; judge by relative residual
+    N, S = w["n"] + w["S"], w["S"]
+    A = sxs0.copy()
+    d = np.arange(N)
+    A[d[:S], d[:S]] += 1.0
+    A[d[S:], d[S:]] += 1e-6
+    for wout in (wout_e, rc.wout):
+        assert _residual(A.T, wout.T, sxt0.T) < 1e-13
+    # downstream forecast parity: engine-trained vs oracle-trained W_out, 100 open-loop steps
+    rng = np.random.default_rng(77)
+    series = syn.ar1_series(w["D"], 100, rng)
+    model = rng.standard_normal((w["S"], 100))
+    rc.x[:] = 0.0
+    eng.state_set(region, np.zeros(w["n"]))
+    worst = 0.0
+    for t in range(100):
+        rc.feedback[:] = series[:, t]
+        rc.local_model[:] = model[:, t]
+        eng.feedback_set(region, series[:, t])
+        eng.local_model_set(region, model[:, t])
+        rc.predict()
+        eng.predict()
+        worst = max(worst, rel_inf(eng.outvec_get(region), rc.outvec))
+    assert worst < 1e-8
+    eng.train_end()
+    eng.close()
+
+
+def test_prior_and_plain_beta_variants(E):
+    w = region_weights(1152, 555, m=450)
+    td, im = _series(w, 3 + 3 * 8, 5)
+    for using_prior, prior_val in ((True, 0.7), (False, 0.0)):
+        rc = c_region(w)
+        eng = single_region_engine(E, w)
+        rc.train_init(8)
+        rc.train_phase(td, im, 3)
+        eng.train_begin([555], 8)
+        eng.train_feed([td], [im], 3)
+        sxs0, sxt0 = rc.sxs.copy(), rc.sxt.copy()
+        assert rc.fit(beta_res=0.05, beta_model=0.5, using_prior=using_prior, prior_val=prior_val) == 0
+        assert eng.train_solve(0.05, 0.5, using_prior, prior_val)[0] == 0
+        N, S = w["n"] + w["S"], w["S"]
+        d = np.arange(N)
+        A, B = sxs0.copy(), sxt0.copy()
+        if using_prior:
+            A[d[:S], d[:S]] += 0.25
+            A[d[S:], d[S:]] += 0.0025
+            B[d[:S], d[:S]] += prior_val * 0.25
+        else:
+            A[d[:S], d[:S]] += 0.5
+            A[d[S:], d[S:]] += 0.05
+        assert _residual(A.T, eng.wout_get(555).T, B.T) < 1e-13
+        assert rel_inf(eng.wout_get(555), rc.wout) < 1e-7   # well conditioned here (beta large)
+        eng.train_end()
+        eng.close()
+
+
+def test_ml_only_training_with_restart_quirk(E):
+    w = region_weights(1152, 555, m=450, ml_only=True)
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    bs, discard = 5, 3
+    td, _ = _series(w, discard + 4 * bs, 9)
+    rc.train_init(bs)
+    rc.train_phase(td, None, discard)
+    eng.train_begin([555], bs)
+    eng.train_feed([td], None, discard)
+    sxs_e, sxt_e = eng.train_gram_get(555)
+    assert rel_inf(sxs_e, rc.sxs) < 1e-12
+    assert rel_inf(sxt_e, rc.sxt) < 1e-12
+    sxs0, sxt0 = rc.sxs.copy(), rc.sxt.copy()
+    assert rc.fit(beta_res=1e-2) == 0
+    assert eng.train_solve(1e-2)[0] == 0
+    A = sxs0 + 1e-2 * np.eye(w["n"])
+    assert _residual(A.T, eng.wout_get(555).T, sxt0.T) < 1e-13
+    eng.train_end()
+    eng.close()
+
+
+def test_wave_of_regions_with_different_shapes_and_slab_boundaries(E, monkeypatch):
+    monkeypatch.setenv("SML_TRAIN_SLAB", "16")   # force several K slabs per phase
+    regions = [0, 1, 2, 3]
+    ws = {r: region_weights(1152, r, m=450) for r in regions}
+    assert len({ws[r]["n"] for r in regions}) > 1
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=288)   # rank 0 owns regions 0..3
+    assert eng.region_indices == regions
+    for r in regions:
+        upload(eng, ws[r])
+    eng.finalize()
+    bs, discard = 10, 4
+    series = {r: _series(ws[r], discard + 5 * bs, 30 + r) for r in regions}
+    eng.train_begin(regions, bs)
+    eng.train_feed([series[r][0] for r in regions], [series[r][1] for r in regions], discard)
+    for r in regions:
+        rc = c_region(ws[r])
+        rc.train_init(bs)
+        rc.train_phase(series[r][0], series[r][1], discard)
+        sxs_e, sxt_e = eng.train_gram_get(r)
+        assert rel_inf(sxs_e, rc.sxs) < 1e-12
+        assert rel_inf(sxt_e, rc.sxt) < 1e-12
+    st = eng.train_stats()
+    assert st["gram_flops_useful"] > 0 and st["gram_ms"] > 0
+    eng.train_end()
+    eng.close()
+
+
+def test_mldivide_matches_dgesv(E):
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=1152)
+    rng = np.random.default_rng(0)
+    for n, k in ((1, 1), (7, 3), (333, 136), (1200, 40)):
+        A = rng.standard_normal((n, n)) + 0.1 * n * np.eye(n)
+        B = rng.standard_normal((n, k))
+        X, info = eng.mldivide(A, B)
+        _, _, Xl, infol = lapack.dgesv(A, B)
+        assert info == 0 and infol == 0
+        assert rel_inf(X, Xl) < 1e-10
+        assert _residual(A, X, B) < 1e-14
+    # singular: LAPACK info > 0, B is not the solution (src/mod_linalg.f90:147-150 prints and continues)
+    A = np.array([[1.0, 2.0], [2.0, 4.0]])
+    _, info = eng.mldivide(A, np.ones((2, 1)))
+    assert info == 2
+    # shape mismatch: 'returning A and B unchanged' (:134-137)
+    B = np.ones((2, 1))
+    X, info = eng.mldivide(np.eye(3), B)
+    assert info == -1 and np.array_equal(X, B)
+    eng.close()
