@@ -110,6 +110,12 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// fire-and-forget global FP64 reduction (RED.E.ADD.F64): no return value, so no scoreboard wait
+__device__ __forceinline__ void red_add_f64(double *p, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles, int kpad)
 {
@@ -159,6 +165,9 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
 
     const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps
     const int g = lane >> 2, q = lane & 3;         // DMMA group / thread-in-group
+    // 8x8 DMMA tiles of this warp that hold real rows / columns (edge tiles of the padded matrix are slivers)
+    const int ma = max(0, min(8, (rowsA - wm * 64 + 7) >> 3));
+    const int nb = max(0, min(4, (rowsB - wn * 32 + 7) >> 3));
     double acc[8][4][2];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
@@ -170,25 +179,48 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
         mbar_wait(&full[s], (kc / SY_STAGES) & 1);
         const double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
         const double *sB = diag ? sA : sA + SY_BK * SY_LDS;
+        if (ma == 8 && nb == 4) {
 #pragma unroll
-        for (int k4 = 0; k4 < SY_BK; k4 += 4) {
-            double af[8], bf[4];
-            const double *pa = sA + (k4 + q) * SY_LDS + wm * 64 + g;
-            const double *pb = sB + (k4 + q) * SY_LDS + wn * 32 + g;
+            for (int k4 = 0; k4 < SY_BK; k4 += 4) {
+                double af[8], bf[4];
+                const double *pa = sA + (k4 + q) * SY_LDS + wm * 64 + g;
+                const double *pb = sB + (k4 + q) * SY_LDS + wn * 32 + g;
 #pragma unroll
-            for (int a = 0; a < 8; ++a) af[a] = pa[a * 8];
+                for (int a = 0; a < 8; ++a) af[a] = pa[a * 8];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
+                for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+                for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                    for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+        } else if (ma > 0 && nb > 0) {
+            // sliver tile: only the DMMA tiles with real rows/columns (warp-uniform predicates)
+#pragma unroll
+            for (int k4 = 0; k4 < SY_BK; k4 += 4) {
+                const double *pa = sA + (k4 + q) * SY_LDS + wm * 64 + g;
+                const double *pb = sB + (k4 + q) * SY_LDS + wn * 32 + g;
+                double bf[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    if (a < ma) {
+                        const double af = pa[a * 8];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (b < nb) dmma884(acc[a][b][0], acc[a][b][1], af, bf[b]);
+                    }
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
-    // epilogue: Gaug[i, j] += acc ; thread holds C[g][2q], C[g][2q+1] of every 8x8 tile
+    // epilogue: Gaug[i, j] += acc ; thread holds C[g][2q], C[g][2q+1] of every 8x8 tile.  Every element of
+    // the lower triangle is owned by exactly one CTA per launch, so a fire-and-forget reduction
+    // (RED.ADD.F64) is deterministic and never stalls on the read of Gaug.
     const int rows_total = ld;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
@@ -197,8 +229,8 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int j = j0 + wn * 32 + b * 8 + 2 * q;
-            if (j < rows_total) t.gram[(size_t)ld * j + i] += acc[a][b][0];
-            if (j + 1 < rows_total) t.gram[(size_t)ld * (j + 1) + i] += acc[a][b][1];
+            if (j < rows_total) red_add_f64(&t.gram[(size_t)ld * j + i], acc[a][b][0]);
+            if (j + 1 < rows_total) red_add_f64(&t.gram[(size_t)ld * (j + 1) + i], acc[a][b][1]);
         }
     }
 }
@@ -268,7 +300,7 @@ struct TrainState {
     TrainRegionDev *d_regs = nullptr;
     int2 *d_tiles = nullptr;
     int ntiles = 0;
-    int ld_max = 0, n_max = 0, ks = 512;
+    int ld_max = 0, n_max = 0, ks = 1024;
     double *d_series_td = nullptr, *d_series_im = nullptr;
     size_t series_td_cap = 0, series_im_cap = 0;
     cusolverDnHandle_t solver = nullptr;

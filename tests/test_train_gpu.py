@@ -27,7 +27,7 @@ def _residual(A, X, B):
     return np.linalg.norm(A @ X - B) / (np.linalg.norm(A) * np.linalg.norm(X) + np.linalg.norm(B))
 
 
-@pytest.mark.parametrize("region,m,bs,nb,discard", [(555, 450, 7, 4, 5), (24 * 3, 450, 16, 3, 2), (556, 1300, 98, 2, 40)])
+@pytest.mark.parametrize("region,m,bs,nb,discard", [(555, 450, 7, 4, 5), (24 * 3, 450, 16, 3, 2), (556, 1300, 98, 7, 40)])
 def test_hybrid_training_parity(E, region, m, bs, nb, discard):
     w = region_weights(1152, region, m=m)
     rc = c_region(w)
