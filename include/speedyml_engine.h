@@ -99,6 +99,17 @@ int sml_processor_decomposition(int irank, int numprocs, int number_of_regions,
 int sml_region_dims(int num_regions, int region, int overlap, int m, double deg, int precip_bool,
                     int sst_bool, int sst_bool_input, int ml_only, int *n, int *k, int *D, int *P,
                     int *S, int *L);
+/* sizes of initialize_slab_ocean_model (src/mod_slab_ocean_reservoir.f90:9-133) for the ocean reservoir of a
+ * region (m = 4000, deg = 6 there): n, k, D = reservoir_numinputs, P = chunk_size_prediction (S is always 0) and
+ * A = logp_end, the length of the time-averaged atmosphere part of its input vector */
+int sml_ocean_region_dims(int num_regions, int region, int overlap, int m, double deg, int *n, int *k,
+                          int *D, int *P, int *A);
+/* ocean maps: sst_map[D/8] offsets in G of the halo'd SST tile (tile_4d_and_logp_to_local_state_input_slab,
+ * src/res_domain.f90:1127-1152); target_map[P] rows of the ocean input vector that form the target
+ * (tile_full_input_to_target_data2d_ocean_model :691-728); atmo_slice0 = 0-based start of
+ * atmo_training_data_idx in the atmosphere input vector (src/mod_slab_ocean_reservoir.f90:1621-1625) */
+int sml_ocean_region_maps(int num_regions, int region, int overlap, int32_t *sst_map, int32_t *target_map,
+                          int *atmo_slice0);
 /* flattened 0-based gather/scatter maps into the global buffers (layout: sml_global_layout):
  *   input_map[D]  : feedback element -> offset in G  (tile_4d_and_logp_to_local_state_input :1081-1125,
  *                   tileoverlapgrid2d for sst/tisr)         input_ms[D] : 0-based mean/std slot, L = sst
@@ -125,6 +136,9 @@ int sml_feedback_get(sml_engine *h, int kind, int region, double *feedback);
 int sml_local_model_set(sml_engine *h, int kind, int region, const double *local_model);
 int sml_local_model_get(sml_engine *h, int kind, int region, double *local_model);
 int sml_outvec_get(sml_engine *h, int kind, int region, double *outvec);
+/* start_prediction_slab seeds reservoir%outvec with the last observed SST/OHTC tile
+ * (src/mod_slab_ocean_reservoir.f90:853-859); the exchange uses it until the first ocean step */
+int sml_outvec_set(sml_engine *h, int kind, int region, const double *outvec);
 int sml_wout_get(sml_engine *h, int kind, int region, double *wout);
 int sml_wout_set(sml_engine *h, int kind, int region, const double *wout);
 
@@ -134,8 +148,14 @@ int sml_wout_set(sml_engine *h, int kind, int region, const double *wout);
 int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, int ld, int length,
                     const int64_t *offsets);
 
-/* ---- predict / predict_ml (src/mod_reservoir.f90:1418-1535; slab :1268-1363) for every local
- * region of the kind: state update + readout + un-standardise; outvec stays on the device ---- */
+/* ---- predict / predict_ml (src/mod_reservoir.f90:1418-1535) for every local region of the kind: state
+ * update + readout + un-standardise; outvec stays on the device.  kind == SML_OCEAN is predict_slab_ml
+ * (src/mod_slab_ocean_reservoir.f90:1318-1363; every output * std(sst) + mean(sst)); the caller decides when
+ * (mod(t*timestep, timestep_slab) == 0, src/parallelmain.f90:238).  The ocean feedback vector is rebuilt by
+ * every sml_step_exchange_end / sml_step_unpack_device(timestep): atmosphere part = mean of the
+ * timestep_slab/timestep-1 slot ring (slot mod(timestep-1, slots)+1), SST part = standardised halo tile of
+ * wholegrid_sst, TISR and OHTC parts as sml_feedback_set left them (src/mpires.f90:594-600,776-781; the
+ * intended semantics of SURVEY.md Appendix C, where the source itself has shape hazards) ---- */
 int sml_predict(sml_engine *h, int kind);
 
 /* ---- sendrecievegrid (src/mpires.f90:218-804), split where the root calls run_model (:565-569).
@@ -161,6 +181,12 @@ int sml_set_sst_prescribed(sml_engine *h, const double *sst_grid);
 int sml_exchange_buffers(sml_engine *h, void **outvec_slab, int64_t *slab_count, void **gathered,
                          int64_t *gathered_count, void **gbuf, int64_t *g_count, void **fbuf,
                          int64_t *f_count);
+/* the same for the ocean reservoirs' outvec slab [nloc][P_ocean] (rows of regions without an ocean reservoir
+ * hold 272.0, src/mpires.f90:323-326): all-gather it after every sml_predict(h, SML_OCEAN) when numprocs > 1 */
+int sml_ocean_exchange_buffers(sml_engine *h, void **ocean_slab, int64_t *slab_count, void **ocean_gathered,
+                               int64_t *gathered_count);
+/* averaged_atmo_input_vec = 0 (initialize_prediction_slab, src/mod_slab_ocean_reservoir.f90:810-811) */
+int sml_ocean_ring_reset(sml_engine *h);
 /* device-only halves of begin/end for callers that keep the grids on the device */
 int sml_step_pack_device(sml_engine *h, int timestep);                 /* gathered -> G (+clamps) */
 int sml_step_unpack_device(sml_engine *h, int timestep);               /* G,F -> feedback, local_model */

@@ -20,7 +20,7 @@ input_xstart input_xend input_ystart input_yend inputxchunk inputychunk input_zs
 tdata_xstart tdata_xend tdata_ystart tdata_yend tdata_zstart tdata_zend pole periodicboundary top bottom
 atmo3d_start atmo3d_end logp_start logp_end precip_start precip_end sst_start sst_end tisr_start tisr_end
 predict_start predict_end logp_mean_std_idx tisr_mean_std_idx precip_mean_std_idx sst_mean_std_idx
-mean_std_length""".split()
+mean_std_length ohtc_start ohtc_end ohtc_mean_std_idx is_ocean""".split()
 
 _DIMS_INT_FIELDS = """local_predictvars local_heightlevels_input local_heightlevels_res
 logp_bool precip_bool precip_input_bool sst_bool sst_bool_input tisr_input_bool
@@ -86,6 +86,9 @@ def lib():
         L.orc_fit_chunk_ml.argtypes = [C.c_void_p, C.c_double]
         L.orc_train_free.argtypes = [C.c_void_p]
         L.orc_setup_region.argtypes = [C.c_int] * 7 + [C.c_double] + [C.c_int] * 4 + [C.POINTER(Grid), C.POINTER(Dims)]
+        L.orc_setup_ocean_region.argtypes = [C.c_int] * 4 + [C.c_double, C.c_int, C.POINTER(Grid), C.POINTER(Dims)]
+        L.orc_predict_slab_ml.argtypes = [C.c_void_p, _dp]
+        L.orc_ocean_feedback.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int, _dp]
         L.orc_tile_full_input_to_target_data2d.argtypes = [C.POINTER(Grid), C.POINTER(Dims), _dp, C.c_int, C.c_int, _dp]
         L.orc_tileoverlapgrid4d.argtypes = [_dp] + [C.c_int] * 7 + [_dp]
         L.orc_tileoverlapgrid2d.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp]
@@ -299,6 +302,39 @@ class Region:
     @property
     def sxt(self):
         return self.view("states_x_trainingdata_aug", (self.P, self.n + self.S))
+
+
+class OceanRegion(Region):
+    """res%reservoir_special / res%grid_special of one region (src/mod_slab_ocean_reservoir.f90)"""
+
+    def __init__(self, num_regions, region, overlap=1, m=4000, deg=6.0, precip_bool=True, nslots=27):
+        self.g, self.d = Grid(), Dims()
+        rc = lib().orc_setup_ocean_region(num_regions, region, overlap, m, float(deg), int(precip_bool),
+                                          C.byref(self.g), C.byref(self.d))
+        if rc:
+            raise ValueError("orc_setup_ocean_region failed")
+        self.h = C.c_void_p(lib().orc_region_new(C.byref(self.g), C.byref(self.d)))
+        self.n, self.D = self.d.n, self.d.reservoir_numinputs
+        self.P, self.S, self.k = self.d.chunk_size_prediction, 0, self.d.k
+        self.L = self.g.mean_std_length
+        self.region, self.num_regions = region, num_regions
+        self.A = self.g.logp_end
+        self.nslots = nslots
+        self.ring = np.zeros((self.A, nslots), order="F")  # averaged_atmo_input_vec, zeroed (:810-811)
+
+    def predict(self):
+        lib().orc_predict_slab_ml(self.h, _d(self.x))
+
+    def build_feedback(self, atmo: Region, timestep: int, wholegrid_sst):
+        sst = np.asfortranarray(wholegrid_sst, dtype=np.float64)
+        lib().orc_ocean_feedback(self.h, atmo.h, _d(self.ring), self.nslots, timestep, _d(sst))
+
+    def target(self, statevec):
+        sv = np.asfortranarray(statevec, dtype=np.float64)
+        out = np.zeros((self.P, sv.shape[1]), order="F")
+        lib().orc_tile_full_input_to_target_data2d(C.byref(self.g), C.byref(self.d), _d(sv), sv.shape[0], sv.shape[1],
+                                                   _d(out))
+        return out
 
 
 def _handles(regs):

@@ -440,6 +440,128 @@ def train_hybrid(reg: Region, phases, batch_size, discard_cols, beta_res, beta_m
     return np.asfortranarray(xsol.T), sxs, sxt, info
 
 
+# --------------------------------------------------------------------------- slab ocean reservoir
+@dataclass
+class OceanRegion:
+    """res%reservoir_special + res%grid_special: initialize_slab_ocean_model
+    (src/mod_slab_ocean_reservoir.f90:9-133) and the offsets of trained_ocean_reservoir_prediction (:1598-1640)"""
+    num_regions: int
+    region: int
+    overlap: int = 1
+    m: int = 4000
+    deg: float = 6.0
+    precip_bool: bool = True   # only decides where the SST slot sits in the copied atmosphere mean/std
+    nslots: int = 27           # timestep_slab/timestep - 1 (:810)
+    rows: np.ndarray = None
+    cols: np.ndarray = None
+    vals: np.ndarray = None
+    win: np.ndarray = None
+    wout: np.ndarray = None
+    mean: np.ndarray = None
+    std: np.ndarray = None
+    feedback: np.ndarray = None
+    outvec: np.ndarray = None
+    leakage: float = 1.0
+
+    def __post_init__(self):
+        R, r, ov = self.num_regions, self.region, self.overlap
+        *_, self.resxchunk, self.resychunk = getxyresextent(R, r)
+        (_, _, _, _, self.inputxchunk, self.inputychunk, _, _) = getoverlapindices(R, r, ov)
+        self.tdata = get_trainingdataindices(R, r, ov)
+        ixy, rxy = self.inputxchunk * self.inputychunk, self.resxchunk * self.resychunk
+        self.P = 2 * rxy                       # sst_size_res + ohtc_res_size (:118)
+        self.D = 4 * ixy + ixy + 3 * ixy       # atmo (lowest level) + logp + sst + tisr + ohtc (:122-127)
+        self.n = int(math.floor(self.m / float(self.D) + 0.5)) * self.D
+        self.k = int((self.deg / float(self.m)) * self.n * self.n)
+        self.A = 5 * ixy                       # logp_end
+        self.sst_start = self.A + 1
+        self.sst_end = self.A + ixy
+        self.tisr_start, self.tisr_end = self.sst_end + 1, self.sst_end + ixy
+        self.ohtc_start, self.ohtc_end = self.tisr_end + 1, self.tisr_end + ixy
+        self.sst_idx = 4 * ZGRID + 2 + (1 if self.precip_bool else 0) + 1  # after logp, tisr, (precip)
+        self.mean_std_length = self.sst_idx
+        self.ring = np.zeros((self.A, self.nslots), order="F")
+        self.ml_only = True
+        self.S = 0
+
+
+def predict_slab_ml(reg: OceanRegion, x):
+    """src/mod_slab_ocean_reservoir.f90:1318-1363; returns (x, outvec)"""
+    x = state_update(reg, x, reg.feedback)
+    x_temp = x.copy()
+    x_temp[1::2] = x_temp[1::2] ** 2
+    outvec = reg.wout @ x_temp
+    return x, outvec * reg.std[reg.sst_idx - 1] + reg.mean[reg.sst_idx - 1]
+
+
+def ocean_feedback(ocean: OceanRegion, atmo: Region, timestep: int, wsst):
+    """SURVEY.md Appendix C intended semantics of src/mpires.f90:594-600,776-781"""
+    ixy = ocean.inputxchunk * ocean.inputychunk
+    a0 = atmo.atmo3d_end - 4 * ixy
+    ocean.ring[:, (timestep - 1) % ocean.nslots] = atmo.feedback[a0:a0 + ocean.A]
+    acc = np.zeros(ocean.A)
+    for k in range(ocean.nslots):      # sum(ring, dim=2), slot order
+        acc = acc + ocean.ring[:, k]
+    ocean.feedback[:ocean.A] = acc / float(ocean.nslots)
+    s = tileoverlapgrid2d(wsst, ocean.num_regions, ocean.region, ocean.overlap).ravel(order="F")
+    ocean.feedback[ocean.sst_start - 1:ocean.sst_end] = (s - ocean.mean[ocean.sst_idx - 1]) / ocean.std[ocean.sst_idx - 1]
+
+
+def tile_full_input_to_target_data_ocean(reg: OceanRegion, statevec):
+    """src/res_domain.f90:691-728 (ohtc_prediction branch); statevec (D, T) -> (P, T)"""
+    ix, iy = reg.inputxchunk, reg.inputychunk
+    T = statevec.shape[1]
+    xs, xe, ys, ye = reg.tdata
+    parts = []
+    for a, b in ((reg.sst_start, reg.sst_end), (reg.ohtc_start, reg.ohtc_end)):
+        t3 = statevec[a - 1:b].reshape((ix, iy, T), order="F")
+        parts.append(t3[xs - 1:xe, ys - 1:ye, :].reshape((-1, T), order="F"))
+    return np.concatenate(parts, axis=0)
+
+
+def train_ml(reg, phases, batch_size, discard_cols, beta_res, target_fn):
+    """ML-only accumulation + fit: reservoir_layer_chunking_ml / chunking_matmul_ml / fit_chunk_ml
+    (src/mod_reservoir.f90:963-1065,1594-1642,1177-1233; slab twins src/mod_slab_ocean_reservoir.f90:869-954,
+    1420-1464,1061-1116).  Unlike the hybrid path, every batch after the first restarts its SpMV operand
+    from the SQUARED copy states(:,batch_size) (:1034 / slab :933)."""
+    from scipy.linalg import lapack
+    n = reg.n
+    sxs = np.zeros((n, n), order="F")
+    sxt = np.zeros((reg.P, n), order="F")
+    for td in phases:
+        x = np.zeros(n)
+        for i in range(discard_cols):
+            x = state_update(reg, x, td[:, i])
+        TL = td.shape[1] - discard_cols
+        nb = TL // batch_size
+        for b in range(nb):
+            states = np.zeros((n, batch_size))
+            for c in range(batch_size):
+                s = b * batch_size + c
+                if s == 0:
+                    states[:, 0] = x
+                    continue
+                u = td[:, discard_cols + s - 1]
+                if c == 0:
+                    # operand = previous batch's last column AFTER the in-place squaring; the leak term uses x
+                    y = coo_mv(reg, prev_last_sq)
+                    xn = np.tanh(y + reg.win @ u)
+                    x = (1.0 - reg.leakage) * x + reg.leakage * xn
+                else:
+                    x = state_update(reg, x, u)
+                states[:, c] = x
+            states[1::2, :] = states[1::2, :] ** 2
+            prev_last_sq = states[:, -1].copy()
+            c0 = discard_cols + b * batch_size
+            target = target_fn(reg, td[:, c0:c0 + batch_size])
+            sxt += target @ states.T
+            sxs += states @ states.T
+    d = np.arange(n)
+    sxs[d, d] += beta_res
+    _, _, xsol, info = lapack.dgesv(sxs.T.copy(order="F"), sxt.T.copy(order="F"))
+    return np.asfortranarray(xsol.T), sxs, sxt, info
+
+
 def pinv_svd(A, thres=1e-2):
     """src/mod_linalg.f90:27-107: Moore-Penrose via SVD, singular values <= thres zeroed"""
     U, s, VT = np.linalg.svd(A, full_matrices=False)

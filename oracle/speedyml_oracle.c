@@ -339,6 +339,59 @@ int orc_setup_region(int num_regions, int region, int overlap, int num_vert_leve
     return 0;
 }
 
+/* slab-ocean reservoir (res%reservoir_special / res%grid_special).
+ * sizes: initialize_slab_ocean_model, src/mod_slab_ocean_reservoir.f90:9-133 (m=4000, deg=6, leakage=1,
+ * always ML-only :26,112-114); vector offsets: trained_ocean_reservoir_prediction :1598-1640.
+ * grid_special starts as a copy of the bottom-level atmosphere grid (same tiling, same mean/std slots). */
+int orc_setup_ocean_region(int num_regions, int region, int overlap, int m, double deg, int precip_bool,
+                           orc_grid *g, orc_dims *d)
+{
+    orc_dims da;
+    if (orc_setup_region(num_regions, region, overlap, 1, 1, 0, 6000, 6.0, precip_bool, 1, 1, 0, g, &da)) return -1;
+    memset(d, 0, sizeof(*d));
+    const int ixy = g->inputxchunk * g->inputychunk, rxy = g->resxchunk * g->resychunk;
+    d->local_predictvars = 4;                      /* :18 full_predictvars */
+    d->local_heightlevels_input = g->inputzchunk;  /* :19 */
+    d->local_heightlevels_res = g->reszchunk;      /* :21 */
+    d->ml_only = 1;                                /* :23 ml_only_ocean */
+    d->m = m;
+    d->deg = deg;
+    d->density = deg / (double)m;                  /* :37 */
+    d->leakage = 1.0;                              /* :41 */
+    d->sst_bool = 1;
+    d->sst_bool_input = 1;
+    d->tisr_input_bool = 1;
+    d->sst_size_res = rxy;                         /* :57 */
+    d->sst_size_input = ixy;                       /* :63 */
+    d->tisr_size_res = rxy;                        /* :75 */
+    d->tisr_size_input = ixy;                      /* :81 */
+    const int atmo_size_input = ixy * d->local_predictvars + ixy; /* :87 (precip_input_bool is .False. :1597) */
+    const int ohtc_input_size = ixy, ohtc_res_size = rxy;         /* :98-108 */
+    d->chunk_size_speedy = 0;                      /* :112-114 */
+    d->chunk_size = d->sst_size_res + ohtc_res_size;            /* :116 */
+    d->chunk_size_prediction = d->sst_size_res + ohtc_res_size; /* :118 */
+    d->locality = atmo_size_input + d->sst_size_input + 0 + d->tisr_size_input + ohtc_input_size - d->chunk_size; /* :122 */
+    d->nodes_per_input = nint_d((double)d->m / ((double)d->chunk_size + (double)d->locality));
+    d->n = d->nodes_per_input * (d->chunk_size + d->locality);
+    d->k = (int)(d->density * d->n * d->n);
+    d->reservoir_numinputs = d->chunk_size + d->locality;
+    /* :1598-1618 */
+    g->atmo3d_start = 1;
+    g->atmo3d_end = ixy * 4;
+    g->logp_start = g->atmo3d_end + 1;
+    g->logp_end = ixy * 4 + ixy;
+    g->precip_start = g->precip_end = 0;
+    g->sst_start = g->logp_end + 1;
+    g->sst_end = g->sst_start + ixy - 1;
+    g->tisr_start = g->sst_end + 1;
+    g->tisr_end = g->tisr_start + ixy - 1;
+    g->ohtc_start = g->tisr_end + 1;
+    g->ohtc_end = g->ohtc_start + ixy - 1;
+    g->ohtc_mean_std_idx = 1; /* :1640 */
+    g->is_ocean = 1;
+    return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* tilers                                                              */
 /* ------------------------------------------------------------------ */
@@ -476,6 +529,21 @@ void orc_tile_full_input_to_target_data2d(const orc_grid *g, const orc_dims *d, 
     const int P = d->chunk_size_prediction;
     const int n4res = nv * g->resxchunk * g->resychunk * d->local_heightlevels_res;
     const int rxy = g->resxchunk * g->resychunk;
+    if (g->is_ocean) {
+        /* tile_full_input_to_target_data2d_ocean_model, src/res_domain.f90:691-728 (ohtc_prediction branch):
+         * interior of the SST block, then interior of the OHTC block */
+        for (int c = 0; c < ncols; ++c) {
+            const double *sv = statevec + (size_t)c * ld;
+            double *t = tiled + (size_t)c * P;
+            size_t e = 0;
+            const double *ss = sv + (g->sst_start - 1), *oh = sv + (g->ohtc_start - 1);
+            for (int y = g->tdata_ystart; y <= g->tdata_yend; ++y)
+                for (int x = g->tdata_xstart; x <= g->tdata_xend; ++x) t[e++] = ss[(x - 1) + (size_t)ixc * (y - 1)];
+            for (int y = g->tdata_ystart; y <= g->tdata_yend; ++y)
+                for (int x = g->tdata_xstart; x <= g->tdata_xend; ++x) t[e++] = oh[(x - 1) + (size_t)ixc * (y - 1)];
+        }
+        return;
+    }
     for (int c = 0; c < ncols; ++c) {
         const double *sv = statevec + (size_t)c * ld;
         double *t = tiled + (size_t)c * P;
@@ -918,6 +986,49 @@ void orc_predict_all(orc_region **regs, int nreg, int ml_only, int nthreads)
     for (int i = 0; i < nreg; ++i) {
         if (ml_only) orc_predict_ml(regs[i], regs[i]->x);
         else orc_predict(regs[i], regs[i]->x);
+    }
+}
+
+/* src/mod_slab_ocean_reservoir.f90:1318-1363 predict_slab_ml: same update and readout (S = 0), then
+ * outvec*std(sst)+mean(sst) on every output (SST and OHTC alike, :1354) */
+void orc_predict_slab_ml(orc_region *r, double *x)
+{
+    const int n = r->d.n, P = r->d.chunk_size_prediction;
+    double *y = (double *)malloc(sizeof(double) * (size_t)n), *temp = (double *)malloc(sizeof(double) * (size_t)n);
+    state_update(r, r->feedback, x, y, temp);
+    readout(r, x, 0);
+    const int si = r->g.sst_mean_std_idx - 1;
+    for (int p = 0; p < P; ++p) {
+        double v = r->outvec[p] * r->std[si];
+        r->outvec[p] = v + r->mean[si];
+    }
+    free(y);
+    free(temp);
+}
+
+/* ocean feedback, intended semantics: src/mpires.f90:594-600 (SST tile, standardised
+ * with grid_special's SST mean/std), :776-781 (ring of the atmosphere reservoir's standardised lowest-level
+ * + logp feedback, slot mod(timestep-1,nslots)+1, mean = sum/nslots even while slots are still zero). */
+void orc_ocean_feedback(orc_region *ocean, const orc_region *atmo, double *ring, int nslots, int timestep,
+                        const double *wholegrid_sst)
+{
+    const orc_grid *g = &ocean->g, *ga = &atmo->g;
+    const int ixy = g->inputxchunk * g->inputychunk;
+    const int A = g->logp_end;
+    const int a0 = ga->atmo3d_end - ixy * 4; /* 0-based start of atmo_training_data_idx (:1621-1625) */
+    const int slot = (timestep - 1) % nslots;
+    for (int e = 0; e < A; ++e) ring[e + (size_t)A * slot] = atmo->feedback[a0 + e];
+    for (int e = 0; e < A; ++e) {
+        double s = 0.0;
+        for (int k = 0; k < nslots; ++k) s += ring[e + (size_t)A * k];
+        ocean->feedback[e] = s / (double)nslots;
+    }
+    double *sst = ocean->feedback + (g->sst_start - 1);
+    orc_tileoverlapgrid2d(wholegrid_sst, g->number_of_regions, g->region, g->overlap, sst);
+    const int si = g->sst_mean_std_idx - 1;
+    for (int e = 0; e < ixy; ++e) {
+        double v = sst[e] - ocean->mean[si];
+        sst[e] = v / ocean->std[si];
     }
 }
 

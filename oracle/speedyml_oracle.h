@@ -41,6 +41,8 @@ typedef struct orc_grid {
     int sst_start, sst_end, tisr_start, tisr_end, predict_start, predict_end;
     int logp_mean_std_idx, tisr_mean_std_idx, precip_mean_std_idx, sst_mean_std_idx;
     int mean_std_length;
+    /* slab-ocean grid_special only (src/mod_slab_ocean_reservoir.f90:1598-1640) */
+    int ohtc_start, ohtc_end, ohtc_mean_std_idx, is_ocean;
 } orc_grid;
 
 /* reservoir_type sizing subset (src/mod_utilities.f90:169-369) */
@@ -75,6 +77,12 @@ int  orc_find_closest_divisor(int target, int number);
 int  orc_setup_region(int num_regions, int region, int overlap, int num_vert_levels, int vert_level,
                       int vert_overlap, int m, double deg, int precip_bool, int slab_ocean_model_bool,
                       int sst_bool_input, int ml_only, orc_grid *g, orc_dims *d);
+
+/* slab-ocean reservoir sizing: initialize_slab_ocean_model (src/mod_slab_ocean_reservoir.f90:9-133) and the
+ * offsets of trained_ocean_reservoir_prediction (:1561-1652); grid_special is a copy of the bottom-level
+ * atmosphere grid with the vector offsets overwritten */
+int  orc_setup_ocean_region(int num_regions, int region, int overlap, int m, double deg, int precip_bool,
+                            orc_grid *g, orc_dims *d);
 
 /* ---- tilers (array copies exactly as the reference slices them) ---- */
 int  orc_tileoverlapgrid4d(const double *grid4d, int nvars, int numregions, int region, int overlap,
@@ -124,6 +132,14 @@ void orc_synchronize(orc_region *r, const double *input, int ld, double *x, int 
 void orc_predict(orc_region *r, double *x);      /* hybrid: uses r->feedback, r->local_model */
 void orc_predict_ml(orc_region *r, double *x);
 void orc_predict_all(orc_region **regs, int nreg, int ml_only, int nthreads);
+/* predict_slab_ml (src/mod_slab_ocean_reservoir.f90:1318-1363): all outputs * std(sst) + mean(sst) */
+void orc_predict_slab_ml(orc_region *r, double *x);
+/* ocean feedback of one hybrid step, intended semantics of SURVEY.md Appendix C (src/mpires.f90:594-600,
+ * 776-781): ring(:, mod(timestep-1,nslots)+1) = atmosphere feedback(atmo3d_end-4*ixy+1 : logp_end) (already
+ * standardised); feedback(1:logp_end) = sum(ring,dim=2)/nslots; feedback(sst_start:sst_end) = standardised
+ * halo'd tile of wholegrid_sst; the TISR and OHTC slots are left as they are.  ring is (logp_end, nslots). */
+void orc_ocean_feedback(orc_region *ocean, const orc_region *atmo, double *ring, int nslots, int timestep,
+                        const double *wholegrid_sst);
 
 /* sendrecievegrid split at the host-model call (src/mpires.f90:218-804) */
 void orc_step_gather(orc_region **regs, int nreg, int precip_bool, int ocean_model,

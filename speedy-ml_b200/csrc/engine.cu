@@ -39,7 +39,11 @@ struct HostRegion {
     RegionDev dev{};
     std::vector<void *> allocs;
     RegionSizes sizes{};
+    OceanSizes osizes{};
     bool sst_in = false;
+    std::vector<int32_t> target_map;   // rows of the input vector that form the training target
+    const int *d_sst_src = nullptr;    // ocean: offsets of the halo'd SST tile in G
+    double sst_mean = 0.0, sst_std = 1.0;
 };
 
 struct KindState {
@@ -81,8 +85,12 @@ struct sml_engine {
     double *d_G = nullptr, *d_F = nullptr, *d_gathered = nullptr;
     double *d_base_sst = nullptr, *d_mask = nullptr, *d_prescribed = nullptr;
     int *d_out_dst = nullptr;
-    int *d_cell_region = nullptr, *d_cell_slot = nullptr, *d_region_ocean_slab = nullptr;
+    int *d_cell_region = nullptr, *d_cell_slot = nullptr;
     double *d_ocean_gathered = nullptr;
+    OceanFb *d_ocean_fb = nullptr;     // one entry per local ocean reservoir
+    double *d_ocean_ring = nullptr;    // averaged_atmo_input_vec of every local ocean reservoir
+    size_t ocean_ring_doubles = 0;
+    int n_ocean_fb = 0, ocean_slots = 27, P_ocean = 0;
     double *h_pin_G = nullptr, *h_pin_F = nullptr;
     bool sst_static_set = false, sst_prescribed_set = false;
     // profiling
@@ -214,7 +222,7 @@ int sml_destroy(sml_engine *h)
     for (int k = 0; k < 2; ++k) free_kind(h->kinds[k]);
     cudaFree(h->d_G); cudaFree(h->d_F); cudaFree(h->d_gathered); cudaFree(h->d_base_sst); cudaFree(h->d_mask);
     cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);
-    cudaFree(h->d_region_ocean_slab); cudaFree(h->d_ocean_gathered);
+    cudaFree(h->d_ocean_gathered); cudaFree(h->d_ocean_fb); cudaFree(h->d_ocean_ring);
     cudaFreeHost(h->h_pin_G); cudaFreeHost(h->h_pin_F);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
@@ -291,6 +299,27 @@ int sml_region_dims(int R, int region, int ov, int m, double deg, int precip, in
     *n = s.n; *k = s.k; *D = s.D; *P = s.P; *S = s.S; *L = s.L;
     return 0;
 }
+int sml_ocean_region_dims(int R, int region, int ov, int m, double deg, int *n, int *k, int *D, int *P, int *A)
+{
+    Tiling t = make_tiling(R);
+    if (!t.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    OceanSizes s = make_ocean_sizes(t, g, m, deg);
+    *n = s.n; *k = s.k; *D = s.D; *P = s.P; *A = s.A;
+    return 0;
+}
+int sml_ocean_region_maps(int R, int region, int ov, int32_t *sst_map, int32_t *target_map, int *atmo_slice0)
+{
+    Tiling t = make_tiling(R);
+    if (!t.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    OceanSizes s = make_ocean_sizes(t, g, 4000, 6.0);
+    OceanMaps m = make_ocean_maps(t, g, s);
+    if (sst_map) std::copy(m.sst_src.begin(), m.sst_src.end(), sst_map);
+    if (target_map) std::copy(m.target_map.begin(), m.target_map.end(), target_map);
+    if (atmo_slice0) *atmo_slice0 = s.atmo_slice0;
+    return 0;
+}
 int sml_region_maps(int R, int region, int ov, int precip, int sst_in, int32_t *input_map, int32_t *input_ms,
                     int32_t *output_map, int32_t *output_ms, int32_t *model_map, int32_t *model_ms,
                     int32_t *target_map)
@@ -348,8 +377,23 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
         hr.sizes = s;
         hr.sst_in = w->sst_bool_input && h->p.slab_ocean_model_bool;
         maps = make_maps(h->tiling, g, s, h->p.precip_bool, hr.sst_in);
+        hr.target_map = maps.target_map;
     } else {
-        FAIL(h, "ocean reservoirs are not supported in this build");
+        // res%reservoir_special: sizes of initialize_slab_ocean_model, always ML-only
+        if (!h->p.slab_ocean_model_bool) FAIL(h, "ocean reservoir uploaded but slab_ocean_model_bool is off");
+        OceanSizes s = make_ocean_sizes(h->tiling, g, 4000, 6.0);
+        if (s.D != D || s.P != P || S != 0)
+            FAIL(h, "ocean region %d: D/P/S = %d/%d/%d but the tiling gives %d/%d/0", w->region, D, P, S, s.D, s.P);
+        if (n % D != 0) FAIL(h, "ocean region %d: n = %d is not a multiple of reservoir_numinputs %d", w->region, n, D);
+        if (w->sst_std == 0.0) FAIL(h, "ocean region %d: sst_std must be the SST slot of grid_special%%std", w->region);
+        hr.osizes = s;
+        OceanMaps om = make_ocean_maps(h->tiling, g, s);
+        hr.target_map = om.target_map;
+        hr.sst_mean = w->sst_mean;
+        hr.sst_std = w->sst_std;
+        if (dev_upload(h, &hr, om.sst_src.data(), om.sst_src.size(), &hr.d_sst_src)) return -1;
+        // predict_slab_ml un-standardises every output with the SST constants (:1354): slot L
+        maps.output_ms.assign(P, L);
     }
     const int ldw = P + (P & 1);
     if (ldw / 2 > NCONS) FAIL(h, "chunk_size_prediction %d too large for the readout kernel", P);
@@ -447,8 +491,18 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
 static int finalize_kind(sml_engine *h, int kind)
 {
     KindState &K = h->kinds[kind];
-    if (!K.any) return 0;
     const int nloc = (int)K.regs.size();
+    if (!K.any) {
+        if (kind == SML_OCEAN && h->p.slab_ocean_model_bool) {
+            // no ocean reservoir on this rank: every region reports 272.0 (src/mpires.f90:323-326)
+            K.P = 2 * h->tiling.fx * h->tiling.fy;
+            K.ldw = K.P;
+            std::vector<double> init((size_t)nloc * K.P, 272.0);
+            CK(h, cudaMalloc(&K.d_out, sizeof(double) * init.size()));
+            CK(h, cudaMemcpy(K.d_out, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice));
+        }
+        return 0;
+    }
     int chunk_rows = 720;
     if (const char *s = getenv("SML_CHUNK_ROWS")) chunk_rows = std::max(64, atoi(s));
     long long xo = 0, fo = 0, lo = 0;
@@ -499,7 +553,6 @@ static int finalize_kind(sml_engine *h, int kind)
     K.xs_cap = (S_max + max_rows + 1) & ~1;
     K.smem_bytes = (size_t)STAGES * K.stage_bytes + ((size_t)K.xs_cap + 2 * NCONS) * 8 + 2 * STAGES * 8;
     if (K.smem_bytes > 227 * 1024) FAIL(h, "step kernel needs %zu B of shared memory", K.smem_bytes);
-    CK(h, cudaFuncSetAttribute(k_step<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.smem_bytes));
 
     std::vector<RegionDev> regs(nloc);
     for (int i = 0; i < nloc; ++i) regs[i] = K.regs[i].dev;
@@ -517,8 +570,12 @@ static int finalize_kind(sml_engine *h, int kind)
     CK(h, cudaMemset(K.d_fb, 0, sizeof(double) * std::max<long long>(1, fo)));
     CK(h, cudaMalloc(&K.d_lm, sizeof(double) * std::max<long long>(1, lo)));
     CK(h, cudaMemset(K.d_lm, 0, sizeof(double) * std::max<long long>(1, lo)));
-    CK(h, cudaMalloc(&K.d_out, sizeof(double) * (size_t)nloc * K.P));
-    CK(h, cudaMemset(K.d_out, 0, sizeof(double) * (size_t)nloc * K.P));
+    {
+        // ocean slab rows of regions without an ocean reservoir stay at 272.0 (src/mpires.f90:323-326)
+        std::vector<double> init((size_t)nloc * K.P, kind == SML_OCEAN ? 272.0 : 0.0);
+        CK(h, cudaMalloc(&K.d_out, sizeof(double) * init.size()));
+        CK(h, cudaMemcpy(K.d_out, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice));
+    }
     CK(h, cudaMalloc(&K.d_partials, sizeof(double) * (size_t)std::max(1, K.nitems) * K.ldw));
     if (K.any_dense) {
         CK(h, cudaMalloc(&K.d_temp, sizeof(double) * std::max<long long>(1, xo)));
@@ -535,8 +592,46 @@ int sml_finalize(sml_engine *h)
     for (int k = 0; k < 2; ++k)
         if (finalize_kind(h, k)) return -1;
     if (!h->kinds[SML_ATMO].any) FAIL(h, "no atmosphere reservoirs uploaded");
+    {
+        // the dynamic shared-memory limit is a property of the kernel, not of a launch: take the larger kind
+        const size_t smem = std::max(h->kinds[SML_ATMO].smem_bytes, h->kinds[SML_OCEAN].smem_bytes);
+        CK(h, cudaFuncSetAttribute(k_step<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const int R = h->p.number_of_regions, P = h->kinds[SML_ATMO].P;
     h->P_atmo = P;
+    h->P_ocean = h->kinds[SML_OCEAN].P > 0 ? h->kinds[SML_OCEAN].P : 2 * h->tiling.fx * h->tiling.fy;
+    if (h->kinds[SML_OCEAN].any) {
+        // feedback assembly of the ocean reservoirs: ring of timestep_slab/timestep - 1 slots
+        // (src/mod_slab_ocean_reservoir.f90:810), zeroed (:811)
+        KindState &KA = h->kinds[SML_ATMO], &KO = h->kinds[SML_OCEAN];
+        if (h->p.timestep <= 0 || h->p.timestep_slab / h->p.timestep - 1 < 1) FAIL(h, "bad timestep / timestep_slab");
+        h->ocean_slots = h->p.timestep_slab / h->p.timestep - 1;
+        std::vector<OceanFb> fbs;
+        size_t ring = 0;
+        for (size_t i = 0; i < KO.regs.size(); ++i) {
+            HostRegion &ho = KO.regs[i];
+            if (!ho.uploaded) continue;
+            const RegionDev &da = KA.regs[i].dev;
+            if (ho.osizes.atmo_slice0 + ho.osizes.A > da.D) FAIL(h, "internal: atmosphere slice of ocean region out of range");
+            OceanFb f{};
+            f.atmo_fb_off = da.fb_off + ho.osizes.atmo_slice0;
+            f.fb_off = ho.dev.fb_off;
+            f.ring_off = (long long)ring;
+            f.A = ho.osizes.A;
+            f.ixy = ho.osizes.ixy;
+            f.sst_src = ho.d_sst_src;
+            f.sst_mean = ho.sst_mean;
+            f.sst_std = ho.sst_std;
+            ring += (size_t)f.A * h->ocean_slots;
+            fbs.push_back(f);
+        }
+        h->n_ocean_fb = (int)fbs.size();
+        h->ocean_ring_doubles = ring;
+        CK(h, cudaMalloc(&h->d_ocean_fb, sizeof(OceanFb) * fbs.size()));
+        CK(h, cudaMemcpy(h->d_ocean_fb, fbs.data(), sizeof(OceanFb) * fbs.size(), cudaMemcpyHostToDevice));
+        CK(h, cudaMalloc(&h->d_ocean_ring, sizeof(double) * ring));
+        CK(h, cudaMemset(h->d_ocean_ring, 0, sizeof(double) * ring));
+    }
     // scatter table for ALL regions of the model (every rank rebuilds the whole grid after the all-gather)
     std::vector<int> out_dst((size_t)R * P);
     std::vector<int> cell_region(XG * YG), cell_slot(XG * YG);
@@ -560,9 +655,6 @@ int sml_finalize(sml_engine *h)
     CK(h, cudaMemcpy(h->d_cell_region, cell_region.data(), sizeof(int) * XG * YG, cudaMemcpyHostToDevice));
     CK(h, cudaMalloc(&h->d_cell_slot, sizeof(int) * XG * YG));
     CK(h, cudaMemcpy(h->d_cell_slot, cell_slot.data(), sizeof(int) * XG * YG, cudaMemcpyHostToDevice));
-    std::vector<int> ocean_slab(R, -1);
-    CK(h, cudaMalloc(&h->d_region_ocean_slab, sizeof(int) * R));
-    CK(h, cudaMemcpy(h->d_region_ocean_slab, ocean_slab.data(), sizeof(int) * R, cudaMemcpyHostToDevice));
     CK(h, cudaMalloc(&h->d_G, sizeof(double) * G_TOTAL));
     CK(h, cudaMemset(h->d_G, 0, sizeof(double) * G_TOTAL));
     CK(h, cudaMalloc(&h->d_F, sizeof(double) * F_TOTAL));
@@ -575,8 +667,11 @@ int sml_finalize(sml_engine *h)
     CK(h, cudaMemset(h->d_mask, 0, sizeof(double) * XG * YG));
     CK(h, cudaMalloc(&h->d_prescribed, sizeof(double) * XG * YG));
     CK(h, cudaMemset(h->d_prescribed, 0, sizeof(double) * XG * YG));
-    CK(h, cudaMalloc(&h->d_ocean_gathered, sizeof(double) * (size_t)R * 8));
-    CK(h, cudaMemset(h->d_ocean_gathered, 0, sizeof(double) * (size_t)R * 8));
+    {
+        std::vector<double> init((size_t)R * h->P_ocean, 272.0);
+        CK(h, cudaMalloc(&h->d_ocean_gathered, sizeof(double) * init.size()));
+        CK(h, cudaMemcpy(h->d_ocean_gathered, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice));
+    }
     CK(h, cudaMallocHost(&h->h_pin_G, sizeof(double) * G_TOTAL));
     CK(h, cudaMallocHost(&h->h_pin_F, sizeof(double) * (F_TOTAL + XG * YG)));
     h->finalized = true;
@@ -613,6 +708,7 @@ int sml_feedback_get(sml_engine *h, int kind, int region, double *v) { return co
 int sml_local_model_set(sml_engine *h, int kind, int region, const double *v) { return copy_vec(h, kind, region, nullptr, v, 2); }
 int sml_local_model_get(sml_engine *h, int kind, int region, double *v) { return copy_vec(h, kind, region, v, nullptr, 2); }
 int sml_outvec_get(sml_engine *h, int kind, int region, double *v) { return copy_vec(h, kind, region, v, nullptr, 3); }
+int sml_outvec_set(sml_engine *h, int kind, int region, const double *v) { return copy_vec(h, kind, region, nullptr, v, 3); }
 
 int sml_wout_get(sml_engine *h, int kind, int region, double *wout)
 {
@@ -781,6 +877,27 @@ int sml_exchange_buffers(sml_engine *h, void **slab, int64_t *slab_count, void *
     return 0;
 }
 
+int sml_ocean_exchange_buffers(sml_engine *h, void **slab, int64_t *slab_count, void **gathered,
+                               int64_t *gathered_count)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    KindState &K = h->kinds[SML_OCEAN];
+    if (!K.d_out) FAIL(h, "slab_ocean_model_bool is off: there is no ocean slab");
+    *slab = K.d_out;
+    *slab_count = (int64_t)K.regs.size() * h->P_ocean;
+    *gathered = h->d_ocean_gathered;
+    *gathered_count = (int64_t)h->p.number_of_regions * h->P_ocean;
+    return 0;
+}
+
+int sml_ocean_ring_reset(sml_engine *h)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (h->d_ocean_ring)
+        CK(h, cudaMemsetAsync(h->d_ocean_ring, 0, sizeof(double) * h->ocean_ring_doubles, h->stream));
+    return 0;
+}
+
 int sml_step_pack_device(sml_engine *h, int timestep)
 {
     (void)timestep;
@@ -796,9 +913,11 @@ int sml_step_pack_device(sml_engine *h, int timestep)
         if (!h->sst_static_set) FAIL(h, "sml_set_sst_static (base_sst_grid, sea_mask) has not been called");
         const int mode = h->p.sst_prescribed ? 1 : 0;
         if (mode == 1 && !h->sst_prescribed_set) FAIL(h, "sst_prescribed is on but sml_set_sst_prescribed was never called");
+        // single rank: the ocean outvec slab already holds every region; otherwise the host all-gathers it
+        const double *ocean_out = (h->p.numprocs == 1) ? h->kinds[SML_OCEAN].d_out : h->d_ocean_gathered;
         k_sst_grid<<<(XG * YG + 255) / 256, 256, 0, h->stream>>>(h->d_G + G_SST, h->d_base_sst, h->d_mask,
                                                                  h->d_prescribed, h->d_cell_region, h->d_cell_slot,
-                                                                 h->d_region_ocean_slab, h->d_ocean_gathered, 8, mode);
+                                                                 ocean_out, h->P_ocean, mode);
         h->launches++;
     }
     CK(h, cudaGetLastError());
@@ -821,13 +940,20 @@ int sml_step_exchange_begin(sml_engine *h, int timestep, double *w4d, double *w2
 
 int sml_step_unpack_device(sml_engine *h, int timestep)
 {
-    (void)timestep;
     if (check_ready(h, SML_ATMO)) return -1;
     CK(h, cudaSetDevice(h->p.device));
     KindState &K = h->kinds[SML_ATMO];
+    if (h->n_ocean_fb > 0 && timestep < 1)
+        FAIL(h, "timestep must be the 1-based hybrid step (it selects the ring slot mod(timestep-1,%d)+1)", h->ocean_slots);
     k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
                                                                    h->p.ml_only ? 0 : 1);
     h->launches++;
+    if (h->n_ocean_fb > 0) {
+        k_build_ocean_inputs<<<h->n_ocean_fb, 128, 0, h->stream>>>(h->d_ocean_fb, h->d_G, K.d_fb,
+                                                                   h->kinds[SML_OCEAN].d_fb, h->d_ocean_ring,
+                                                                   (timestep - 1) % h->ocean_slots, h->ocean_slots);
+        h->launches++;
+    }
     CK(h, cudaGetLastError());
     return 0;
 }

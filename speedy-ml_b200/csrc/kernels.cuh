@@ -305,23 +305,19 @@ __global__ void k_scatter_grid(const double *__restrict__ gathered, const int *_
     G[dst] = v;
 }
 
-// wholegrid_sst (src/mpires.f90:288-290, 315-328, 470-484).  mode 0: reference -- base grid, ocean tiles
-// (first fx*fy outputs of each ocean reservoir) or 272.0 for regions without one; mode 1: prescribed field.
+// wholegrid_sst (src/mpires.f90:288-290, 315-328, 470-484).  mode 0: reference -- every cell takes the first
+// fx*fy outputs of its region's ocean reservoir (tile_full_2d_grid_with_local_res, src/res_domain.f90:828-850);
+// regions without one hold 272.0 in their slab row (:323-326, 383); mode 1: prescribed field.
 __global__ void k_sst_grid(double *__restrict__ sst, const double *__restrict__ base, const double *__restrict__ mask,
                            const double *__restrict__ prescribed, const int *__restrict__ cell_region,
-                           const int *__restrict__ cell_slot, const int *__restrict__ region_ocean_slab,
-                           const double *__restrict__ ocean_gathered, int ocean_P, int mode)
+                           const int *__restrict__ cell_slot, const double *__restrict__ ocean_out, int ocean_P,
+                           int mode)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= 96 * 48) return;
     double v;
-    if (mode == 1) {
-        v = prescribed[e];
-    } else {
-        const int r = cell_region[e];
-        const int slab = region_ocean_slab[r];
-        v = (slab >= 0) ? ocean_gathered[(size_t)slab * ocean_P + cell_slot[e]] : 272.0;
-    }
+    if (mode == 1) v = prescribed[e];
+    else v = ocean_out[(size_t)cell_region[e] * ocean_P + cell_slot[e]];
     if (mask[e] > 0.0) v = base[e];
     if (v < 272.0) v = 272.0;
     sst[e] = v;
@@ -348,6 +344,35 @@ __global__ void k_build_inputs(const RegionDev *__restrict__ regs, const double 
             if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
             lm_pool[R.lm_off + s] = v;
         }
+}
+
+// ocean reservoir feedback (src/mpires.f90:594-600, 776-781; intended semantics):
+//   ring(:, slot) = the atmosphere reservoir's standardised lowest-level + logp feedback
+//   feedback(1:A) = sum(ring, dim=2) / nslots   (slot order, divides by nslots even while slots are zero)
+//   feedback(sst) = (halo'd tile of wholegrid_sst - mean_sst) / std_sst ;  TISR / OHTC slots untouched.
+struct OceanFb {
+    long long atmo_fb_off;  // atmosphere feedback of the same region + atmo_slice0
+    long long fb_off;       // ocean feedback
+    long long ring_off;     // ring [nslots][A]
+    int A, ixy;
+    const int *sst_src;     // [ixy] offsets into G
+    double sst_mean, sst_std;
+};
+
+__global__ void k_build_ocean_inputs(const OceanFb *__restrict__ O, const double *__restrict__ G,
+                                     const double *__restrict__ atmo_fb, double *__restrict__ ocean_fb,
+                                     double *__restrict__ ring, int slot, int nslots)
+{
+    const OceanFb o = O[blockIdx.x];
+    double *rg = ring + o.ring_off;
+    for (int e = threadIdx.x; e < o.A; e += blockDim.x) {
+        rg[(size_t)slot * o.A + e] = atmo_fb[o.atmo_fb_off + e];
+        double s = 0.0;
+        for (int k = 0; k < nslots; ++k) s = __dadd_rn(s, rg[(size_t)k * o.A + e]);
+        ocean_fb[o.fb_off + e] = __ddiv_rn(s, (double)nslots);
+    }
+    for (int e = threadIdx.x; e < o.ixy; e += blockDim.x)
+        ocean_fb[o.fb_off + o.A + e] = __ddiv_rn(__dsub_rn(G[o.sst_src[e]], o.sst_mean), o.sst_std);
 }
 
 }  // namespace sml

@@ -208,6 +208,57 @@ inline RegionMaps make_maps(const Tiling &t, const RegionGeom &g, const RegionSi
     return m;
 }
 
+// ---- slab-ocean reservoir (res%reservoir_special / res%grid_special) ------------------------------------
+// initialize_slab_ocean_model (src/mod_slab_ocean_reservoir.f90:9-133): input vector
+//   [ atmosphere lowest level (var,lx,ly) 4*ixy | logp ixy | sst ixy | tisr ixy | ohtc ixy ],  D = 8*ixy,
+//   output [ sst(rx,ry) | ohtc(rx,ry) ], P = 2*fx*fy, always ML-only (S = 0); offsets :1598-1618.
+struct OceanSizes {
+    int n, k, D, P, q;
+    int ixy;       // halo tile points
+    int A;         // logp_end: length of the time-averaged atmosphere part (5*ixy)
+    int sst_off, tisr_off, ohtc_off;  // 0-based offsets in the ocean input vector
+    int atmo_slice0;  // 0-based start of atmo_training_data_idx (:1621-1625) in the ATMOSPHERE input vector
+};
+
+inline OceanSizes make_ocean_sizes(const Tiling &t, const RegionGeom &g, int m, double deg)
+{
+    OceanSizes s{};
+    s.ixy = g.ixc * g.iyc;
+    s.A = NVAR * s.ixy + s.ixy;
+    s.sst_off = s.A;
+    s.tisr_off = s.sst_off + s.ixy;
+    s.ohtc_off = s.tisr_off + s.ixy;
+    s.D = s.ohtc_off + s.ixy;
+    s.P = 2 * t.fx * t.fy;
+    s.q = (int)std::floor((double)m / (double)s.D + 0.5);
+    s.n = s.q * s.D;
+    s.k = (int)((deg / (double)m) * s.n * s.n);
+    s.atmo_slice0 = NVAR * s.ixy * ZG - NVAR * s.ixy;  // atmo3d_end - 4*ixy: the lowest level is the last z slab
+    return s;
+}
+
+struct OceanMaps {
+    std::vector<int32_t> sst_src;     // [ixy] offsets into G of the halo'd SST tile (tileoverlapgrid2d)
+    std::vector<int32_t> target_map;  // [P] rows of the ocean input vector (tile_full_input_to_target_data2d_ocean_model, src/res_domain.f90:691-728)
+};
+
+inline OceanMaps make_ocean_maps(const Tiling &t, const RegionGeom &g, const OceanSizes &s)
+{
+    OceanMaps m;
+    m.sst_src.assign(s.ixy, 0);
+    for (int ly = 0; ly < g.iyc; ++ly)
+        for (int lx = 0; lx < g.ixc; ++lx)
+            m.sst_src[lx + g.ixc * ly] = (int32_t)(G_SST + off2(g.gx[lx], g.iys - 1 + ly));
+    m.target_map.assign(s.P, 0);
+    int e = 0;
+    for (int blk = 0; blk < 2; ++blk) {
+        const int base = blk == 0 ? s.sst_off : s.ohtc_off;
+        for (int ry = 0; ry < t.fy; ++ry)
+            for (int rx = 0; rx < t.fx; ++rx) m.target_map[e++] = base + (g.tdx0 + rx) + g.ixc * (g.tdy0 + ry);
+    }
+    return m;
+}
+
 // processor_decomposition (src/res_domain.f90:31-62)
 inline std::vector<int32_t> regions_of_rank(int irank, int numprocs, int nregions)
 {

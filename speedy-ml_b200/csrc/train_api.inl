@@ -95,13 +95,9 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         bad = bad || alloc((size_t)d.ld * T.ks * 8, &p); d.slab = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xa = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xb = (double *)p;
-        // target rows (tile_full_input_to_target_data2d) from the tiling
-        std::vector<int32_t> tmap(d.R.P, 0);
-        if (kind == SML_ATMO) {
-            RegionGeom g = make_geom(h->tiling, regions[i], h->p.overlap);
-            RegionMaps m = make_maps(h->tiling, g, K.regs[li].sizes, h->p.precip_bool, K.regs[li].sst_in);
-            tmap = m.target_map;
-        }
+        // target rows (tile_full_input_to_target_data2d / _ocean_model), flattened at upload
+        const std::vector<int32_t> &tmap = K.regs[li].target_map;
+        if ((int)tmap.size() != d.R.P) { h->err = "internal: target map size"; train_release(T); return -1; }
         bad = bad || alloc(sizeof(int) * d.R.P, &p);
         if (!bad) {
             cudaMemcpyAsync(p, tmap.data(), sizeof(int) * d.R.P, cudaMemcpyHostToDevice, h->stream);

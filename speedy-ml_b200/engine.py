@@ -58,6 +58,8 @@ _SIGNATURES = {
     "sml_region_dims": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
                         + [C.POINTER(C.c_int)] * 6, C.c_int),
     "sml_region_maps": ([C.c_int] * 5 + [_ip] * 7, C.c_int),
+    "sml_ocean_region_dims": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [C.POINTER(C.c_int)] * 5, C.c_int),
+    "sml_ocean_region_maps": ([C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int)], C.c_int),
     "sml_global_layout": ([_lp, _lp, _lp], C.c_int),
     "sml_region_upload": ([C.c_void_p, C.POINTER(SmlRegionWeights)], C.c_int),
     "sml_finalize": ([C.c_void_p], C.c_int),
@@ -68,6 +70,7 @@ _SIGNATURES = {
     "sml_local_model_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_local_model_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_outvec_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_outvec_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_wout_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_wout_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_synchronize": ([C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _lp], C.c_int),
@@ -77,6 +80,8 @@ _SIGNATURES = {
     "sml_set_sst_static": ([C.c_void_p, _dp, _dp], C.c_int),
     "sml_set_sst_prescribed": ([C.c_void_p, _dp], C.c_int),
     "sml_exchange_buffers": ([C.c_void_p] + [C.POINTER(C.c_void_p), _lp] * 4, C.c_int),
+    "sml_ocean_exchange_buffers": ([C.c_void_p] + [C.POINTER(C.c_void_p), _lp] * 2, C.c_int),
+    "sml_ocean_ring_reset": ([C.c_void_p], C.c_int),
     "sml_step_pack_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_step_unpack_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_begin": ([C.c_void_p, C.c_int, _ip, C.c_int, C.c_int], C.c_int),
@@ -198,6 +203,26 @@ def region_maps(num_regions, region, overlap=1, precip_bool=True, sst_bool_input
                                       *[_i(a) for a in arrs]):
         raise ValueError("unsupported region count")
     return dict(zip(("input_map", "input_ms", "output_map", "output_ms", "model_map", "model_ms", "target_map"), arrs))
+
+
+def ocean_region_dims(num_regions, region, overlap=1, m=4000, deg=6.0):
+    """initialize_slab_ocean_model sizes -> dict(n, k, D, P, S=0, A)"""
+    v = [C.c_int() for _ in range(5)]
+    if load_library().sml_ocean_region_dims(num_regions, region, overlap, m, float(deg), *[C.byref(a) for a in v]):
+        raise ValueError("unsupported region count")
+    d = dict(zip(("n", "k", "D", "P", "A"), (a.value for a in v)))
+    d["S"] = 0
+    return d
+
+
+def ocean_region_maps(num_regions, region, overlap=1):
+    d = ocean_region_dims(num_regions, region, overlap)
+    sst = np.zeros(d["D"] // 8, np.int32)
+    tgt = np.zeros(d["P"], np.int32)
+    a0 = C.c_int()
+    if load_library().sml_ocean_region_maps(num_regions, region, overlap, _i(sst), _i(tgt), C.byref(a0)):
+        raise ValueError("unsupported region count")
+    return dict(sst_map=sst, target_map=tgt, atmo_slice0=a0.value)
 
 
 def global_layout():
@@ -332,6 +357,11 @@ class Engine:
     def outvec_get(self, region, kind=ATMO):
         return self._get(self.lib.sml_outvec_get, kind, region, self.dims[(kind, region)]["P"])
 
+    def outvec_set(self, region, v, kind=ATMO):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        assert v.size == self.dims[(kind, region)]["P"]
+        self._ck(self.lib.sml_outvec_set(self.h, kind, region, _d(v)))
+
     def wout_get(self, region, kind=ATMO):
         d = self.dims[(kind, region)]
         out = np.zeros((d["P"], d["n"] + d["S"]), order="F")
@@ -407,6 +437,17 @@ class Engine:
         self._ck(self.lib.sml_exchange_buffers(self.h, *args))
         names = ("outvec_slab", "gathered", "G", "F")
         return {n: DeviceArray(p.value, c.value, self) for n, p, c in zip(names, ptrs, cnts)}
+
+    def ocean_exchange_buffers(self):
+        """-> dict of DeviceArray: ocean_slab [nloc*P_ocean], ocean_gathered [R*P_ocean]"""
+        ptrs = [C.c_void_p() for _ in range(2)]
+        cnts = [C.c_int64() for _ in range(2)]
+        self._ck(self.lib.sml_ocean_exchange_buffers(self.h, C.byref(ptrs[0]), C.byref(cnts[0]), C.byref(ptrs[1]),
+                                                     C.byref(cnts[1])))
+        return {n: DeviceArray(p.value, c.value, self) for n, p, c in zip(("ocean_slab", "ocean_gathered"), ptrs, cnts)}
+
+    def ocean_ring_reset(self):
+        self._ck(self.lib.sml_ocean_ring_reset(self.h))
 
     # -- training: chunking_matmul / fit_chunk_hybrid   mod_reservoir.f90:1645,1235
     def train_begin(self, regions, batch_size, kind=ATMO):
