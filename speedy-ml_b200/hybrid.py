@@ -1,0 +1,151 @@
+"""The hybrid step loop of src/parallelmain.f90:206-273 over one engine shard per rank.
+
+`HybridStepper` is the host-side sequencing the reference spreads over parallelmain.f90 (region loop calling
+predict, :226-251) and mpires.f90:sendrecievegrid (:218-804): predict on every local region, exchange of the
+outvec slabs, assembly of the global grids with the clamps, the host model (SPEEDY's run_model, a callable
+here) on rank 0, and the rebuild of every region's feedback / local_model.
+
+Ranks are one process per GPU.  The data path has ONE collective per step -- the all-gather of the outvec
+slabs (1152 x 136 doubles in total) -- plus the broadcast of rank 0's host-model forecast and the date's TISR
+field; every rank then rebuilds the whole grid and gathers its own halo'd inputs locally.  Regions are sharded
+as processor_decomposition (src/res_domain.f90:31-62) does; with number_of_regions divisible by the rank count
+the shards are contiguous ascending blocks, so rank-major all-gather order IS region order (`slab_rows`).
+
+The stepper only needs the small `shard` protocol below, so the multi-rank sequencing is testable on CPU with
+the gloo backend (tests/test_multirank_gloo.py drives it with an oracle-backed shard); on a GPU box the shard
+is `EngineShard`, a thin view of speedy-ml_b200.engine.Engine whose buffers are engine-owned device memory.
+
+shard protocol:  predict() . ocean_predict() . pack(t) . unpack(t) . exchange_begin(t) -> (w4d, w2d, wp, wsst)
+                 exchange_end(t, f4d, f2d, tisr) . load_forecast(f4d, f2d, tisr) [rank 0, stages H2D]
+                 tensors: slab, gathered, F, tisr_dev, (ocean_slab, ocean_gathered) or None
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine as E
+
+
+def slab_rows(number_of_regions: int, numprocs: int):
+    """region id of every row of the all-gathered outvec buffer (rank-major order)."""
+    rows = []
+    for r in range(numprocs):
+        rows += E.processor_decomposition(r, numprocs, number_of_regions)
+    return rows
+
+
+def check_contiguous_sharding(number_of_regions: int, numprocs: int):
+    """the engine indexes the gathered buffer by region id: require rank-major order == region order"""
+    rows = slab_rows(number_of_regions, numprocs)
+    if rows != list(range(number_of_regions)):
+        raise ValueError(f"{number_of_regions} regions over {numprocs} ranks is not a contiguous sharding "
+                         "(processor_decomposition puts the remainder regions out of order)")
+    return number_of_regions // numprocs
+
+
+def ocean_step_due(t: int, timestep: int = 6, timestep_slab: int = 168) -> bool:
+    """src/parallelmain.f90:238: the ocean reservoirs step when mod(t*timestep, timestep_slab) == 0"""
+    return (t * timestep) % timestep_slab == 0
+
+
+class EngineShard:
+    """the stepper's view of one Engine (one rank's regions on one B200)"""
+
+    def __init__(self, eng: "E.Engine", torch_module, ocean: bool = False):
+        self.eng = eng
+        torch = torch_module
+        bufs = eng.exchange_buffers()
+        self.slab = torch.as_tensor(bufs["outvec_slab"], device="cuda")
+        self.gathered = torch.as_tensor(bufs["gathered"], device="cuda")
+        self.F = torch.as_tensor(bufs["F"], device="cuda")
+        self.G = torch.as_tensor(bufs["G"], device="cuda")
+        lay = E.global_layout()
+        self.lay = lay
+        self.tisr_dev = self.G[lay["tisr"]:]
+        self.ocean_slab = self.ocean_gathered = None
+        if ocean:
+            ob = eng.ocean_exchange_buffers()
+            self.ocean_slab = torch.as_tensor(ob["ocean_slab"], device="cuda")
+            self.ocean_gathered = torch.as_tensor(ob["ocean_gathered"], device="cuda")
+        self._pin_f = torch.empty(lay["f_total"], dtype=torch.float64).pin_memory()
+        self._pin_t = torch.empty(E.XGRID * E.YGRID, dtype=torch.float64).pin_memory()
+        self._torch = torch
+
+    def predict(self):
+        self.eng.predict()
+
+    def ocean_predict(self):
+        self.eng.predict(kind=E.OCEAN)
+
+    def pack(self, t):
+        self.eng.step_pack_device(t)
+
+    def unpack(self, t):
+        self.eng.step_unpack_device(t)
+
+    def exchange_begin(self, t):
+        return self.eng.step_exchange_begin(t)
+
+    def exchange_end(self, t, f4d, f2d, tisr):
+        self.eng.step_exchange_end(t, f4d, f2d, tisr)
+
+    def load_forecast(self, f4d, f2d, tisr):
+        """rank 0, multi-rank runs: stage the host model's output for the broadcast (pinned -> device, async)"""
+        torch, lay = self._torch, self.lay
+        self._pin_f[:lay["w2d"]] = torch.from_numpy(np.asarray(f4d).ravel(order="F"))
+        self._pin_f[lay["w2d"]:] = torch.from_numpy(np.asarray(f2d).ravel(order="F"))
+        self._pin_t[:] = torch.from_numpy(np.asarray(tisr).ravel(order="F"))
+        self.F.copy_(self._pin_f, non_blocking=True)
+        self.tisr_dev.copy_(self._pin_t, non_blocking=True)
+
+
+class HybridStepper:
+    """one hybrid step = parallelmain's region loop + sendrecievegrid, over `world` ranks"""
+
+    def __init__(self, shard, rank: int = 0, world: int = 1, dist=None, timestep: int = 6, timestep_slab: int = 168):
+        self.s, self.rank, self.world, self.dist = shard, rank, world, dist
+        self.timestep, self.timestep_slab = timestep, timestep_slab
+        if world > 1 and dist is None:
+            raise ValueError("multi-rank stepping needs torch.distributed")
+
+    # ---- the exchange of the outvec slabs (the path's only data collective)
+    def _gather_outvecs(self, ocean_stepped: bool):
+        if self.world == 1:
+            return
+        self.dist.all_gather_into_tensor(self.s.gathered, self.s.slab)
+        if ocean_stepped and self.s.ocean_slab is not None:
+            self.dist.all_gather_into_tensor(self.s.ocean_gathered, self.s.ocean_slab)
+
+    def _predict(self, t):
+        self.s.predict()
+        stepped = self.s.ocean_slab is not None and ocean_step_due(t, self.timestep, self.timestep_slab)
+        if stepped:
+            self.s.ocean_predict()
+        return stepped or (t == 1 and self.s.ocean_slab is not None)  # first step publishes the seeded ocean outvecs
+
+    def device_step(self, t: int):
+        """everything resident on the device; the forecast buffer F keeps what the last host step left"""
+        stepped = self._predict(t)
+        self._gather_outvecs(stepped)
+        self.s.pack(t)
+        self.s.unpack(t)
+
+    def step(self, t: int, host_model, tisr_grid):
+        """the reference-facing step: host buffers, the host model (run_model) between begin and end.
+        host_model(w4d, w2d, wsst) -> (forecast_4d, forecast_2d); tisr_grid is the date's global TISR field."""
+        stepped = self._predict(t)
+        self._gather_outvecs(stepped)
+        if self.rank == 0:
+            w4d, w2d, wp, wsst = self.s.exchange_begin(t)
+            f4d, f2d = host_model(w4d, w2d, wsst)
+            if self.world == 1:
+                self.s.exchange_end(t, f4d, f2d, tisr_grid)
+                return (w4d, w2d, wp, wsst)
+            self.s.load_forecast(f4d, f2d, tisr_grid)
+        else:
+            self.s.pack(t)
+            w4d = w2d = wp = wsst = None
+        self.dist.broadcast(self.s.F, 0)
+        self.dist.broadcast(self.s.tisr_dev, 0)
+        self.s.unpack(t)
+        return (w4d, w2d, wp, wsst) if self.rank == 0 else None
