@@ -313,6 +313,7 @@ def run_gpu(args):
     H.check_contiguous_sharding(R_TOTAL, world)
     shard = H.EngineShard(eng, torch)
     stepper = H.HybridStepper(shard, rank=rank, world=world, dist=dist if world > 1 else None)
+    stepper_ovl = H.HybridStepper(shard, rank=rank, world=world, dist=dist if world > 1 else None)
     lay = E.global_layout()
     # start from climatology: G holds the "previous hybrid grid", F its host forecast
     g0 = np.concatenate([F["clim4d"].ravel(order="F"), F["clim2d"].ravel(order="F"), np.zeros(96 * 48),
@@ -329,7 +330,7 @@ def run_gpu(args):
     device_step = stepper.device_step
 
     def e2e_step(t):
-        stepper.step(t, host_model, F["tisr"])
+        (stepper_ovl if args.overlap else stepper).step(t, host_model, F["tisr"])
 
     def barrier():
         if world > 1:
@@ -354,9 +355,15 @@ def run_gpu(args):
         return ms, wall
 
     # ---- e2e first (it also leaves a consistent F on the device), then the device-resident measure
+    if args.overlap:
+        stepper_ovl.overlap = True
+        eng.set_overlap(True)
     for i in range(args.warmup):
         e2e_step(i + 1)
     e2e_ms, e2e_wall = timed(e2e_step, args.steps, args.warmup + 1)
+    if args.overlap:
+        eng.set_overlap(False)
+        stepper_ovl.overlap = False
     for i in range(args.warmup):
         device_step(i + 1)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -397,7 +404,9 @@ def run_gpu(args):
                        "value_path": "device-resident: predict + all-gather + scatter/clamp + feedback rebuild; "
                                      "host model excluded (F resident)",
                        "e2e_path": "sml_predict + sml_step_exchange_begin (D2H) + host model stub + "
-                                   "sml_step_exchange_end (H2D), wall clock",
+                                   "sml_step_exchange_end (H2D), wall clock; "
+                                   + ("overlapped mode: the next predict's state update and x~ readout run while the "
+                                      "host model works (SURVEY.md Appendix D)" if args.overlap else "sequential mode"),
                        "state_finite": finite, "setup_s": round(t_gen, 1)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((lay["f_total"] + 96 * 48) * 8),
                     "d2h_bytes_per_step": int(lay["tisr"] * 8), "ms_per_step": e2e_wall / args.steps,
@@ -432,6 +441,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false",
+                    help="e2e in the sequential (reference-order) mode instead of the overlapped one")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     if args.warmup < 3:

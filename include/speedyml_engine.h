@@ -169,6 +169,24 @@ int sml_step_exchange_begin(sml_engine *h, int timestep, double *wholegrid4d, do
                             double *wholegrid_precip, double *wholegrid_sst);
 int sml_step_exchange_end(sml_engine *h, int timestep, const double *forecast_4d,
                           const double *forecast_2d, const double *tisr_grid);
+/* ---- overlapped step (optional).  feedback(t) depends only on the gathered outvec grid,
+ * TISR and SST -- not on run_model's forecast -- and local_model(t) enters only the first S columns of the next
+ * readout (the reference computes that split itself as v_p / v_ml, src/mod_reservoir.f90:1458-1461).  With
+ * sml_set_overlap(h, 1):
+ *   sml_set_tisr(h, tisr)            the date's TISR field, before the exchange begins
+ *   sml_step_exchange_begin(...)     additionally rebuilds every feedback vector and launches the NEXT predict's
+ *                                    state update + W_out[:, S:]*x~ while only the grid copy-out is waited for
+ *   (host: NetCDF output, run_model)
+ *   sml_step_exchange_end(...)       uploads the forecast, builds local_model, adds W_out[:, 0:S]*local_model,
+ *                                    un-standardises: outvec of step t+1 is complete (tisr may be NULL)
+ *   sml_predict(h, SML_ATMO)         of step t+1 then only consumes that result.
+ * Summation order differs from the fused readout (v_p + v_ml instead of one dot product): equal within 1e-13,
+ * not bit-identical; reservoir state/feedback are bit-identical.  sml_state_get after exchange_end returns x(t+1).
+ * Multi-rank callers use the device-only pieces: sml_step_pack_device, sml_step_predict_ahead,
+ * (broadcast of F), sml_step_unpack_device. ---- */
+int sml_set_overlap(sml_engine *h, int on);
+int sml_set_tisr(sml_engine *h, const double *tisr_grid);
+int sml_step_predict_ahead(sml_engine *h, int timestep);
 /* static fields of the exchange: base_sst_grid and sea_mask (src/mod_reservoir.f90:847-887) */
 int sml_set_sst_static(sml_engine *h, const double *base_sst_grid, const double *sea_mask);
 /* sst_prescribed == 1: the SST field (96x48) the next exchanges start from instead of ocean-reservoir

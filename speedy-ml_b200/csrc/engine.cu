@@ -52,6 +52,7 @@ struct KindState {
     std::vector<HostRegion> regs;
     RegionDev *d_regs = nullptr;
     StepItem *d_items = nullptr;
+    StepItem *d_items_split = nullptr;  // same chunks without the S local_model columns (overlapped step)
     std::vector<StepItem> items;
     int nitems = 0;
     double *d_x[2] = {nullptr, nullptr};
@@ -99,6 +100,16 @@ struct sml_engine {
     bool profile = false;
     int64_t launches = 0;
     TrainState train;
+    // overlapped step: the state update and the W_out[:, S:]*x~ partials of the NEXT
+    // predict run while the host model works on this step's grids; the S model columns are added when its
+    // forecast arrives
+    bool overlap = false;
+    bool ahead_pending = false;  // ML part of the next predict launched, model part still missing
+    bool ahead_done = false;     // next predict complete: the next sml_predict(ATMO) only consumes it
+    bool tisr_fresh = false;     // sml_set_tisr has been called for the step being exchanged
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
+    double *h_pin_tisr = nullptr;
 };
 
 #define FAIL(h, ...)                                      \
@@ -207,7 +218,7 @@ static void free_kind(KindState &K)
 {
     for (auto &r : K.regs)
         for (void *p : r.allocs) cudaFree(p);
-    cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
+    cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_items_split); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
     cudaFree(K.d_lm); cudaFree(K.d_out); cudaFree(K.d_partials); cudaFree(K.d_temp); cudaFree(K.d_fb_offs);
     cudaFree(K.d_in); cudaFree(K.d_in_offs);
 }
@@ -223,7 +234,11 @@ int sml_destroy(sml_engine *h)
     cudaFree(h->d_G); cudaFree(h->d_F); cudaFree(h->d_gathered); cudaFree(h->d_base_sst); cudaFree(h->d_mask);
     cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);
     cudaFree(h->d_ocean_gathered); cudaFree(h->d_ocean_fb); cudaFree(h->d_ocean_ring);
-    cudaFreeHost(h->h_pin_G); cudaFreeHost(h->h_pin_F);
+    cudaFreeHost(h->h_pin_G); cudaFreeHost(h->h_pin_F); cudaFreeHost(h->h_pin_tisr);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+    if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
+    if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
     delete h;
@@ -560,6 +575,16 @@ static int finalize_kind(sml_engine *h, int kind)
     CK(h, cudaMemcpy(K.d_regs, regs.data(), sizeof(RegionDev) * nloc, cudaMemcpyHostToDevice));
     CK(h, cudaMalloc(&K.d_items, sizeof(StepItem) * std::max(1, K.nitems)));
     CK(h, cudaMemcpy(K.d_items, K.items.data(), sizeof(StepItem) * K.nitems, cudaMemcpyHostToDevice));
+    {
+        std::vector<StepItem> split = K.items;
+        for (StepItem &it : split) {
+            it.col0 = K.regs[it.reg].dev.S + it.row0;
+            it.ncols = it.nrows;
+            it.xs_off = 0;
+        }
+        CK(h, cudaMalloc(&K.d_items_split, sizeof(StepItem) * std::max(1, K.nitems)));
+        CK(h, cudaMemcpy(K.d_items_split, split.data(), sizeof(StepItem) * K.nitems, cudaMemcpyHostToDevice));
+    }
     CK(h, cudaMalloc(&K.d_fb_offs, sizeof(long long) * nloc));
     CK(h, cudaMemcpy(K.d_fb_offs, fb_offs.data(), sizeof(long long) * nloc, cudaMemcpyHostToDevice));
     for (int b = 0; b < 2; ++b) {
@@ -674,6 +699,11 @@ int sml_finalize(sml_engine *h)
     }
     CK(h, cudaMallocHost(&h->h_pin_G, sizeof(double) * G_TOTAL));
     CK(h, cudaMallocHost(&h->h_pin_F, sizeof(double) * (F_TOTAL + XG * YG)));
+    CK(h, cudaMallocHost(&h->h_pin_tisr, sizeof(double) * XG * YG));
+    CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(h, cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
     h->finalized = true;
     return 0;
 }
@@ -757,6 +787,13 @@ int sml_predict(sml_engine *h, int kind)
     if (check_ready(h, kind)) return -1;
     CK(h, cudaSetDevice(h->p.device));
     KindState &K = h->kinds[kind];
+    if (kind == SML_ATMO) {
+        if (h->ahead_pending) FAIL(h, "overlapped step: sml_step_exchange_end / sml_step_unpack_device has not closed the previous step");
+        if (h->ahead_done) {  // this predict was computed while the host model ran
+            h->ahead_done = false;
+            return 0;
+        }
+    }
     cudaEvent_t *ev = nullptr;
     if (h->profile && h->ev_used < PROFILE_RING) {
         while ((int)h->ev.size() < 3 * (h->ev_used + 1)) {
@@ -770,7 +807,8 @@ int sml_predict(sml_engine *h, int kind)
     if (launch_step(h, K, K.d_items, K.nitems, K.d_fb, K.d_fb_offs, 0, 1)) return -1;
     K.cur ^= 1;
     if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
-    k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1);
+    k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1, 0,
+                                                                     K.d_lm);
     h->launches++;
     CK(h, cudaGetLastError());
     if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
@@ -924,12 +962,66 @@ int sml_step_pack_device(sml_engine *h, int timestep)
     return 0;
 }
 
+// feedback of every local region from G (needs this step's TISR in G), the ocean ring, then the state update and
+// the x~ columns of the readout of the NEXT predict (split-order)
+int sml_step_predict_ahead(sml_engine *h, int timestep)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    if (!h->overlap) FAIL(h, "sml_step_predict_ahead needs sml_set_overlap(h, 1)");
+    if (h->ahead_pending || h->ahead_done) FAIL(h, "overlapped step: the previous look-ahead predict was never consumed");
+    if (!h->tisr_fresh) FAIL(h, "overlapped step: call sml_set_tisr with the date's TISR field before the exchange begins");
+    KindState &K = h->kinds[SML_ATMO];
+    if (h->n_ocean_fb > 0 && timestep < 1) FAIL(h, "timestep must be the 1-based hybrid step");
+    k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm, 0, 1);
+    h->launches++;
+    if (h->n_ocean_fb > 0) {
+        k_build_ocean_inputs<<<h->n_ocean_fb, 128, 0, h->stream>>>(h->d_ocean_fb, h->d_G, K.d_fb,
+                                                                   h->kinds[SML_OCEAN].d_fb, h->d_ocean_ring,
+                                                                   (timestep - 1) % h->ocean_slots, h->ocean_slots);
+        h->launches++;
+    }
+    cudaEvent_t *ev = nullptr;
+    if (h->profile && h->ev_used < PROFILE_RING) {
+        while ((int)h->ev.size() < 3 * (h->ev_used + 1)) {
+            cudaEvent_t e;
+            CK(h, cudaEventCreate(&e));
+            h->ev.push_back(e);
+        }
+        ev = &h->ev[3 * h->ev_used++];
+    }
+    if (ev) CK(h, cudaEventRecord(ev[0], h->stream));
+    if (launch_step(h, K, K.d_items_split, K.nitems, K.d_fb, K.d_fb_offs, 0, 1)) return -1;
+    K.cur ^= 1;
+    if (ev) {
+        CK(h, cudaEventRecord(ev[1], h->stream));
+        CK(h, cudaEventRecord(ev[2], h->stream));
+    }
+    h->tisr_fresh = false;
+    h->ahead_pending = true;
+    return 0;
+}
+
 int sml_step_exchange_begin(sml_engine *h, int timestep, double *w4d, double *w2d, double *wprecip, double *wsst)
 {
     if (sml_step_pack_device(h, timestep)) return -1;
-    if (w4d || w2d || wprecip || wsst) {
+    const bool copy_out = w4d || w2d || wprecip || wsst;
+    if (h->overlap) {
+        // D2H of the grids on the copy stream, the look-ahead predict on the main stream; the host only
+        // waits for the copy
+        if (copy_out) {
+            CK(h, cudaEventRecord(h->ev_pack, h->stream));
+            CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pack, 0));
+            CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->copy_stream));
+            CK(h, cudaEventRecord(h->ev_d2h, h->copy_stream));
+        }
+        if (sml_step_predict_ahead(h, timestep)) return -1;
+        if (copy_out) CK(h, cudaEventSynchronize(h->ev_d2h));
+    } else if (copy_out) {
         CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
+    }
+    if (copy_out) {
         if (w4d) std::memcpy(w4d, h->h_pin_G + G_W4D, sizeof(double) * G_W2D);
         if (w2d) std::memcpy(w2d, h->h_pin_G + G_W2D, sizeof(double) * XG * YG);
         if (wprecip) std::memcpy(wprecip, h->h_pin_G + G_PRECIP, sizeof(double) * XG * YG);
@@ -943,10 +1035,23 @@ int sml_step_unpack_device(sml_engine *h, int timestep)
     if (check_ready(h, SML_ATMO)) return -1;
     CK(h, cudaSetDevice(h->p.device));
     KindState &K = h->kinds[SML_ATMO];
+    if (h->overlap && h->ahead_pending) {
+        // the forecast is in F: local_model, then v_p = W_out[:, 0:S]*local_model joins the partials
+        k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
+                                                                       h->p.ml_only ? 0 : 1, 0);
+        h->launches++;
+        k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1, 1,
+                                                                         K.d_lm);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        h->ahead_pending = false;
+        h->ahead_done = true;
+        return 0;
+    }
     if (h->n_ocean_fb > 0 && timestep < 1)
         FAIL(h, "timestep must be the 1-based hybrid step (it selects the ring slot mod(timestep-1,%d)+1)", h->ocean_slots);
     k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
-                                                                   h->p.ml_only ? 0 : 1);
+                                                                   h->p.ml_only ? 0 : 1, 1);
     h->launches++;
     if (h->n_ocean_fb > 0) {
         k_build_ocean_inputs<<<h->n_ocean_fb, 128, 0, h->stream>>>(h->d_ocean_fb, h->d_G, K.d_fb,
@@ -962,18 +1067,51 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const 
 {
     if (check_ready(h, SML_ATMO)) return -1;
     CK(h, cudaSetDevice(h->p.device));
-    if (!tisr) FAIL(h, "tisr_grid is required");
+    const bool ahead = h->overlap && h->ahead_pending;
+    if (!tisr && !ahead) FAIL(h, "tisr_grid is required");
+    // the forecast goes up on the copy stream in the overlapped mode (the main stream is busy with the look-ahead
+    // predict); its pinned staging is free again: the last copy from it finished before this step's pack ran
+    cudaStream_t up = ahead ? h->copy_stream : h->stream;
     if (!h->p.ml_only) {
         if (!f4d || !f2d) FAIL(h, "hybrid mode needs forecast_4d and forecast_2d");
         std::memcpy(h->h_pin_F + F_F4D, f4d, sizeof(double) * G_W2D);
         std::memcpy(h->h_pin_F + F_F2D, f2d, sizeof(double) * XG * YG);
-        CK(h, cudaMemcpyAsync(h->d_F, h->h_pin_F, sizeof(double) * F_TOTAL, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(h->d_F, h->h_pin_F, sizeof(double) * F_TOTAL, cudaMemcpyHostToDevice, up));
+    }
+    if (ahead) {
+        CK(h, cudaEventRecord(h->ev_h2d, h->copy_stream));
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_h2d, 0));
+        return sml_step_unpack_device(h, timestep);
     }
     std::memcpy(h->h_pin_F + F_TOTAL, tisr, sizeof(double) * XG * YG);
     CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_F + F_TOTAL, sizeof(double) * XG * YG, cudaMemcpyHostToDevice,
                           h->stream));
     if (sml_step_unpack_device(h, timestep)) return -1;
     CK(h, cudaStreamSynchronize(h->stream));  // pinned staging is reused by the next call
+    return 0;
+}
+
+int sml_set_overlap(sml_engine *h, int on)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (h->ahead_pending) FAIL(h, "cannot switch modes between sml_step_exchange_begin and _end");
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->overlap = on != 0;
+    h->ahead_done = false;
+    h->tisr_fresh = false;
+    return 0;
+}
+
+// get_tisr_by_date's field for the step being exchanged (src/mpires.f90:751-753, 1676-1708): in the overlapped mode
+// the feedback is rebuilt before the host model returns, so TISR has to be on the device when the exchange begins
+int sml_set_tisr(sml_engine *h, const double *tisr)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (!tisr) FAIL(h, "tisr_grid is required");
+    CK(h, cudaSetDevice(h->p.device));
+    std::memcpy(h->h_pin_tisr, tisr, sizeof(double) * XG * YG);
+    CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_tisr, sizeof(double) * XG * YG, cudaMemcpyHostToDevice, h->stream));
+    h->tisr_fresh = true;
     return 0;
 }
 

@@ -273,12 +273,21 @@ __global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__
 
 // partials of a region summed in item order, then unstandardize_state_vec_res (src/res_domain.f90:1424-1475):
 // v*std then +mean, two roundings (src/mod_utilities.f90:799-829).  One block per region.
+// model_part != 0 (split-order readout of the overlapped step): the partials hold only W_out[:, S:]*x~ (the
+// reference's v_ml, src/mod_reservoir.f90:1460) and this kernel adds v_p = W_out[:, 0:S]*local_model (:1459)
+// once the host model's forecast has arrived.
 __global__ void k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ partials, int ldw_max,
-                                 double *__restrict__ out_pool, int unstandardize)
+                                 double *__restrict__ out_pool, int unstandardize, int model_part,
+                                 const double *__restrict__ lm_pool)
 {
     const RegionDev R = regs[blockIdx.x];
     for (int p = threadIdx.x; p < R.P; p += blockDim.x) {
         double v = 0.0;
+        if (model_part) {
+            const double *lm = lm_pool + R.lm_off;
+            const double *w = R.wout + p;
+            for (int j = 0; j < R.S; ++j) v = fma(w[(size_t)j * R.ldw], lm[j], v);
+        }
         for (int c = 0; c < R.nitems; ++c) v += partials[(size_t)(R.item0 + c) * ldw_max + p];
         if (unstandardize) {
             const int ms = R.out_ms[p];
@@ -328,15 +337,16 @@ __global__ void k_sst_grid(double *__restrict__ sst, const double *__restrict__ 
 // src/mod_utilities.f90:1307-1329).  grid: (nregions), threads stride over D then S.
 __global__ void k_build_inputs(const RegionDev *__restrict__ regs, const double *__restrict__ G,
                                const double *__restrict__ F, double *__restrict__ fb_pool,
-                               double *__restrict__ lm_pool, int do_model)
+                               double *__restrict__ lm_pool, int do_model, int do_feedback)
 {
     const RegionDev R = regs[blockIdx.x];
-    for (int d = threadIdx.x; d < R.D; d += blockDim.x) {
-        double v = G[R.fb_src[d]];
-        const int ms = R.fb_ms[d];
-        if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
-        fb_pool[R.fb_off + d] = v;
-    }
+    if (do_feedback)
+        for (int d = threadIdx.x; d < R.D; d += blockDim.x) {
+            double v = G[R.fb_src[d]];
+            const int ms = R.fb_ms[d];
+            if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
+            fb_pool[R.fb_off + d] = v;
+        }
     if (do_model)
         for (int s = threadIdx.x; s < R.S; s += blockDim.x) {
             double v = F[R.lm_src[s]];

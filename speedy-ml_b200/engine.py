@@ -77,6 +77,9 @@ _SIGNATURES = {
     "sml_predict": ([C.c_void_p, C.c_int], C.c_int),
     "sml_step_exchange_begin": ([C.c_void_p, C.c_int, _dp, _dp, _dp, _dp], C.c_int),
     "sml_step_exchange_end": ([C.c_void_p, C.c_int, _dp, _dp, _dp], C.c_int),
+    "sml_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_set_tisr": ([C.c_void_p, _dp], C.c_int),
+    "sml_step_predict_ahead": ([C.c_void_p, C.c_int], C.c_int),
     "sml_set_sst_static": ([C.c_void_p, _dp, _dp], C.c_int),
     "sml_set_sst_prescribed": ([C.c_void_p, _dp], C.c_int),
     "sml_exchange_buffers": ([C.c_void_p] + [C.POINTER(C.c_void_p), _lp] * 4, C.c_int),
@@ -415,11 +418,22 @@ class Engine:
         self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, _d(w4d), _d(w2d), _d(wp), _d(wsst)))
         return w4d, w2d, wp, wsst
 
-    def step_exchange_end(self, timestep, forecast_4d, forecast_2d, tisr_grid):
+    def step_exchange_end(self, timestep, forecast_4d, forecast_2d, tisr_grid=None):
         f4 = _farr(forecast_4d, (4, XGRID, YGRID, ZGRID)) if forecast_4d is not None else None
         f2 = _farr(forecast_2d, (XGRID, YGRID)) if forecast_2d is not None else None
-        ti = _farr(tisr_grid, (XGRID, YGRID))
+        ti = _farr(tisr_grid, (XGRID, YGRID)) if tisr_grid is not None else None
         self._ck(self.lib.sml_step_exchange_end(self.h, timestep, _d(f4), _d(f2), _d(ti)))
+
+    # -- overlapped step: the next predict runs while the host model works
+    def set_overlap(self, on=True):
+        self._ck(self.lib.sml_set_overlap(self.h, int(on)))
+
+    def set_tisr(self, tisr_grid):
+        ti = _farr(tisr_grid, (XGRID, YGRID))
+        self._ck(self.lib.sml_set_tisr(self.h, _d(ti)))
+
+    def step_predict_ahead(self, timestep):
+        self._ck(self.lib.sml_step_predict_ahead(self.h, timestep))
 
     def step_pack_device(self, timestep=0):
         self._ck(self.lib.sml_step_pack_device(self.h, timestep))

@@ -94,19 +94,35 @@ class EngineShard:
         torch, lay = self._torch, self.lay
         self._pin_f[:lay["w2d"]] = torch.from_numpy(np.asarray(f4d).ravel(order="F"))
         self._pin_f[lay["w2d"]:] = torch.from_numpy(np.asarray(f2d).ravel(order="F"))
-        self._pin_t[:] = torch.from_numpy(np.asarray(tisr).ravel(order="F"))
         self.F.copy_(self._pin_f, non_blocking=True)
-        self.tisr_dev.copy_(self._pin_t, non_blocking=True)
+        if tisr is not None:
+            self._pin_t[:] = torch.from_numpy(np.asarray(tisr).ravel(order="F"))
+            self.tisr_dev.copy_(self._pin_t, non_blocking=True)
+
+    # overlapped mode
+    def set_overlap(self, on):
+        self.eng.set_overlap(on)
+
+    def set_tisr(self, tisr):
+        self.eng.set_tisr(tisr)
+
+    def predict_ahead(self, t):
+        self.eng.step_predict_ahead(t)
 
 
 class HybridStepper:
     """one hybrid step = parallelmain's region loop + sendrecievegrid, over `world` ranks"""
 
-    def __init__(self, shard, rank: int = 0, world: int = 1, dist=None, timestep: int = 6, timestep_slab: int = 168):
+    def __init__(self, shard, rank: int = 0, world: int = 1, dist=None, timestep: int = 6, timestep_slab: int = 168,
+                 overlap: bool = False):
         self.s, self.rank, self.world, self.dist = shard, rank, world, dist
         self.timestep, self.timestep_slab = timestep, timestep_slab
         if world > 1 and dist is None:
             raise ValueError("multi-rank stepping needs torch.distributed")
+        # overlap: the next step's state update and x~ readout run while the host model works (Appendix D)
+        self.overlap = overlap
+        if overlap:
+            self.s.set_overlap(True)
 
     # ---- the exchange of the outvec slabs (the path's only data collective)
     def _gather_outvecs(self, ocean_stepped: bool):
@@ -135,17 +151,22 @@ class HybridStepper:
         host_model(w4d, w2d, wsst) -> (forecast_4d, forecast_2d); tisr_grid is the date's global TISR field."""
         stepped = self._predict(t)
         self._gather_outvecs(stepped)
+        if self.overlap:
+            self.s.set_tisr(tisr_grid)          # every rank holds the TISR table (get_tisr_by_date)
         if self.rank == 0:
-            w4d, w2d, wp, wsst = self.s.exchange_begin(t)
+            w4d, w2d, wp, wsst = self.s.exchange_begin(t)   # overlap: also launches the next predict's ML part
             f4d, f2d = host_model(w4d, w2d, wsst)
             if self.world == 1:
-                self.s.exchange_end(t, f4d, f2d, tisr_grid)
+                self.s.exchange_end(t, f4d, f2d, None if self.overlap else tisr_grid)
                 return (w4d, w2d, wp, wsst)
-            self.s.load_forecast(f4d, f2d, tisr_grid)
+            self.s.load_forecast(f4d, f2d, None if self.overlap else tisr_grid)
         else:
             self.s.pack(t)
+            if self.overlap:
+                self.s.predict_ahead(t)
             w4d = w2d = wp = wsst = None
         self.dist.broadcast(self.s.F, 0)
-        self.dist.broadcast(self.s.tisr_dev, 0)
+        if not self.overlap:
+            self.dist.broadcast(self.s.tisr_dev, 0)
         self.s.unpack(t)
         return (w4d, w2d, wp, wsst) if self.rank == 0 else None

@@ -323,3 +323,89 @@ def test_readout_properties_full_tiling(E, small_model):
     # (o - mean)/std is linear in W_out
     assert rel_inf((o2 - mean_vec) / std_vec, 2.0 * (o1 - mean_vec) / std_vec) < 1e-12
     eng.wout_set(r, saved)
+
+
+def _reset_small_model(ws, eng, rcs, seed):
+    rng = np.random.default_rng(seed)
+    for w, rc in zip(ws, rcs):
+        fb = rng.standard_normal(w["D"])
+        lm = rng.standard_normal(w["S"])
+        x0 = 0.1 * rng.standard_normal(w["n"])
+        rc.feedback[:], rc.local_model[:], rc.x[:] = fb, lm, x0
+        eng.feedback_set(w["region"], fb)
+        eng.local_model_set(w["region"], lm)
+        eng.state_set(w["region"], x0)
+
+
+def test_overlapped_step_matches_sequential_and_oracle(E, small_model):
+    """the next predict's state update + x~ readout runs while the host model works; only the
+    summation order of the readout changes (v_p + v_ml).  Grids must agree with the sequential engine loop to
+    1e-12 and with the oracle to the loop tolerance; feedback vectors bit-identical given identical grids."""
+    ws, eng, rcs = small_model
+    G = initial_grids()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    eng.set_sst_prescribed(G["base_sst"])
+    nsteps = 6
+
+    def tisr_of(t):
+        return np.asfortranarray(G["tisr"] * (1.0 + 0.01 * t))
+
+    def run(overlap):
+        _reset_small_model(ws, eng, rcs, 33)
+        eng.set_overlap(overlap)
+        grids = []
+        for t in range(1, nsteps + 1):
+            eng.predict()
+            if overlap:
+                eng.set_tisr(tisr_of(t))
+            g = eng.step_exchange_begin(t)
+            f4, f2 = oc.host_stub(g[0], g[1], G["clim4d"], G["clim2d"])
+            eng.step_exchange_end(t, f4, f2, None if overlap else tisr_of(t))
+            grids.append(g)
+        fb = {r: eng.feedback_get(r) for r in (0, 555, 1151)}
+        lm = {r: eng.local_model_get(r) for r in (0, 555, 1151)}
+        eng.set_overlap(False)
+        return grids, fb, lm
+
+    seq, fb_s, lm_s = run(False)
+    ovl, fb_o, lm_o = run(True)
+    for t in range(nsteps):
+        for a, b in zip(ovl[t], seq[t]):
+            assert rel_inf(a, b) < (1e-14 if t == 0 else 1e-11)
+    for r in fb_s:
+        assert rel_inf(fb_o[r], fb_s[r]) < 1e-11 and rel_inf(lm_o[r], lm_s[r]) < 1e-11
+    # oracle closed loop from the same start
+    _reset_small_model(ws, eng, rcs, 33)
+    sst_mean = np.array([w["mean"][-1] for w in ws])
+    sst_std = np.array([w["std"][-1] for w in ws])
+    has = np.ones(len(rcs), dtype=np.int32)
+    oo = np.zeros((len(rcs), 4))
+    for i, w in enumerate(ws):
+        xs, xe, ys, ye, *_ = oc.getxyresextent(1152, w["region"])
+        oo[i] = G["base_sst"][xs - 1:xe, ys - 1:ye].ravel(order="F")
+    for t in range(1, nsteps + 1):
+        oc.predict_all(rcs, nthreads=8)
+        gc = oc.step_gather(rcs, True, True, G["base_sst"], G["sea_mask"], ocean_out=oo, has_ocean=has)
+        for a, b in zip(ovl[t - 1], gc):
+            assert rel_inf(a, b) < TOL_LOOP
+        f4, f2 = oc.host_stub(gc[0], gc[1], G["clim4d"], G["clim2d"])
+        oc.step_scatter(rcs, True, True, False, *gc, f4, f2, tisr_of(t), sst_mean, sst_std, nthreads=8)
+
+
+def test_overlapped_step_protocol_errors(E, small_model):
+    ws, eng, rcs = small_model
+    G = initial_grids()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    eng.set_sst_prescribed(G["base_sst"])
+    eng.set_overlap(True)
+    eng.predict()
+    with pytest.raises(E.EngineError):          # TISR must be on the device before the exchange begins
+        eng.step_exchange_begin(1)
+    eng.set_tisr(G["tisr"])
+    g = eng.step_exchange_begin(1)
+    with pytest.raises(E.EngineError):          # predict before the step was closed
+        eng.predict()
+    f4, f2 = oc.host_stub(g[0], g[1], G["clim4d"], G["clim2d"])
+    eng.step_exchange_end(1, f4, f2)
+    eng.predict()                               # consumes the look-ahead result
+    eng.set_overlap(False)
