@@ -312,6 +312,8 @@ def run_gpu(args):
     H = importlib.import_module("speedy-ml_b200.hybrid")
     H.check_contiguous_sharding(R_TOTAL, world)
     shard = H.EngineShard(eng, torch)
+    if world > 1 and args.peer:
+        shard.attach_peers(dist)   # fused all-gather: peer stores from the readout kernel over NVLink
     stepper = H.HybridStepper(shard, rank=rank, world=world, dist=dist if world > 1 else None)
     stepper_ovl = H.HybridStepper(shard, rank=rank, world=world, dist=dist if world > 1 else None)
     lay = E.global_layout()
@@ -382,6 +384,9 @@ def run_gpu(args):
     ov = eng.outvec_get(my_regions[0])
     finite = bool(np.isfinite(x).all() and np.isfinite(ov).all())
 
+    eng_peer = eng.peer_attached()
+    if eng_peer:
+        eng.peer_check()
     ms_per_step = dev_ms / args.steps
     value = SIM_DAYS_PER_STEP / (ms_per_step * 1e-3)
     e2e_value = SIM_DAYS_PER_STEP / (e2e_wall / args.steps * 1e-3)  # wall clock: host work is inside
@@ -400,6 +405,9 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "regions": R_TOTAL, "regions_per_gpu": len(my_regions),
                        "reservoir_m": M_RES, "degree": 6, "overlap": 1, "sim_days_per_step": SIM_DAYS_PER_STEP,
                        "sharding": f"processor_decomposition over {world} rank(s)",
+                       "exchange": ("none (single rank)" if world == 1 else
+                                    "fused all-gather: peer stores from the readout kernel over NVLink (CUDA IPC)"
+                                    if eng_peer else "NCCL all_gather_into_tensor of the outvec slabs"),
                        "l2": "per-GPU weights streamed every step (8.1 GB / n_gpus) exceed the 126 MB L2; no flush",
                        "value_path": "device-resident: predict + all-gather + scatter/clamp + feedback rebuild; "
                                      "host model excluded (F resident)",
@@ -441,6 +449,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-peer", dest="peer", action="store_false",
+                    help="multi-GPU: NCCL all-gather of the outvec slabs instead of the fused peer-store exchange")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="e2e in the sequential (reference-order) mode instead of the overlapped one")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

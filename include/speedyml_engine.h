@@ -199,6 +199,18 @@ int sml_set_sst_prescribed(sml_engine *h, const double *sst_grid);
 int sml_exchange_buffers(sml_engine *h, void **outvec_slab, int64_t *slab_count, void **gathered,
                          int64_t *gathered_count, void **gbuf, int64_t *g_count, void **fbuf,
                          int64_t *f_count);
+/* ---- fused all-gather over NVLink (ranks of ONE node, one process per GPU).  After sml_finalize every rank
+ * exports the CUDA IPC handle of its exchange block (64 bytes), the host passes all handles to all ranks (any
+ * transport) and attaches them in rank order.  From then on the readout-finish kernel of sml_predict(h, SML_ATMO)
+ * stores every outvec straight into every rank's gathered buffer (peer stores) and publishes a step flag; the
+ * pack kernel of sml_step_exchange_begin / sml_step_pack_device waits for all flags.  No host collective is
+ * needed for the atmosphere slabs any more (sml_exchange_buffers' gathered buffer is then unused).  Requires
+ * number_of_regions divisible by numprocs (contiguous shards) and numprocs <= 8.  sml_peer_check reports a rank
+ * that never published (the wait gives up after ~10 s instead of hanging). ---- */
+int sml_peer_export(sml_engine *h, void *handle64);
+int sml_peer_attach(sml_engine *h, const void *handles /* numprocs x 64 bytes, rank order */, int count);
+int sml_peer_attached(const sml_engine *h);
+int sml_peer_check(sml_engine *h);
 /* the same for the ocean reservoirs' outvec slab [nloc][P_ocean] (rows of regions without an ocean reservoir
  * hold 272.0, src/mpires.f90:323-326): all-gather it after every sml_predict(h, SML_OCEAN) when numprocs > 1 */
 int sml_ocean_exchange_buffers(sml_engine *h, void **ocean_slab, int64_t *slab_count, void **ocean_gathered,

@@ -110,6 +110,14 @@ struct sml_engine {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_pack = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
     double *h_pin_tisr = nullptr;
+    // peer exchange (fused all-gather over NVLink; kernels.cuh PeerTable)
+    void *d_xchg = nullptr;            // this rank's exchange block: [2][R*P] doubles + MAX_PEERS flags
+    size_t xchg_flags_off = 0;         // byte offset of the flags inside the block
+    PeerTable peers{};                 // world == 0/1: not attached
+    std::vector<void *> peer_mapped;   // cudaIpcOpenMemHandle results to close
+    unsigned long long peer_seq = 0;   // number of atmosphere predicts published so far
+    unsigned int *d_done = nullptr;
+    int *d_peer_err = nullptr;
 };
 
 #define FAIL(h, ...)                                      \
@@ -234,6 +242,8 @@ int sml_destroy(sml_engine *h)
     cudaFree(h->d_G); cudaFree(h->d_F); cudaFree(h->d_gathered); cudaFree(h->d_base_sst); cudaFree(h->d_mask);
     cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);
     cudaFree(h->d_ocean_gathered); cudaFree(h->d_ocean_fb); cudaFree(h->d_ocean_ring);
+    for (void *m : h->peer_mapped) cudaIpcCloseMemHandle(m);
+    cudaFree(h->d_xchg); cudaFree(h->d_done); cudaFree(h->d_peer_err);
     cudaFreeHost(h->h_pin_G); cudaFreeHost(h->h_pin_F); cudaFreeHost(h->h_pin_tisr);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
@@ -700,6 +710,16 @@ int sml_finalize(sml_engine *h)
     CK(h, cudaMallocHost(&h->h_pin_G, sizeof(double) * G_TOTAL));
     CK(h, cudaMallocHost(&h->h_pin_F, sizeof(double) * (F_TOTAL + XG * YG)));
     CK(h, cudaMallocHost(&h->h_pin_tisr, sizeof(double) * XG * YG));
+    CK(h, cudaMalloc(&h->d_done, sizeof(unsigned int)));
+    CK(h, cudaMemset(h->d_done, 0, sizeof(unsigned int)));
+    CK(h, cudaMalloc(&h->d_peer_err, sizeof(int)));
+    CK(h, cudaMemset(h->d_peer_err, 0, sizeof(int)));
+    if (h->p.numprocs > 1) {
+        h->xchg_flags_off = (sizeof(double) * 2 * (size_t)R * P + 255) / 256 * 256;
+        const size_t bytes = h->xchg_flags_off + sizeof(unsigned long long) * MAX_PEERS;
+        CK(h, cudaMalloc(&h->d_xchg, bytes));
+        CK(h, cudaMemset(h->d_xchg, 0, bytes));
+    }
     CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CK(h, cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
     CK(h, cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
@@ -782,6 +802,27 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
     return 0;
 }
 
+// partials -> outvec slab (+ the model columns in the overlapped mode); for the atmosphere kind with peers attached
+// the same kernel pushes the outvecs into every rank's gathered buffer and publishes the step
+static int launch_finish(sml_engine *h, KindState &K, int model_part)
+{
+    PeerTable pt{};
+    unsigned long long seq = 0;
+    long long peer_off = 0;
+    if (&K == &h->kinds[SML_ATMO] && h->peers.world > 1) {
+        pt = h->peers;
+        seq = ++h->peer_seq;
+        const long long RP = (long long)h->p.number_of_regions * K.P;
+        // rank-major == region order (contiguous shards): this rank's rows start at local_ids[0]
+        peer_off = (long long)(seq & 1) * RP + (long long)h->local_ids[0] * K.P;
+    }
+    k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1,
+                                                                     model_part, K.d_lm, pt, seq, peer_off, h->d_done);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
 int sml_predict(sml_engine *h, int kind)
 {
     if (check_ready(h, kind)) return -1;
@@ -807,10 +848,7 @@ int sml_predict(sml_engine *h, int kind)
     if (launch_step(h, K, K.d_items, K.nitems, K.d_fb, K.d_fb_offs, 0, 1)) return -1;
     K.cur ^= 1;
     if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
-    k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1, 0,
-                                                                     K.d_lm);
-    h->launches++;
-    CK(h, cudaGetLastError());
+    if (launch_finish(h, K, 0)) return -1;
     if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
     return 0;
 }
@@ -942,28 +980,105 @@ int sml_step_pack_device(sml_engine *h, int timestep)
     if (check_ready(h, SML_ATMO)) return -1;
     CK(h, cudaSetDevice(h->p.device));
     KindState &K = h->kinds[SML_ATMO];
-    const int total = h->p.number_of_regions * K.P;
-    const double *gathered = (h->p.numprocs == 1) ? K.d_out : h->d_gathered;
-    k_scatter_grid<<<(total + 255) / 256, 256, 0, h->stream>>>(gathered, h->d_out_dst, total, h->d_G, G_PRECIP,
-                                                                G_SST, G_W2D);
-    h->launches++;
+    PackArgs a{};
+    a.total = h->p.number_of_regions * K.P;
+    a.out_dst = h->d_out_dst;
+    a.G = h->d_G;
+    a.precip_lo = G_PRECIP; a.precip_hi = G_SST; a.w4d_hi = G_W2D; a.sst_off = G_SST;
+    a.nsc = (a.total + 255) / 256;
+    a.err = h->d_peer_err;
+    if (h->p.numprocs == 1) {
+        a.gathered = K.d_out;
+    } else if (h->peers.world > 1) {
+        // fused all-gather: wait for every rank's flag of this step, read this step's half of the exchange block
+        a.gathered = (const double *)h->d_xchg + (size_t)(h->peer_seq & 1) * a.total;
+        a.my_flags = (const unsigned long long *)((const char *)h->d_xchg + h->xchg_flags_off);
+        a.world = h->peers.world;
+        a.seq = h->peer_seq;
+    } else {
+        a.gathered = h->d_gathered;  // filled by the host's collective (NCCL all-gather)
+    }
+    a.sst_mode = -1;
     if (h->p.slab_ocean_model_bool) {
         if (!h->sst_static_set) FAIL(h, "sml_set_sst_static (base_sst_grid, sea_mask) has not been called");
-        const int mode = h->p.sst_prescribed ? 1 : 0;
-        if (mode == 1 && !h->sst_prescribed_set) FAIL(h, "sst_prescribed is on but sml_set_sst_prescribed was never called");
+        a.sst_mode = h->p.sst_prescribed ? 1 : 0;
+        if (a.sst_mode == 1 && !h->sst_prescribed_set) FAIL(h, "sst_prescribed is on but sml_set_sst_prescribed was never called");
+        a.base = h->d_base_sst; a.mask = h->d_mask; a.prescribed = h->d_prescribed;
+        a.cell_region = h->d_cell_region; a.cell_slot = h->d_cell_slot;
         // single rank: the ocean outvec slab already holds every region; otherwise the host all-gathers it
-        const double *ocean_out = (h->p.numprocs == 1) ? h->kinds[SML_OCEAN].d_out : h->d_ocean_gathered;
-        k_sst_grid<<<(XG * YG + 255) / 256, 256, 0, h->stream>>>(h->d_G + G_SST, h->d_base_sst, h->d_mask,
-                                                                 h->d_prescribed, h->d_cell_region, h->d_cell_slot,
-                                                                 ocean_out, h->P_ocean, mode);
-        h->launches++;
+        a.ocean_out = (h->p.numprocs == 1) ? h->kinds[SML_OCEAN].d_out : h->d_ocean_gathered;
+        a.ocean_P = h->P_ocean;
     }
+    const int nsst = (a.sst_mode >= 0) ? (XG * YG + 255) / 256 : 0;
+    k_pack_grids<<<a.nsc + nsst, 256, 0, h->stream>>>(a);
+    h->launches++;
     CK(h, cudaGetLastError());
     return 0;
 }
 
-// feedback of every local region from G (needs this step's TISR in G), the ocean ring, then the state update and
-// the x~ columns of the readout of the NEXT predict (split-order)
+// ---- peer exchange set-up: every rank exports the IPC handle of its exchange block, the host passes all of them
+// around (any transport: torch.distributed all_gather_object, MPI_Allgather of 64 bytes) and attaches them
+int sml_peer_export(sml_engine *h, void *handle64)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (!h->d_xchg) FAIL(h, "peer exchange needs numprocs > 1");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(h, cudaSetDevice(h->p.device));
+    cudaIpcMemHandle_t hd;
+    CK(h, cudaIpcGetMemHandle(&hd, h->d_xchg));
+    std::memcpy(handle64, &hd, 64);
+    return 0;
+}
+
+int sml_peer_attach(sml_engine *h, const void *handles, int count)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (!h->d_xchg) FAIL(h, "peer exchange needs numprocs > 1");
+    if (count != h->p.numprocs) FAIL(h, "sml_peer_attach: %d handles for %d ranks", count, h->p.numprocs);
+    if (count > MAX_PEERS) FAIL(h, "peer exchange supports up to %d ranks of one node", MAX_PEERS);
+    if (h->peers.world > 1) FAIL(h, "peers are already attached");
+    CK(h, cudaSetDevice(h->p.device));
+    PeerTable pt{};
+    pt.world = count;
+    pt.rank = h->p.irank;
+    for (int k = 0; k < count; ++k) {
+        void *base = nullptr;
+        if (k == h->p.irank) {
+            base = h->d_xchg;
+        } else {
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, (const char *)handles + 64 * (size_t)k, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (void *m : h->peer_mapped) cudaIpcCloseMemHandle(m);
+                h->peer_mapped.clear();
+                FAIL(h, "cudaIpcOpenMemHandle(rank %d): %s -- ranks must be on one node with peer access; use the host "
+                        "collective (sml_exchange_buffers) instead", k, cudaGetErrorString(e));
+            }
+            h->peer_mapped.push_back(base);
+        }
+        pt.gathered[k] = (double *)base;
+        pt.flags[k] = (unsigned long long *)((char *)base + h->xchg_flags_off);
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->peers = pt;
+    h->peer_seq = 0;
+    return 0;
+}
+
+int sml_peer_attached(const sml_engine *h) { return h && h->peers.world > 1 ? 1 : 0; }
+
+// a peer that never published its step shows up here (the pack kernel gives up after ~10 s instead of hanging)
+int sml_peer_check(sml_engine *h)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    int err = 0;
+    CK(h, cudaMemcpyAsync(&err, h->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (err) FAIL(h, "peer exchange timed out: a rank did not publish its outvecs");
+    return 0;
+}
+
 int sml_step_predict_ahead(sml_engine *h, int timestep)
 {
     if (check_ready(h, SML_ATMO)) return -1;
@@ -1040,10 +1155,7 @@ int sml_step_unpack_device(sml_engine *h, int timestep)
         k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
                                                                        h->p.ml_only ? 0 : 1, 0);
         h->launches++;
-        k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1, 1,
-                                                                         K.d_lm);
-        h->launches++;
-        CK(h, cudaGetLastError());
+        if (launch_finish(h, K, 1)) return -1;
         h->ahead_pending = false;
         h->ahead_done = true;
         return 0;

@@ -4,9 +4,10 @@
 //                    W_out readout partials; W_out tiles arrive by TMA bulk copies (cp.async.bulk,
 //                    mbarrier complete_tx) through a multi-stage shared-memory ring.
 //  k_win_dense       fallback W_in*u for regions whose W_in is not one-non-zero-per-row.
-//  k_readout_finish  fixed-order reduction of the partials + un-standardise -> outvec slab.
-//  k_scatter_grid    outvec slabs of all regions -> global grids, with the exchange clamps.
-//  k_sst_grid        wholegrid_sst assembly (ocean tiles / 272 K / land mask / floor).
+//  k_readout_finish  fixed-order reduction of the partials + un-standardise -> outvec slab, pushed into every
+//                    rank's gathered buffer over NVLink (fused all-gather) when peers are attached.
+//  k_pack_grids      outvec slabs of all regions -> global grids with the exchange clamps, and the wholegrid_sst
+//                    assembly (ocean tiles / 272 K / land mask / floor); waits for the peers' step flags.
 //  k_build_inputs    global grids -> every region's feedback and local_model (gather + standardise).
 //
 // Reference statements each kernel reproduces are cited at the kernel.
@@ -95,6 +96,37 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 __device__ __forceinline__ void consumer_bar()
 {
     asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer exchange over NVLink (one process per GPU, buffers mapped with CUDA IPC): every rank owns an exchange
+// block  [2][R*P] doubles (the all-gathered outvecs, double-buffered by step parity) + MAX_PEERS step flags.
+// The readout-finish kernel stores each region's outvec straight into EVERY rank's block and, once all local
+// regions are out, publishes the step number in every rank's flag slot; the pack kernel of each rank waits for
+// all slots to reach the step.  This replaces the per-step NCCL all-gather (1152 x 136 doubles in total).
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 8;
+struct PeerTable {
+    int world, rank;
+    double *gathered[MAX_PEERS];             // rank k's [2][R*P] buffer as mapped into this process
+    unsigned long long *flags[MAX_PEERS];    // rank k's flags[MAX_PEERS]; slot r is written by rank r
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_cg_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,7 +310,8 @@ __global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__
 // once the host model's forecast has arrived.
 __global__ void k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ partials, int ldw_max,
                                  double *__restrict__ out_pool, int unstandardize, int model_part,
-                                 const double *__restrict__ lm_pool)
+                                 const double *__restrict__ lm_pool, PeerTable pt, unsigned long long seq,
+                                 long long peer_off, unsigned int *__restrict__ done_counter)
 {
     const RegionDev R = regs[blockIdx.x];
     for (int p = threadIdx.x; p < R.P; p += blockDim.x) {
@@ -294,42 +327,86 @@ __global__ void k_readout_finish(const RegionDev *__restrict__ regs, const doubl
             if (ms >= 0) v = __dadd_rn(__dmul_rn(v, R.std[ms]), R.mean[ms]);
         }
         out_pool[R.out_off + p] = v;
+        // fused all-gather: the outvec goes straight into every rank's gathered buffer (peer stores over NVLink)
+        if (pt.world > 1) {
+            const long long dst = peer_off + R.out_off + p;
+            for (int k = 0; k < pt.world; ++k) pt.gathered[k][dst] = v;
+        }
+    }
+    if (pt.world > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int old = atomicAdd(done_counter, 1u);
+            if (old == gridDim.x - 1) {  // every local region's outvec is on its way: publish the step
+                *done_counter = 0;
+                __threadfence_system();
+                for (int k = 0; k < pt.world; ++k) st_release_sys(pt.flags[k] + pt.rank, seq);
+            }
+        }
     }
 }
 
-// tile_full_grid_with_local_state_vec_res1d for every region of the model (src/res_domain.f90:791-826) +
-// the root's clamps: q < 1e-6 -> 1e-6 (src/mpires.f90:460-462), precip < 1e-5 -> 0 (:486-490).
-__global__ void k_scatter_grid(const double *__restrict__ gathered, const int *__restrict__ out_dst, int total,
-                               double *__restrict__ G, long long precip_lo, long long precip_hi, long long w4d_hi)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int dst = out_dst[i];
-    double v = gathered[i];
-    if (dst < w4d_hi) {
-        if ((dst & 3) == 3 && v < 0.000001) v = 0.000001;
-    } else if (dst >= precip_lo && dst < precip_hi) {
-        if (v < 0.00001) v = 0.0;
-    }
-    G[dst] = v;
-}
+// k_pack_grids: the root's grid assembly of sendrecievegrid in one launch.
+//  blocks [0, nsc): tile_full_grid_with_local_state_vec_res1d for every region of the model
+//     (src/res_domain.f90:791-826) + the clamps: q < 1e-6 -> 1e-6 (src/mpires.f90:460-462), precip < 1e-5 -> 0
+//     (:486-490).  With peers, first wait until every rank has published this step's outvecs.
+//  blocks [nsc, ..): wholegrid_sst (src/mpires.f90:288-290, 315-328, 470-484).  mode 0: every cell takes the first
+//     fx*fy outputs of its region's ocean reservoir (tile_full_2d_grid_with_local_res, src/res_domain.f90:828-850);
+//     regions without one hold 272.0 in their slab row (:323-326, 383); mode 1: prescribed field; mode -1: no SST.
+struct PackArgs {
+    const double *gathered;
+    const int *out_dst;
+    int total;
+    double *G;
+    long long precip_lo, precip_hi, w4d_hi, sst_off;
+    int nsc;
+    // peers
+    const unsigned long long *my_flags;
+    int world;
+    unsigned long long seq;
+    int *err;
+    // sst
+    const double *base, *mask, *prescribed, *ocean_out;
+    const int *cell_region, *cell_slot;
+    int ocean_P, sst_mode;
+};
 
-// wholegrid_sst (src/mpires.f90:288-290, 315-328, 470-484).  mode 0: reference -- every cell takes the first
-// fx*fy outputs of its region's ocean reservoir (tile_full_2d_grid_with_local_res, src/res_domain.f90:828-850);
-// regions without one hold 272.0 in their slab row (:323-326, 383); mode 1: prescribed field.
-__global__ void k_sst_grid(double *__restrict__ sst, const double *__restrict__ base, const double *__restrict__ mask,
-                           const double *__restrict__ prescribed, const int *__restrict__ cell_region,
-                           const int *__restrict__ cell_slot, const double *__restrict__ ocean_out, int ocean_P,
-                           int mode)
+__global__ void k_pack_grids(PackArgs a)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 96 * 48) return;
+    if ((int)blockIdx.x < a.nsc) {
+        if (a.world > 1) {
+            if ((int)threadIdx.x < a.world) {
+                const long long t0 = clock64();
+                while (ld_acquire_sys(a.my_flags + threadIdx.x) < a.seq) {
+                    if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; report instead of hanging
+                        *a.err = 1;
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= a.total) return;
+        const int dst = a.out_dst[i];
+        double v = ld_cg_f64(a.gathered + i);
+        if (dst < a.w4d_hi) {
+            if ((dst & 3) == 3 && v < 0.000001) v = 0.000001;
+        } else if (dst >= a.precip_lo && dst < a.precip_hi) {
+            if (v < 0.00001) v = 0.0;
+        }
+        a.G[dst] = v;
+        return;
+    }
+    const int e = (blockIdx.x - a.nsc) * blockDim.x + threadIdx.x;
+    if (e >= 96 * 48 || a.sst_mode < 0) return;
     double v;
-    if (mode == 1) v = prescribed[e];
-    else v = ocean_out[(size_t)cell_region[e] * ocean_P + cell_slot[e]];
-    if (mask[e] > 0.0) v = base[e];
+    if (a.sst_mode == 1) v = a.prescribed[e];
+    else v = a.ocean_out[(size_t)a.cell_region[e] * a.ocean_P + a.cell_slot[e]];
+    if (a.mask[e] > 0.0) v = a.base[e];
     if (v < 272.0) v = 272.0;
-    sst[e] = v;
+    a.G[a.sst_off + e] = v;
 }
 
 // feedback / local_model from the global buffers (src/mpires.f90:581-604, 749-775):

@@ -85,6 +85,10 @@ _SIGNATURES = {
     "sml_exchange_buffers": ([C.c_void_p] + [C.POINTER(C.c_void_p), _lp] * 4, C.c_int),
     "sml_ocean_exchange_buffers": ([C.c_void_p] + [C.POINTER(C.c_void_p), _lp] * 2, C.c_int),
     "sml_ocean_ring_reset": ([C.c_void_p], C.c_int),
+    "sml_peer_export": ([C.c_void_p, C.c_void_p], C.c_int),
+    "sml_peer_attach": ([C.c_void_p, C.c_void_p, C.c_int], C.c_int),
+    "sml_peer_attached": ([C.c_void_p], C.c_int),
+    "sml_peer_check": ([C.c_void_p], C.c_int),
     "sml_step_pack_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_step_unpack_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_begin": ([C.c_void_p, C.c_int, _ip, C.c_int, C.c_int], C.c_int),
@@ -451,6 +455,23 @@ class Engine:
         self._ck(self.lib.sml_exchange_buffers(self.h, *args))
         names = ("outvec_slab", "gathered", "G", "F")
         return {n: DeviceArray(p.value, c.value, self) for n, p, c in zip(names, ptrs, cnts)}
+
+    # -- fused all-gather over NVLink (CUDA IPC peer stores from the readout-finish kernel)
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.sml_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, handles):
+        """handles: list of the 64-byte exports of every rank, in rank order"""
+        blob = b"".join(handles)
+        self._ck(self.lib.sml_peer_attach(self.h, blob, len(handles)))
+
+    def peer_attached(self) -> bool:
+        return bool(self.lib.sml_peer_attached(self.h))
+
+    def peer_check(self):
+        self._ck(self.lib.sml_peer_check(self.h))
 
     def ocean_exchange_buffers(self):
         """-> dict of DeviceArray: ocean_slab [nloc*P_ocean], ocean_gathered [R*P_ocean]"""

@@ -71,6 +71,19 @@ class EngineShard:
         self._pin_t = torch.empty(E.XGRID * E.YGRID, dtype=torch.float64).pin_memory()
         self._torch = torch
 
+    @property
+    def peer_attached(self):
+        return self.eng.peer_attached()
+
+    def attach_peers(self, dist):
+        """exchange the CUDA IPC handles of the ranks' exchange blocks and switch the atmosphere all-gather to
+        peer stores from the readout kernel (ranks of one node)"""
+        mine = self.eng.peer_export()
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, mine)
+        self.eng.peer_attach(handles)
+        dist.barrier()
+
     def predict(self):
         self.eng.predict()
 
@@ -128,7 +141,8 @@ class HybridStepper:
     def _gather_outvecs(self, ocean_stepped: bool):
         if self.world == 1:
             return
-        self.dist.all_gather_into_tensor(self.s.gathered, self.s.slab)
+        if not getattr(self.s, "peer_attached", False):   # else: pushed by the readout kernel over NVLink
+            self.dist.all_gather_into_tensor(self.s.gathered, self.s.slab)
         if ocean_stepped and self.s.ocean_slab is not None:
             self.dist.all_gather_into_tensor(self.s.ocean_gathered, self.s.ocean_slab)
 

@@ -1,0 +1,124 @@
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU):
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mr_gpu_check.py
+Runs the same closed hybrid loop (small reservoirs on the full 1152-region tiling) with
+  (a) the host collective (NCCL all-gather of the outvec slabs),
+  (b) the fused all-gather (peer stores from the readout kernel over NVLink, CUDA IPC),
+  (c) (b) in the overlapped mode,
+and requires on rank 0: (a) == (b) bit for bit, (c) within 1e-11 of (a), and (a) within 1e-10 of the
+single-process CPU oracle.  Prints MULTIGPU_OK on success (tests/test_multigpu.py looks for it)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import c_region, initial_grids, oc, region_weights, rel_inf  # noqa: E402
+
+E = importlib.import_module("speedy-ml_b200.engine")
+H = importlib.import_module("speedy-ml_b200.hybrid")
+R, M, NSTEPS = 1152, 300, 6
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    G = initial_grids()
+    eng = E.Engine(number_of_regions=R, irank=rank, numprocs=world, device=local, sst_prescribed=True, stream=stream)
+    ws = {r: region_weights(R, r, m=M, with_dense_win=False) for r in eng.region_indices}
+    for r, w in ws.items():
+        eng.region_upload(r, w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"], win_compact=w["winc"],
+                          win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"])
+    eng.finalize()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    eng.set_sst_prescribed(G["base_sst"])
+    shard = H.EngineShard(eng, torch)
+
+    def reset():
+        rng = np.random.default_rng(5)
+        draws = [(rng.standard_normal(576), rng.standard_normal(132), 0.1 * rng.standard_normal(700)) for _ in range(R)]
+        for r, w in ws.items():
+            fb, lm, x0 = draws[r]
+            eng.feedback_set(r, fb[:w["D"]])
+            eng.local_model_set(r, lm[:w["S"]])
+            eng.state_set(r, x0[:w["n"]])
+        return draws
+
+    def host_model(w4d, w2d, wsst):
+        return oc.host_stub(w4d, w2d, G["clim4d"], G["clim2d"])
+
+    def run(overlap):
+        reset()
+        st = H.HybridStepper(shard, rank=rank, world=world, dist=dist, overlap=overlap)
+        out = []
+        for t in range(1, NSTEPS + 1):
+            g = st.step(t, host_model, G["tisr"])
+            if rank == 0:
+                out.append([a.copy() for a in g])
+        torch.cuda.synchronize()
+        fbs = {r: eng.feedback_get(r) for r in list(ws)[:3]}
+        if overlap:
+            eng.set_overlap(False)
+        dist.barrier()
+        return out, fbs
+
+    nccl, fb_nccl = run(False)
+    assert not eng.peer_attached()
+    shard.attach_peers(dist)
+    assert eng.peer_attached()
+    peer, fb_peer = run(False)
+    ovl, fb_ovl = run(True)
+    eng.peer_check()
+    ok = True
+    for r in fb_nccl:
+        ok &= np.array_equal(fb_nccl[r], fb_peer[r]) and rel_inf(fb_ovl[r], fb_nccl[r]) < 1e-11
+    if rank == 0:
+        for t in range(NSTEPS):
+            for a, b, c in zip(nccl[t], peer[t], ovl[t]):
+                ok &= np.array_equal(a, b)
+                ok &= rel_inf(c, a) < 1e-11
+        # single-process oracle of the whole model
+        all_ws = [region_weights(R, r, m=M, with_dense_win=False) for r in range(R)]
+        rcs = [c_region(w) for w in all_ws]
+        draws = reset()
+        for w, rc in zip(all_ws, rcs):
+            fb, lm, x0 = draws[w["region"]]
+            rc.feedback[:], rc.local_model[:], rc.x[:] = fb[:w["D"]], lm[:w["S"]], x0[:w["n"]]
+        sst_mean = np.array([w["mean"][-1] for w in all_ws])
+        sst_std = np.array([w["std"][-1] for w in all_ws])
+        has = np.ones(R, dtype=np.int32)
+        oo = np.zeros((R, 4))
+        for i in range(R):
+            xs, xe, ys, ye, *_ = oc.getxyresextent(R, i)
+            oo[i] = G["base_sst"][xs - 1:xe, ys - 1:ye].ravel(order="F")
+        worst = 0.0
+        for t in range(NSTEPS):
+            oc.predict_all(rcs, nthreads=8)
+            gc = oc.step_gather(rcs, True, True, G["base_sst"], G["sea_mask"], ocean_out=oo, has_ocean=has)
+            for a, b in zip(nccl[t], gc):
+                worst = max(worst, rel_inf(a, b))
+            f4, f2 = oc.host_stub(gc[0], gc[1], G["clim4d"], G["clim2d"])
+            oc.step_scatter(rcs, True, True, False, *gc, f4, f2, G["tisr"], sst_mean, sst_std, nthreads=8)
+        ok &= worst < 1e-10
+        print(f"rank0: nccl==peer bitwise, overlap within 1e-11, oracle worst rel err {worst:.2e}, ok={ok}")
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    eng.close()
+    dist.destroy_process_group()
+    if int(flag.item()) != 1:
+        raise SystemExit("MULTIGPU_FAILED")
+    if rank == 0:
+        print("MULTIGPU_OK")
+
+
+if __name__ == "__main__":
+    main()
