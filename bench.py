@@ -292,7 +292,10 @@ def run_gpu(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
 
-    eng = E.Engine(number_of_regions=R_TOTAL, irank=rank, numprocs=world, device=local_rank, sst_prescribed=True,
+    # --emulate-world W (single process): this GPU carries rank 0's shard of a W-rank run, no exchange -- isolates
+    # the per-rank step cost at that scale (diagnostic; not a bench line)
+    eng_world = args.emulate_world if (world == 1 and args.emulate_world > 1) else world
+    eng = E.Engine(number_of_regions=R_TOTAL, irank=rank, numprocs=eng_world, device=local_rank, sst_prescribed=True,
                    stream=stream)
     my_regions = eng.region_indices
     t_gen = time.perf_counter()
@@ -310,7 +313,7 @@ def run_gpu(args):
     eng.set_sst_static(F["base_sst"], F["sea_mask"])
     eng.set_sst_prescribed(F["base_sst"])
     H = importlib.import_module("speedy-ml_b200.hybrid")
-    H.check_contiguous_sharding(R_TOTAL, world)
+    H.check_contiguous_sharding(R_TOTAL, eng_world)
     shard = H.EngineShard(eng, torch)
     if world > 1 and args.peer:
         shard.attach_peers(dist)   # fused all-gather: peer stores from the readout kernel over NVLink
@@ -375,6 +378,7 @@ def run_gpu(args):
     eng.profile(True)
     dev_ms, dev_wall = timed(device_step, args.steps, 1)
     k_step_ms, k_fin_ms, k_cnt = eng.kernel_times()
+    pack_ms, unpack_ms, ph_cnt = eng.phase_times()
     eng.profile(False)
     launches = eng.kernel_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
@@ -415,7 +419,9 @@ def run_gpu(args):
                                    "sml_step_exchange_end (H2D), wall clock; "
                                    + ("overlapped mode: the next predict's state update and x~ readout run while the "
                                       "host model works (SURVEY.md Appendix D)" if args.overlap else "sequential mode"),
-                       "state_finite": finite, "setup_s": round(t_gen, 1)},
+                       "state_finite": finite, "setup_s": round(t_gen, 1),
+                       **({"emulate_world": eng_world, "note": "DIAGNOSTIC: one rank's shard of an emulated "
+                           f"{eng_world}-rank run, not a whole-model number"} if eng_world != world else {})},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((lay["f_total"] + 96 * 48) * 8),
                     "d2h_bytes_per_step": int(lay["tisr"] * 8), "ms_per_step": e2e_wall / args.steps,
                     "ms_per_step_device_events": e2e_ms / args.steps},
@@ -424,7 +430,10 @@ def run_gpu(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms_per_launch": step_kernel_ms,
-                         "finish_kernel_ms_per_launch": k_fin_ms / max(1, k_cnt), "launches_timed": k_cnt},
+                         "finish_kernel_ms_per_launch": k_fin_ms / max(1, k_cnt), "launches_timed": k_cnt,
+                         "pack_kernel_ms_per_launch": pack_ms / max(1, ph_cnt),
+                         "unpack_kernel_ms_per_launch": unpack_ms / max(1, ph_cnt),
+                         "chunk_rows": eng.step_chunk_rows()},
             "clocks": clocks,
             "wall_ms_per_step": dev_wall / args.steps,
         }
@@ -449,6 +458,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=0)
     ap.add_argument("--no-peer", dest="peer", action="store_false",
                     help="multi-GPU: NCCL all-gather of the outvec slabs instead of the fused peer-store exchange")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",

@@ -16,6 +16,7 @@
 #include "train.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -60,7 +61,8 @@ struct KindState {
     double *d_fb = nullptr, *d_lm = nullptr, *d_out = nullptr, *d_partials = nullptr, *d_temp = nullptr;
     long long *d_fb_offs = nullptr;
     long long x_total = 0, fb_total = 0, lm_total = 0;
-    int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0;
+    int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0, chunk_rows = 0;
+    int *d_order = nullptr;  // launch order of the items: largest first
     size_t smem_bytes = 0;
     bool any_dense = false;
     int64_t alg_bytes = 0;
@@ -98,6 +100,10 @@ struct sml_engine {
     std::vector<cudaEvent_t> ev;  // ring of (start, step done, finish done) triples
     int ev_used = 0;              // triples recorded since the last read
     bool profile = false;
+    struct PhaseTimer {
+        std::vector<cudaEvent_t> ev;  // (start, stop) pairs
+        int used = 0;
+    } pt_pack, pt_unpack;
     int64_t launches = 0;
     TrainState train;
     // overlapped step: the state update and the W_out[:, S:]*x~ partials of the NEXT
@@ -226,7 +232,7 @@ static void free_kind(KindState &K)
 {
     for (auto &r : K.regs)
         for (void *p : r.allocs) cudaFree(p);
-    cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_items_split); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
+    cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_items_split); cudaFree(K.d_order); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
     cudaFree(K.d_lm); cudaFree(K.d_out); cudaFree(K.d_partials); cudaFree(K.d_temp); cudaFree(K.d_fb_offs);
     cudaFree(K.d_in); cudaFree(K.d_in_offs);
 }
@@ -250,6 +256,8 @@ int sml_destroy(sml_engine *h)
     if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
     if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->pt_pack.ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->pt_unpack.ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -528,8 +536,11 @@ static int finalize_kind(sml_engine *h, int kind)
         }
         return 0;
     }
+    // rows per CTA of the step kernel: 8-9 chunks per region.  Measured on B200 (profiles/round1_summary.md): 360..1027
+    // rows differ by < 3 % at every shard size (1152..144 regions per GPU), 720 is best or within noise of the best
     int chunk_rows = 720;
     if (const char *s = getenv("SML_CHUNK_ROWS")) chunk_rows = std::max(64, atoi(s));
+    K.chunk_rows = chunk_rows;
     long long xo = 0, fo = 0, lo = 0;
     int S_max = 0, max_rows = 0;
     K.items.clear();
@@ -585,6 +596,14 @@ static int finalize_kind(sml_engine *h, int kind)
     CK(h, cudaMemcpy(K.d_regs, regs.data(), sizeof(RegionDev) * nloc, cudaMemcpyHostToDevice));
     CK(h, cudaMalloc(&K.d_items, sizeof(StepItem) * std::max(1, K.nitems)));
     CK(h, cudaMemcpy(K.d_items, K.items.data(), sizeof(StepItem) * K.nitems, cudaMemcpyHostToDevice));
+    {
+        // launch order: largest items first so that the last CTAs to start are the cheapest (LPT)
+        std::vector<int> order(K.nitems);
+        for (int i = 0; i < K.nitems; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return K.items[a].ncols > K.items[b].ncols; });
+        CK(h, cudaMalloc(&K.d_order, sizeof(int) * std::max(1, K.nitems)));
+        CK(h, cudaMemcpy(K.d_order, order.data(), sizeof(int) * K.nitems, cudaMemcpyHostToDevice));
+    }
     {
         std::vector<StepItem> split = K.items;
         for (StepItem &it : split) {
@@ -794,12 +813,30 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
         h->launches++;
     }
     const size_t smem = do_readout ? K.smem_bytes : 0;
-    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool,
-                                                          u_offs, u_t, K.d_lm, K.d_temp, K.d_partials, K.ldw,
-                                                          K.stage_cols, K.stage_bytes, K.xs_cap, do_readout);
+    // the full item list is launched largest-first; partial lists (one region's synchronize) in place.
+    // partials are indexed by the item's position in the FULL list (k_readout_finish reads item0 + c)
+    static const bool no_lpt = getenv("SML_NO_LPT") != nullptr;  // A/B switch for profiles/
+    const bool full = !no_lpt && (d_items == K.d_items || d_items == K.d_items_split) && nitems == K.nitems;
+    const int item_base = full ? 0 : (int)(d_items - K.d_items);
+    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, full ? K.d_order : nullptr, item_base,
+                                                          K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm,
+                                                          K.d_temp, K.d_partials, K.ldw, K.stage_cols, K.stage_bytes,
+                                                          K.xs_cap, do_readout);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
+}
+
+// CUDA-event bracket of one phase of the step (only while profiling)
+static cudaEvent_t *phase_events(sml_engine *h, sml_engine::PhaseTimer &t)
+{
+    if (!h->profile || t.used >= PROFILE_RING) return nullptr;
+    while ((int)t.ev.size() < 2 * (t.used + 1)) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        t.ev.push_back(e);
+    }
+    return &t.ev[2 * t.used++];
 }
 
 // partials -> outvec slab (+ the model columns in the overlapped mode); for the atmosphere kind with peers attached
@@ -845,6 +882,8 @@ int sml_predict(sml_engine *h, int kind)
         ev = &h->ev[3 * h->ev_used++];
     }
     if (ev) CK(h, cudaEventRecord(ev[0], h->stream));
+    // the finish stays a separate launch: folding it into the step kernel's tail (last chunk of a region reduces)
+    // was measured 2.6 % slower -- the fence + atomic round trip idles every CTA slot for ~1 us per chunk
     if (launch_step(h, K, K.d_items, K.nitems, K.d_fb, K.d_fb_offs, 0, 1)) return -1;
     K.cur ^= 1;
     if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
@@ -1010,7 +1049,10 @@ int sml_step_pack_device(sml_engine *h, int timestep)
         a.ocean_P = h->P_ocean;
     }
     const int nsst = (a.sst_mode >= 0) ? (XG * YG + 255) / 256 : 0;
+    cudaEvent_t *pe = phase_events(h, h->pt_pack);
+    if (pe) CK(h, cudaEventRecord(pe[0], h->stream));
     k_pack_grids<<<a.nsc + nsst, 256, 0, h->stream>>>(a);
+    if (pe) CK(h, cudaEventRecord(pe[1], h->stream));
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -1162,8 +1204,11 @@ int sml_step_unpack_device(sml_engine *h, int timestep)
     }
     if (h->n_ocean_fb > 0 && timestep < 1)
         FAIL(h, "timestep must be the 1-based hybrid step (it selects the ring slot mod(timestep-1,%d)+1)", h->ocean_slots);
+    cudaEvent_t *pe = phase_events(h, h->pt_unpack);
+    if (pe) CK(h, cudaEventRecord(pe[0], h->stream));
     k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
                                                                    h->p.ml_only ? 0 : 1, 1);
+    if (pe) CK(h, cudaEventRecord(pe[1], h->stream));
     h->launches++;
     if (h->n_ocean_fb > 0) {
         k_build_ocean_inputs<<<h->n_ocean_fb, 128, 0, h->stream>>>(h->d_ocean_fb, h->d_G, K.d_fb,
@@ -1233,6 +1278,30 @@ int sml_profile(sml_engine *h, int on)
     if (!h) return -1;
     h->profile = on != 0;
     h->ev_used = 0;
+    h->pt_pack.used = 0;
+    h->pt_unpack.used = 0;
+    return 0;
+}
+// CUDA-event time of the pack (grid assembly, incl. the wait for the peers' outvecs) and unpack (feedback rebuild)
+// kernels since the last call, for the share-of-step table in profiles/
+int sml_phase_times(sml_engine *h, double *pack_ms_sum, double *unpack_ms_sum, int *count)
+{
+    if (!h) return -1;
+    *pack_ms_sum = *unpack_ms_sum = 0.0;
+    *count = std::min(h->pt_pack.used, h->pt_unpack.used);
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->pt_pack.used; ++i) {
+        float a = 0.f;
+        CK(h, cudaEventElapsedTime(&a, h->pt_pack.ev[2 * i], h->pt_pack.ev[2 * i + 1]));
+        *pack_ms_sum += a;
+    }
+    for (int i = 0; i < h->pt_unpack.used; ++i) {
+        float a = 0.f;
+        CK(h, cudaEventElapsedTime(&a, h->pt_unpack.ev[2 * i], h->pt_unpack.ev[2 * i + 1]));
+        *unpack_ms_sum += a;
+    }
+    h->pt_pack.used = 0;
+    h->pt_unpack.used = 0;
     return 0;
 }
 int sml_kernel_times(sml_engine *h, double *step_ms_sum, double *finish_ms_sum, int *count)
@@ -1254,6 +1323,7 @@ int sml_kernel_times(sml_engine *h, double *step_ms_sum, double *finish_ms_sum, 
     return 0;
 }
 int64_t sml_kernel_launch_count(const sml_engine *h) { return h ? h->launches : 0; }
+int sml_step_chunk_rows(const sml_engine *h, int kind) { return (h && kind >= 0 && kind < 2) ? h->kinds[kind].chunk_rows : 0; }
 int64_t sml_predict_algorithmic_bytes(const sml_engine *h, int kind)
 {
     if (!h || kind < 0 || kind > 1) return 0;

@@ -179,8 +179,8 @@ __device__ __forceinline__ double update_row(const RegionDev &R, int row, const 
 // ---------------------------------------------------------------------------------------------
 template <int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 2)
-k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, const double *__restrict__ x_old,
-       double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
+k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, const int *__restrict__ order,
+       int item_base, const double *__restrict__ x_old, double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
        const double *__restrict__ lm_pool, const double *__restrict__ temp_pool, double *__restrict__ partials,
        int ldw_max, int stage_cols, int stage_bytes, int xs_cap, int do_readout)
 {
@@ -190,7 +190,8 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
     uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * NCONS);
     uint64_t *empty = full + STAGES;
 
-    const StepItem it = items[blockIdx.x];
+    const int item = order ? order[blockIdx.x] : (int)blockIdx.x;  // largest-first launch order
+    const StepItem it = items[item];
     const RegionDev R = regs[it.reg];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -284,7 +285,7 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
     for (int p = tid; p < ldw; p += NCONS) {
         double sum = 0.0;
         for (int g = 0; g < cpi; ++g) sum += red[g * ldw + p];
-        partials[(size_t)blockIdx.x * ldw_max + p] = sum;
+        partials[(size_t)(item_base + item) * ldw_max + p] = sum;
     }
 }
 

@@ -100,6 +100,8 @@ _SIGNATURES = {
     "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_profile": ([C.c_void_p, C.c_int], C.c_int),
     "sml_kernel_times": ([C.c_void_p, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
+    "sml_phase_times": ([C.c_void_p, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
+    "sml_step_chunk_rows": ([C.c_void_p, C.c_int], C.c_int),
     "sml_kernel_launch_count": ([C.c_void_p], C.c_int64),
     "sml_predict_algorithmic_bytes": ([C.c_void_p, C.c_int], C.c_int64),
 }
@@ -558,6 +560,15 @@ class Engine:
         a, b, c = C.c_double(), C.c_double(), C.c_int()
         self._ck(self.lib.sml_kernel_times(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def phase_times(self):
+        """-> (sum of pack-kernel ms, sum of unpack-kernel ms, count) since the last call (profiling on)"""
+        a, b, c = C.c_double(), C.c_double(), C.c_int()
+        self._ck(self.lib.sml_phase_times(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def step_chunk_rows(self, kind=ATMO):
+        return int(self.lib.sml_step_chunk_rows(self.h, kind))
 
     def kernel_launch_count(self):
         return int(self.lib.sml_kernel_launch_count(self.h))
