@@ -816,9 +816,9 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
     // the full item list is launched largest-first; partial lists (one region's synchronize) in place.
     // partials are indexed by the item's position in the FULL list (k_readout_finish reads item0 + c)
     static const bool no_lpt = getenv("SML_NO_LPT") != nullptr;  // A/B switch for profiles/
-    const bool full = !no_lpt && (d_items == K.d_items || d_items == K.d_items_split) && nitems == K.nitems;
+    const bool full = (d_items == K.d_items || d_items == K.d_items_split) && nitems == K.nitems;
     const int item_base = full ? 0 : (int)(d_items - K.d_items);
-    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, full ? K.d_order : nullptr, item_base,
+    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, (full && !no_lpt) ? K.d_order : nullptr, item_base,
                                                           K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm,
                                                           K.d_temp, K.d_partials, K.ldw, K.stage_cols, K.stage_bytes,
                                                           K.xs_cap, do_readout);
