@@ -231,6 +231,11 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
                    const int64_t *im_off, int ncols, int discard_cols);
 int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using_prior,
                     double prior_val, int32_t *info_per_region);
+/* sml_train_solve factorises the regularised Gram (symmetric positive definite for ridge > 0) of every region of
+ * the wave by a batched blocked Cholesky on the FP64 tensor cores and falls back, per region, to LU with partial
+ * pivoting -- what dgesv does -- when a pivot is not positive; info keeps dgesv's meaning either way.
+ * by_cholesky: regions of the current wave that stayed on the Cholesky path. */
+int sml_train_solver_stats(sml_engine *h, int *by_cholesky);
 int sml_train_gram_get(sml_engine *h, int region, double *states_x_states_aug,
                        double *states_x_trainingdata_aug);
 int sml_train_end(sml_engine *h);

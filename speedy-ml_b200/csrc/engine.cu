@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "resdomain.hpp"
 #include "train.cuh"
+#include "chol.cuh"
 
 #include <algorithm>
 #include <functional>

@@ -25,6 +25,10 @@ struct TrainRegionDev {
     const int *target_map;    // [P] rows of the input vector that form the target
     int ld;                   // padded N+P (multiple of 16)
     int pad0;
+    // ridge solve (chol.cuh)
+    double *linv;             // [ceil(N/128)][2][128*128]: inverse of every diagonal block of L, and its transpose
+    double *dsave;            // [ld] diagonal of the regularised A (restored if the region falls back to LU)
+    int *chol_info;           // 0: on the Cholesky path; > 0: non-positive pivot at that column; < 0: not eligible
 };
 
 // one reservoir step for every region of the wave: reads input column in_col, writes the new state to the
@@ -308,6 +312,7 @@ struct TrainState {
     double gram_ms = 0.0;             // CUDA-event time of the Gram kernels
     double stategen_ms = 0.0;
     double solve_ms = 0.0;
+    int solved_by_cholesky = 0;
 };
 
 inline void train_release(TrainState &t)

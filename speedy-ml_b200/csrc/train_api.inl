@@ -95,6 +95,9 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         bad = bad || alloc((size_t)d.ld * T.ks * 8, &p); d.slab = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xa = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xb = (double *)p;
+        bad = bad || alloc((size_t)((N + CH_NB - 1) / CH_NB) * CH_LINV * 8, &p); d.linv = (double *)p;
+        bad = bad || alloc((size_t)d.ld * 8, &p); d.dsave = (double *)p;
+        bad = bad || alloc(sizeof(int), &p); d.chol_info = (int *)p;
         // target rows (tile_full_input_to_target_data2d / _ocean_model), flattened at upload
         const std::vector<int32_t> &tmap = K.regs[li].target_map;
         if ((int)tmap.size() != d.R.P) { h->err = "internal: target map size"; train_release(T); return -1; }
@@ -118,6 +121,8 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     CK(h, cudaMalloc(&T.d_tiles, sizeof(int2) * tiles.size()));
     CK(h, cudaMemcpy(T.d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
     CK(h, cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    CK(h, cudaFuncSetAttribute(k_chol_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    CK(h, cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_DIAG_SMEM));
     CK(h, cudaStreamSynchronize(h->stream));
     T.active = true;
     return 0;
@@ -236,10 +241,18 @@ int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using
     if (!T.active) FAIL(h, "sml_train_solve without sml_train_begin");
     CK(h, cudaSetDevice(h->p.device));
     KindState &K = h->kinds[T.kind];
+    const int nw = (int)T.regs.size();
+    // SML_SOLVER=lu forces dgesv-style LU with partial pivoting for every region (the fallback path)
+    const char *solver_env = getenv("SML_SOLVER");
+    const bool force_lu = solver_env && std::string(solver_env) == "lu";
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     CK(h, cudaEventRecord(e0, h->stream));
-    for (size_t i = 0; i < T.regs.size(); ++i) {
+
+    // ---- ridge terms, prior, lower -> upper mirror (the upper triangle keeps A for the LU fallback)
+    std::vector<int> init_info(nw, 0);
+    int kb_max = 0, P_max = 0;
+    for (int i = 0; i < nw; ++i) {
         TrainRegionDev &d = T.regs[i].dev;
         const int N = d.R.n + d.R.S, S = d.R.S, P = d.R.P, ld = d.ld;
         double add_model, add_res, prior_add = 0.0;
@@ -258,18 +271,81 @@ int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using
         const dim3 mg((ld + 31) / 32, (ld + 31) / 32);
         k_train_ridge_mirror<<<mg, dim3(32, 8), 0, h->stream>>>(d.gram, ld, N, S, P, add_model, add_res, prior_add, ml_first_n);
         h->launches++;
-        CK(h, cudaGetLastError());
-        int info = 0;
-        if (device_dgesv(h, d.gram, ld, d.gram + (size_t)ld * N, ld, N, P, &info)) return -1;
-        if (info_per_region) info_per_region[i] = info;
-        if (info == 0) {
-            // reservoir%wout = transpose(b_trans) (:1313)
-            double *wout = const_cast<double *>(K.regs[T.regs[i].local].dev.wout);
-            k_train_store_wout<<<(N + 127) / 128, 128, 0, h->stream>>>(d.gram + (size_t)ld * N, ld, N, P, wout, d.R.ldw);
-            h->launches++;
+        // the tile kernels address operands in 16-byte units: N must be a multiple of 4 (every reservoir size the
+        // reference derives is); anything else goes straight to LU
+        init_info[i] = (force_lu || (N % 4) != 0) ? -1 : 0;
+        CK(h, cudaMemcpyAsync(d.chol_info, &init_info[i], sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        kb_max = std::max(kb_max, (N + CH_NB - 1) / CH_NB);
+        P_max = std::max(P_max, P);
+    }
+    CK(h, cudaGetLastError());
+
+    // ---- batched left-looking Cholesky of the first N columns of every Gaug of the wave (chol.cuh)
+    if (!force_lu) {
+        k_chol_save_diag<<<dim3((T.ld_max + 255) / 256, nw), 256, 0, h->stream>>>(T.d_regs);
+        h->launches++;
+        const int nt = (T.ld_max + CH_NB - 1) / CH_NB;
+        for (int k = 0; k < kb_max; ++k) {
+            if (k > 0) {
+                k_chol_gemm<<<dim3(nt - k, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, CH_UPDATE, k);
+                h->launches++;
+            }
+            k_chol_diag<<<nw, 256, CH_DIAG_SMEM, h->stream>>>(T.d_regs, k);
+            k_chol_gemm<<<dim3(nt - k, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, CH_TRSM, k);
+            h->launches += 2;
         }
-        // 'something went wrong with dgesv' is print-and-continue in the reference (src/mod_linalg.f90:147-150):
-        // W_out is left untouched and info is reported
+        CK(h, cudaGetLastError());
+    }
+    std::vector<int> chol(nw, -1);
+    for (int i = 0; i < nw; ++i)
+        CK(h, cudaMemcpyAsync(&chol[i], T.regs[i].dev.chol_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+
+    // ---- regions on the Cholesky path: L^T into the upper triangle, then the back substitution W L = Z
+    bool any_chol = false;
+    for (int i = 0; i < nw; ++i) {
+        if (chol[i] != 0) continue;
+        any_chol = true;
+        TrainRegionDev &d = T.regs[i].dev;
+        const dim3 mg((d.ld + 31) / 32, (d.ld + 31) / 32);
+        k_train_ridge_mirror<<<mg, dim3(32, 8), 0, h->stream>>>(d.gram, d.ld, d.R.n + d.R.S, d.R.S, d.R.P, 0.0, 0.0, 0.0, -1);
+        h->launches++;
+    }
+    if (any_chol) {
+        const int ptiles = (P_max + CH_NB - 1) / CH_NB;
+        for (int k = kb_max - 1; k >= 0; --k) {
+            k_chol_gemm<<<dim3(ptiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, CH_BACK_UPDATE, k);
+            k_chol_gemm<<<dim3(ptiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, CH_BACK_TRI, k);
+            h->launches += 2;
+        }
+        CK(h, cudaGetLastError());
+    }
+    for (int i = 0; i < nw; ++i) {
+        TrainRegionDev &d = T.regs[i].dev;
+        const int N = d.R.n + d.R.S, P = d.R.P, ld = d.ld;
+        double *wout = const_cast<double *>(K.regs[T.regs[i].local].dev.wout);
+        int info = 0;
+        if (chol[i] == 0) {
+            k_chol_store_wout<<<N, 64, 0, h->stream>>>(T.d_regs, i, wout, d.R.ldw);
+            h->launches++;
+        } else {
+            // not positive definite (ridge 0 / rank-deficient Gram) or not eligible: restore A and do what dgesv does
+            if (chol[i] > 0) {
+                const dim3 mg((ld + 31) / 32, (ld + 31) / 32);
+                k_chol_restore<<<mg, dim3(32, 8), 0, h->stream>>>(d.gram, d.dsave, ld);
+                h->launches++;
+            }
+            if (device_dgesv(h, d.gram, ld, d.gram + (size_t)ld * N, ld, N, P, &info)) return -1;
+            if (info == 0) {
+                // reservoir%wout = transpose(b_trans) (:1313)
+                k_train_store_wout<<<(N + 127) / 128, 128, 0, h->stream>>>(d.gram + (size_t)ld * N, ld, N, P, wout, d.R.ldw);
+                h->launches++;
+            }
+            // 'something went wrong with dgesv' is print-and-continue in the reference (src/mod_linalg.f90:147-150):
+            // W_out is left untouched and info is reported
+        }
+        if (info_per_region) info_per_region[i] = info;
+        T.solved_by_cholesky += chol[i] == 0 ? 1 : 0;
     }
     CK(h, cudaEventRecord(e1, h->stream));
     CK(h, cudaEventSynchronize(e1));
@@ -277,6 +353,15 @@ int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using
     cudaEventElapsedTime(&ms, e0, e1);
     T.solve_ms += ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+// how many regions of the current wave the Cholesky path solved (the rest went through LU)
+int sml_train_solver_stats(sml_engine *h, int *by_cholesky)
+{
+    if (!h) return -1;
+    *by_cholesky = h->train.solved_by_cholesky;
     return 0;
 }
 

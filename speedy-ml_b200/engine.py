@@ -94,6 +94,7 @@ _SIGNATURES = {
     "sml_train_begin": ([C.c_void_p, C.c_int, _ip, C.c_int, C.c_int], C.c_int),
     "sml_train_feed": ([C.c_void_p, _dp, _lp, _dp, _lp, C.c_int, C.c_int], C.c_int),
     "sml_train_solve": ([C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, _ip], C.c_int),
+    "sml_train_solver_stats": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
     "sml_train_gram_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
     "sml_train_end": ([C.c_void_p], C.c_int),
     "sml_train_stats": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
@@ -521,6 +522,12 @@ class Engine:
         info = np.zeros(len(self._train_regions), dtype=np.int32)
         self._ck(self.lib.sml_train_solve(self.h, beta_res, beta_model, int(using_prior), prior_val, _i(info)))
         return info
+
+    def train_solver_stats(self):
+        """-> number of regions of the current wave solved by the Cholesky path (the rest fell back to LU)"""
+        n = C.c_int()
+        self._ck(self.lib.sml_train_solver_stats(self.h, C.byref(n)))
+        return n.value
 
     def train_gram_get(self, region):
         d = self.dims[(self._train_kind, region)]

@@ -173,3 +173,78 @@ def test_mldivide_matches_dgesv(E):
     X, info = eng.mldivide(np.eye(3), B)
     assert info == -1 and np.array_equal(X, B)
     eng.close()
+
+
+def _train_small(E, eng, rc, w, region, bs=8, discard=3, nbatch=3, seed=5):
+    td, im = _series(w, discard + nbatch * bs, seed)
+    rc.train_init(bs)
+    rc.train_phase(td, im, discard)
+    eng.train_begin([region], bs)
+    eng.train_feed([td], [im], discard)
+    return rc.sxs.copy(), rc.sxt.copy()
+
+
+def test_solver_paths_cholesky_lu_and_fallback(E, monkeypatch):
+    """fit_chunk's system is SPD for ridge > 0: the engine factorises it by batched Cholesky (chol.cuh) and falls
+    back to dgesv-style LU when a pivot is not positive.  All three routes must solve the reference's system."""
+    region = 555
+    w = region_weights(1152, region, m=1300)          # N = 1284: 11 panels of 128, last one partial
+    N, S = w["n"] + w["S"], w["S"]
+    d = np.arange(N)
+    results = {}
+    for route in ("cholesky", "lu", "fallback"):
+        if route == "lu":
+            monkeypatch.setenv("SML_SOLVER", "lu")
+        else:
+            monkeypatch.delenv("SML_SOLVER", raising=False)
+        rc = c_region(w)
+        eng = single_region_engine(E, w)
+        sxs0, sxt0 = _train_small(E, eng, rc, w, region)
+        A, B = sxs0.copy(), sxt0.copy()
+        if route == "fallback":
+            # plain-beta variant with a negative "ridge": A is indefinite, Cholesky must bail out and LU must solve it
+            beta_res, beta_model, using_prior = -50.0, -50.0, False
+            A[d, d] += -50.0
+        else:
+            beta_res, beta_model, using_prior = 1e-3, 1.0, True
+            A[d[:S], d[:S]] += 1.0
+            A[d[S:], d[S:]] += 1e-6
+        info = eng.train_solve(beta_res, beta_model, using_prior, 0.0)
+        assert info[0] == 0
+        assert eng.train_solver_stats() == (1 if route == "cholesky" else 0)
+        wout = eng.wout_get(region)
+        assert _residual(A.T, wout.T, B.T) < 1e-13
+        assert rc.fit(beta_res=beta_res, beta_model=beta_model, using_prior=using_prior, prior_val=0.0) == 0
+        assert _residual(A.T, rc.wout.T, B.T) < 1e-13
+        results[route] = wout
+        eng.train_end()
+        eng.close()
+    # same system, two factorizations: agreement is limited by cond(A) * eps, the residuals above are the criterion
+    assert rel_inf(results["cholesky"] @ np.ones(N), results["lu"] @ np.ones(N)) < 1e-6
+
+
+def test_solver_wave_mixed_shapes(E):
+    """a wave whose regions have different N (different panel counts, different partial last panels)"""
+    regions = [0, 1, 2, 3]
+    ws = {r: region_weights(1152, r, m=450) for r in regions}
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=288)
+    for r in regions:
+        upload(eng, ws[r])
+    eng.finalize()
+    bs, discard = 10, 4
+    series = {r: _series(ws[r], discard + 4 * bs, 60 + r) for r in regions}
+    eng.train_begin(regions, bs)
+    eng.train_feed([series[r][0] for r in regions], [series[r][1] for r in regions], discard)
+    grams = {r: eng.train_gram_get(r) for r in regions}
+    info = eng.train_solve(1e-3, 1.0, True, 0.0)
+    assert list(info) == [0, 0, 0, 0] and eng.train_solver_stats() == 4
+    for r in regions:
+        w = ws[r]
+        N, S = w["n"] + w["S"], w["S"]
+        d = np.arange(N)
+        A, B = grams[r][0].copy(), grams[r][1].copy()
+        A[d[:S], d[:S]] += 1.0
+        A[d[S:], d[S:]] += 1e-6
+        assert _residual(A.T, eng.wout_get(r).T, B.T) < 1e-13
+    eng.train_end()
+    eng.close()
