@@ -128,6 +128,16 @@ int sml_global_layout(int64_t off[5], int64_t *g_total, int64_t *f_total);
 int sml_region_upload(sml_engine *h, const sml_region_weights *w);
 int sml_finalize(sml_engine *h); /* after the last upload: builds the batched step plan */
 
+/* ---- reservoir construction on the device (gen_res, src/mod_reservoir.f90:182-212): after the unscaled adjacency
+ * of every region has been uploaded (makesparse -> mklsparse, src/mod_linalg.f90:180-218) and sml_finalize,
+ *   sml_sparse_eigen   replaces sparse_eigen (ARPACK dnaupd/dneupd, src/mod_linalg.f90:220-514): the largest-
+ *                      magnitude eigenvalue of every local adjacency -- the Perron root of a non-negative matrix --
+ *                      by batched power iteration; eigs[nloc] in local order; returns 1 if maxit was reached
+ *   sml_adjacency_scale applies vals *= factor[i] (factor = radius / eig, :193-195) to the device copy; the host
+ *                      applies the same factor to reservoir%vals ---- */
+int sml_sparse_eigen(sml_engine *h, int kind, int maxit, double tol, double *eigs, int *iterations);
+int sml_adjacency_scale(sml_engine *h, int kind, const double *factor);
+
 /* ---- per-region state (reservoir%current_state / saved_state / feedback / local_model / outvec) ---- */
 int sml_state_set(sml_engine *h, int kind, int region, const double *x);
 int sml_state_get(sml_engine *h, int kind, int region, double *x);

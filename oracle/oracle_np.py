@@ -562,6 +562,23 @@ def train_ml(reg, phases, batch_size, discard_cols, beta_res, target_fn):
     return np.asfortranarray(xsol.T), sxs, sxt, info
 
 
+def sparse_eigen(n, rows, cols, vals, nev=6):
+    """src/mod_linalg.f90:220-514: ARPACK dnaupd/dneupd (which='LM', nev=6) on the COO matrix, then
+    eigs = maxval(d) over the whole (ncv,3) work array -- real parts, imaginary parts and residuals (:246,511).
+    Restated with a dense eigen-decomposition (test sizes only): take the nev largest-magnitude eigenvalues and
+    the max over their real and imaginary parts (residuals of converged pairs are ~0)."""
+    A = np.zeros((n, n))
+    np.add.at(A, (rows - 1, cols - 1), vals)      # duplicates sum, like the COO handle
+    lam = np.linalg.eigvals(A)
+    top = lam[np.argsort(-np.abs(lam))[:nev]]
+    return float(max(top.real.max(), top.imag.max(), 0.0))
+
+
+def gen_res_scale(vals, eigs, radius):
+    """src/mod_reservoir.f90:193-195: newvals = (vals/eigs)*radius"""
+    return (vals / eigs) * radius
+
+
 def pinv_svd(A, thres=1e-2):
     """src/mod_linalg.f90:27-107: Moore-Penrose via SVD, singular values <= thres zeroed"""
     U, s, VT = np.linalg.svd(A, full_matrices=False)

@@ -15,8 +15,10 @@
 #include "resdomain.hpp"
 #include "train.cuh"
 #include "chol.cuh"
+#include "genres.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <functional>
 #include <cstdio>
 #include <cstdlib>
@@ -854,8 +856,11 @@ static int launch_finish(sml_engine *h, KindState &K, int model_part)
         // rank-major == region order (contiguous shards): this rank's rows start at local_ids[0]
         peer_off = (long long)(seq & 1) * RP + (long long)h->local_ids[0] * K.P;
     }
-    k_readout_finish<<<(unsigned)K.regs.size(), 160, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1,
-                                                                     model_part, K.d_lm, pt, seq, peer_off, h->d_done);
+    if (K.P > FIN_PMAX) FAIL(h, "chunk_size_prediction %d exceeds the finish kernel's %d outputs", K.P, FIN_PMAX);
+    // sequential mode: one group of threads sums the partials; overlapped mode: 4 groups share the model columns
+    const int threads = model_part ? FIN_GROUPS * FIN_PMAX : FIN_PMAX;
+    k_readout_finish<<<(unsigned)K.regs.size(), threads, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1,
+                                                                         model_part, K.d_lm, pt, seq, peer_off, h->d_done);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -1270,6 +1275,69 @@ int sml_set_tisr(sml_engine *h, const double *tisr)
     std::memcpy(h->h_pin_tisr, tisr, sizeof(double) * XG * YG);
     CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_tisr, sizeof(double) * XG * YG, cudaMemcpyHostToDevice, h->stream));
     h->tisr_fresh = true;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ reservoir construction (gen_res) */
+// sparse_eigen for every local region of the kind: power iteration until the estimate moves by less than tol
+// (relative) in every region, at most maxit iterations.  eigs[nloc] in local order (0 where there is no reservoir).
+int sml_sparse_eigen(sml_engine *h, int kind, int maxit, double tol, double *eigs, int *iterations)
+{
+    if (check_ready(h, kind)) return -1;
+    if (maxit < 1 || !eigs) FAIL(h, "sml_sparse_eigen: bad arguments");
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[kind];
+    const int nloc = (int)K.regs.size();
+    const int nblk = (K.n_max + GR_BLOCK - 1) / GR_BLOCK;
+    double *x = nullptr, *y = nullptr, *part = nullptr, *lam = nullptr;
+    CK(h, cudaMalloc(&x, sizeof(double) * std::max<long long>(1, K.x_total)));
+    CK(h, cudaMalloc(&y, sizeof(double) * std::max<long long>(1, K.x_total)));
+    CK(h, cudaMalloc(&part, sizeof(double) * (size_t)nloc * nblk));
+    CK(h, cudaMalloc(&lam, sizeof(double) * 2 * nloc));
+    CK(h, cudaMemsetAsync(lam, 0, sizeof(double) * 2 * nloc, h->stream));
+    k_eig_init<<<nloc, 256, 0, h->stream>>>(K.d_regs, x);
+    h->launches++;
+    std::vector<double> hl(2 * nloc, 0.0);
+    int it = 0;
+    bool done = false;
+    while (it < maxit && !done) {
+        const int burst = std::min(8, maxit - it);  // check convergence every few iterations (one D2H each)
+        for (int b = 0; b < burst; ++b) {
+            k_eig_spmv<<<dim3(nblk, nloc), GR_BLOCK, 0, h->stream>>>(K.d_regs, x, y, part, nblk);
+            k_eig_normalize<<<nloc, 256, 0, h->stream>>>(K.d_regs, y, x, part, nblk, lam);
+            h->launches += 2;
+        }
+        it += burst;
+        CK(h, cudaMemcpyAsync(hl.data(), lam, sizeof(double) * 2 * nloc, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        done = true;
+        for (int i = 0; i < nloc; ++i)
+            if (K.regs[i].uploaded && std::fabs(hl[2 * i] - hl[2 * i + 1]) > tol * std::fabs(hl[2 * i])) done = false;
+    }
+    for (int i = 0; i < nloc; ++i) eigs[i] = K.regs[i].uploaded ? hl[2 * i] : 0.0;
+    if (iterations) *iterations = it;
+    cudaFree(x); cudaFree(y); cudaFree(part); cudaFree(lam);
+    CK(h, cudaGetLastError());
+    return done ? 0 : 1;  // 1: not converged within maxit (eigs hold the last estimates)
+}
+
+// reservoir%vals = (reservoir%vals / eigs) * radius on the device copy (src/mod_reservoir.f90:193-195): the
+// caller passes factor[i] = radius / eigs[i] and applies the same factor to its host copy of vals
+int sml_adjacency_scale(sml_engine *h, int kind, const double *factor)
+{
+    if (check_ready(h, kind)) return -1;
+    if (!factor) FAIL(h, "sml_adjacency_scale: factor is required");
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[kind];
+    const int nloc = (int)K.regs.size();
+    double *df = nullptr;
+    CK(h, cudaMalloc(&df, sizeof(double) * nloc));
+    CK(h, cudaMemcpyAsync(df, factor, sizeof(double) * nloc, cudaMemcpyHostToDevice, h->stream));
+    k_adj_scale<<<dim3(32, nloc), 256, 0, h->stream>>>(K.d_regs, df);
+    h->launches++;
+    CK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(df);
+    CK(h, cudaGetLastError());
     return 0;
 }
 

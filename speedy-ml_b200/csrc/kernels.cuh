@@ -309,29 +309,52 @@ __global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__
 // model_part != 0 (split-order readout of the overlapped step): the partials hold only W_out[:, S:]*x~ (the
 // reference's v_ml, src/mod_reservoir.f90:1460) and this kernel adds v_p = W_out[:, 0:S]*local_model (:1459)
 // once the host model's forecast has arrived.
-__global__ void k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ partials, int ldw_max,
-                                 double *__restrict__ out_pool, int unstandardize, int model_part,
-                                 const double *__restrict__ lm_pool, PeerTable pt, unsigned long long seq,
-                                 long long peer_off, unsigned int *__restrict__ done_counter)
+constexpr int FIN_GROUPS = 4;     // column groups of the model-part GEMV
+constexpr int FIN_PMAX = 160;     // threads per group >= P rounded up to a warp multiple
+
+__global__ void __launch_bounds__(FIN_GROUPS *FIN_PMAX)
+k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ partials, int ldw_max,
+                 double *__restrict__ out_pool, int unstandardize, int model_part,
+                 const double *__restrict__ lm_pool, PeerTable pt, unsigned long long seq,
+                 long long peer_off, unsigned int *__restrict__ done_counter)
 {
+    __shared__ double s_vp[FIN_GROUPS][FIN_PMAX];
     const RegionDev R = regs[blockIdx.x];
-    for (int p = threadIdx.x; p < R.P; p += blockDim.x) {
-        double v = 0.0;
-        if (model_part) {
-            const double *lm = lm_pool + R.lm_off;
+    const int grp = threadIdx.x / FIN_PMAX, p0 = threadIdx.x % FIN_PMAX;
+    if (model_part) {
+        // v_p = W_out[:, 0:S] * local_model: group g takes columns g, g+4, ...; 4 independent FMA chains per thread
+        // keep the loads in flight; the groups are combined in fixed order below (deterministic)
+        const double *lm = lm_pool + R.lm_off;
+        for (int p = p0; p < R.P; p += FIN_PMAX) {
             const double *w = R.wout + p;
-            for (int j = 0; j < R.S; ++j) v = fma(w[(size_t)j * R.ldw], lm[j], v);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int j = grp;
+            for (; j + 3 * FIN_GROUPS < R.S; j += 4 * FIN_GROUPS) {
+                a0 = fma(w[(size_t)j * R.ldw], lm[j], a0);
+                a1 = fma(w[(size_t)(j + FIN_GROUPS) * R.ldw], lm[j + FIN_GROUPS], a1);
+                a2 = fma(w[(size_t)(j + 2 * FIN_GROUPS) * R.ldw], lm[j + 2 * FIN_GROUPS], a2);
+                a3 = fma(w[(size_t)(j + 3 * FIN_GROUPS) * R.ldw], lm[j + 3 * FIN_GROUPS], a3);
+            }
+            for (; j < R.S; j += FIN_GROUPS) a0 = fma(w[(size_t)j * R.ldw], lm[j], a0);
+            if (p < FIN_PMAX) s_vp[grp][p] = (a0 + a1) + (a2 + a3);
         }
-        for (int c = 0; c < R.nitems; ++c) v += partials[(size_t)(R.item0 + c) * ldw_max + p];
-        if (unstandardize) {
-            const int ms = R.out_ms[p];
-            if (ms >= 0) v = __dadd_rn(__dmul_rn(v, R.std[ms]), R.mean[ms]);
-        }
-        out_pool[R.out_off + p] = v;
-        // fused all-gather: the outvec goes straight into every rank's gathered buffer (peer stores over NVLink)
-        if (pt.world > 1) {
-            const long long dst = peer_off + R.out_off + p;
-            for (int k = 0; k < pt.world; ++k) pt.gathered[k][dst] = v;
+        __syncthreads();
+    }
+    if (grp == 0) {
+        for (int p = p0; p < R.P; p += FIN_PMAX) {
+            double v = 0.0;
+            if (model_part) v = (s_vp[0][p] + s_vp[1][p]) + (s_vp[2][p] + s_vp[3][p]);
+            for (int c = 0; c < R.nitems; ++c) v += partials[(size_t)(R.item0 + c) * ldw_max + p];
+            if (unstandardize) {
+                const int ms = R.out_ms[p];
+                if (ms >= 0) v = __dadd_rn(__dmul_rn(v, R.std[ms]), R.mean[ms]);
+            }
+            out_pool[R.out_off + p] = v;
+            // fused all-gather: the outvec goes straight into every rank's gathered buffer (peer stores over NVLink)
+            if (pt.world > 1) {
+                const long long dst = peer_off + R.out_off + p;
+                for (int k = 0; k < pt.world; ++k) pt.gathered[k][dst] = v;
+            }
         }
     }
     if (pt.world > 1) {

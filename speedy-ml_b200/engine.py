@@ -63,6 +63,8 @@ _SIGNATURES = {
     "sml_global_layout": ([_lp, _lp, _lp], C.c_int),
     "sml_region_upload": ([C.c_void_p, C.POINTER(SmlRegionWeights)], C.c_int),
     "sml_finalize": ([C.c_void_p], C.c_int),
+    "sml_sparse_eigen": ([C.c_void_p, C.c_int, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)], C.c_int),
+    "sml_adjacency_scale": ([C.c_void_p, C.c_int, _dp], C.c_int),
     "sml_state_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_state_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_feedback_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
@@ -334,6 +336,29 @@ class Engine:
     def finalize(self):
         self._ck(self.lib.sml_finalize(self.h))
 
+    # -- gen_res: sparse_eigen + rescale to the target spectral radius   mod_reservoir.f90:182-212
+    def sparse_eigen(self, kind=ATMO, maxit=500, tol=1e-13):
+        """-> (eigs[nloc] in local region order, iterations, converged)"""
+        eigs = np.zeros(self.num_of_regions_on_proc)
+        it = C.c_int()
+        rc = self._ck(self.lib.sml_sparse_eigen(self.h, kind, maxit, tol, _d(eigs), C.byref(it)), allow_positive=True)
+        return eigs, it.value, rc == 0
+
+    def adjacency_scale(self, factor, kind=ATMO):
+        factor = np.ascontiguousarray(factor, dtype=np.float64)
+        assert factor.size == self.num_of_regions_on_proc
+        self._ck(self.lib.sml_adjacency_scale(self.h, kind, _d(factor)))
+
+    def gen_res(self, radius, kind=ATMO, maxit=500, tol=1e-13):
+        """spectral radius of every local adjacency, then vals <- vals / eig * radius on the device.
+        Returns the factors radius/eig so the host can scale reservoir%vals the same way."""
+        eigs, it, ok = self.sparse_eigen(kind, maxit, tol)
+        if not ok:
+            raise EngineError(f"sparse_eigen did not converge in {it} iterations")
+        factor = np.where(eigs > 0, radius / np.where(eigs > 0, eigs, 1.0), 1.0)
+        self.adjacency_scale(factor, kind)
+        return factor, eigs
+
     # -- reservoir%current_state / feedback / local_model / outvec
     def _get(self, fn, kind, region, size):
         out = np.zeros(size)
@@ -414,14 +439,21 @@ class Engine:
         s = _farr(sst_grid, (XGRID, YGRID))
         self._ck(self.lib.sml_set_sst_prescribed(self.h, _d(s)))
 
-    def step_exchange_begin(self, timestep, copy_out=True):
+    def step_exchange_begin(self, timestep, copy_out=True, reuse=False):
+        """-> (wholegrid4d, wholegrid2d, wholegrid_precip, wholegrid_sst).  reuse=True returns the same four
+        arrays on every call (overwritten by the next call) instead of allocating 1.3 MB per step."""
         if not copy_out:
             self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, None, None, None, None))
             return None
-        w4d = np.zeros((4, XGRID, YGRID, ZGRID), order="F")
-        w2d = np.zeros((XGRID, YGRID), order="F")
-        wp = np.zeros((XGRID, YGRID), order="F")
-        wsst = np.zeros((XGRID, YGRID), order="F")
+        if reuse and getattr(self, "_grids", None) is not None:
+            w4d, w2d, wp, wsst = self._grids
+        else:
+            w4d = np.empty((4, XGRID, YGRID, ZGRID), order="F")
+            w2d = np.empty((XGRID, YGRID), order="F")
+            wp = np.empty((XGRID, YGRID), order="F")
+            wsst = np.empty((XGRID, YGRID), order="F")
+            if reuse:
+                self._grids = (w4d, w2d, wp, wsst)
         self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, _d(w4d), _d(w2d), _d(wp), _d(wsst)))
         return w4d, w2d, wp, wsst
 

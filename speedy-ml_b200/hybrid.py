@@ -70,6 +70,9 @@ class EngineShard:
         self._pin_f = torch.empty(lay["f_total"], dtype=torch.float64).pin_memory()
         self._pin_t = torch.empty(E.XGRID * E.YGRID, dtype=torch.float64).pin_memory()
         self._torch = torch
+        self._pin_f_np = self._pin_f.numpy()
+        self._pin_t_np = self._pin_t.numpy()
+        self.reuse_grids = False    # True: exchange_begin returns the same host arrays every step
 
     @property
     def peer_attached(self):
@@ -97,19 +100,21 @@ class EngineShard:
         self.eng.step_unpack_device(t)
 
     def exchange_begin(self, t):
-        return self.eng.step_exchange_begin(t)
+        return self.eng.step_exchange_begin(t, reuse=self.reuse_grids)
 
     def exchange_end(self, t, f4d, f2d, tisr):
         self.eng.step_exchange_end(t, f4d, f2d, tisr)
 
     def load_forecast(self, f4d, f2d, tisr):
         """rank 0, multi-rank runs: stage the host model's output for the broadcast (pinned -> device, async)"""
-        torch, lay = self._torch, self.lay
-        self._pin_f[:lay["w2d"]] = torch.from_numpy(np.asarray(f4d).ravel(order="F"))
-        self._pin_f[lay["w2d"]:] = torch.from_numpy(np.asarray(f2d).ravel(order="F"))
+        lay = self.lay
+        # the pinned staging is free: the previous step's copy out of it precedes this step's grid assembly in
+        # stream order, and exchange_begin has just waited for the copy-out of those grids
+        np.copyto(self._pin_f_np[:lay["w2d"]], np.asarray(f4d).reshape(-1, order="F"))
+        np.copyto(self._pin_f_np[lay["w2d"]:], np.asarray(f2d).reshape(-1, order="F"))
         self.F.copy_(self._pin_f, non_blocking=True)
         if tisr is not None:
-            self._pin_t[:] = torch.from_numpy(np.asarray(tisr).ravel(order="F"))
+            np.copyto(self._pin_t_np, np.asarray(tisr).reshape(-1, order="F"))
             self.tisr_dev.copy_(self._pin_t, non_blocking=True)
 
     # overlapped mode
