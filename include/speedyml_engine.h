@@ -263,6 +263,7 @@ int sml_mldivide(sml_engine *h, double *A, int lda, double *B, int ldb, int n, i
 int sml_profile(sml_engine *h, int on);
 int sml_kernel_times(sml_engine *h, double *step_ms_sum, double *finish_ms_sum, int *count);
 int sml_phase_times(sml_engine *h, double *pack_ms_sum, double *unpack_ms_sum, int *count);
+int sml_sync_times(sml_engine *h, double *update_ms_sum, int64_t *steps); /* update-only launches of sml_synchronize */
 int sml_step_chunk_rows(const sml_engine *h, int kind); /* rows per CTA the step plan chose */
 int64_t sml_kernel_launch_count(const sml_engine *h);
 /* algorithmic bytes one sml_predict(kind) moves */

@@ -107,6 +107,8 @@ struct sml_engine {
         std::vector<cudaEvent_t> ev;  // (start, stop) pairs
         int used = 0;
     } pt_pack, pt_unpack;
+    double sync_ms_sum = 0.0;   // update-only launches of sml_synchronize while profiling (tools/sweep.py)
+    long long sync_steps = 0;
     int64_t launches = 0;
     TrainState train;
     // overlapped step: the state update and the W_out[:, S:]*x~ partials of the NEXT
@@ -948,6 +950,12 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
         items = K.d_items + K.regs[first].dev.item0;
         nitems = K.regs[first].dev.nitems;
     }
+    cudaEvent_t se0 = nullptr, se1 = nullptr;
+    if (h->profile) {
+        CK(h, cudaEventCreate(&se0));
+        CK(h, cudaEventCreate(&se1));
+        CK(h, cudaEventRecord(se0, h->stream));
+    }
     for (int t = 0; t < length; ++t) {
         if (region != SML_ALL_REGIONS) {
             // the untouched regions keep their state: copy theirs forward is avoided by updating only
@@ -961,7 +969,16 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
             K.cur ^= 1;
         }
     }
+    if (se0) CK(h, cudaEventRecord(se1, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (se0) {
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, se0, se1));
+        h->sync_ms_sum += ms;
+        h->sync_steps += length;
+        cudaEventDestroy(se0);
+        cudaEventDestroy(se1);
+    }
     return 0;
 }
 
@@ -1389,6 +1406,16 @@ int sml_kernel_times(sml_engine *h, double *step_ms_sum, double *finish_ms_sum, 
         *finish_ms_sum += b;
     }
     h->ev_used = 0;
+    return 0;
+}
+// CUDA-event time of the update-only step launches issued by sml_synchronize while profiling, and their count
+int sml_sync_times(sml_engine *h, double *ms_sum, int64_t *steps)
+{
+    if (!h) return -1;
+    *ms_sum = h->sync_ms_sum;
+    *steps = h->sync_steps;
+    h->sync_ms_sum = 0.0;
+    h->sync_steps = 0;
     return 0;
 }
 int64_t sml_kernel_launch_count(const sml_engine *h) { return h ? h->launches : 0; }

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "sml_profile": ([C.c_void_p, C.c_int], C.c_int),
     "sml_kernel_times": ([C.c_void_p, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
     "sml_phase_times": ([C.c_void_p, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
+    "sml_sync_times": ([C.c_void_p, _dp, _lp], C.c_int),
     "sml_step_chunk_rows": ([C.c_void_p, C.c_int], C.c_int),
     "sml_kernel_launch_count": ([C.c_void_p], C.c_int64),
     "sml_predict_algorithmic_bytes": ([C.c_void_p, C.c_int], C.c_int64),
@@ -605,6 +606,12 @@ class Engine:
         a, b, c = C.c_double(), C.c_double(), C.c_int()
         self._ck(self.lib.sml_phase_times(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def sync_times(self):
+        """-> (ms of the update-only launches issued by synchronize while profiling, number of steps)"""
+        a, n = C.c_double(), C.c_int64()
+        self._ck(self.lib.sml_sync_times(self.h, C.byref(a), C.byref(n)))
+        return a.value, n.value
 
     def step_chunk_rows(self, kind=ATMO):
         return int(self.lib.sml_step_chunk_rows(self.h, kind))

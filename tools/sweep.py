@@ -2,8 +2,8 @@
 """BASELINE.json configs[4]: reservoir-size and adjacency-degree sweep on one B200.
 
 For each (m, degree): 1152 regions of the T30 tiling (true class mix, SST input on 70 %), synthetic weights;
-  * update  : the state update alone (ELL SpMV + compact W_in + tanh + leak) -- update-only launches of k_step,
-              timed as the difference of two synchronize(ALL) calls of different length (cancels the input upload);
+  * update  : the state update alone (ELL SpMV + compact W_in + tanh + leak) -- the update-only launches of k_step
+              that synchronize(ALL) issues, bracketed by CUDA events inside the engine;
   * step    : the fused update + readout kernel (CUDA events inside the engine, as bench.py does);
   * readout : step - update.
 Bytes are the algorithmic ones of DESIGN.md section 4.1; the roof is MEASURED_PEAKS.json's copy bandwidth.
@@ -14,7 +14,6 @@ import importlib
 import json
 import os
 import sys
-import time
 
 import numpy as np
 
@@ -57,18 +56,13 @@ def point(m, deg, nregions, steps):
     eng.finalize()
     assert eng.predict_algorithmic_bytes() == upd_bytes + rd_bytes
     rng = np.random.default_rng(0)
-    T1, T2 = 4, 4 + steps
-    inputs = [np.asfortranarray(rng.standard_normal((D, T2))) for (_, D) in dims]
-
-    def sync_time(T):
-        best = 1e9
-        for _ in range(3):
-            t0 = time.perf_counter()
-            eng.synchronize_all(inputs, T)
-            best = min(best, time.perf_counter() - t0)
-        return best
-
-    upd_ms = (sync_time(T2) - sync_time(T1)) / (T2 - T1) * 1e3
+    inputs = [np.asfortranarray(rng.standard_normal((D, steps))) for (_, D) in dims]
+    eng.synchronize_all(inputs, 3)               # warm-up
+    eng.profile(True)
+    eng.synchronize_all(inputs, steps)           # update-only launches, bracketed by CUDA events in the engine
+    upd_ms, nsteps = eng.sync_times()
+    eng.profile(False)
+    upd_ms /= nsteps
     for _ in range(3):
         eng.predict()
     eng.profile(True)
