@@ -25,6 +25,9 @@ namespace sml {
 
 constexpr int CH_NB = 128;                       // panel width = tile size
 constexpr int CH_LINV = 2 * CH_NB * CH_NB;       // doubles per panel: Linv (row c, col m) then LinvT
+constexpr int CH_SB = 32;                        // sub-block of the diagonal-block kernel
+constexpr int CH_LD = CH_NB + 1;
+constexpr int CH_TLD = 3 * CH_SB + 1;
 enum CholOp { CH_UPDATE = 0, CH_TRSM = 1, CH_BACK_UPDATE = 2, CH_BACK_TRI = 3 };
 
 // C(128x128) = sum_kk Aop[i, kk] * Bop[j, kk], kk in [0, kvalid), kvalid % 4 == 0.
@@ -204,18 +207,54 @@ k_chol_gemm(const TrainRegionDev *__restrict__ T, int op, int k)
     }
 }
 
-// Diagonal block of panel k: unblocked Cholesky of the nb x nb block in shared memory, then its inverse.
-// One array holds both: the lower triangle is L, the strictly upper triangle collects X^T (X = L^-1), the
-// diagonal of X sits in dinv.  Writes L back (lower part only: the upper triangle of Gaug still holds A),
-// and the zero-padded 128 x 128 blocks Linv (element (c, m) at c + 128 m) and LinvT.
+// Diagonal block of panel k: Cholesky of the nb x nb block in shared memory, then its inverse, both blocked by 32.
+//   factor : per 32-wide sub-panel -- one warp factorises the 32 x 32 diagonal block in registers (lane = row,
+//            columns exchanged by shuffles), threads-per-row solve the rows below it, all threads apply the rank-32
+//            update to the trailing block;
+//   invert : X = L^-1.  Warp b inverts diagonal sub-block b (lane = column, forward substitution in registers);
+//            the off-diagonal blocks follow by block rows, X_ij = -X_ii (sum_m L_im X_mj), with all threads.
+// One array holds both: the lower triangle is L, the strictly upper triangle collects X^T, diag(X) sits in dinv.
+// Writes L back (lower part only: the upper triangle of Gaug still holds A), and the zero-padded 128 x 128 blocks
+// Linv (element (c, m) at c + 128 m) and LinvT.
 // A non-positive or non-finite pivot sets info = 1-based column (dpotrf convention) and the region drops out.
+// Cholesky of one 32 x 32 diagonal sub-block by one warp, entirely in registers: lane i holds row i, the column
+// being eliminated travels by shuffles.  Rows/columns beyond w are padded with the identity.  Returns the 1-based
+// column of the first non-positive / non-finite pivot, or 0 (then the factor is written back).
+__device__ __noinline__ int chol32_warp(double *__restrict__ Sb, int LD, int w, int lane)
+{
+    double a[CH_SB];
+    const int i = lane;
+#pragma unroll
+    for (int c = 0; c < CH_SB; ++c) a[c] = (i < w && c < w && c <= i) ? Sb[i * LD + c] : ((i == c) ? 1.0 : 0.0);
+    int failcol = 0;
+#pragma unroll
+    for (int j = 0; j < CH_SB; ++j) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (failcol == 0 && (!(d > 0.0) || !isfinite(d))) failcol = j + 1;
+        const double r = sqrt(d);
+        const double l = (i == j) ? r : a[j] / r;   // lanes above the diagonal carry zeros
+        a[j] = l;
+#pragma unroll
+        for (int c = j + 1; c < CH_SB; ++c) {
+            const double lc = __shfl_sync(0xffffffffu, l, c);
+            if (i >= c) a[c] = fma(-l, lc, a[c]);
+        }
+    }
+    if (failcol) return failcol;
+#pragma unroll
+    for (int c = 0; c < CH_SB; ++c)
+        if (i < w && c < w && c <= i) Sb[i * LD + c] = a[c];
+    return 0;
+}
+
 __global__ void __launch_bounds__(256, 1)
 k_chol_diag(const TrainRegionDev *__restrict__ T, int k)
 {
     extern __shared__ __align__(16) double ch_s[];
-    constexpr int LD = CH_NB + 1;
-    double *S = ch_s;                // [128][129]
-    double *dinv = ch_s + CH_NB * LD;
+    constexpr int LD = CH_LD;
+    double *S = ch_s;                      // [128][129]
+    double *dinv = ch_s + CH_NB * LD;      // [128]
+    double *Tm = dinv + CH_NB;             // [32][97] scratch of the inversion
     __shared__ int s_fail;
     const TrainRegionDev &t = T[blockIdx.x];
     if (*t.chol_info != 0) return;
@@ -224,61 +263,123 @@ k_chol_diag(const TrainRegionDev *__restrict__ T, int k)
     if (j0 >= N) return;
     const int nb = min(CH_NB, N - j0);
     double *G = t.gram + (size_t)j0 * ld + j0;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_fail = 0;
     for (int e = tid; e < nb * nb; e += nt) {
         const int i = e % nb, c = e / nb;
         S[i * LD + c] = (i >= c) ? G[(size_t)c * ld + i] : 0.0;
     }
     __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        const double d = S[j * LD + j];
-        if (!(d > 0.0) || !isfinite(d)) {  // uniform across the CTA: every thread reads the same value
-            if (tid == 0) *t.chol_info = j0 + j + 1;
+
+    // ---------------- blocked factorisation
+    for (int b0 = 0; b0 < nb; b0 += CH_SB) {
+        const int w = min(CH_SB, nb - b0);
+        if (warp == 0) {
+            const int failcol = chol32_warp(S + b0 * LD + b0, LD, w, lane);
+            if (failcol && lane == 0) s_fail = b0 + failcol;
+        }
+        __syncthreads();
+        if (s_fail) {
+            if (tid == 0) *t.chol_info = j0 + s_fail;
             return;
         }
-        const double r = sqrt(d);
-        __syncthreads();
-        for (int i = j + tid; i < nb; i += nt) S[i * LD + j] = (i == j) ? r : S[i * LD + j] / r;
-        __syncthreads();
-        const int w = nb - j - 1;
-        for (int e = tid; e < w * w; e += nt) {
-            const int i = j + 1 + e % w, c = j + 1 + e / w;
-            if (i >= c) S[i * LD + c] -= S[i * LD + j] * S[c * LD + j];
+        const int below = nb - b0 - w;   // rows under the sub-block; > 0 only when w == 32
+        if (below > 0) {
+            if (tid < below) {
+                const int r = b0 + CH_SB + tid;
+                double x[CH_SB];
+#pragma unroll
+                for (int c = 0; c < CH_SB; ++c) {
+                    double v = S[r * LD + b0 + c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) v = fma(-x[m], S[(b0 + c) * LD + b0 + m], v);
+                    x[c] = v / S[(b0 + c) * LD + b0 + c];
+                }
+#pragma unroll
+                for (int c = 0; c < CH_SB; ++c) S[r * LD + b0 + c] = x[c];
+            }
+            __syncthreads();
+            const int t0 = b0 + CH_SB;
+            for (int e = tid; e < below * below; e += nt) {
+                const int i = t0 + e % below, c = t0 + e / below;
+                if (i < c) continue;
+                const double *ri = S + i * LD + b0, *rc = S + c * LD + b0;
+                double v = S[i * LD + c];
+#pragma unroll 8
+                for (int m = 0; m < CH_SB; ++m) v = fma(-ri[m], rc[m], v);
+                S[i * LD + c] = v;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
-    // inverse: thread c solves L x = e_c; x_i is kept at S[c][i] (i > c), x_c in dinv[c]
-    if (tid < nb) {
-        const int c = tid;
-        const double xc = 1.0 / S[c * LD + c];
-        dinv[c] = xc;
-        for (int i = c + 1; i < nb; ++i) {
-            double s = S[i * LD + c] * xc;
-            for (int m = c + 1; m < i; ++m) s = fma(S[i * LD + m], S[c * LD + m], s);
-            S[c * LD + i] = -s / S[i * LD + i];
+
+    // ---------------- inverse of the diagonal sub-blocks: warp b, lane = column
+    if (warp < (nb + CH_SB - 1) / CH_SB) {
+        const int b0 = warp * CH_SB, w = min(CH_SB, nb - b0), c = lane;
+        double x[CH_SB];
+        // branch-free so that x[] stays in registers: x[m] = 0 for m < c makes the full-length dot product exact
+#pragma unroll
+        for (int i = 0; i < CH_SB; ++i) {
+            const bool in = i < w;
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < i; ++m) acc = fma(in ? S[(b0 + i) * LD + b0 + m] : 0.0, x[m], acc);
+            const double dii = in ? S[(b0 + i) * LD + b0 + i] : 1.0;
+            x[i] = (i == c) ? 1.0 / dii : ((i > c) ? -acc / dii : 0.0);
+        }
+        __syncwarp();
+        if (c < w) {
+#pragma unroll
+            for (int i = 0; i < CH_SB; ++i) {
+                if (i == c) dinv[b0 + c] = x[i];                                // static index keeps x[] in registers
+                else if (i > c && i < w) S[(b0 + c) * LD + b0 + i] = x[i];      // X[b0+i][b0+c] kept transposed
+            }
         }
     }
     __syncthreads();
+    // X[m][c] for m >= c (all already computed): dinv on the diagonal, else the transposed store
+#define CH_X(m, c) (((m) == (c)) ? dinv[(c)] : S[(c) * LD + (m)])
+    for (int r0 = CH_SB; r0 < nb; r0 += CH_SB) {
+        const int w = min(CH_SB, nb - r0);
+        // Tm[i][c] = sum_{m=c}^{r0-1} L[r0+i][m] X[m][c],  i < w, c < r0
+        for (int e = tid; e < w * r0; e += nt) {
+            const int i = e % w, c = e / w;
+            const double *Lrow = S + (r0 + i) * LD;
+            double acc = Lrow[c] * dinv[c];
+            for (int m = c + 1; m < r0; ++m) acc = fma(Lrow[m], S[c * LD + m], acc);
+            Tm[i * CH_TLD + c] = acc;
+        }
+        __syncthreads();
+        // X[r0+i][c] = -sum_{m<=i} X_ii[i][m] Tm[m][c]
+        for (int e = tid; e < w * r0; e += nt) {
+            const int i = e % w, c = e / w;
+            double acc = dinv[r0 + i] * Tm[i * CH_TLD + c];
+            for (int m = 0; m < i; ++m) acc = fma(S[(r0 + m) * LD + r0 + i], Tm[m * CH_TLD + c], acc);
+            S[c * LD + r0 + i] = -acc;
+        }
+        __syncthreads();
+    }
+
     double *linv = t.linv + (size_t)k * CH_LINV, *linvT = linv + CH_NB * CH_NB;
     for (int e = tid; e < CH_NB * CH_NB; e += nt) {
         const int r = e % CH_NB, m = e / CH_NB;  // element (row r, col m)
         double x = 0.0, xt = 0.0;
         if (r < nb && m < nb) {
             if (r == m) x = xt = dinv[r];
-            else if (r > m) x = S[m * LD + r];   // X[r][m]
-            else xt = S[r * LD + m];             // X^T[r][m] = X[m][r]
+            else if (r > m) x = CH_X(r, m);      // X[r][m]
+            else xt = CH_X(m, r);                // X^T[r][m] = X[m][r]
         }
         linv[e] = x;
         linvT[e] = xt;
     }
+#undef CH_X
     for (int e = tid; e < nb * nb; e += nt) {
         const int i = e % nb, c = e / nb;
         if (i >= c) G[(size_t)c * ld + i] = S[i * LD + c];
     }
 }
 
-constexpr size_t CH_DIAG_SMEM = (size_t)(CH_NB * (CH_NB + 1) + CH_NB) * 8;
+constexpr size_t CH_DIAG_SMEM = (size_t)(CH_NB * CH_LD + CH_NB + CH_SB * CH_TLD) * 8;
 
 // diagonal of the regularised A, saved before the factorisation overwrites it (LU fallback)
 __global__ void k_chol_save_diag(const TrainRegionDev *__restrict__ T)

@@ -66,6 +66,8 @@ struct KindState {
     long long x_total = 0, fb_total = 0, lm_total = 0;
     int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0, chunk_rows = 0;
     int *d_order = nullptr;  // launch order of the items: largest first
+    int *d_one_region = nullptr;  // region index for one region's synchronize
+    int one_region = -1;
     size_t smem_bytes = 0;
     bool any_dense = false;
     int64_t alg_bytes = 0;
@@ -237,7 +239,7 @@ static void free_kind(KindState &K)
 {
     for (auto &r : K.regs)
         for (void *p : r.allocs) cudaFree(p);
-    cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_items_split); cudaFree(K.d_order); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
+    cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_items_split); cudaFree(K.d_order); cudaFree(K.d_one_region); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
     cudaFree(K.d_lm); cudaFree(K.d_out); cudaFree(K.d_partials); cudaFree(K.d_temp); cudaFree(K.d_fb_offs);
     cudaFree(K.d_in); cudaFree(K.d_in_offs);
 }
@@ -602,7 +604,7 @@ static int finalize_kind(sml_engine *h, int kind)
     CK(h, cudaMalloc(&K.d_items, sizeof(StepItem) * std::max(1, K.nitems)));
     CK(h, cudaMemcpy(K.d_items, K.items.data(), sizeof(StepItem) * K.nitems, cudaMemcpyHostToDevice));
     {
-        // launch order: largest items first so that the last CTAs to start are the cheapest (LPT)
+        // optional launch order (SML_LPT): largest items first so that the last CTAs to start are the cheapest
         std::vector<int> order(K.nitems);
         for (int i = 0; i < K.nitems; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return K.items[a].ncols > K.items[b].ncols; });
@@ -817,13 +819,48 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
         k_win_dense<<<grid, 256, 0, h->stream>>>(K.d_regs, u_pool, u_offs, u_t, K.d_temp);
         h->launches++;
     }
-    const size_t smem = do_readout ? K.smem_bytes : 0;
+    if (!do_readout) {
+        // update-only step (synchronize): the dedicated latency-tolerant kernel, all regions or one region's slice
+        // rows per thread: measured 0.200 / 0.206 / 0.151 ms for 1 / 2 / 4 at the bench config (profiles/round1_summary.md)
+        static const int rpt = getenv("SML_UPDATE_RPT") ? atoi(getenv("SML_UPDATE_RPT")) : 4;  // A/B switch
+        const int RPT = (rpt == 1 || rpt == 2 || rpt == 8) ? rpt : 4;
+        const bool all = d_items == K.d_items && nitems == K.nitems;
+        int nreg = (int)K.regs.size();
+        const int *list = nullptr;
+        if (!all) {
+            if (!K.d_one_region) CK(h, cudaMalloc(&K.d_one_region, sizeof(int)));
+            const int reg = K.items[(int)(d_items - K.d_items)].reg;
+            if (reg != K.one_region) {
+                CK(h, cudaMemcpyAsync(K.d_one_region, &reg, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+                CK(h, cudaStreamSynchronize(h->stream));
+                K.one_region = reg;
+            }
+            list = K.d_one_region;
+            nreg = 1;
+        }
+        dim3 grid((K.n_max + 256 * RPT - 1) / (256 * RPT), (unsigned)nreg);
+        if (RPT == 1)
+            k_update<1><<<grid, 256, 0, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp);
+        else if (RPT == 2)
+            k_update<2><<<grid, 256, 0, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp);
+        else if (RPT == 8)
+            k_update<8><<<grid, 256, 0, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp);
+        else
+            k_update<4><<<grid, 256, 0, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        return 0;
+    }
+    const size_t smem = K.smem_bytes;
     // the full item list is launched largest-first; partial lists (one region's synchronize) in place.
     // partials are indexed by the item's position in the FULL list (k_readout_finish reads item0 + c)
-    static const bool no_lpt = getenv("SML_NO_LPT") != nullptr;  // A/B switch for profiles/
+    // CTAs are launched in region-major item order: neighbouring CTAs stream neighbouring W_out columns.  A
+    // largest-first (LPT) order was measured 1.8 % slower (1.2794 vs 1.2559 ms per launch, same box) and is off
+    // unless SML_LPT is set
+    static const bool lpt = getenv("SML_LPT") != nullptr;
     const bool full = (d_items == K.d_items || d_items == K.d_items_split) && nitems == K.nitems;
     const int item_base = full ? 0 : (int)(d_items - K.d_items);
-    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, (full && !no_lpt) ? K.d_order : nullptr, item_base,
+    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, (full && lpt) ? K.d_order : nullptr, item_base,
                                                           K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm,
                                                           K.d_temp, K.d_partials, K.ldw, K.stage_cols, K.stage_bytes,
                                                           K.xs_cap, do_readout);

@@ -190,7 +190,7 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
     uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * NCONS);
     uint64_t *empty = full + STAGES;
 
-    const int item = order ? order[blockIdx.x] : (int)blockIdx.x;  // largest-first launch order
+    const int item = order ? order[blockIdx.x] : (int)blockIdx.x;  // optional launch-order permutation
     const StepItem it = items[item];
     const RegionDev R = regs[it.reg];
     const int tid = threadIdx.x;
@@ -286,6 +286,77 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
         double sum = 0.0;
         for (int g = 0; g < cpi; ++g) sum += red[g * ldw + p];
         partials[(size_t)(item_base + item) * ldw_max + p] = sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_update: the state update alone (synchronize, src/mod_reservoir.f90:1354-1381; slab :1237-1266).
+// The fused kernel hides this phase behind the W_out stream; on its own it is a latency problem (four dependent
+// global loads per row), so this variant keeps more loads in flight: 256-thread CTAs at high occupancy, RPT rows
+// per thread (rows 256 apart, so every load stays coalesced), ELL slots fetched three at a time for all of the
+// thread's rows before the x gathers.  Accumulation order per row is the entry order, as in update_row.
+// grid (ceil(n_max / (256*RPT)), regions); region_list selects regions (one region's synchronize) or is null.
+// ---------------------------------------------------------------------------------------------
+template <int RPT>
+__global__ void __launch_bounds__(256)
+k_update(const RegionDev *__restrict__ regs, const int *__restrict__ region_list, const double *__restrict__ x_old,
+         double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
+         const double *__restrict__ temp_pool)
+{
+    const int reg = region_list ? region_list[blockIdx.y] : (int)blockIdx.y;
+    const RegionDev &R = regs[reg];
+    const int n = R.n;
+    const int base = blockIdx.x * (256 * RPT) + threadIdx.x;
+    if (base >= n) return;
+    const double *__restrict__ xo = x_old + R.x_off;
+    const double *__restrict__ u = u_pool + u_offs[reg] + (long long)u_t * R.D;
+    const int *__restrict__ ecol = R.ell_col;
+    const double *__restrict__ eval = R.ell_val;
+    const int W = R.ell_w;
+    int row[RPT];
+    bool ok[RPT];
+    double acc[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = base + i * 256;
+        ok[i] = r < n;
+        row[i] = ok[i] ? r : base;  // out-of-range lanes recompute a valid row and drop the result
+        acc[i] = 0.0;
+    }
+    for (int s = 0; s < W; s += 3) {
+        int c[RPT][3];
+        double v[RPT][3], xv[RPT][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const bool in = s + j < W;
+                c[i][j] = in ? __ldg(ecol + (size_t)(s + j) * n + row[i]) : 0;
+                v[i][j] = in ? __ldg(eval + (size_t)(s + j) * n + row[i]) : 0.0;
+            }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) xv[i][j] = xo[c[i][j]];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+                if (s + j < W) acc[i] = fma(v[i][j], xv[i][j], acc[i]);
+    }
+    double t[RPT], xr[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        if (R.win_mode == 0) t[i] = __dmul_rn(__ldg(R.winc + row[i]), u[__ldg(R.wcol + row[i])]);
+        else t[i] = temp_pool[R.x_off + row[i]];
+        xr[i] = xo[row[i]];
+    }
+    double *__restrict__ xn = x_new + R.x_off;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const double xt = tanh(__dadd_rn(acc[i], t[i]));
+        const double xv2 = __dadd_rn(__dmul_rn(1.0 - R.leak, xr[i]), __dmul_rn(R.leak, xt));
+        if (ok[i]) xn[row[i]] = xv2;
     }
 }
 
