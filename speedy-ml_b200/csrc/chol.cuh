@@ -11,8 +11,9 @@
 // Y R^T was.  All O(N^3) work runs through one FP64 tensor-core (DMMA) tile-GEMM with TMA-fed operands:
 //     UPDATE      A[i-tile, blk k] -= L[i-tile, 0:j0] L[blk k, 0:j0]^T              (K = j0)
 //     TRSM        L[rows below, blk k]  = A[rows below, blk k] Linv_k^T             (K = nb)
-//     BACK_UPDATE W[:, blk k] -= W[:, cols right of k] L[rows below k, blk k]       (K = N - j0 - nb)
 //     BACK_TRI    W[:, blk k]  = W[:, blk k] Linv_k                                 (K = nb)
+//     BACK_UPDATE W[:, blk j] -= W[:, blk k] L[blk k, blk j]   for every j < k      (K = nb; right-looking, so
+//                 each step is k*ceil(P/128) independent tiles instead of one long-K tile)
 // with the 128 x 128 diagonal blocks factorised and inverted in shared memory by k_chol_diag.
 // BACK_UPDATE needs L^T with the K index along a column; after the factorisation L is mirrored into the upper
 // triangle once (k_train_ridge_mirror without ridge terms).  Until then the upper triangle still holds the
@@ -78,20 +79,26 @@ k_chol_gemm(const TrainRegionDev *__restrict__ T, int op, int k)
         C = G + (size_t)j0 * ld + i0;
         ni = rowsA; nj = nb;
     } else {
-        const int p0 = blockIdx.x * CH_NB;
-        if (p0 >= P) return;
+        const int ptiles = (P + CH_NB - 1) / CH_NB;
+        const int p0 = (blockIdx.x % ptiles) * CH_NB;
         const int np = min(CH_NB, P - p0);
         transposed = true;
-        C = G + (size_t)j0 * ld + N + p0;   // W[p0 + j, j0 + i] at C[i*ld + j]
-        ni = nb; nj = np;
         if (op == CH_BACK_UPDATE) {
-            const int m0 = j0 + nb;         // K index kk <-> column m0 + kk; L^T lives in the upper triangle
-            A = G + (size_t)m0 * ld + j0; lda = ld; rowsA = CH_NB;
-            B = G + (size_t)m0 * ld + N + p0; ldb = ld; rowsB = np;
-            kvalid = N - m0;
-            if (kvalid <= 0) return;
+            // block column jt < k of W receives the contribution of the just-solved block k:
+            //   W[p, c] -= sum_{m in blk k} W[p, m] L[m, c]; L^T lives in the upper triangle: U[c, m] at G[m*ld + c]
+            const int jt = blockIdx.x / ptiles;
+            if (jt >= k) return;
+            const int c0 = jt * CH_NB;
+            A = G + (size_t)j0 * ld + c0; lda = ld; rowsA = CH_NB;        // rows c of block jt, K index m - j0
+            B = G + (size_t)j0 * ld + N + p0; ldb = ld; rowsB = np;       // rows p, same K index
+            kvalid = nb;
             mode = 0;
+            C = G + (size_t)c0 * ld + N + p0;   // W[p0 + j, c0 + i] at C[i*ld + j]
+            ni = CH_NB; nj = np;
         } else {
+            if (blockIdx.x >= (unsigned)ptiles) return;
+            C = G + (size_t)j0 * ld + N + p0;   // W[p0 + j, j0 + i] at C[i*ld + j]
+            ni = nb; nj = np;
             A = linv + CH_NB * CH_NB; lda = CH_NB; rowsA = CH_NB;  // LinvT: element (c, c') = Linv[c', c]
             B = G + (size_t)j0 * ld + N + p0; ldb = ld; rowsB = np;
             kvalid = nb;

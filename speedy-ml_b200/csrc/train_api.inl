@@ -314,9 +314,12 @@ int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using
     if (any_chol) {
         const int ptiles = (P_max + CH_NB - 1) / CH_NB;
         for (int k = kb_max - 1; k >= 0; --k) {
-            k_chol_gemm<<<dim3(ptiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, CH_BACK_UPDATE, k);
             k_chol_gemm<<<dim3(ptiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, CH_BACK_TRI, k);
-            h->launches += 2;
+            h->launches++;
+            if (k > 0) {
+                k_chol_gemm<<<dim3(ptiles * k, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, CH_BACK_UPDATE, k);
+                h->launches++;
+            }
         }
         CK(h, cudaGetLastError());
     }
