@@ -168,6 +168,12 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
  * intended semantics of SURVEY.md Appendix C, where the source itself has shape hazards) ---- */
 int sml_predict(sml_engine *h, int kind);
 
+/* model_parameters%outvec_component_contribs (src/mod_reservoir.f90:1458-1461): when on, every atmosphere predict also
+ * keeps reservoir%v_p = wout(:,1:chunk_size_speedy)*local_model and reservoir%v_ml = wout(:,chunk_size_speedy+1:)*x~
+ * (standardised units).  The readout then runs in split order (outvec = unstandardise(v_p + v_ml)). */
+int sml_set_contribs(sml_engine *h, int on);
+int sml_contribs_get(sml_engine *h, int region, double *v_p, double *v_ml);
+
 /* ---- sendrecievegrid (src/mpires.f90:218-804), split where the root calls run_model (:565-569).
  * begin: gathers the outvecs into the global grids, applies the clamps (:456-490) and returns them
  *        (rank 0 arrays may be NULL to skip the copy-out): wholegrid4d[4*96*48*8], wholegrid2d[96*48],

@@ -123,6 +123,9 @@ struct sml_engine {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_pack = nullptr, ev_d2h = nullptr, ev_h2d = nullptr;
     double *h_pin_tisr = nullptr;
+    // outvec_component_contribs (src/mod_reservoir.f90:1458-1461): v_p and v_ml of every local atmosphere region
+    bool contribs = false;
+    double *d_vp = nullptr, *d_vml = nullptr;
     // peer exchange (fused all-gather over NVLink; kernels.cuh PeerTable)
     void *d_xchg = nullptr;            // this rank's exchange block: [2][R*P] doubles + MAX_PEERS flags
     size_t xchg_flags_off = 0;         // byte offset of the flags inside the block
@@ -256,7 +259,7 @@ int sml_destroy(sml_engine *h)
     cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);
     cudaFree(h->d_ocean_gathered); cudaFree(h->d_ocean_fb); cudaFree(h->d_ocean_ring);
     for (void *m : h->peer_mapped) cudaIpcCloseMemHandle(m);
-    cudaFree(h->d_xchg); cudaFree(h->d_done); cudaFree(h->d_peer_err);
+    cudaFree(h->d_xchg); cudaFree(h->d_done); cudaFree(h->d_peer_err); cudaFree(h->d_vp); cudaFree(h->d_vml);
     cudaFreeHost(h->h_pin_G); cudaFreeHost(h->h_pin_F); cudaFreeHost(h->h_pin_tisr);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
@@ -888,18 +891,21 @@ static int launch_finish(sml_engine *h, KindState &K, int model_part)
     PeerTable pt{};
     unsigned long long seq = 0;
     long long peer_off = 0;
-    if (&K == &h->kinds[SML_ATMO] && h->peers.world > 1) {
+    const bool atmo = &K == &h->kinds[SML_ATMO];
+    if (atmo && h->peers.world > 1) {
         pt = h->peers;
         seq = ++h->peer_seq;
         const long long RP = (long long)h->p.number_of_regions * K.P;
         // rank-major == region order (contiguous shards): this rank's rows start at local_ids[0]
         peer_off = (long long)(seq & 1) * RP + (long long)h->local_ids[0] * K.P;
     }
-    if (K.P > FIN_PMAX) FAIL(h, "chunk_size_prediction %d exceeds the finish kernel's %d outputs", K.P, FIN_PMAX);
     // sequential mode: one group of threads sums the partials; overlapped mode: 4 groups share the model columns
     const int threads = model_part ? FIN_GROUPS * FIN_PMAX : FIN_PMAX;
-    k_readout_finish<<<(unsigned)K.regs.size(), threads, 0, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1,
-                                                                         model_part, K.d_lm, pt, seq, peer_off, h->d_done);
+    const size_t fsmem = model_part ? sizeof(double) * FIN_GROUPS * ((K.P + 1) & ~1) : 0;
+    k_readout_finish<<<(unsigned)K.regs.size(), threads, fsmem, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1,
+                                                                         model_part, K.d_lm, pt, seq, peer_off, h->d_done,
+                                                                         (atmo && h->contribs && model_part) ? h->d_vp : nullptr,
+                                                                         (atmo && h->contribs && model_part) ? h->d_vml : nullptr);
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -929,10 +935,12 @@ int sml_predict(sml_engine *h, int kind)
     if (ev) CK(h, cudaEventRecord(ev[0], h->stream));
     // the finish stays a separate launch: folding it into the step kernel's tail (last chunk of a region reduces)
     // was measured 2.6 % slower -- the fence + atomic round trip idles every CTA slot for ~1 us per chunk
-    if (launch_step(h, K, K.d_items, K.nitems, K.d_fb, K.d_fb_offs, 0, 1)) return -1;
+    // with outvec_component_contribs the readout runs in split order (v_p + v_ml) so that both halves exist
+    const bool split = kind == SML_ATMO && h->contribs;
+    if (launch_step(h, K, split ? K.d_items_split : K.d_items, K.nitems, K.d_fb, K.d_fb_offs, 0, 1)) return -1;
     K.cur ^= 1;
     if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
-    if (launch_finish(h, K, 0)) return -1;
+    if (launch_finish(h, K, split ? 1 : 0)) return -1;
     if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
     return 0;
 }
@@ -1305,6 +1313,38 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const 
                           h->stream));
     if (sml_step_unpack_device(h, timestep)) return -1;
     CK(h, cudaStreamSynchronize(h->stream));  // pinned staging is reused by the next call
+    return 0;
+}
+
+// model_parameters%outvec_component_contribs (src/mod_reservoir.f90:1458-1461): keep v_p = wout(:,1:S)*local_model and
+// v_ml = wout(:,S+1:)*x~ of every local atmosphere region (standardised units, as the reference stores them).  The
+// readout then runs in split order, outvec = unstandardise(v_p + v_ml): equal to the fused order within 1e-13.
+int sml_set_contribs(sml_engine *h, int on)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    KindState &K = h->kinds[SML_ATMO];
+    if (on && !h->d_vp) {
+        const size_t bytes = sizeof(double) * K.regs.size() * K.P;
+        CK(h, cudaMalloc(&h->d_vp, bytes));
+        CK(h, cudaMalloc(&h->d_vml, bytes));
+        CK(h, cudaMemset(h->d_vp, 0, bytes));
+        CK(h, cudaMemset(h->d_vml, 0, bytes));
+    }
+    h->contribs = on != 0;
+    return 0;
+}
+
+int sml_contribs_get(sml_engine *h, int region, double *v_p, double *v_ml)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (!h->contribs) FAIL(h, "sml_set_contribs(h, 1) has not been called");
+    int li;
+    if (local_of(h, SML_ATMO, region, &li)) return -1;
+    const RegionDev &d = h->kinds[SML_ATMO].regs[li].dev;
+    CK(h, cudaMemcpyAsync(v_p, h->d_vp + d.out_off, sizeof(double) * d.P, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(v_ml, h->d_vml + d.out_off, sizeof(double) * d.P, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -381,16 +381,18 @@ __global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__
 // reference's v_ml, src/mod_reservoir.f90:1460) and this kernel adds v_p = W_out[:, 0:S]*local_model (:1459)
 // once the host model's forecast has arrived.
 constexpr int FIN_GROUPS = 4;     // column groups of the model-part GEMV
-constexpr int FIN_PMAX = 160;     // threads per group >= P rounded up to a warp multiple
+constexpr int FIN_PMAX = 160;     // threads per group (outputs are strided over them: any chunk_size_prediction)
 
 __global__ void __launch_bounds__(FIN_GROUPS *FIN_PMAX)
 k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ partials, int ldw_max,
                  double *__restrict__ out_pool, int unstandardize, int model_part,
                  const double *__restrict__ lm_pool, PeerTable pt, unsigned long long seq,
-                 long long peer_off, unsigned int *__restrict__ done_counter)
+                 long long peer_off, unsigned int *__restrict__ done_counter, double *__restrict__ vp_pool,
+                 double *__restrict__ vml_pool)
 {
-    __shared__ double s_vp[FIN_GROUPS][FIN_PMAX];
+    extern __shared__ double s_vp[];   // [FIN_GROUPS][pstride], overlapped mode only
     const RegionDev R = regs[blockIdx.x];
+    const int pstride = (R.P + 1) & ~1;
     const int grp = threadIdx.x / FIN_PMAX, p0 = threadIdx.x % FIN_PMAX;
     if (model_part) {
         // v_p = W_out[:, 0:S] * local_model: group g takes columns g, g+4, ...; 4 independent FMA chains per thread
@@ -407,14 +409,22 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
                 a3 = fma(w[(size_t)(j + 3 * FIN_GROUPS) * R.ldw], lm[j + 3 * FIN_GROUPS], a3);
             }
             for (; j < R.S; j += FIN_GROUPS) a0 = fma(w[(size_t)j * R.ldw], lm[j], a0);
-            if (p < FIN_PMAX) s_vp[grp][p] = (a0 + a1) + (a2 + a3);
+            s_vp[grp * pstride + p] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
     }
     if (grp == 0) {
         for (int p = p0; p < R.P; p += FIN_PMAX) {
             double v = 0.0;
-            if (model_part) v = (s_vp[0][p] + s_vp[1][p]) + (s_vp[2][p] + s_vp[3][p]);
+            if (model_part) v = (s_vp[p] + s_vp[pstride + p]) + (s_vp[2 * pstride + p] + s_vp[3 * pstride + p]);
+            if (vp_pool) {
+                // reservoir%v_p / reservoir%v_ml (outvec_component_contribs, src/mod_reservoir.f90:1458-1461): the two
+                // halves of the readout, in standardised units as the reference keeps them
+                double vml = 0.0;
+                for (int c = 0; c < R.nitems; ++c) vml += partials[(size_t)(R.item0 + c) * ldw_max + p];
+                vp_pool[R.out_off + p] = v;
+                vml_pool[R.out_off + p] = vml;
+            }
             for (int c = 0; c < R.nitems; ++c) v += partials[(size_t)(R.item0 + c) * ldw_max + p];
             if (unstandardize) {
                 const int ms = R.out_ms[p];

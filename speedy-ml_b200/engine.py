@@ -77,6 +77,8 @@ _SIGNATURES = {
     "sml_wout_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_synchronize": ([C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _lp], C.c_int),
     "sml_predict": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_set_contribs": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_contribs_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
     "sml_step_exchange_begin": ([C.c_void_p, C.c_int, _dp, _dp, _dp, _dp], C.c_int),
     "sml_step_exchange_end": ([C.c_void_p, C.c_int, _dp, _dp, _dp], C.c_int),
     "sml_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
@@ -430,6 +432,16 @@ class Engine:
     # -- predict / predict_ml for every local region   mod_reservoir.f90:1418,1491
     def predict(self, kind=ATMO):
         self._ck(self.lib.sml_predict(self.h, kind))
+
+    # -- outvec_component_contribs: reservoir%v_p, reservoir%v_ml   mod_reservoir.f90:1458-1461
+    def set_contribs(self, on=True):
+        self._ck(self.lib.sml_set_contribs(self.h, int(on)))
+
+    def contribs_get(self, region):
+        P = self.dims[(ATMO, region)]["P"]
+        vp, vml = np.zeros(P), np.zeros(P)
+        self._ck(self.lib.sml_contribs_get(self.h, region, _d(vp), _d(vml)))
+        return vp, vml
 
     # -- sendrecievegrid   mpires.f90:218
     def set_sst_static(self, base_sst_grid, sea_mask):

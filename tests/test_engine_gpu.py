@@ -409,3 +409,62 @@ def test_overlapped_step_protocol_errors(E, small_model):
     eng.step_exchange_end(1, f4, f2)
     eng.predict()                               # consumes the look-ahead result
     eng.set_overlap(False)
+
+
+def test_outvec_component_contribs(E):
+    """reservoir%v_p / reservoir%v_ml (src/mod_reservoir.f90:1458-1461): the two halves of the readout"""
+    region = 556
+    w = region_weights(1152, region, m=1300)
+    rc = c_region(w)
+    eng = single_region_engine(E, w)
+    rng = np.random.default_rng(8)
+    x0, fb, lm = 0.3 * rng.standard_normal(w["n"]), rng.standard_normal(w["D"]), rng.standard_normal(w["S"])
+    rc.x[:], rc.feedback[:], rc.local_model[:] = x0, fb, lm
+    eng.state_set(region, x0)
+    eng.feedback_set(region, fb)
+    eng.local_model_set(region, lm)
+    with pytest.raises(E.EngineError):
+        eng.contribs_get(region)
+    eng.set_contribs(True)
+    rc.predict()
+    eng.predict()
+    xt = rc.x.copy()
+    xt[1::2] **= 2                                    # x_temp(2:n:2) squared
+    S = w["S"]
+    v_p = w["wout"][:, :S] @ lm
+    v_ml = w["wout"][:, S:] @ xt
+    vp_e, vml_e = eng.contribs_get(region)
+    assert rel_inf(vp_e, v_p) < 1e-13 and rel_inf(vml_e, v_ml) < 1e-13
+    assert rel_inf(eng.outvec_get(region), rc.outvec) < TOL_STEP * 10     # split order vs the oracle's fused order
+    eng.set_contribs(False)
+    eng.close()
+
+
+@pytest.mark.parametrize("R,region", [(288, 145), (288, 0), (576, 300)])
+def test_other_tilings_predict_and_exchange(E, R, region):
+    """288 regions -> 4x4 tiles (P = 544, the tiling of the reference's unit test), 576 -> 4x2: the engine takes its
+    sizes from the tiling, nothing is specialised to 1152"""
+    m = 2600 if R == 288 else 1500
+    w = region_weights(R, region, m=m, with_dense_win=False)
+    assert w["n"] > 0
+    rc = c_region(w)
+    eng = E.Engine(number_of_regions=R, irank=region, numprocs=R, sst_prescribed=True)
+    eng.region_upload(region, w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"], win_compact=w["winc"],
+                      win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"])
+    eng.finalize()
+    rng = np.random.default_rng(R + region)
+    x0, fb, lm = 0.3 * rng.standard_normal(w["n"]), rng.standard_normal(w["D"]), rng.standard_normal(w["S"])
+    rc.x[:], rc.feedback[:], rc.local_model[:] = x0, fb, lm
+    eng.state_set(region, x0)
+    eng.feedback_set(region, fb)
+    eng.local_model_set(region, lm)
+    rc.predict()
+    eng.predict()
+    assert rel_inf(eng.state_get(region), rc.x) < TOL_STEP
+    assert rel_inf(eng.outvec_get(region), rc.outvec) < TOL_STEP * 10
+    # overlapped (split-order) finish with this P as well
+    eng.state_set(region, x0)
+    eng.set_contribs(True)
+    eng.predict()
+    assert rel_inf(eng.outvec_get(region), rc.outvec) < TOL_STEP * 10
+    eng.close()
