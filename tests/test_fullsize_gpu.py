@@ -20,7 +20,8 @@ from helpers import oc, rel_inf  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-SAMPLE = [0, 5, 23, 24 * 47, 24 * 47 + 23, 555, 556, 557, 558, 700, 1128, 1151]
+SAMPLE = [0, 5, 23, 24 * 47, 24 * 47 + 23, 555, 556, 557, 558, 700, 24 * 46, 24 * 20 + 23]   # distinct ids
+assert len(set(SAMPLE)) == len(SAMPLE)   # the oracle's scatter runs one thread per listed region
 
 
 @pytest.fixture(scope="module")
