@@ -57,5 +57,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_DRIVER = os.path.join(LIB_DIR, "replay_main")
+
+
+def build_host_driver(force: bool = False) -> str:
+    """the compiled host program on the C++ host layer (g++ only; links the engine library)"""
+    srcs = [os.path.join(HERE, "drivers", "replay_main.cpp"), os.path.join(HERE, "host", "speedyml_host.hpp"),
+            os.path.join(os.path.dirname(HERE), "include", "speedyml_engine.h")]
+    if not force and os.path.exists(HOST_DRIVER) and all(os.path.getmtime(s) < os.path.getmtime(HOST_DRIVER) for s in srcs) \
+            and os.path.getmtime(LIB) < os.path.getmtime(HOST_DRIVER):
+        return HOST_DRIVER
+    build()
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cuda_lib = "/usr/local/cuda/lib64"
+    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-o", HOST_DRIVER, srcs[0], "-L" + LIB_DIR, "-lspeedyml_b200",
+           "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + cuda_lib, "-L" + cuda_lib]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed for speedy-ml_b200/drivers/replay_main.cpp")
+    return HOST_DRIVER
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
