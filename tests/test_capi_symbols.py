@@ -46,3 +46,24 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("import oracle", "from oracle", "oracle_c", "oracle_np", "speedyml_oracle", "orc_"):
                     assert needle not in src, f"{f} uses the oracle ({needle})"
+
+
+def test_cpp_host_driver_builds_and_fails_loudly_without_gpu(tmp_path):
+    """the compiled host program on speedy-ml_b200/host/speedyml_host.hpp links against the same C ABI (g++ only)"""
+    import subprocess
+
+    import numpy as np
+    import torch
+    build = importlib.import_module("speedy-ml_b200.build")
+    exe = build.build_host_driver()
+    assert os.access(exe, os.X_OK)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 2 and "usage" in p.stderr
+    if torch.cuda.is_available():
+        return
+    case = tmp_path / "empty.bin"
+    with open(case, "wb") as f:
+        f.write(b"SMLCASE1")
+        np.array([1152, 1, 1, 1, 0, 1, 1152, 1, 0], dtype=np.int32).tofile(f)
+    p = subprocess.run([exe, str(case), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert p.returncode == 1 and "no CUDA device" in p.stderr      # no CPU fallback in the compiled host either
