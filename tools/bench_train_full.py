@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[2]: ridge-regression training of ALL 1152 W_out on one B200 -- Gram accumulation + solve
+in region waves sized to HBM.
+
+Every region is trained at the reference's default length: 6 interleaved phases (trainingdata(:, i::6),
+src/mod_reservoir.f90:289-301) of `--cols` columns each (2000 -> 1960 kept states per phase after the 40-column
+discard, batch 98), then fit_chunk_hybrid (beta_res = 1e-3, beta_model = 1, squared).  The synthetic series is one
+standardised AR(1) draw per phase shared by the regions of a wave (the arithmetic does not depend on the values).
+Reports wall time, CUDA-event time of the Gram and solve kernels, useful Gram TFLOP/s.  One JSON line.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--wave", type=int, default=192)
+    ap.add_argument("--regions", type=int, default=1152)
+    ap.add_argument("--phases", type=int, default=6)
+    ap.add_argument("--cols", type=int, default=2000)
+    ap.add_argument("--discard", type=int, default=40)
+    ap.add_argument("--batch", type=int, default=98)
+    args = ap.parse_args()
+    E = importlib.import_module("speedy-ml_b200.engine")
+    syn = importlib.import_module("speedy-ml_b200.synthetic")
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=1152 // args.regions)
+    regions = eng.region_indices
+    dims = {}
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        for w in ex.map(bench.gen_region, regions):
+            eng.region_upload(w["region"], w["rows"], w["cols"], w["vals"], None, w["mean"], w["std"],
+                              win_compact=w["winc"], win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"],
+                              S=w["S"], P=w["P"])
+            dims[w["region"]] = (w["D"], w["S"], w["n"], w["P"])
+    eng.finalize()
+    setup = time.perf_counter() - t0
+    rng = np.random.default_rng(3)
+    D_max = max(d[0] for d in dims.values())
+    S_max = max(d[1] for d in dims.values())
+    phases = [(syn.ar1_series(D_max, args.cols, rng), np.asfortranarray(rng.standard_normal((S_max, args.cols))))
+              for _ in range(args.phases)]
+    tot = dict(gram_flops_useful=0.0, gram_ms=0.0, stategen_ms=0.0, solve_ms=0.0)
+    by_chol = 0
+    bad = 0
+    t0 = time.perf_counter()
+    for i0 in range(0, len(regions), args.wave):
+        wave = regions[i0:i0 + args.wave]
+        eng.train_begin(wave, args.batch)
+        for td, im in phases:
+            eng.train_feed([td[:dims[r][0]] for r in wave], [im[:dims[r][1]] for r in wave], args.discard)
+        info = eng.train_solve(1e-3, 1.0, True, 0.0)
+        bad += int(np.count_nonzero(info))
+        by_chol += eng.train_solver_stats()
+        st = eng.train_stats()
+        for k in tot:
+            tot[k] += st[k]
+        eng.train_end()
+    wall = time.perf_counter() - t0
+    w = eng.wout_get(regions[-1])
+    out = {"workload": f"ridge training of {len(regions)} W_out (m=6000), {args.phases} phases x {args.cols} columns, "
+                       f"waves of {args.wave}", "wall_s": wall, "gram_s": tot["gram_ms"] / 1e3,
+           "stategen_s": tot["stategen_ms"] / 1e3, "solve_s": tot["solve_ms"] / 1e3,
+           "gram_tflops_useful": tot["gram_flops_useful"] / (tot["gram_ms"] * 1e-3) / 1e12,
+           "solve_ms_per_region": tot["solve_ms"] / len(regions), "solved_by_cholesky": by_chol, "dgesv_info_nonzero": bad,
+           "wout_finite": bool(np.isfinite(w).all()), "setup_s": round(setup, 1)}
+    print(json.dumps(out))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
