@@ -120,9 +120,16 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(SY_THREADS, 1)
+// WM x WN consumer warps, each owning a (128/WM) x (128/WN) sub-tile; <2,4> = 8 warps with 64 accumulators per thread
+// (fewest shared-memory loads per DMMA), <4,4> = 16 warps with 32 (more warps per scheduler to cover the DMMA
+// issue bubbles).  Launch with (WM*WN + 1) * 32 threads.
+template <int WM, int WN>
+__global__ void __launch_bounds__((WM * WN + 1) * 32, 1)
 k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles, int kpad)
 {
+    constexpr int NCW = WM * WN;               // consumer warps
+    constexpr int TR = SY_BM / WM, TC = SY_BM / WN;   // warp sub-tile
+    constexpr int TA = TR / 8, TB = TC / 8;    // 8 x 8 DMMA tiles per warp
     extern __shared__ __align__(128) unsigned char sy_smem[];
     double *stage0 = reinterpret_cast<double *>(sy_smem);
     uint64_t *full = reinterpret_cast<uint64_t *>(sy_smem + (size_t)SY_STAGES * SY_STAGE_DOUBLES * 8);
@@ -141,14 +148,14 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
     if (tid == 0) {
         for (int s = 0; s < SY_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], SY_CONS_WARPS);
+            mbar_init(&empty[s], NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == SY_CONS_WARPS) {
+    if (warp == NCW) {
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)SY_BK * (rowsA + (diag ? 0 : rowsB)) * 8u;
             for (int kc = 0; kc < nchunks; ++kc) {
@@ -167,52 +174,52 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
         return;
     }
 
-    const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps
+    const int wm = warp / WN, wn = warp % WN;
     const int g = lane >> 2, q = lane & 3;         // DMMA group / thread-in-group
     // 8x8 DMMA tiles of this warp that hold real rows / columns (edge tiles of the padded matrix are slivers)
-    const int ma = max(0, min(8, (rowsA - wm * 64 + 7) >> 3));
-    const int nb = max(0, min(4, (rowsB - wn * 32 + 7) >> 3));
-    double acc[8][4][2];
+    const int ma = max(0, min(TA, (rowsA - wm * TR + 7) >> 3));
+    const int nb = max(0, min(TB, (rowsB - wn * TC + 7) >> 3));
+    double acc[TA][TB][2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < TA; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < TB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     for (int kc = 0; kc < nchunks; ++kc) {
         const int s = kc % SY_STAGES;
         mbar_wait(&full[s], (kc / SY_STAGES) & 1);
         const double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
         const double *sB = diag ? sA : sA + SY_BK * SY_LDS;
-        if (ma == 8 && nb == 4) {
+        if (ma == TA && nb == TB) {
 #pragma unroll
             for (int k4 = 0; k4 < SY_BK; k4 += 4) {
-                double af[8], bf[4];
-                const double *pa = sA + (k4 + q) * SY_LDS + wm * 64 + g;
-                const double *pb = sB + (k4 + q) * SY_LDS + wn * 32 + g;
+                double af[TA], bf[TB];
+                const double *pa = sA + (k4 + q) * SY_LDS + wm * TR + g;
+                const double *pb = sB + (k4 + q) * SY_LDS + wn * TC + g;
 #pragma unroll
-                for (int a = 0; a < 8; ++a) af[a] = pa[a * 8];
+                for (int a = 0; a < TA; ++a) af[a] = pa[a * 8];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
+                for (int b = 0; b < TB; ++b) bf[b] = pb[b * 8];
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
+                for (int a = 0; a < TA; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                    for (int b = 0; b < TB; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
             }
         } else if (ma > 0 && nb > 0) {
             // sliver tile: only the DMMA tiles with real rows/columns (warp-uniform predicates)
 #pragma unroll
             for (int k4 = 0; k4 < SY_BK; k4 += 4) {
-                const double *pa = sA + (k4 + q) * SY_LDS + wm * 64 + g;
-                const double *pb = sB + (k4 + q) * SY_LDS + wn * 32 + g;
-                double bf[4];
+                const double *pa = sA + (k4 + q) * SY_LDS + wm * TR + g;
+                const double *pb = sB + (k4 + q) * SY_LDS + wn * TC + g;
+                double bf[TB];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
+                for (int b = 0; b < TB; ++b) bf[b] = pb[b * 8];
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
+                for (int a = 0; a < TA; ++a) {
                     if (a < ma) {
                         const double af = pa[a * 8];
 #pragma unroll
-                        for (int b = 0; b < 4; ++b)
+                        for (int b = 0; b < TB; ++b)
                             if (b < nb) dmma884(acc[a][b][0], acc[a][b][1], af, bf[b]);
                     }
                 }
@@ -227,12 +234,12 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
     // (RED.ADD.F64) is deterministic and never stalls on the read of Gaug.
     const int rows_total = ld;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int i = i0 + wm * 64 + a * 8 + g;
+    for (int a = 0; a < TA; ++a) {
+        const int i = i0 + wm * TR + a * 8 + g;
         if (i >= rows_total) continue;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int j = j0 + wn * 32 + b * 8 + 2 * q;
+        for (int b = 0; b < TB; ++b) {
+            const int j = j0 + wn * TC + b * 8 + 2 * q;
             if (j < rows_total) red_add_f64(&t.gram[(size_t)ld * j + i], acc[a][b][0]);
             if (j + 1 < rows_total) red_add_f64(&t.gram[(size_t)ld * (j + 1) + i], acc[a][b][1]);
         }

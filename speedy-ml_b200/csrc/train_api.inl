@@ -120,7 +120,8 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     T.ntiles = (int)tiles.size();
     CK(h, cudaMalloc(&T.d_tiles, sizeof(int2) * tiles.size()));
     CK(h, cudaMemcpy(T.d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
-    CK(h, cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    CK(h, cudaFuncSetAttribute(k_syrk_dmma<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    CK(h, cudaFuncSetAttribute(k_syrk_dmma<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     CK(h, cudaFuncSetAttribute(k_chol_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     CK(h, cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_DIAG_SMEM));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -214,7 +215,10 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
         k_train_fill<<<dim3(kpad, nw), 128, 0, h->stream>>>(T.d_regs, discard_cols + s0, nc, kpad);
         h->launches++;
         CK(h, cudaEventRecord(e1, h->stream));
-        k_syrk_dmma<<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
+        // warp layout of the Gram kernel: A/B switch SML_SYRK_WARPS=16 -> 4 x 4 warps of 32 x 32, default 2 x 4 of 64 x 32
+        static const bool w16 = getenv("SML_SYRK_WARPS") && atoi(getenv("SML_SYRK_WARPS")) == 16;
+        if (w16) k_syrk_dmma<4, 4><<<dim3(T.ntiles, nw), 17 * 32, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
+        else k_syrk_dmma<2, 4><<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
         h->launches++;
         CK(h, cudaEventRecord(e2, h->stream));
         CK(h, cudaGetLastError());

@@ -540,28 +540,28 @@ class Engine:
         self._ck(self.lib.sml_train_begin(self.h, kind, _i(regions), regions.size, batch_size))
 
     def train_feed(self, trainingdata_by_region, imperfect_by_region, discard_cols):
-        tds, tdo, ims, imo, pt, pi = [], [], [], [], 0, 0
-        ncols = None
-        for r, td in zip(self._train_regions, trainingdata_by_region):
-            td = _farr(td)
-            ncols = td.shape[1] if ncols is None else ncols
-            assert td.shape == (self.dims[(self._train_kind, r)]["D"], ncols)
-            tds.append(td.ravel(order="F"))
-            tdo.append(pt)
-            pt += td.size
+        """one phase for the wave: per-region (D_i, ncols) series and (S_i, ncols) imperfect-model series.  The arrays
+        are handed over in place (offsets relative to the first one), not concatenated."""
+        def in_place(arrays, key):
+            keep, offs, base = [], [], None
+            for r, a in zip(self._train_regions, arrays):
+                a = _farr(a)
+                assert a.shape == (self.dims[(self._train_kind, r)][key], ncols), (a.shape, key)
+                keep.append(a)
+                addr = a.ctypes.data
+                base = addr if base is None else base
+                assert (addr - base) % 8 == 0
+                offs.append((addr - base) // 8)
+            return keep, np.asarray(offs, dtype=np.int64)
+
+        ncols = np.shape(trainingdata_by_region[0])[1]
+        tds, tdo = in_place(trainingdata_by_region, "D")
         if imperfect_by_region is not None:
-            for r, im in zip(self._train_regions, imperfect_by_region):
-                im = _farr(im)
-                assert im.shape == (self.dims[(self._train_kind, r)]["S"], ncols)
-                ims.append(im.ravel(order="F"))
-                imo.append(pi)
-                pi += im.size
-        td = np.concatenate(tds)
-        tdo = np.asarray(tdo, dtype=np.int64)
-        im = np.concatenate(ims) if ims else None
-        imo = np.asarray(imo, dtype=np.int64) if ims else None
-        self._ck(self.lib.sml_train_feed(self.h, _d(td), tdo.ctypes.data_as(_lp), _d(im),
-                                         imo.ctypes.data_as(_lp) if imo is not None else None, ncols, discard_cols))
+            ims, imo = in_place(imperfect_by_region, "S")
+            im_ptr, imo_ptr = _d(ims[0]), imo.ctypes.data_as(_lp)
+        else:
+            ims, im_ptr, imo_ptr = None, None, None
+        self._ck(self.lib.sml_train_feed(self.h, _d(tds[0]), tdo.ctypes.data_as(_lp), im_ptr, imo_ptr, ncols, discard_cols))
 
     def train_solve(self, beta_res, beta_model=1.0, using_prior=True, prior_val=0.0):
         info = np.zeros(len(self._train_regions), dtype=np.int32)
