@@ -126,6 +126,12 @@ int sml_global_layout(int64_t off[5], int64_t *g_total, int64_t *f_total);
 /* ---- weights: mklsparse (src/mod_linalg.f90:10-25) + trained_reservoir_prediction
  *      (src/mod_reservoir.f90:1783-1886); slab twin src/mod_slab_ocean_reservoir.f90:1561-1652 ---- */
 int sml_region_upload(sml_engine *h, const sml_region_weights *w);
+/* the same straight from the file write_trained_res produces (src/mod_reservoir.f90:1703-1738; read_trained_res
+ * src/mod_io.f90:2938-2983): one NetCDF-classic container per region with win, wout (float), rows, cols (int), vals,
+ * mean, std (float), read without any NetCDF library and widened to FP64.  sml_trained_res_dims only reads the header
+ * (errors: sml_last_error(NULL)). */
+int sml_trained_res_dims(const char *path, int *n, int *k, int *D, int *P, int *S, int *L);
+int sml_region_upload_file(sml_engine *h, const char *path, int region, int kind, int sst_bool_input, double leakage);
 int sml_finalize(sml_engine *h); /* after the last upload: builds the batched step plan */
 
 /* ---- reservoir construction on the device (gen_res, src/mod_reservoir.f90:182-212): after the unscaled adjacency

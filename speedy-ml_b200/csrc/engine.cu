@@ -16,6 +16,7 @@
 #include "train.cuh"
 #include "chol.cuh"
 #include "genres.cuh"
+#include "ncfile.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -529,6 +530,78 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
     hr.uploaded = true;
     K.any = true;
     return 0;
+}
+
+/* ------------------------------------------------------------------ weight container (read_trained_res) */
+// the seven variables of write_trained_res' NetCDF-classic file, widened to FP64 (src/mod_io.f90:2938-2983)
+namespace {
+struct TrainedRes {
+    int n = 0, D = 0, P = 0, N = 0, k = 0, L = 0;
+    std::vector<double> win, wout, vals, mean, std;
+    std::vector<int32_t> rows, cols;
+};
+void load_trained_res(const char *path, TrainedRes &t, bool dims_only)
+{
+    NcClassicFile f(path);
+    const auto &vw = f.var("win");   // Fortran win(n, D) -> file shape (D, n)
+    const auto &vo = f.var("wout");  // Fortran wout(P, n+S) -> file shape (n+S, P)
+    if (vw.shape.size() != 2 || vo.shape.size() != 2) throw std::runtime_error("win / wout must be two-dimensional");
+    t.D = (int)vw.shape[0]; t.n = (int)vw.shape[1];
+    t.N = (int)vo.shape[0]; t.P = (int)vo.shape[1];
+    t.k = (int)f.var("rows").count();
+    t.L = (int)f.var("mean").count();
+    if (f.var("cols").count() != t.k || f.var("vals").count() != t.k || f.var("std").count() != t.L)
+        throw std::runtime_error("rows/cols/vals or mean/std lengths disagree");
+    if (t.N < t.n) throw std::runtime_error("wout has fewer columns than the reservoir has nodes");
+    if (dims_only) return;
+    t.win = f.read_real("win");
+    t.wout = f.read_real("wout");
+    t.rows = f.read_int("rows");
+    t.cols = f.read_int("cols");
+    t.vals = f.read_real("vals");
+    t.mean = f.read_real("mean");
+    t.std = f.read_real("std");
+}
+}  // namespace
+
+extern "C" int sml_trained_res_dims(const char *path, int *n, int *k, int *D, int *P, int *S, int *L)
+{
+    try {
+        TrainedRes t;
+        load_trained_res(path, t, true);
+        *n = t.n; *k = t.k; *D = t.D; *P = t.P; *S = t.N - t.n; *L = t.L;
+        return 0;
+    } catch (const std::exception &e) {
+        g_create_err = e.what();
+        return -1;
+    }
+}
+
+// read_trained_res + mklsparse for one region straight from its file (trained_reservoir_prediction,
+// src/mod_reservoir.f90:1783-1886); sst_mean/sst_std default to the last mean/std slot (the SST slot)
+extern "C" int sml_region_upload_file(sml_engine *h, const char *path, int region, int kind, int sst_bool_input,
+                                      double leakage)
+{
+    if (!h || !path) return -1;
+    TrainedRes t;
+    try {
+        load_trained_res(path, t, false);
+    } catch (const std::exception &e) {
+        FAIL(h, "%s: %s", path, e.what());
+    }
+    sml_region_weights w{};
+    w.region = region;
+    w.kind = kind;
+    w.n = t.n; w.k = t.k; w.D = t.D; w.P = t.P; w.S = t.N - t.n; w.L = t.L;
+    w.sst_bool_input = sst_bool_input;
+    w.leakage = leakage;
+    w.sst_mean = t.mean.back();
+    w.sst_std = t.std.back();
+    w.rows = t.rows.data(); w.cols = t.cols.data(); w.vals = t.vals.data();
+    w.win_dense = t.win.data();
+    w.wout = t.wout.data();
+    w.mean = t.mean.data(); w.std = t.std.data();
+    return sml_region_upload(h, &w);
 }
 
 static int finalize_kind(sml_engine *h, int kind)

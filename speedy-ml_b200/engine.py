@@ -62,6 +62,8 @@ _SIGNATURES = {
     "sml_ocean_region_maps": ([C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int)], C.c_int),
     "sml_global_layout": ([_lp, _lp, _lp], C.c_int),
     "sml_region_upload": ([C.c_void_p, C.POINTER(SmlRegionWeights)], C.c_int),
+    "sml_trained_res_dims": ([C.c_char_p] + [C.POINTER(C.c_int)] * 6, C.c_int),
+    "sml_region_upload_file": ([C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double], C.c_int),
     "sml_finalize": ([C.c_void_p], C.c_int),
     "sml_sparse_eigen": ([C.c_void_p, C.c_int, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)], C.c_int),
     "sml_adjacency_scale": ([C.c_void_p, C.c_int, _dp], C.c_int),
@@ -240,6 +242,15 @@ def ocean_region_maps(num_regions, region, overlap=1):
     return dict(sst_map=sst, target_map=tgt, atmo_slice0=a0.value)
 
 
+def trained_res_dims(path):
+    """header of a write_trained_res file -> dict(n, k, D, P, S, L)"""
+    v = [C.c_int() for _ in range(6)]
+    lib = load_library()
+    if lib.sml_trained_res_dims(os.fsencode(path), *[C.byref(a) for a in v]):
+        raise EngineError(lib.sml_last_error(None).decode())
+    return dict(zip(("n", "k", "D", "P", "S", "L"), (a.value for a in v)))
+
+
 def global_layout():
     off = (C.c_int64 * 5)()
     g, f = C.c_int64(), C.c_int64()
@@ -335,6 +346,12 @@ class Engine:
         w.rows, w.cols, w.vals, w.mean, w.std = _i(rows), _i(cols), _d(vals), _d(mean), _d(std)
         self._ck(self.lib.sml_region_upload(self.h, C.byref(w)))
         self.dims[(kind, region)] = dict(n=n, D=Dw, P=Pw, S=Sw, L=mean.size)
+
+    def region_upload_file(self, path, region, kind=ATMO, sst_bool_input=True, leakage=1.0):
+        """read_trained_res + mklsparse from the region's NetCDF-classic weight file (float32 -> FP64 on the way)"""
+        d = trained_res_dims(path)
+        self._ck(self.lib.sml_region_upload_file(self.h, os.fsencode(path), region, kind, int(sst_bool_input), float(leakage)))
+        self.dims[(kind, region)] = dict(n=d["n"], D=d["D"], P=d["P"], S=d["S"], L=d["L"])
 
     def finalize(self):
         self._ck(self.lib.sml_finalize(self.h))
