@@ -251,6 +251,17 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
  * inputs are pre-noised. */
 int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const double *im,
                    const int64_t *im_off, int ncols, int discard_cols);
+/* training data on the device: instead of per-region series, upload the conditioned GLOBAL series of
+ * the training period once -- column t = [wholegrid4d | wholegrid2d(logp) | precip | sst | tisr] in the layout of
+ * sml_global_layout (physical units after get_training_data's conditioning, src/mod_reservoir.f90:362-389: q in g/kg
+ * floored at 1e-6, precip log(1 + p/eps), SST floored at 272) and, for hybrid training, F = [forecast_4d | forecast_2d],
+ * the SPEEDY forecast valid at t.  sml_train_feed_global then tiles and standardises every region's input, imperfect-
+ * model and target columns on the fly with the arithmetic of the forecast exchange (tile_4d_and_logp_to_local_state_input
+ * + standardize_state_vec_input, src/res_domain.f90:1081-1125,1211-1268).  Inputs are noise-free (SURVEY.md 8c quirk 7:
+ * per-region pre-noised series go through sml_train_feed).  phase column c = global column first_col + stride*c. */
+int sml_train_global_series(sml_engine *h, const double *G_series, const double *F_series, int ncols_total);
+int sml_train_feed_global(sml_engine *h, int first_col, int stride, int ncols, int discard_cols);
+int sml_train_global_release(sml_engine *h);
 int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using_prior,
                     double prior_val, int32_t *info_per_region);
 /* sml_train_solve factorises the regularised Gram (symmetric positive definite for ridge > 0) of every region of

@@ -31,12 +31,33 @@ struct TrainRegionDev {
     int *chol_info;           // 0: on the Cholesky path; > 0: non-positive pivot at that column; < 0: not eligible
 };
 
+// Device-resident global training series (sml_train_global_series): column t is the conditioned global state at time
+// t in the layout of the exchange buffers, G = [w4d | w2d | precip | sst | tisr] and F = [f4d | f2d].  With it the
+// training kernels tile and standardise every region's input, imperfect-model and target columns on the fly --
+// the arithmetic of tile_4d_and_logp_to_local_state_input + standardize_state_vec_input (src/res_domain.f90:1081-1125,
+// 1211-1268) exactly as k_build_inputs does it for the forecast -- instead of reading per-region series.
+struct GlobalSeries {
+    const double *G = nullptr;   // [ncols_total][g_len]; null: per-region series (TrainRegionDev::td / im)
+    const double *F = nullptr;   // [ncols_total][f_len]
+    long long g_len = 0, f_len = 0;
+    int first = 0, stride = 1;   // phase column c <-> global column first + stride * c
+};
+
+__device__ __forceinline__ double series_input(const GlobalSeries &gs, const RegionDev &R, int col, int c)
+{
+    double v = gs.G[(size_t)(gs.first + gs.stride * col) * gs.g_len + R.fb_src[c]];
+    const int ms = R.fb_ms[c];
+    if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
+    return v;
+}
+
 // one reservoir step for every region of the wave: reads input column in_col, writes the new state to the
 // other ping-pong buffer and (out_col >= 0) x~ into slab column out_col.  gather_col >= 0 takes the SpMV
 // operand from slab column gather_col instead of the state -- the ML-only restart of the reference, which
 // feeds the squared copy states(:,batch_size) back (src/mod_reservoir.f90:1034; slab ocean :933).
 // reservoir_layer_chunking_hybrid/_ml, src/mod_reservoir.f90:963-1175.   grid (ceil(n_max/256), nwave)
-__global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity, int in_col, int out_col, int gather_col)
+__global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity, int in_col, int out_col, int gather_col,
+                               GlobalSeries gs)
 {
     const TrainRegionDev &t = T[blockIdx.y];
     const RegionDev &R = t.R;
@@ -45,7 +66,7 @@ __global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity,
     const double *xo = parity ? t.xb : t.xa;
     double *xn = parity ? t.xa : t.xb;
     const double *gsrc = (gather_col >= 0) ? t.slab + (size_t)t.ld * gather_col + R.S : xo;
-    const double *u = t.td + (size_t)R.D * in_col;
+    const double *u = gs.G ? nullptr : t.td + (size_t)R.D * in_col;
     const int n = R.n;
     const int *__restrict__ ec = R.ell_col + row;
     const double *__restrict__ ev = R.ell_val + row;
@@ -53,10 +74,12 @@ __global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity,
     for (int s = 0; s < R.ell_w; ++s) acc = fma(__ldg(ev + (size_t)s * n), gsrc[__ldg(ec + (size_t)s * n)], acc);
     double tw;
     if (R.win_mode == 0) {
-        tw = __dmul_rn(__ldg(R.winc + row), u[__ldg(R.wcol + row)]);
+        const int wc = __ldg(R.wcol + row);
+        tw = __dmul_rn(__ldg(R.winc + row), gs.G ? series_input(gs, R, in_col, wc) : u[wc]);
     } else {
         tw = 0.0;
-        for (int i = 0; i < R.D; ++i) tw = fma(R.win_dense[(size_t)i * n + row], u[i], tw);
+        for (int i = 0; i < R.D; ++i)
+            tw = fma(R.win_dense[(size_t)i * n + row], gs.G ? series_input(gs, R, in_col, i) : u[i], tw);
     }
     const double xt = tanh(__dadd_rn(acc, tw));
     const double xv = __dadd_rn(__dmul_rn(1.0 - R.leak, xo[row]), __dmul_rn(R.leak, xt));
@@ -77,7 +100,7 @@ __global__ void k_train_store_state(const TrainRegionDev *__restrict__ T, int pa
 // imperfect-model rows and target rows of slab columns [0, ncols): series column = first_series_col + c.
 // chunking_matmul :1668 (imperfect), tile_full_input_to_target_data2d src/res_domain.f90:602-651 (target).
 // Columns [ncols, kpad) are zeroed entirely (K padding of the tensor-core kernel).  grid (kpad, nwave)
-__global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_series_col, int ncols, int kpad)
+__global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_series_col, int ncols, int kpad, GlobalSeries gs)
 {
     const TrainRegionDev &t = T[blockIdx.y];
     const RegionDev &R = t.R;
@@ -89,8 +112,20 @@ __global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_ser
         return;
     }
     const int sc = first_series_col + c;
-    for (int i = threadIdx.x; i < R.S; i += blockDim.x) col[i] = t.im[(size_t)R.S * sc + i];
-    for (int p = threadIdx.x; p < R.P; p += blockDim.x) col[N + p] = t.td[(size_t)R.D * sc + t.target_map[p]];
+    if (gs.G) {
+        // imperfect model: tile_4d_and_logp_full_grid_to_local_res_vec + standardize_state_vec_res of the forecast grid
+        const double *Fc = gs.F ? gs.F + (size_t)(gs.first + gs.stride * sc) * gs.f_len : nullptr;
+        for (int i = threadIdx.x; i < R.S; i += blockDim.x) {
+            double v = Fc[R.lm_src[i]];
+            const int ms = R.lm_ms[i];
+            if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
+            col[i] = v;
+        }
+        for (int p = threadIdx.x; p < R.P; p += blockDim.x) col[N + p] = series_input(gs, R, sc, t.target_map[p]);
+    } else {
+        for (int i = threadIdx.x; i < R.S; i += blockDim.x) col[i] = t.im[(size_t)R.S * sc + i];
+        for (int p = threadIdx.x; p < R.P; p += blockDim.x) col[N + p] = t.td[(size_t)R.D * sc + t.target_map[p]];
+    }
     for (int i = N + R.P + threadIdx.x; i < t.ld; i += blockDim.x) col[i] = 0.0;
 }
 
@@ -320,6 +355,12 @@ struct TrainState {
     double stategen_ms = 0.0;
     double solve_ms = 0.0;
     int solved_by_cholesky = 0;
+};
+
+// global training series, kept across waves (sml_train_global_series / sml_train_global_release)
+struct TrainGlobal {
+    double *d_G = nullptr, *d_F = nullptr;
+    int ncols_total = 0;
 };
 
 inline void train_release(TrainState &t)

@@ -129,6 +129,79 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     return 0;
 }
 
+// state generation + Gram accumulation of one phase for the wave; inputs come either from the per-region series
+// already placed in T.regs[i].dev.td / im, or from the device-resident global series gs
+static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const GlobalSeries &gs)
+{
+    TrainState &T = h->train;
+    const int nw = (int)T.regs.size();
+    std::vector<TrainRegionDev> devs(nw);
+    for (int i = 0; i < nw; ++i) {
+        TrainRegionDev &d = T.regs[i].dev;
+        CK(h, cudaMemsetAsync(d.xa, 0, (size_t)d.R.n * 8, h->stream));  // x = 0 at the start of every phase (:1091)
+        devs[i] = d;
+    }
+    CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * nw, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    const dim3 ugrid((T.n_max + 255) / 256, nw);
+    int parity = 0;
+    // discard loop (:1093-1106)
+    for (int i = 0; i < discard_cols; ++i) {
+        k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, i, -1, -1, gs);
+        parity ^= 1;
+        h->launches++;
+    }
+    const int TL = ncols - discard_cols;
+    const int bs = T.batch_size;
+    const int kept = (TL / bs) * bs;  // states 1..kept enter the Gram
+    // state s (1-based) pairs with series column discard+s (1-based) = discard+s-1 (0-based); it is produced
+    // from state s-1 with input column discard+s-1 (1-based) = discard+s-2 (0-based)
+    for (int s0 = 0; s0 < kept; s0 += T.ks) {
+        const int nc = std::min(T.ks, kept - s0);
+        const int kpad = (nc + SY_BK - 1) / SY_BK * SY_BK;
+        CK(h, cudaEventRecord(e0, h->stream));
+        for (int c = 0; c < nc; ++c) {
+            const int s = s0 + c;  // 0-based state index
+            if (s == 0) {
+                k_train_store_state<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, 0);
+            } else {
+                // ML-only paths restart every batch from the squared copy (SpMV operand only)
+                // (at a slab boundary the previous slab was full, its last column is still intact)
+                int gather = -1;
+                if (!T.hybrid && (s % bs) == 0) gather = (c > 0) ? c - 1 : T.ks - 1;
+                k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, discard_cols + s - 1, c, gather, gs);
+                parity ^= 1;
+            }
+            h->launches++;
+        }
+        k_train_fill<<<dim3(kpad, nw), 128, 0, h->stream>>>(T.d_regs, discard_cols + s0, nc, kpad, gs);
+        h->launches++;
+        CK(h, cudaEventRecord(e1, h->stream));
+        // warp layout of the Gram kernel: A/B switch SML_SYRK_WARPS=16 -> 4 x 4 warps of 32 x 32, default 2 x 4 of 64 x 32
+        static const bool w16 = getenv("SML_SYRK_WARPS") && atoi(getenv("SML_SYRK_WARPS")) == 16;
+        if (w16) k_syrk_dmma<4, 4><<<dim3(T.ntiles, nw), 17 * 32, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
+        else k_syrk_dmma<2, 4><<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
+        h->launches++;
+        CK(h, cudaEventRecord(e2, h->stream));
+        CK(h, cudaGetLastError());
+        CK(h, cudaEventSynchronize(e2));
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        T.stategen_ms += a;
+        T.gram_ms += b;
+        for (auto &r : T.regs) {
+            const double N = r.dev.R.n + r.dev.R.S, P = r.dev.R.P;
+            T.gram_flops_useful += (N * (N + 1.0) + 2.0 * P * N) * nc;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return 0;
+}
+
 int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const double *im, const int64_t *im_off,
                    int ncols, int discard_cols)
 {
@@ -159,7 +232,6 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
         T.series_im_cap = im_total;
     }
     size_t pt = 0, pi = 0;
-    std::vector<TrainRegionDev> devs(nw);
     for (int i = 0; i < nw; ++i) {
         TrainRegionDev &d = T.regs[i].dev;
         const size_t tsz = (size_t)d.R.D * ncols, isz = (size_t)d.R.S * ncols;
@@ -173,68 +245,61 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
         } else {
             d.im = nullptr;
         }
-        CK(h, cudaMemsetAsync(d.xa, 0, (size_t)d.R.n * 8, h->stream));  // x = 0 at the start of every phase (:1091)
-        devs[i] = d;
     }
-    CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * nw, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
+    return train_run_phase(h, ncols, discard_cols, GlobalSeries{});
+}
 
-    cudaEvent_t e0, e1, e2;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-    const dim3 ugrid((T.n_max + 255) / 256, nw);
-    int parity = 0;
-    // discard loop (:1093-1106)
-    for (int i = 0; i < discard_cols; ++i) {
-        k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, i, -1, -1);
-        parity ^= 1;
-        h->launches++;
+// The conditioned global series of the whole training period, uploaded ONCE and kept on the device across waves
+// and phases (12 000 six-hourly states of the T30 grid are 30 GB: G 1.33 MB + F 1.22 MB per column).
+int sml_train_global_series(sml_engine *h, const double *G_series, const double *F_series, int ncols_total)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (!G_series || ncols_total < 1) FAIL(h, "sml_train_global_series: bad arguments");
+    if (!h->p.ml_only && !F_series) FAIL(h, "hybrid training needs the forecast series F");
+    CK(h, cudaSetDevice(h->p.device));
+    TrainGlobal &TG = h->train_global;
+    cudaFree(TG.d_G); cudaFree(TG.d_F);
+    TG = TrainGlobal{};
+    if (cudaMalloc(&TG.d_G, sizeof(double) * (size_t)G_TOTAL * ncols_total) != cudaSuccess)
+        FAIL(h, "the global series does not fit in HBM (%d columns)", ncols_total);
+    CK(h, cudaMemcpy(TG.d_G, G_series, sizeof(double) * (size_t)G_TOTAL * ncols_total, cudaMemcpyHostToDevice));
+    if (F_series) {
+        if (cudaMalloc(&TG.d_F, sizeof(double) * (size_t)F_TOTAL * ncols_total) != cudaSuccess)
+            FAIL(h, "the global forecast series does not fit in HBM (%d columns)", ncols_total);
+        CK(h, cudaMemcpy(TG.d_F, F_series, sizeof(double) * (size_t)F_TOTAL * ncols_total, cudaMemcpyHostToDevice));
     }
-    const int TL = ncols - discard_cols;
-    const int bs = T.batch_size;
-    const int kept = (TL / bs) * bs;  // states 1..kept enter the Gram
-    // state s (1-based) pairs with series column discard+s (1-based) = discard+s-1 (0-based); it is produced
-    // from state s-1 with input column discard+s-1 (1-based) = discard+s-2 (0-based)
-    for (int s0 = 0; s0 < kept; s0 += T.ks) {
-        const int nc = std::min(T.ks, kept - s0);
-        const int kpad = (nc + SY_BK - 1) / SY_BK * SY_BK;
-        CK(h, cudaEventRecord(e0, h->stream));
-        for (int c = 0; c < nc; ++c) {
-            const int s = s0 + c;  // 0-based state index
-            if (s == 0) {
-                k_train_store_state<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, 0);
-            } else {
-                // ML-only paths restart every batch from the squared copy (SpMV operand only)
-                // (at a slab boundary the previous slab was full, its last column is still intact)
-                int gather = -1;
-                if (!T.hybrid && (s % bs) == 0) gather = (c > 0) ? c - 1 : T.ks - 1;
-                k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, discard_cols + s - 1, c, gather);
-                parity ^= 1;
-            }
-            h->launches++;
-        }
-        k_train_fill<<<dim3(kpad, nw), 128, 0, h->stream>>>(T.d_regs, discard_cols + s0, nc, kpad);
-        h->launches++;
-        CK(h, cudaEventRecord(e1, h->stream));
-        // warp layout of the Gram kernel: A/B switch SML_SYRK_WARPS=16 -> 4 x 4 warps of 32 x 32, default 2 x 4 of 64 x 32
-        static const bool w16 = getenv("SML_SYRK_WARPS") && atoi(getenv("SML_SYRK_WARPS")) == 16;
-        if (w16) k_syrk_dmma<4, 4><<<dim3(T.ntiles, nw), 17 * 32, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
-        else k_syrk_dmma<2, 4><<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
-        h->launches++;
-        CK(h, cudaEventRecord(e2, h->stream));
-        CK(h, cudaGetLastError());
-        CK(h, cudaEventSynchronize(e2));
-        float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, e0, e1);
-        cudaEventElapsedTime(&b, e1, e2);
-        T.stategen_ms += a;
-        T.gram_ms += b;
-        for (auto &r : T.regs) {
-            const double N = r.dev.R.n + r.dev.R.S, P = r.dev.R.P;
-            T.gram_flops_useful += (N * (N + 1.0) + 2.0 * P * N) * nc;
-        }
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    TG.ncols_total = ncols_total;
     return 0;
+}
+
+int sml_train_global_release(sml_engine *h)
+{
+    if (!h) return -1;
+    cudaFree(h->train_global.d_G); cudaFree(h->train_global.d_F);
+    h->train_global = TrainGlobal{};
+    return 0;
+}
+
+// one phase from the resident global series: phase column c is global column first_col + stride*c
+// (trainingdata(:, i::timestep), src/mod_reservoir.f90:289-301)
+int sml_train_feed_global(sml_engine *h, int first_col, int stride, int ncols, int discard_cols)
+{
+    if (!h) return -1;
+    TrainState &T = h->train;
+    if (!T.active) FAIL(h, "sml_train_feed_global without sml_train_begin");
+    if (T.kind != SML_ATMO) FAIL(h, "the global series feeds atmosphere reservoirs (the ocean inputs are time-averaged on the host)");
+    TrainGlobal &TG = h->train_global;
+    if (!TG.d_G) FAIL(h, "sml_train_global_series has not been called");
+    if (T.hybrid && !TG.d_F) FAIL(h, "hybrid training needs the forecast series F");
+    if (first_col < 0 || stride < 1 || ncols < 1 || first_col + (long long)stride * (ncols - 1) >= TG.ncols_total)
+        FAIL(h, "phase (first %d, stride %d, %d columns) runs past the %d resident columns", first_col, stride, ncols, TG.ncols_total);
+    if (discard_cols < 0 || ncols - discard_cols < T.batch_size) FAIL(h, "phase too short: %d columns, discard %d, batch %d", ncols, discard_cols, T.batch_size);
+    CK(h, cudaSetDevice(h->p.device));
+    GlobalSeries gs;
+    gs.G = TG.d_G; gs.F = TG.d_F;
+    gs.g_len = G_TOTAL; gs.f_len = F_TOTAL;
+    gs.first = first_col; gs.stride = stride;
+    return train_run_phase(h, ncols, discard_cols, gs);
 }
 
 int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using_prior, double prior_val,

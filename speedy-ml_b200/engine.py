@@ -99,6 +99,9 @@ _SIGNATURES = {
     "sml_step_unpack_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_begin": ([C.c_void_p, C.c_int, _ip, C.c_int, C.c_int], C.c_int),
     "sml_train_feed": ([C.c_void_p, _dp, _lp, _dp, _lp, C.c_int, C.c_int], C.c_int),
+    "sml_train_global_series": ([C.c_void_p, _dp, _dp, C.c_int], C.c_int),
+    "sml_train_feed_global": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
+    "sml_train_global_release": ([C.c_void_p], C.c_int),
     "sml_train_solve": ([C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, _ip], C.c_int),
     "sml_train_solver_stats": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
     "sml_train_gram_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
@@ -579,6 +582,21 @@ class Engine:
         else:
             ims, im_ptr, imo_ptr = None, None, None
         self._ck(self.lib.sml_train_feed(self.h, _d(tds[0]), tdo.ctypes.data_as(_lp), im_ptr, imo_ptr, ncols, discard_cols))
+
+    def train_global_series(self, G_series, F_series=None):
+        """G_series (g_total, T), F_series (f_total, T) column-major: the conditioned global series, kept on the device"""
+        lay = global_layout()
+        G = _farr(G_series)
+        assert G.shape[0] == lay["g_total"]
+        F = _farr(F_series) if F_series is not None else None
+        assert F is None or F.shape == (lay["f_total"], G.shape[1])
+        self._ck(self.lib.sml_train_global_series(self.h, _d(G), _d(F), G.shape[1]))
+
+    def train_feed_global(self, first_col, stride, ncols, discard_cols):
+        self._ck(self.lib.sml_train_feed_global(self.h, first_col, stride, ncols, discard_cols))
+
+    def train_global_release(self):
+        self._ck(self.lib.sml_train_global_release(self.h))
 
     def train_solve(self, beta_res, beta_model=1.0, using_prior=True, prior_val=0.0):
         info = np.zeros(len(self._train_regions), dtype=np.int32)

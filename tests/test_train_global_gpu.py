@@ -1,0 +1,84 @@
+"""Training from the device-resident GLOBAL series (sml_train_global_series / sml_train_feed_global):
+the engine tiles and standardises every region's input, imperfect-model and target columns on the fly.  The oracle
+builds the same per-region series column by column with the reference's tilers (the feedback construction of
+sendrecievegrid), trains on them, and the Gram must agree to 1e-12; feeding those per-region series through
+sml_train_feed must give the BIT-identical Gram.  -m gpu."""
+import importlib
+
+import numpy as np
+import pytest
+
+from helpers import c_region, initial_grids, oc, region_weights, rel_inf, syn
+
+pytestmark = pytest.mark.gpu
+
+
+def test_global_series_feed_matches_oracle_tiling_and_per_region_feed():
+    E = importlib.import_module("speedy-ml_b200.engine")
+    regions = [0, 1, 2, 3]                                   # south-pole + interior tiles of the first x column
+    ws = {r: region_weights(1152, r, m=450, with_dense_win=False) for r in regions}
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=288)
+    for r in regions:
+        w = ws[r]
+        eng.region_upload(r, w["rows"], w["cols"], w["vals"], None, w["mean"], w["std"], win_compact=w["winc"],
+                          win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"], S=w["S"], P=w["P"])
+    eng.finalize()
+    lay = E.global_layout()
+    F0 = initial_grids()
+    rng = np.random.default_rng(17)
+    T = 64
+    G = np.zeros((lay["g_total"], T), order="F")
+    F = np.zeros((lay["f_total"], T), order="F")
+    for t in range(T):
+        w4d = F0["clim4d"] * (1.0 + 0.02 * rng.standard_normal(F0["clim4d"].shape))
+        w4d[3] = np.maximum(w4d[3], 0.000001)
+        w2d = F0["clim2d"] + 0.01 * rng.standard_normal((96, 48))
+        wp = np.log1p(np.abs(rng.standard_normal((96, 48))))        # log(1 + p/eps)-like, >= 0
+        wsst = np.maximum(F0["base_sst"] + rng.standard_normal((96, 48)), 272.0)
+        tisr = np.abs(F0["tisr"] * (1.0 + 0.1 * rng.standard_normal((96, 48))))
+        G[:, t] = np.concatenate([a.ravel(order="F") for a in (w4d, w2d, wp, wsst, tisr)])
+        f4 = 0.97 * w4d + 0.03 * F0["clim4d"]
+        f2 = 0.97 * w2d
+        F[:, t] = np.concatenate([f4.ravel(order="F"), f2.ravel(order="F")])
+
+    # oracle: per-region series through the reference's tilers + standardisation, column by column
+    rcs = [c_region(ws[r]) for r in regions]
+    sst_mean = np.array([ws[r]["mean"][-1] for r in regions])
+    sst_std = np.array([ws[r]["std"][-1] for r in regions])
+    td = {r: np.zeros((ws[r]["D"], T), order="F") for r in regions}
+    im = {r: np.zeros((ws[r]["S"], T), order="F") for r in regions}
+    o = lay
+    for t in range(T):
+        g = G[:, t]
+        grids = (g[:o["w2d"]].reshape((4, 96, 48, 8), order="F"), g[o["w2d"]:o["precip"]].reshape((96, 48), order="F"),
+                 g[o["precip"]:o["sst"]].reshape((96, 48), order="F"), g[o["sst"]:o["tisr"]].reshape((96, 48), order="F"))
+        f4 = F[:o["w2d"], t].reshape((4, 96, 48, 8), order="F")
+        f2 = F[o["w2d"]:, t].reshape((96, 48), order="F")
+        tisr = g[o["tisr"]:].reshape((96, 48), order="F")
+        oc.step_scatter(rcs, True, True, False, *grids, f4, f2, tisr, sst_mean, sst_std, nthreads=2)
+        for r, rc in zip(regions, rcs):
+            td[r][:, t] = rc.feedback
+            im[r][:, t] = rc.local_model
+
+    first, stride, ncols, discard, bs = 1, 2, 27, 3, 6       # phase = columns 1, 3, 5, ...
+    sel = first + stride * np.arange(ncols)
+    for rc, r in zip(rcs, regions):
+        rc.train_init(bs)
+        rc.train_phase(np.asfortranarray(td[r][:, sel]), np.asfortranarray(im[r][:, sel]), discard)
+
+    eng.train_global_series(G, F)
+    eng.train_begin(regions, bs)
+    eng.train_feed_global(first, stride, ncols, discard)
+    gram_global = {r: eng.train_gram_get(r) for r in regions}
+    with pytest.raises(E.EngineError):                        # runs past the resident columns
+        eng.train_feed_global(first, stride, T, discard)
+    eng.train_end()
+    eng.train_begin(regions, bs)
+    eng.train_feed([np.asfortranarray(td[r][:, sel]) for r in regions], [np.asfortranarray(im[r][:, sel]) for r in regions], discard)
+    gram_local = {r: eng.train_gram_get(r) for r in regions}
+    eng.train_end()
+    eng.train_global_release()
+    for rc, r in zip(rcs, regions):
+        assert rel_inf(gram_global[r][0], rc.sxs) < 1e-12 and rel_inf(gram_global[r][1], rc.sxt) < 1e-12
+        assert np.array_equal(gram_global[r][0], gram_local[r][0]) and np.array_equal(gram_global[r][1], gram_local[r][1])
+    eng.close()
