@@ -272,6 +272,9 @@ int sml_train_solver_stats(sml_engine *h, int *by_cholesky);
 int sml_train_gram_get(sml_engine *h, int region, double *states_x_states_aug,
                        double *states_x_trainingdata_aug);
 int sml_train_end(sml_engine *h);
+/* sml_train_end keeps the wave's device blocks for the next sml_train_begin (allocating ~350 MB per region anew for
+ * every wave costs more than the solve); sml_train_trim returns them to the allocator */
+int sml_train_trim(sml_engine *h);
 /* measurement: useful Gram flops N(N+1)K + 2PNK accumulated by sml_train_feed and the CUDA-event time (ms) of
  * the Gram kernels, the state generation and the solves of the current wave */
 int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms,

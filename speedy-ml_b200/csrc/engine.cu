@@ -115,6 +115,7 @@ struct sml_engine {
     int64_t launches = 0;
     TrainState train;
     TrainGlobal train_global;
+    TrainPool train_pool;
     // overlapped step: the state update and the W_out[:, S:]*x~ partials of the NEXT
     // predict run while the host model works on this step's grids; the S model columns are added when its
     // forecast arrives
@@ -255,6 +256,7 @@ int sml_destroy(sml_engine *h)
     cudaSetDevice(h->p.device);
     cudaDeviceSynchronize();
     train_release(h->train);
+    h->train_pool.drop_all();
     cudaFree(h->train_global.d_G); cudaFree(h->train_global.d_F);
     if (h->train.solver) cusolverDnDestroy(h->train.solver);
     for (int k = 0; k < 2; ++k) free_kind(h->kinds[k]);

@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
+#include <map>
 #include <vector>
 
 namespace sml {
@@ -335,7 +336,26 @@ __global__ void k_train_store_wout(const double *__restrict__ X, int ldx, int N,
 struct TrainRegionHost {
     int local = -1, region = -1;
     TrainRegionDev dev{};
-    std::vector<void *> allocs;
+    std::vector<std::pair<void *, size_t>> allocs;
+};
+
+// device buffers of finished waves, reused by the next sml_train_begin (a wave is ~350 MB per region: cudaMalloc /
+// cudaFree of thousands of such blocks cost more than the solve)
+struct TrainPool {
+    std::multimap<size_t, void *> free_blocks;
+    void *take(size_t bytes)
+    {
+        auto it = free_blocks.find(bytes);
+        if (it == free_blocks.end()) return nullptr;
+        void *p = it->second;
+        free_blocks.erase(it);
+        return p;
+    }
+    void drop_all()
+    {
+        for (auto &b : free_blocks) cudaFree(b.second);
+        free_blocks.clear();
+    }
 };
 
 struct TrainState {
@@ -363,10 +383,13 @@ struct TrainGlobal {
     int ncols_total = 0;
 };
 
-inline void train_release(TrainState &t)
+inline void train_release(TrainState &t, TrainPool *pool = nullptr)
 {
     for (auto &r : t.regs)
-        for (void *p : r.allocs) cudaFree(p);
+        for (auto &a : r.allocs) {
+            if (pool) pool->free_blocks.emplace(a.second, a.first);
+            else cudaFree(a.first);
+        }
     t.regs.clear();
     cudaFree(t.d_regs); t.d_regs = nullptr;
     cudaFree(t.d_tiles); t.d_tiles = nullptr;

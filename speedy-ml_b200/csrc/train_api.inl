@@ -80,12 +80,21 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         T.n_max = std::max(T.n_max, d.R.n);
         T.hybrid = d.R.S > 0;
         auto alloc = [&](size_t bytes, void **p) -> int {
+            if ((*p = h->train_pool.take(bytes)) != nullptr) {  // a block of a finished wave
+                tr.allocs.emplace_back(*p, bytes);
+                return 0;
+            }
             cudaError_t e = cudaMalloc(p, bytes);
+            if (e != cudaSuccess) {  // blocks of other sizes may be hoarding the memory: give them back and retry
+                cudaGetLastError();
+                h->train_pool.drop_all();
+                e = cudaMalloc(p, bytes);
+            }
             if (e != cudaSuccess) {
                 h->err = std::string("training wave does not fit in HBM (cudaMalloc: ") + cudaGetErrorString(e) + "); use fewer regions per wave";
                 return -1;
             }
-            tr.allocs.push_back(*p);
+            tr.allocs.emplace_back(*p, bytes);
             return 0;
         };
         void *p = nullptr;
@@ -108,7 +117,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         }
         d.target_map = (const int *)p;
         T.regs.push_back(tr);
-        if (bad) { train_release(T); return -1; }
+        if (bad) { train_release(T); h->train_pool.drop_all(); return -1; }
         devs.push_back(d);
     }
     CK(h, cudaMalloc(&T.d_regs, sizeof(TrainRegionDev) * devs.size()));
@@ -260,6 +269,7 @@ int sml_train_global_series(sml_engine *h, const double *G_series, const double 
     TrainGlobal &TG = h->train_global;
     cudaFree(TG.d_G); cudaFree(TG.d_F);
     TG = TrainGlobal{};
+    h->train_pool.drop_all();  // blocks kept from finished waves must not stand in the way
     if (cudaMalloc(&TG.d_G, sizeof(double) * (size_t)G_TOTAL * ncols_total) != cudaSuccess)
         FAIL(h, "the global series does not fit in HBM (%d columns)", ncols_total);
     CK(h, cudaMemcpy(TG.d_G, G_series, sizeof(double) * (size_t)G_TOTAL * ncols_total, cudaMemcpyHostToDevice));
@@ -269,6 +279,16 @@ int sml_train_global_series(sml_engine *h, const double *G_series, const double 
         CK(h, cudaMemcpy(TG.d_F, F_series, sizeof(double) * (size_t)F_TOTAL * ncols_total, cudaMemcpyHostToDevice));
     }
     TG.ncols_total = ncols_total;
+    return 0;
+}
+
+// give the device blocks kept from finished waves back to the allocator (they are reused by the next
+// sml_train_begin otherwise; sml_destroy frees them in any case)
+int sml_train_trim(sml_engine *h)
+{
+    if (!h) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    h->train_pool.drop_all();
     return 0;
 }
 
@@ -476,7 +496,7 @@ int sml_train_end(sml_engine *h)
     CK(h, cudaSetDevice(h->p.device));
     cudaStreamSynchronize(h->stream);
     cusolverDnHandle_t keep = h->train.solver;
-    train_release(h->train);
+    train_release(h->train, &h->train_pool);  // the next wave reuses the blocks
     h->train.solver = keep;
     return 0;
 }

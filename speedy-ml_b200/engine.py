@@ -106,6 +106,7 @@ _SIGNATURES = {
     "sml_train_solver_stats": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
     "sml_train_gram_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
     "sml_train_end": ([C.c_void_p], C.c_int),
+    "sml_train_trim": ([C.c_void_p], C.c_int),
     "sml_train_stats": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
     "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_profile": ([C.c_void_p, C.c_int], C.c_int),
@@ -625,6 +626,10 @@ class Engine:
 
     def train_end(self):
         self._ck(self.lib.sml_train_end(self.h))
+
+    def train_trim(self):
+        """return the device blocks kept from finished waves to the allocator"""
+        self._ck(self.lib.sml_train_trim(self.h))
 
     # -- mldivide(A, B)   mod_linalg.f90:109
     def mldivide(self, A, B):
