@@ -24,6 +24,17 @@ H = importlib.import_module("speedy-ml_b200.hybrid")
 R, M, NSTEPS = 1152, 300, 6
 
 
+def reset_engine(eng, ws):
+    rng = np.random.default_rng(5)
+    draws = [(rng.standard_normal(576), rng.standard_normal(132), 0.1 * rng.standard_normal(700)) for _ in range(R)]
+    for r, w in ws.items():
+        fb, lm, x0 = draws[r]
+        eng.feedback_set(r, fb[:w["D"]])
+        eng.local_model_set(r, lm[:w["S"]])
+        eng.state_set(r, x0[:w["n"]])
+    return draws
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -44,14 +55,7 @@ def main():
     shard = H.EngineShard(eng, torch)
 
     def reset():
-        rng = np.random.default_rng(5)
-        draws = [(rng.standard_normal(576), rng.standard_normal(132), 0.1 * rng.standard_normal(700)) for _ in range(R)]
-        for r, w in ws.items():
-            fb, lm, x0 = draws[r]
-            eng.feedback_set(r, fb[:w["D"]])
-            eng.local_model_set(r, lm[:w["S"]])
-            eng.state_set(r, x0[:w["n"]])
-        return draws
+        return reset_engine(eng, ws)
 
     def host_model(w4d, w2d, wsst):
         return oc.host_stub(w4d, w2d, G["clim4d"], G["clim2d"])
@@ -110,6 +114,75 @@ def main():
             oc.step_scatter(rcs, True, True, False, *gc, f4, f2, G["tisr"], sst_mean, sst_std, nthreads=8)
         ok &= worst < 1e-10
         print(f"rank0: nccl==peer bitwise, overlap within 1e-11, oracle worst rel err {worst:.2e}, ok={ok}")
+    eng.close()
+
+    # ---- coupled model: ocean reservoirs on the 'ocean' regions; their slabs are all-gathered by NCCL after each
+    # ocean step, the atmosphere slabs by peer stores.  Rank 0 compares the grids with a single-process oracle.
+    from helpers import c_ocean, ocean_weights, sst_input_mask
+    eng = E.Engine(number_of_regions=R, irank=rank, numprocs=world, device=local, sst_prescribed=False, stream=stream)
+    for r, w in ws.items():
+        eng.region_upload(r, w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"], win_compact=w["winc"],
+                          win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"])
+    wos = {r: ocean_weights(R, r, m=M, mean=ws[r]["mean"], std=ws[r]["std"], with_dense_win=False)
+           for r in ws if sst_input_mask(r)}
+    for r, w in wos.items():
+        eng.region_upload(r, w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"], win_compact=w["winc"],
+                          win_col=w["wcol"], D=w["D"], kind=E.OCEAN)
+    eng.finalize()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    shard2 = H.EngineShard(eng, torch, ocean=True)
+    shard2.attach_peers(dist)
+    rng = np.random.default_rng(9)
+    odraw = {r: (rng.standard_normal(128), 285.0 + 5.0 * rng.random(8)) for r in range(R)}   # same stream on every rank
+    draws = reset_engine(eng, ws)
+    for r, w in wos.items():
+        eng.feedback_set(r, odraw[r][0][:w["D"]], kind=E.OCEAN)
+        eng.outvec_set(r, odraw[r][1], kind=E.OCEAN)
+    NS2 = 30
+    st = H.HybridStepper(shard2, rank=rank, world=world, dist=dist)
+    cgrids = []
+    for t in range(1, NS2 + 1):
+        g = st.step(t, host_model, G["tisr"])
+        if rank == 0 and t in (1, 2, 27, 28, 29, 30):
+            cgrids.append((t, [a.copy() for a in g]))
+    torch.cuda.synchronize()
+    eng.peer_check()
+    if rank == 0:
+        all_ws = [region_weights(R, r, m=M, with_dense_win=False) for r in range(R)]
+        all_wos = {r: ocean_weights(R, r, m=M, mean=all_ws[r]["mean"], std=all_ws[r]["std"], with_dense_win=False)
+                   for r in range(R) if sst_input_mask(r)}
+        rcs = [c_region(w) for w in all_ws]
+        cos = {r: c_ocean(w) for r, w in all_wos.items()}
+        for w, rc in zip(all_ws, rcs):
+            fb, lm, x0 = draws[w["region"]]
+            rc.feedback[:], rc.local_model[:], rc.x[:] = fb[:w["D"]], lm[:w["S"]], x0[:w["n"]]
+        for r, co in cos.items():
+            co.feedback[:] = odraw[r][0][:all_wos[r]["D"]]
+            co.outvec[:] = odraw[r][1]
+            co.x[:] = 0.0
+        sst_mean = np.array([w["mean"][-1] for w in all_ws])
+        sst_std = np.array([w["std"][-1] for w in all_ws])
+        has = np.array([1 if r in cos else 0 for r in range(R)], dtype=np.int32)
+        want = dict(cgrids)
+        worst2 = 0.0
+        for t in range(1, NS2 + 1):
+            oc.predict_all(rcs, nthreads=8)
+            if (t * 6) % 168 == 0:
+                for co in cos.values():
+                    co.predict()
+            oo = np.zeros((R, 4))
+            for r, co in cos.items():
+                oo[r] = co.outvec[:4]
+            gc = oc.step_gather(rcs, True, True, G["base_sst"], G["sea_mask"], ocean_out=oo, has_ocean=has)
+            if t in want:
+                for a, b in zip(want[t], gc):
+                    worst2 = max(worst2, rel_inf(a, b))
+            f4, f2 = oc.host_stub(gc[0], gc[1], G["clim4d"], G["clim2d"])
+            oc.step_scatter(rcs, True, True, False, *gc, f4, f2, G["tisr"], sst_mean, sst_std, nthreads=8)
+            for r, co in cos.items():
+                co.build_feedback(rcs[r], t, gc[3])
+        ok &= worst2 < 1e-10
+        print(f"rank0: coupled 2-rank loop (ocean slabs over NCCL, atmosphere over peer stores) vs oracle: {worst2:.2e}, ok={ok}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     eng.close()

@@ -226,3 +226,48 @@ def test_ocean_training_gram_and_fit(E):
         res = np.linalg.norm(A.T @ X - B.T) / (np.linalg.norm(A) * np.linalg.norm(X) + np.linalg.norm(B))
         assert res < 1e-13
     eng.close()
+
+
+def test_coupled_loop_overlapped_mode_matches_sequential(E, coupled_model):
+    """the overlapped step with ocean reservoirs: the ocean ring/SST feedback is rebuilt inside exchange_begin, the
+    ocean reservoirs still step on the caller's schedule; grids must match the sequential engine loop"""
+    ws, wos, eng, rcs, cos = coupled_model
+    G = initial_grids()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    rng = np.random.default_rng(5)
+    start = {w["region"]: (0.1 * rng.standard_normal(w["n"]), rng.standard_normal(w["D"]), rng.standard_normal(w["S"])) for w in ws}
+    ostart = {r: (0.1 * rng.standard_normal(wos[r]["n"]), rng.standard_normal(wos[r]["D"]), 285.0 + 5.0 * rng.random(8)) for r in wos}
+
+    def run(overlap):
+        for r, (x0, fb, lm) in start.items():
+            eng.state_set(r, x0)
+            eng.feedback_set(r, fb)
+            eng.local_model_set(r, lm)
+        for r, (x0, fb, ov) in ostart.items():
+            eng.state_set(r, x0, kind=E.OCEAN)
+            eng.feedback_set(r, fb, kind=E.OCEAN)
+            eng.outvec_set(r, ov, kind=E.OCEAN)
+        eng.ocean_ring_reset()
+        eng.set_overlap(overlap)
+        out = []
+        for t in range(1, 31):                                 # one ocean step at t = 28, ring wraps
+            eng.predict()
+            if (t * 6) % 168 == 0:
+                eng.predict(kind=E.OCEAN)
+            if overlap:
+                eng.set_tisr(G["tisr"])
+            g = eng.step_exchange_begin(t)
+            f4, f2 = oc.host_stub(g[0], g[1], G["clim4d"], G["clim2d"])
+            eng.step_exchange_end(t, f4, f2, None if overlap else G["tisr"])
+            out.append([a.copy() for a in g])
+        ofb = {r: eng.feedback_get(r, kind=E.OCEAN) for r in (0, 3, 555)}
+        eng.set_overlap(False)
+        return out, ofb
+
+    seq, ofb_seq = run(False)
+    ovl, ofb_ovl = run(True)
+    for t in range(30):
+        for a, b in zip(ovl[t], seq[t]):
+            assert rel_inf(a, b) < 1e-10
+    for r in ofb_seq:
+        assert rel_inf(ofb_ovl[r], ofb_seq[r]) < 1e-10
