@@ -24,6 +24,7 @@ module speedyml_gpu
   public :: gpu_engine_create, gpu_engine_finalize, gpu_engine_destroy
   public :: mklsparse, synchronize, predict, predict_ml, predict_slab_ml, sendrecievegrid
   public :: gpu_train_begin, gpu_train_phase, gpu_fit_chunk, gpu_train_end, mldivide
+  public :: gen_res, read_trained_res, gpu_train_global_series, gpu_train_phase_global, gpu_set_overlap, gpu_set_tisr
 
   integer(c_int), parameter :: SML_ATMO = 0, SML_OCEAN = 1, SML_ALL_REGIONS = -1
 
@@ -172,6 +173,48 @@ module speedyml_gpu
      integer(c_int) function sml_train_end(h) bind(C, name='sml_train_end')
        import :: c_ptr, c_int
        type(c_ptr), value :: h
+     end function
+     integer(c_int) function sml_sparse_eigen(h, kind, maxit, tol, eigs, iterations) bind(C, name='sml_sparse_eigen')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: kind, maxit
+       real(c_double), value :: tol
+       real(c_double), intent(out) :: eigs(*)
+       integer(c_int), intent(out) :: iterations
+     end function
+     integer(c_int) function sml_adjacency_scale(h, kind, factor) bind(C, name='sml_adjacency_scale')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: kind
+       real(c_double), intent(in) :: factor(*)
+     end function
+     integer(c_int) function sml_region_upload_file(h, path, region, kind, sst_bool_input, leakage) bind(C, name='sml_region_upload_file')
+       import :: c_ptr, c_int, c_double, c_char
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: path(*)
+       integer(c_int), value :: region, kind, sst_bool_input
+       real(c_double), value :: leakage
+     end function
+     integer(c_int) function sml_train_global_series(h, g_series, f_series, ncols_total) bind(C, name='sml_train_global_series')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: g_series(*), f_series(*)
+       integer(c_int), value :: ncols_total
+     end function
+     integer(c_int) function sml_train_feed_global(h, first_col, stride, ncols, discard_cols) bind(C, name='sml_train_feed_global')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: first_col, stride, ncols, discard_cols
+     end function
+     integer(c_int) function sml_set_overlap(h, on) bind(C, name='sml_set_overlap')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: on
+     end function
+     integer(c_int) function sml_set_tisr(h, tisr) bind(C, name='sml_set_tisr')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: tisr(*)
      end function
      integer(c_int) function sml_mldivide(h, A, lda, B, ldb, n, nrhs) bind(C, name='sml_mldivide')
        import :: c_ptr, c_int, c_double
@@ -428,6 +471,66 @@ contains
 
   subroutine gpu_train_end()
     call ck(sml_train_end(h), 'sml_train_end')
+  end subroutine
+
+  !> gen_res(reservoir), src/mod_reservoir.f90:182-212, for every local reservoir at once: after makesparse + mklsparse
+  !> of the unscaled adjacency and gpu_engine_finalize, the spectral radii come from the device (replaces the ARPACK
+  !> sparse_eigen, src/mod_linalg.f90:220-514) and vals = (vals/eig)*radius is applied on both sides
+  subroutine gen_res(reservoirs, kind)
+    type(reservoir_type), intent(inout) :: reservoirs(:)
+    integer, intent(in), optional :: kind
+    real(kind=dp), allocatable :: eigs(:), factor(:)
+    integer(c_int) :: k, iters, rc
+    integer :: i
+    k = SML_ATMO
+    if (present(kind)) k = kind
+    allocate(eigs(size(reservoirs)), factor(size(reservoirs)))
+    rc = sml_sparse_eigen(h, k, 500, 1.0d-13, eigs, iters)
+    call ck(rc, 'sml_sparse_eigen')
+    if (rc == 1) print *, 'sparse_eigen did not converge in', iters, 'iterations'
+    do i = 1, size(reservoirs)
+       factor(i) = 1.0_dp
+       if (eigs(i) > 0.0_dp) factor(i) = reservoirs(i)%radius / eigs(i)
+       reservoirs(i)%vals = reservoirs(i)%vals * factor(i)
+    end do
+    call ck(sml_adjacency_scale(h, k, factor), 'sml_adjacency_scale')
+  end subroutine
+
+  !> read_trained_res + mklsparse in one call (src/mod_io.f90:2938-2983, src/mod_reservoir.f90:1852): the engine reads
+  !> the NetCDF-classic file write_trained_res produced itself and uploads it (float32 -> real(dp) widening)
+  subroutine read_trained_res(reservoir, filename, kind)
+    type(reservoir_type), intent(in) :: reservoir
+    character(len=*), intent(in) :: filename
+    integer, intent(in), optional :: kind
+    integer(c_int) :: k
+    k = SML_ATMO
+    if (present(kind)) k = kind
+    call ck(sml_region_upload_file(h, trim(filename)//c_null_char, reservoir%assigned_region, k, &
+                                   merge(1, 0, reservoir%sst_bool_input), reservoir%leakage), 'sml_region_upload_file')
+  end subroutine
+
+  !> the conditioned global series of the training period, resident on the device for all waves and phases;
+  !> g_series(g_total, ncols), f_series(f_total, ncols) in the layout of sml_global_layout
+  subroutine gpu_train_global_series(g_series, f_series)
+    real(kind=dp), intent(in) :: g_series(:,:), f_series(:,:)
+    call ck(sml_train_global_series(h, g_series, f_series, size(g_series, 2)), 'sml_train_global_series')
+  end subroutine
+
+  !> one phase trainingdata(:, i::timestep) from the resident series (first_col is 0-based)
+  subroutine gpu_train_phase_global(first_col, stride, ncols, discard_cols)
+    integer, intent(in) :: first_col, stride, ncols, discard_cols
+    call ck(sml_train_feed_global(h, first_col, stride, ncols, discard_cols), 'sml_train_feed_global')
+  end subroutine
+
+  !> overlapped step: the next predict's state update and x~ readout run while run_model works (call gpu_set_tisr
+  !> with get_tisr_by_date's field before every sendrecievegrid)
+  subroutine gpu_set_overlap(on)
+    logical, intent(in) :: on
+    call ck(sml_set_overlap(h, merge(1, 0, on)), 'sml_set_overlap')
+  end subroutine
+  subroutine gpu_set_tisr(tisr_grid)
+    real(kind=dp), intent(in) :: tisr_grid(:,:)
+    call ck(sml_set_tisr(h, tisr_grid), 'sml_set_tisr')
   end subroutine
 
   !> mldivide(A,B), src/mod_linalg.f90:109-151: A*X = B, B becomes X when info == 0

@@ -67,3 +67,23 @@ def test_cpp_host_driver_builds_and_fails_loudly_without_gpu(tmp_path):
         np.array([1152, 1, 1, 1, 0, 1, 1152, 1, 0], dtype=np.int32).tofile(f)
     p = subprocess.run([exe, str(case), str(tmp_path / "out.bin")], capture_output=True, text=True)
     assert p.returncode == 1 and "no CUDA device" in p.stderr      # no CPU fallback in the compiled host either
+
+
+def test_fortran_shim_binds_only_declared_symbols_with_matching_arity():
+    """speedyml_gpu.f90 cannot be compiled here (no Fortran front-end); at least keep it in step with the header:
+    every bind(C, name=...) must be a declared entry point with the same number of arguments"""
+    hdr = open(os.path.join(ROOT, "include", "speedyml_engine.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(sml_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    f90 = open(os.path.join(ROOT, "speedy-ml_b200", "fortran", "speedyml_gpu.f90")).read()
+    f90 = re.sub(r"&\s*\n\s*", " ", f90)
+    bound = re.findall(r"function\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name='(\w+)'\)", f90)
+    assert len(bound) >= 30
+    for fname, fargs, cname in bound:
+        assert fname == cname
+        assert cname in decl, f"{cname} bound in the Fortran layer but not declared in the header"
+        n = len([a for a in fargs.split(",") if a.strip()])
+        assert n == decl[cname], f"{cname}: {n} Fortran arguments vs {decl[cname]} in the header"
