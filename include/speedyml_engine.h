@@ -209,6 +209,13 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *forecast_4d
 int sml_set_overlap(sml_engine *h, int on);
 int sml_set_tisr(sml_engine *h, const double *tisr_grid);
 int sml_step_predict_ahead(sml_engine *h, int timestep);
+/* zero-copy variants for hosts that can work in place: sml_step_exchange_begin_view returns pointers into the engine's
+ * pinned staging instead of copying into caller arrays (valid until the next begin); sml_forecast_staging returns the
+ * pinned arrays sml_step_exchange_end uploads from -- pass the same pointers to sml_step_exchange_end and the
+ * intermediate copy is skipped.  The device<->host transfers themselves are unchanged. */
+int sml_step_exchange_begin_view(sml_engine *h, int timestep, const double **wholegrid4d, const double **wholegrid2d,
+                                 const double **wholegrid_precip, const double **wholegrid_sst);
+int sml_forecast_staging(sml_engine *h, double **forecast_4d, double **forecast_2d, double **tisr_grid);
 /* static fields of the exchange: base_sst_grid and sea_mask (src/mod_reservoir.f90:847-887) */
 int sml_set_sst_static(sml_engine *h, const double *base_sst_grid, const double *sea_mask);
 /* sst_prescribed == 1: the SST field (96x48) the next exchanges start from instead of ocean-reservoir

@@ -1332,6 +1332,42 @@ int sml_step_exchange_begin(sml_engine *h, int timestep, double *w4d, double *w2
     return 0;
 }
 
+// zero-copy variant for hosts that can consume the grids in place: the same as sml_step_exchange_begin, but instead of
+// copying into caller arrays it returns pointers into the engine's pinned staging (valid until the next begin)
+int sml_step_exchange_begin_view(sml_engine *h, int timestep, const double **w4d, const double **w2d,
+                                 const double **wprecip, const double **wsst)
+{
+    if (!w4d || !w2d || !wprecip || !wsst) return -1;
+    if (sml_step_pack_device(h, timestep)) return -1;
+    if (h->overlap) {
+        CK(h, cudaEventRecord(h->ev_pack, h->stream));
+        CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pack, 0));
+        CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(h, cudaEventRecord(h->ev_d2h, h->copy_stream));
+        if (sml_step_predict_ahead(h, timestep)) return -1;
+        CK(h, cudaEventSynchronize(h->ev_d2h));
+    } else {
+        CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    *w4d = h->h_pin_G + G_W4D;
+    *w2d = h->h_pin_G + G_W2D;
+    *wprecip = h->h_pin_G + G_PRECIP;
+    *wsst = h->h_pin_G + G_SST;
+    return 0;
+}
+
+// the pinned staging sml_step_exchange_end uploads from: a host model that writes its forecast (and the TISR field)
+// straight into these arrays and passes the same pointers to sml_step_exchange_end saves the intermediate copy
+int sml_forecast_staging(sml_engine *h, double **forecast_4d, double **forecast_2d, double **tisr_grid)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (forecast_4d) *forecast_4d = h->h_pin_F + F_F4D;
+    if (forecast_2d) *forecast_2d = h->h_pin_F + F_F2D;
+    if (tisr_grid) *tisr_grid = h->h_pin_F + F_TOTAL;
+    return 0;
+}
+
 int sml_step_unpack_device(sml_engine *h, int timestep)
 {
     if (check_ready(h, SML_ATMO)) return -1;
@@ -1376,8 +1412,8 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const 
     cudaStream_t up = ahead ? h->copy_stream : h->stream;
     if (!h->p.ml_only) {
         if (!f4d || !f2d) FAIL(h, "hybrid mode needs forecast_4d and forecast_2d");
-        std::memcpy(h->h_pin_F + F_F4D, f4d, sizeof(double) * G_W2D);
-        std::memcpy(h->h_pin_F + F_F2D, f2d, sizeof(double) * XG * YG);
+        if (f4d != h->h_pin_F + F_F4D) std::memcpy(h->h_pin_F + F_F4D, f4d, sizeof(double) * G_W2D);
+        if (f2d != h->h_pin_F + F_F2D) std::memcpy(h->h_pin_F + F_F2D, f2d, sizeof(double) * XG * YG);
         CK(h, cudaMemcpyAsync(h->d_F, h->h_pin_F, sizeof(double) * F_TOTAL, cudaMemcpyHostToDevice, up));
     }
     if (ahead) {
@@ -1385,7 +1421,7 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const 
         CK(h, cudaStreamWaitEvent(h->stream, h->ev_h2d, 0));
         return sml_step_unpack_device(h, timestep);
     }
-    std::memcpy(h->h_pin_F + F_TOTAL, tisr, sizeof(double) * XG * YG);
+    if (tisr != h->h_pin_F + F_TOTAL) std::memcpy(h->h_pin_F + F_TOTAL, tisr, sizeof(double) * XG * YG);
     CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_F + F_TOTAL, sizeof(double) * XG * YG, cudaMemcpyHostToDevice,
                           h->stream));
     if (sml_step_unpack_device(h, timestep)) return -1;

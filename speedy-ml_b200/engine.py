@@ -82,6 +82,8 @@ _SIGNATURES = {
     "sml_set_contribs": ([C.c_void_p, C.c_int], C.c_int),
     "sml_contribs_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
     "sml_step_exchange_begin": ([C.c_void_p, C.c_int, _dp, _dp, _dp, _dp], C.c_int),
+    "sml_step_exchange_begin_view": ([C.c_void_p, C.c_int] + [C.POINTER(_dp)] * 4, C.c_int),
+    "sml_forecast_staging": ([C.c_void_p] + [C.POINTER(_dp)] * 3, C.c_int),
     "sml_step_exchange_end": ([C.c_void_p, C.c_int, _dp, _dp, _dp], C.c_int),
     "sml_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
     "sml_set_tisr": ([C.c_void_p, _dp], C.c_int),
@@ -490,6 +492,27 @@ class Engine:
                 self._grids = (w4d, w2d, wp, wsst)
         self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, _d(w4d), _d(w2d), _d(wp), _d(wsst)))
         return w4d, w2d, wp, wsst
+
+    def step_exchange_begin_view(self, timestep):
+        """zero-copy: the four grids as read-only views of the engine's pinned staging (valid until the next begin)"""
+        p = [_dp() for _ in range(4)]
+        self._ck(self.lib.sml_step_exchange_begin_view(self.h, timestep, *[C.byref(a) for a in p]))
+        shapes = ((4, XGRID, YGRID, ZGRID), (XGRID, YGRID), (XGRID, YGRID), (XGRID, YGRID))
+        out = []
+        for ptr, shp in zip(p, shapes):
+            a = np.ctypeslib.as_array(ptr, shape=(int(np.prod(shp)),)).reshape(shp, order="F")
+            a.flags.writeable = False
+            out.append(a)
+        return tuple(out)
+
+    def forecast_staging(self):
+        """(forecast_4d, forecast_2d, tisr) views of the pinned staging step_exchange_end uploads from: write the host
+        model's output into them and pass them to step_exchange_end to skip the intermediate copy"""
+        p = [_dp() for _ in range(3)]
+        self._ck(self.lib.sml_forecast_staging(self.h, *[C.byref(a) for a in p]))
+        shapes = ((4, XGRID, YGRID, ZGRID), (XGRID, YGRID), (XGRID, YGRID))
+        return tuple(np.ctypeslib.as_array(ptr, shape=(int(np.prod(shp)),)).reshape(shp, order="F")
+                     for ptr, shp in zip(p, shapes))
 
     def step_exchange_end(self, timestep, forecast_4d, forecast_2d, tisr_grid=None):
         f4 = _farr(forecast_4d, (4, XGRID, YGRID, ZGRID)) if forecast_4d is not None else None

@@ -73,6 +73,7 @@ class EngineShard:
         self._pin_f_np = self._pin_f.numpy()
         self._pin_t_np = self._pin_t.numpy()
         self.reuse_grids = False    # True: exchange_begin returns the same host arrays every step
+        self.zero_copy = False      # True: exchange_begin returns views of the pinned staging (no host copy)
 
     @property
     def peer_attached(self):
@@ -100,7 +101,18 @@ class EngineShard:
         self.eng.step_unpack_device(t)
 
     def exchange_begin(self, t):
+        if self.zero_copy:
+            return self.eng.step_exchange_begin_view(t)      # views of the engine's pinned staging
         return self.eng.step_exchange_begin(t, reuse=self.reuse_grids)
+
+    def forecast_buffers(self, world):
+        """(forecast_4d, forecast_2d) arrays the host model may write in place: the engine's pinned upload staging on a
+        single rank, this shard's pinned broadcast staging otherwise"""
+        if world == 1:
+            return self.eng.forecast_staging()[:2]
+        lay = self.lay
+        return (self._pin_f_np[:lay["w2d"]].reshape((4, E.XGRID, E.YGRID, E.ZGRID), order="F"),
+                self._pin_f_np[lay["w2d"]:].reshape((E.XGRID, E.YGRID), order="F"))
 
     def exchange_end(self, t, f4d, f2d, tisr):
         self.eng.step_exchange_end(t, f4d, f2d, tisr)
@@ -110,8 +122,9 @@ class EngineShard:
         lay = self.lay
         # the pinned staging is free: the previous step's copy out of it precedes this step's grid assembly in
         # stream order, and exchange_begin has just waited for the copy-out of those grids
-        np.copyto(self._pin_f_np[:lay["w2d"]], np.asarray(f4d).reshape(-1, order="F"))
-        np.copyto(self._pin_f_np[lay["w2d"]:], np.asarray(f2d).reshape(-1, order="F"))
+        if not np.shares_memory(f4d, self._pin_f_np):        # else: the host model wrote into the staging in place
+            np.copyto(self._pin_f_np[:lay["w2d"]], np.asarray(f4d).reshape(-1, order="F"))
+            np.copyto(self._pin_f_np[lay["w2d"]:], np.asarray(f2d).reshape(-1, order="F"))
         self.F.copy_(self._pin_f, non_blocking=True)
         if tisr is not None:
             np.copyto(self._pin_t_np, np.asarray(tisr).reshape(-1, order="F"))

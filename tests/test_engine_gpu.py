@@ -468,3 +468,30 @@ def test_other_tilings_predict_and_exchange(E, R, region):
     eng.predict()
     assert rel_inf(eng.outvec_get(region), rc.outvec) < TOL_STEP * 10
     eng.close()
+
+
+def test_zero_copy_staging_views(E, small_model):
+    """sml_step_exchange_begin_view / sml_forecast_staging: same grids and same feedback as the copying entry points"""
+    ws, eng, rcs = small_model
+    G = initial_grids()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    eng.set_sst_prescribed(G["base_sst"])
+    _reset_small_model(ws, eng, rcs, 44)
+    eng.predict()
+    copies = eng.step_exchange_begin(1)
+    views = eng.step_exchange_begin_view(1)
+    for a, b in zip(views, copies):
+        assert np.array_equal(a, b) and not a.flags.writeable
+    f4, f2 = oc.host_stub(copies[0], copies[1], G["clim4d"], G["clim2d"])
+    eng.step_exchange_end(1, f4, f2, G["tisr"])
+    fb_copy = {r: (eng.feedback_get(r), eng.local_model_get(r)) for r in (0, 555, 1151)}
+    s4, s2, st = eng.forecast_staging()
+    s4[...] = f4
+    s2[...] = f2
+    st[...] = G["tisr"]
+    for r in fb_copy:                                   # scramble, then rebuild from the staging written in place
+        eng.feedback_set(r, np.zeros(ws[r]["D"]))
+        eng.local_model_set(r, np.zeros(ws[r]["S"]))
+    eng.step_exchange_end(1, s4, s2, st)
+    for r, (fb, lm) in fb_copy.items():
+        assert np.array_equal(eng.feedback_get(r), fb) and np.array_equal(eng.local_model_get(r), lm)
