@@ -269,6 +269,13 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
 int sml_train_global_series(sml_engine *h, const double *G_series, const double *F_series, int ncols_total);
 int sml_train_feed_global(sml_engine *h, int first_col, int stride, int ncols, int discard_cols);
 int sml_train_global_release(sml_engine *h);
+/* grid%mean / grid%std of every local region from the resident series (get_training_data, src/mod_reservoir.f90:413-470;
+ * formulas: standardize_data_5d_logp_tisr src/mod_utilities.f90:1144-1193 two-pass population std, standardize_data_3d
+ * :894-912 for precip, standardize_sst_data_3d :853-892 with its std > 0.2 gate -> sst_bool_input).  The series may be
+ * uploaded before any region is (the constants are inputs of sml_region_upload).  Returns L, the slot count; mean and
+ * std are [nloc][L] in local region order. */
+int sml_conditioning_stats(sml_engine *h, int first_col, int stride, int ncols, double *mean, double *std,
+                           int32_t *sst_bool_input);
 int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using_prior,
                     double prior_val, int32_t *info_per_region);
 /* sml_train_solve factorises the regularised Gram (symmetric positive definite for ridge > 0) of every region of

@@ -579,6 +579,50 @@ def gen_res_scale(vals, eigs, radius):
     return (vals / eigs) * radius
 
 
+def conditioning_stats(w4d_t, logp_t, tisr_t, precip_t, sst_t, numregions, region, overlap):
+    """grid%mean / grid%std of one region from its training window (get_training_data, src/mod_reservoir.f90:413-470).
+    Inputs are the conditioned global series, time last: w4d_t (4,96,48,8,T), 2-D fields (96,48,T); precip_t / sst_t may
+    be None.  Slot order: (var, level) var-major, logp, tisr, [precip], [sst].  Formulas:
+      standardize_data_5d_logp_tisr (src/mod_utilities.f90:1144-1193): mean = sum/size, std = sqrt(sum((x-mean)**2)/size)
+      standardize_data_3d (:894-912, precip):  std = sqrt((sum(x**2) - sum(x)**2/size)/size)
+      standardize_sst_data_3d (:853-892): two-pass std, kept only if sum(x**2)-sum(x)**2/size > 0 and std > 0.2,
+                                          else mean = std = 0 and any_change = .False.
+    Returns (mean, std, sst_any_change)."""
+    T = w4d_t.shape[-1]
+
+    def tile2(f):   # (96,48,T) -> halo block (ixc, iyc, T)
+        return np.stack([tileoverlapgrid2d(f[:, :, t], numregions, region, overlap) for t in range(T)], axis=-1)
+
+    def two_pass(x):
+        m = np.sum(x) / x.size
+        return m, math.sqrt(np.sum((x - m) ** 2) / x.size)
+
+    loc4 = np.stack([tileoverlapgrid4d(w4d_t[..., t], numregions, region, overlap) for t in range(T)], axis=-1)
+    mean, std = [], []
+    for v in range(4):
+        for z in range(ZGRID):
+            m, sd = two_pass(loc4[v, :, :, z, :])
+            mean.append(m); std.append(sd)
+    for f in (logp_t, tisr_t):
+        m, sd = two_pass(tile2(f))
+        mean.append(m); std.append(sd)
+    if precip_t is not None:
+        x = tile2(precip_t)
+        mean.append(np.sum(x) / x.size)
+        std.append(math.sqrt((np.sum(x ** 2) - np.sum(x) ** 2 / x.size) / x.size))
+    any_change = True
+    if sst_t is not None:
+        x = tile2(sst_t)
+        m, sd = 0.0, 0.0
+        any_change = False
+        if (np.sum(x ** 2) - np.sum(x) ** 2 / x.size) > 0:
+            m_, sd_ = two_pass(x)
+            if sd_ > 0.2:
+                m, sd, any_change = m_, sd_, True
+        mean.append(m); std.append(sd)
+    return np.array(mean), np.array(std), any_change
+
+
 def pinv_svd(A, thres=1e-2):
     """src/mod_linalg.f90:27-107: Moore-Penrose via SVD, singular values <= thres zeroed"""
     U, s, VT = np.linalg.svd(A, full_matrices=False)

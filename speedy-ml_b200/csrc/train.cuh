@@ -377,6 +377,87 @@ struct TrainState {
     int solved_by_cholesky = 0;
 };
 
+// Per-region standardisation constants from the resident global series (get_training_data, src/mod_reservoir.f90:
+// 413-470): for every (variable, level) slot the mean and the population standard deviation over the region's halo
+// block and all columns of the window --
+//   kind 0 (atmosphere levels, logp, tisr; standardize_data_5d_logp_tisr, src/mod_utilities.f90:1144-1193):
+//          mean = sum/N, std = sqrt(sum((x-mean)^2)/N)
+//   kind 1 (precip; standardize_data_3d :894-912): std = sqrt((sum(x^2) - sum(x)^2/N)/N)
+//   kind 2 (SST; standardize_sst_data_3d :853-892): as kind 0 if sum(x^2)-sum(x)^2/N > 0 and std > 0.2, else
+//          mean = std = 0 and the region gets no SST input (any_change = .False.)
+// One block per (slot, region); fixed-order tree reductions, so the result is deterministic.
+struct StatSlot {
+    int first_cell;   // index into the region's cell list
+    int ncells;
+    long long base;   // offset of the slot's 2-D field (or of (var, level)) in a G column; element = base + cell*cstride
+    int cstride;
+    int kind;
+};
+
+__global__ void __launch_bounds__(256)
+k_cond_stats(const double *__restrict__ Gs, long long g_len, int first, int stride, int ncols,
+             const StatSlot *__restrict__ slots, int L, const int *__restrict__ cells, double *__restrict__ mean_out,
+             double *__restrict__ std_out, int *__restrict__ sst_flag)
+{
+    __shared__ double r1[256], r2[256];
+    __shared__ double s_mean;
+    const int region = blockIdx.y, l = blockIdx.x;
+    const StatSlot sl = slots[(size_t)region * L + l];
+    const int *cl = cells + sl.first_cell;
+    const long long total = (long long)sl.ncells * ncols;
+    double a = 0.0, b = 0.0;
+    for (long long e = threadIdx.x; e < total; e += 256) {
+        const int c = (int)(e / sl.ncells), k = (int)(e % sl.ncells);
+        const double x = Gs[(size_t)(first + stride * c) * g_len + sl.base + (long long)cl[k] * sl.cstride];
+        a += x;
+        b = fma(x, x, b);
+    }
+    r1[threadIdx.x] = a;
+    r2[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            r1[threadIdx.x] += r1[threadIdx.x + o];
+            r2[threadIdx.x] += r2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    const double S1 = r1[0], Sq = r2[0], N = (double)total;
+    if (threadIdx.x == 0) s_mean = S1 / N;
+    __syncthreads();
+    const double mean = s_mean;
+    double v = 0.0;
+    for (long long e = threadIdx.x; e < total; e += 256) {
+        const int c = (int)(e / sl.ncells), k = (int)(e % sl.ncells);
+        const double x = Gs[(size_t)(first + stride * c) * g_len + sl.base + (long long)cl[k] * sl.cstride];
+        const double d = x - mean;
+        v = fma(d, d, v);
+    }
+    __syncthreads();
+    r1[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) r1[threadIdx.x] += r1[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double m = mean, sd;
+        const double onepass = Sq - S1 * S1 / N;
+        if (sl.kind == 1) {
+            sd = sqrt(onepass / N);
+        } else {
+            sd = sqrt(r1[0] / N);
+            if (sl.kind == 2) {
+                const bool keep = onepass > 0.0 && sd > 0.2;
+                if (!keep) m = sd = 0.0;
+                sst_flag[region] = keep ? 1 : 0;
+            }
+        }
+        mean_out[(size_t)region * L + l] = m;
+        std_out[(size_t)region * L + l] = sd;
+    }
+}
+
 // global training series, kept across waves (sml_train_global_series / sml_train_global_release)
 struct TrainGlobal {
     double *d_G = nullptr, *d_F = nullptr;

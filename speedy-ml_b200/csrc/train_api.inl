@@ -262,7 +262,7 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
 // and phases (12 000 six-hourly states of the T30 grid are 30 GB: G 1.33 MB + F 1.22 MB per column).
 int sml_train_global_series(sml_engine *h, const double *G_series, const double *F_series, int ncols_total)
 {
-    if (check_ready(h, SML_ATMO)) return -1;
+    if (!h) return -1;  // needs no uploaded region: the statistics that parameterise the uploads come from this series
     if (!G_series || ncols_total < 1) FAIL(h, "sml_train_global_series: bad arguments");
     if (!h->p.ml_only && !F_series) FAIL(h, "hybrid training needs the forecast series F");
     CK(h, cudaSetDevice(h->p.device));
@@ -290,6 +290,64 @@ int sml_train_trim(sml_engine *h)
     CK(h, cudaSetDevice(h->p.device));
     h->train_pool.drop_all();
     return 0;
+}
+
+// mean/std of every local region from the resident series, window = columns first_col + stride*c, c < ncols.
+// mean / std: [nloc][L] with L = 32 + logp + tisr (+ precip) (+ sst), the slot order of grid%mean
+// (src/mod_reservoir.f90:414-436); sst_bool_input[nloc]: standardize_sst_data_3d's any_change (1 when there is no SST slot).
+int sml_conditioning_stats(sml_engine *h, int first_col, int stride, int ncols, double *mean, double *std,
+                           int32_t *sst_bool_input)
+{
+    if (!h) return -1;
+    TrainGlobal &TG = h->train_global;
+    if (!TG.d_G) FAIL(h, "sml_train_global_series has not been called");
+    if (first_col < 0 || stride < 1 || ncols < 1 || first_col + (long long)stride * (ncols - 1) >= TG.ncols_total)
+        FAIL(h, "window (first %d, stride %d, %d columns) runs past the %d resident columns", first_col, stride, ncols, TG.ncols_total);
+    CK(h, cudaSetDevice(h->p.device));
+    const int nloc = (int)h->local_ids.size();
+    const bool precip = h->p.precip_bool, sst = h->p.slab_ocean_model_bool;
+    const int L = NVAR * ZG + 2 + (precip ? 1 : 0) + (sst ? 1 : 0);
+    std::vector<StatSlot> slots((size_t)nloc * L);
+    std::vector<int> cells;
+    for (int i = 0; i < nloc; ++i) {
+        RegionGeom g = make_geom(h->tiling, h->local_ids[i], h->p.overlap);
+        const int first_cell = (int)cells.size();
+        for (int ly = 0; ly < g.iyc; ++ly)
+            for (int lx = 0; lx < g.ixc; ++lx) cells.push_back((int)off2(g.gx[lx], g.iys - 1 + ly));
+        const int nc = g.ixc * g.iyc;
+        int l = 0;
+        for (int v = 0; v < NVAR; ++v)
+            for (int z = 0; z < ZG; ++z)
+                slots[(size_t)i * L + l++] = StatSlot{first_cell, nc, G_W4D + v + (long long)NVAR * XG * YG * z, NVAR, 0};
+        slots[(size_t)i * L + l++] = StatSlot{first_cell, nc, G_W2D, 1, 0};    // logp
+        slots[(size_t)i * L + l++] = StatSlot{first_cell, nc, G_TISR, 1, 0};   // tisr
+        if (precip) slots[(size_t)i * L + l++] = StatSlot{first_cell, nc, G_PRECIP, 1, 1};
+        if (sst) slots[(size_t)i * L + l++] = StatSlot{first_cell, nc, G_SST, 1, 2};
+    }
+    StatSlot *d_slots = nullptr;
+    int *d_cells = nullptr, *d_flag = nullptr;
+    double *d_mean = nullptr, *d_std = nullptr;
+    CK(h, cudaMalloc(&d_slots, sizeof(StatSlot) * slots.size()));
+    CK(h, cudaMalloc(&d_cells, sizeof(int) * cells.size()));
+    CK(h, cudaMalloc(&d_flag, sizeof(int) * nloc));
+    CK(h, cudaMalloc(&d_mean, sizeof(double) * slots.size()));
+    CK(h, cudaMalloc(&d_std, sizeof(double) * slots.size()));
+    CK(h, cudaMemcpyAsync(d_slots, slots.data(), sizeof(StatSlot) * slots.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(d_cells, cells.data(), sizeof(int) * cells.size(), cudaMemcpyHostToDevice, h->stream));
+    std::vector<int> ones(nloc, 1);
+    CK(h, cudaMemcpyAsync(d_flag, ones.data(), sizeof(int) * nloc, cudaMemcpyHostToDevice, h->stream));
+    k_cond_stats<<<dim3(L, nloc), 256, 0, h->stream>>>(TG.d_G, G_TOTAL, first_col, stride, ncols, d_slots, L, d_cells, d_mean,
+                                                       d_std, d_flag);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(mean, d_mean, sizeof(double) * slots.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(std, d_std, sizeof(double) * slots.size(), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int> flags(nloc, 1);
+    CK(h, cudaMemcpyAsync(flags.data(), d_flag, sizeof(int) * nloc, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (sst_bool_input) std::copy(flags.begin(), flags.end(), sst_bool_input);
+    cudaFree(d_slots); cudaFree(d_cells); cudaFree(d_flag); cudaFree(d_mean); cudaFree(d_std);
+    return L;
 }
 
 int sml_train_global_release(sml_engine *h)

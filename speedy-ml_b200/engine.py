@@ -104,6 +104,7 @@ _SIGNATURES = {
     "sml_train_global_series": ([C.c_void_p, _dp, _dp, C.c_int], C.c_int),
     "sml_train_feed_global": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_train_global_release": ([C.c_void_p], C.c_int),
+    "sml_conditioning_stats": ([C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip], C.c_int),
     "sml_train_solve": ([C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, _ip], C.c_int),
     "sml_train_solver_stats": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
     "sml_train_gram_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
@@ -618,6 +619,17 @@ class Engine:
 
     def train_feed_global(self, first_col, stride, ncols, discard_cols):
         self._ck(self.lib.sml_train_feed_global(self.h, first_col, stride, ncols, discard_cols))
+
+    def conditioning_stats(self, first_col, stride, ncols):
+        """-> (mean (nloc, L), std (nloc, L), sst_bool_input (nloc,)) of every local region from the resident series"""
+        Lmax = 36
+        mean = np.zeros(self.num_of_regions_on_proc * Lmax)
+        std = np.zeros(self.num_of_regions_on_proc * Lmax)
+        flag = np.zeros(self.num_of_regions_on_proc, dtype=np.int32)
+        L = self._ck(self.lib.sml_conditioning_stats(self.h, first_col, stride, ncols, _d(mean), _d(std), _i(flag)),
+                     allow_positive=True)
+        n = self.num_of_regions_on_proc
+        return mean[:n * L].reshape(n, L), std[:n * L].reshape(n, L), flag.astype(bool)
 
     def train_global_release(self):
         self._ck(self.lib.sml_train_global_release(self.h))

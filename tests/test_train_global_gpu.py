@@ -82,3 +82,39 @@ def test_global_series_feed_matches_oracle_tiling_and_per_region_feed():
         assert rel_inf(gram_global[r][0], rc.sxs) < 1e-12 and rel_inf(gram_global[r][1], rc.sxt) < 1e-12
         assert np.array_equal(gram_global[r][0], gram_local[r][0]) and np.array_equal(gram_global[r][1], gram_local[r][1])
     eng.close()
+
+
+def test_conditioning_stats_from_resident_series():
+    """grid%mean / grid%std of every local region computed on the device from the resident global series vs the
+    reference's formulas restated in NumPy (two-pass population std; one-pass form for precip; SST gate std > 0.2)"""
+    from helpers import on
+    E = importlib.import_module("speedy-ml_b200.engine")
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=288)      # regions 0..3; no region is uploaded
+    regions = eng.region_indices
+    lay = E.global_layout()
+    F0 = initial_grids()
+    rng = np.random.default_rng(23)
+    T = 40
+    w4d_t = np.stack([F0["clim4d"] * (1.0 + 0.03 * rng.standard_normal(F0["clim4d"].shape)) for _ in range(T)], axis=-1)
+    logp_t = np.stack([F0["clim2d"] + 0.01 * rng.standard_normal((96, 48)) for _ in range(T)], axis=-1)
+    precip_t = np.stack([np.log1p(np.abs(rng.standard_normal((96, 48)))) for _ in range(T)], axis=-1)
+    sst_t = np.stack([np.maximum(F0["base_sst"] + rng.standard_normal((96, 48)), 272.0) for _ in range(T)], axis=-1)
+    sst_t[0:4, 0:3, :] = 272.0          # region 0's whole halo block (x 96,1,2,3 wraps; rows 1..3): constant -> no SST input
+    sst_t[95, 0:3, :] = 272.0
+    tisr_t = np.stack([np.abs(F0["tisr"] * (1.0 + 0.1 * rng.standard_normal((96, 48)))) for _ in range(T)], axis=-1)
+    G = np.zeros((lay["g_total"], T), order="F")
+    for t in range(T):
+        G[:, t] = np.concatenate([a.ravel(order="F") for a in (w4d_t[..., t], logp_t[..., t], precip_t[..., t], sst_t[..., t], tisr_t[..., t])])
+    eng.train_global_series(G, np.zeros((lay["f_total"], T), order="F"))
+    first, stride, ncols = 2, 3, 12
+    sel = first + stride * np.arange(ncols)
+    mean, std, sst_in = eng.conditioning_stats(first, stride, ncols)
+    assert mean.shape == (4, 36)
+    for i, r in enumerate(regions):
+        m, s, any_change = on.conditioning_stats(w4d_t[..., sel], logp_t[..., sel], tisr_t[..., sel], precip_t[..., sel],
+                                                 sst_t[..., sel], 1152, r, 1)
+        assert rel_inf(mean[i], m) < 1e-12 and rel_inf(std[i], s) < 1e-11
+        assert bool(sst_in[i]) == any_change
+    assert not sst_in[0] and mean[0, 35] == 0.0 and std[0, 35] == 0.0 and sst_in[1]
+    eng.train_global_release()
+    eng.close()
