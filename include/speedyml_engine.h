@@ -269,6 +269,11 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
 int sml_train_global_series(sml_engine *h, const double *G_series, const double *F_series, int ncols_total);
 int sml_train_feed_global(sml_engine *h, int first_col, int stride, int ncols, int discard_cols);
 int sml_train_global_release(sml_engine *h);
+/* when the uploaded series is RAW (hourly, physical units as read from the reanalysis): apply get_training_data's
+ * conditioning in place on the device (src/mod_reservoir.f90:362-395) -- q*1000 floored at 1e-6, TISR and precip
+ * floored at 0, total_precip_over_a_period(period) (src/mod_utilities.f90:1688-1729) then log(1 + p/precip_epsilon),
+ * SST floored at 272 K.  Once per upload. */
+int sml_condition_series(sml_engine *h, int period, double precip_epsilon);
 /* grid%mean / grid%std of every local region from the resident series (get_training_data, src/mod_reservoir.f90:413-470;
  * formulas: standardize_data_5d_logp_tisr src/mod_utilities.f90:1144-1193 two-pass population std, standardize_data_3d
  * :894-912 for precip, standardize_sst_data_3d :853-892 with its std > 0.2 gate -> sst_bool_input).  The series may be

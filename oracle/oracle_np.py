@@ -579,6 +579,32 @@ def gen_res_scale(vals, eigs, radius):
     return (vals / eigs) * radius
 
 
+def total_precip_over_a_period(precip, period):
+    """src/mod_utilities.f90:1688-1729; precip (..., T) hourly: out[t] = sum(copy[t-period : t]) (period+1 values, 1-based
+    inclusive), sum(copy[1 : t]) while t - period < 1"""
+    out = np.empty_like(precip)
+    T = precip.shape[-1]
+    for t in range(1, T + 1):
+        lo = 1 if t - period < 1 else t - period
+        acc = np.zeros(precip.shape[:-1])
+        for k in range(lo, t + 1):          # Fortran sum over the slice, first to last
+            acc = acc + precip[..., k - 1]
+        out[..., t - 1] = acc
+    return out
+
+
+def condition_raw_series(w4d_t, tisr_t, precip_t, sst_t, period, eps):
+    """get_training_data's conditioning (src/mod_reservoir.f90:362-395) on raw series (time last); returns copies"""
+    w4d = w4d_t.copy()
+    w4d[3] = w4d[3] * 1000.0
+    w4d[3][w4d[3] < 0.000001] = 0.000001
+    tisr = np.where(tisr_t < 0.0, 0.0, tisr_t)
+    p = np.where(precip_t < 0.0, 0.0, precip_t)
+    p = np.log(1 + total_precip_over_a_period(p, period) / eps)
+    sst = np.where(sst_t < 272.0, 272.0, sst_t)
+    return w4d, tisr, p, sst
+
+
 def conditioning_stats(w4d_t, logp_t, tisr_t, precip_t, sst_t, numregions, region, overlap):
     """grid%mean / grid%std of one region from its training window (get_training_data, src/mod_reservoir.f90:413-470).
     Inputs are the conditioned global series, time last: w4d_t (4,96,48,8,T), 2-D fields (96,48,T); precip_t / sst_t may

@@ -458,10 +458,54 @@ k_cond_stats(const double *__restrict__ Gs, long long g_len, int first, int stri
     }
 }
 
+// get_training_data's conditioning of the raw (hourly, physical-unit) series, in place on the resident copy
+// (src/mod_reservoir.f90:362-395):
+//   specific humidity: *1000 (g/kg), floored at 1e-6 (:365-368);   TISR: negative -> 0 (:373-375)
+//   precip: negative -> 0 (:380-382); total over the hybrid time step, total_precip_over_a_period
+//           (src/mod_utilities.f90:1688-1729: sum(copy(t-period : t)), i.e. period+1 hourly values, sum(copy(1:t)) while
+//           t - period < 1); then log(1 + p/precip_epsilon) (:387)
+//   SST: floored at 272 K (:390-394)
+// One thread per grid cell walks the time axis; the windowed precip sum runs from the last column backwards so that
+// the original values it needs are still in place.
+__global__ void k_condition_series(double *__restrict__ Gs, long long g_len, int ncols, int period, double eps,
+                                   long long off_w2d, long long off_precip, long long off_sst, long long off_tisr,
+                                   int do_precip, int do_sst)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g_len) return;
+    if (e < off_w2d) {
+        if ((e & 3) == 3)  // var index is the fastest one: q is variable 4
+            for (int t = 0; t < ncols; ++t) {
+                double v = Gs[(size_t)t * g_len + e] * 1000.0;
+                if (v < 0.000001) v = 0.000001;
+                Gs[(size_t)t * g_len + e] = v;
+            }
+    } else if (e >= off_tisr) {
+        for (int t = 0; t < ncols; ++t)
+            if (Gs[(size_t)t * g_len + e] < 0.0) Gs[(size_t)t * g_len + e] = 0.0;
+    } else if (e >= off_sst) {
+        if (do_sst)
+            for (int t = 0; t < ncols; ++t)
+                if (Gs[(size_t)t * g_len + e] < 272.0) Gs[(size_t)t * g_len + e] = 272.0;
+    } else if (e >= off_precip) {
+        if (do_precip) {
+            for (int t = 0; t < ncols; ++t)
+                if (Gs[(size_t)t * g_len + e] < 0.0) Gs[(size_t)t * g_len + e] = 0.0;
+            for (int t = ncols - 1; t >= 0; --t) {
+                const int t0 = (t - period < 0) ? 0 : t - period;   // 1-based: t-period < 1 -> 1..t, else t-period..t
+                double s = 0.0;
+                for (int k = t0; k <= t; ++k) s += Gs[(size_t)k * g_len + e];   // Fortran sum: first to last
+                Gs[(size_t)t * g_len + e] = log(1.0 + s / eps);
+            }
+        }
+    }
+}
+
 // global training series, kept across waves (sml_train_global_series / sml_train_global_release)
 struct TrainGlobal {
     double *d_G = nullptr, *d_F = nullptr;
     int ncols_total = 0;
+    bool conditioned = false;
 };
 
 inline void train_release(TrainState &t, TrainPool *pool = nullptr)

@@ -292,6 +292,26 @@ int sml_train_trim(sml_engine *h)
     return 0;
 }
 
+// get_training_data's conditioning (unit conversion, floors, precip accumulation + log transform) applied in place to the
+// resident RAW series; call once, before sml_conditioning_stats / sml_train_feed_global
+int sml_condition_series(sml_engine *h, int period, double precip_epsilon)
+{
+    if (!h) return -1;
+    TrainGlobal &TG = h->train_global;
+    if (!TG.d_G) FAIL(h, "sml_train_global_series has not been called");
+    if (TG.conditioned) FAIL(h, "the resident series has already been conditioned");
+    if (period < 1 || !(precip_epsilon > 0.0)) FAIL(h, "sml_condition_series: bad period / precip_epsilon");
+    CK(h, cudaSetDevice(h->p.device));
+    k_condition_series<<<(unsigned)((G_TOTAL + 255) / 256), 256, 0, h->stream>>>(TG.d_G, G_TOTAL, TG.ncols_total, period,
+                                                                                 precip_epsilon, G_W2D, G_PRECIP, G_SST, G_TISR,
+                                                                                 h->p.precip_bool, h->p.slab_ocean_model_bool);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    TG.conditioned = true;
+    return 0;
+}
+
 // mean/std of every local region from the resident series, window = columns first_col + stride*c, c < ncols.
 // mean / std: [nloc][L] with L = 32 + logp + tisr (+ precip) (+ sst), the slot order of grid%mean
 // (src/mod_reservoir.f90:414-436); sst_bool_input[nloc]: standardize_sst_data_3d's any_change (1 when there is no SST slot).

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "sml_train_global_series": ([C.c_void_p, _dp, _dp, C.c_int], C.c_int),
     "sml_train_feed_global": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_train_global_release": ([C.c_void_p], C.c_int),
+    "sml_condition_series": ([C.c_void_p, C.c_int, C.c_double], C.c_int),
     "sml_conditioning_stats": ([C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip], C.c_int),
     "sml_train_solve": ([C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, _ip], C.c_int),
     "sml_train_solver_stats": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
@@ -619,6 +620,10 @@ class Engine:
 
     def train_feed_global(self, first_col, stride, ncols, discard_cols):
         self._ck(self.lib.sml_train_feed_global(self.h, first_col, stride, ncols, discard_cols))
+
+    def condition_series(self, period=6, precip_epsilon=0.001):
+        """get_training_data's unit conversion, floors and precip accumulation + log transform, in place on the device"""
+        self._ck(self.lib.sml_condition_series(self.h, period, precip_epsilon))
 
     def conditioning_stats(self, first_col, stride, ncols):
         """-> (mean (nloc, L), std (nloc, L), sst_bool_input (nloc,)) of every local region from the resident series"""

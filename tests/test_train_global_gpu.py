@@ -118,3 +118,35 @@ def test_conditioning_stats_from_resident_series():
     assert not sst_in[0] and mean[0, 35] == 0.0 and std[0, 35] == 0.0 and sst_in[1]
     eng.train_global_release()
     eng.close()
+
+
+def test_condition_raw_series_on_device():
+    """unit conversion, floors, precip accumulation over the time step and log transform (get_training_data,
+    src/mod_reservoir.f90:362-395) applied in place to the resident raw series"""
+    from helpers import on
+    E = importlib.import_module("speedy-ml_b200.engine")
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=288)
+    lay = E.global_layout()
+    rng = np.random.default_rng(31)
+    T, period, eps = 30, 6, 0.001
+    w4d_t = rng.standard_normal((4, 96, 48, 8, T))
+    w4d_t[3] = 0.004 * rng.standard_normal((96, 48, 8, T))            # kg/kg, some negative
+    logp_t = 0.05 * rng.standard_normal((96, 48, T))
+    precip_t = np.where(rng.random((96, 48, T)) < 0.6, 0.0, 0.002 * rng.standard_normal((96, 48, T)))
+    sst_t = 280.0 + 10.0 * rng.standard_normal((96, 48, T))
+    tisr_t = 1.0e5 * rng.standard_normal((96, 48, T))
+    G = np.zeros((lay["g_total"], T), order="F")
+    for t in range(T):
+        G[:, t] = np.concatenate([a.ravel(order="F") for a in (w4d_t[..., t], logp_t[..., t], precip_t[..., t], sst_t[..., t], tisr_t[..., t])])
+    eng.train_global_series(G, np.zeros((lay["f_total"], T), order="F"))
+    eng.condition_series(period, eps)
+    with pytest.raises(E.EngineError):
+        eng.condition_series(period, eps)                              # once per upload
+    w4c, tisrc, pc, sstc = on.condition_raw_series(w4d_t, tisr_t, precip_t, sst_t, period, eps)
+    # read the conditioned series back through the statistics of a region whose halo we can slice: compare all slots
+    mean, std, _ = eng.conditioning_stats(0, 1, T)
+    for i, r in enumerate(eng.region_indices):
+        m, s, _ = on.conditioning_stats(w4c, logp_t, tisrc, pc, sstc, 1152, r, 1)
+        assert rel_inf(mean[i], m) < 1e-12 and rel_inf(std[i], s) < 1e-11
+    assert pc.min() >= 0.0 and w4c[3].min() >= 0.000001 and sstc.min() >= 272.0
+    eng.close()
