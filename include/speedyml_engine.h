@@ -269,6 +269,15 @@ int sml_train_feed(sml_engine *h, const double *td, const int64_t *td_off, const
 int sml_train_global_series(sml_engine *h, const double *G_series, const double *F_series, int ncols_total);
 int sml_train_feed_global(sml_engine *h, int first_col, int stride, int ncols, int discard_cols);
 int sml_train_global_release(sml_engine *h);
+/* multiplicative Gaussian input noise for sml_train_feed_global (gaussian_noise_1d_function / _precip,
+ * src/mod_utilities.f90:1387-1464; reservoir%noisemag = 0.2): u*(1 + noisemag*g), precip rows noised in linear space and
+ * transformed back; targets and the imperfect model stay noise-free as in the reference.  The N(0,1) draws come from a
+ * counter-based generator keyed by (seed, region, column, element) -- reproducible, but not the Fortran random_number
+ * stream.  noisemag = 0 (default) switches it off.  sml_train_noise_sample returns, for one region of the current wave,
+ * the clean / Gaussian / noised input vector [D] of a phase column (inspection hook used by the tests). */
+int sml_train_set_noise(sml_engine *h, double noisemag, unsigned long long seed, double precip_epsilon);
+int sml_train_noise_sample(sml_engine *h, int region, int first_col, int stride, int col, double *clean, double *gauss,
+                           double *noisy);
 /* when the uploaded series is RAW (hourly, physical units as read from the reanalysis): apply get_training_data's
  * conditioning in place on the device (src/mod_reservoir.f90:362-395) -- q*1000 floored at 1e-6, TISR and precip
  * floored at 0, total_precip_over_a_period(period) (src/mod_utilities.f90:1688-1729) then log(1 + p/precip_epsilon),

@@ -579,6 +579,24 @@ def gen_res_scale(vals, eigs, radius):
     return (vals / eigs) * radius
 
 
+def gaussian_noise_1d_function_precip(inputdata, gaussnoise, noisemag, precip_start, precip_end, mean_p, std_p, eps):
+    """src/mod_utilities.f90:1410-1464 with the N(0,1) draws passed in (1-based inclusive precip range; 0 if none):
+    noisy = x + g*noisemag*x everywhere except precip, which is un-standardised, taken back to linear space
+    (eps*(e**t - 1)), noised, made non-negative, log-transformed and standardised again."""
+    x = np.asarray(inputdata, dtype=np.float64)
+    g = np.asarray(gaussnoise, dtype=np.float64)
+    out = x + g * noisemag * x
+    if precip_start > 0:
+        sl = slice(precip_start - 1, precip_end)
+        t = x[sl] * std_p + mean_p
+        t = eps * (math.e ** t - 1)
+        t = t + g[sl] * noisemag * t
+        t = np.abs(t)
+        t = np.log(1 + t / eps)
+        out[sl] = (t - mean_p) / std_p
+    return out
+
+
 def total_precip_over_a_period(precip, period):
     """src/mod_utilities.f90:1688-1729; precip (..., T) hourly: out[t] = sum(copy[t-period : t]) (period+1 values, 1-based
     inclusive), sum(copy[1 : t]) while t - period < 1"""

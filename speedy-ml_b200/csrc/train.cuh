@@ -30,6 +30,8 @@ struct TrainRegionDev {
     double *linv;             // [ceil(N/128)][2][128*128]: inverse of every diagonal block of L, and its transpose
     double *dsave;            // [ld] diagonal of the regularised A (restored if the region falls back to LU)
     int *chol_info;           // 0: on the Cholesky path; > 0: non-positive pivot at that column; < 0: not eligible
+    int region;               // reservoir%assigned_region (keys the input-noise generator)
+    int precip_off, precip_len;  // rows of the input vector that hold precip (noised in linear space), -1 / 0 if none
 };
 
 // Device-resident global training series (sml_train_global_series): column t is the conditioned global state at time
@@ -42,7 +44,48 @@ struct GlobalSeries {
     const double *F = nullptr;   // [ncols_total][f_len]
     long long g_len = 0, f_len = 0;
     int first = 0, stride = 1;   // phase column c <-> global column first + stride * c
+    // multiplicative input noise of the training state generation (gaussian_noise_1d_function(_precip),
+    // src/mod_utilities.f90:1387-1464; reservoir%noisemag = 0.2, src/res_domain.f90:1607-1616); 0: off
+    double noisemag = 0.0, precip_eps = 0.001;
+    unsigned long long seed = 0;
 };
+
+// Counter-based standard normal: the draw for (seed, region, global column, input element) is a pure function of those
+// four numbers (splitmix64 finaliser twice, Box-Muller), so every row that reads input element c sees the same noise
+// and a run is reproducible.  This is the engine's generator; the reference's random_number stream cannot be reproduced.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double counter_gauss(unsigned long long seed, int region, int col, int c)
+{
+    const unsigned long long k = mix64(seed ^ ((unsigned long long)(unsigned)region << 42) ^ ((unsigned long long)(unsigned)col << 21) ^
+                                       (unsigned long long)(unsigned)c);
+    const unsigned long long a = mix64(k), b = mix64(k ^ 0xD1B54A32D192ED03ULL);
+    const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740993.0);   // (0, 1)
+    const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);           // [0, 1)
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// the input element the state update sees: standardised value, then the multiplicative noise -- precip in linear space
+__device__ __forceinline__ double noised_value(const GlobalSeries &gs, const RegionDev &R, int region, int precip_off,
+                                               int precip_len, int col, int c, double v, double g)
+{
+    const double nm = gs.noisemag;
+    if (c >= precip_off && c < precip_off + precip_len) {
+        const int ms = R.fb_ms[c];
+        double t = __dadd_rn(__dmul_rn(v, R.std[ms]), R.mean[ms]);
+        t = __dmul_rn(gs.precip_eps, exp(t) - 1.0);
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(g, nm), t));
+        t = fabs(t);
+        t = log(1.0 + t / gs.precip_eps);
+        return __ddiv_rn(__dsub_rn(t, R.mean[ms]), R.std[ms]);
+    }
+    return __dadd_rn(v, __dmul_rn(__dmul_rn(g, nm), v));
+}
 
 __device__ __forceinline__ double series_input(const GlobalSeries &gs, const RegionDev &R, int col, int c)
 {
@@ -50,6 +93,29 @@ __device__ __forceinline__ double series_input(const GlobalSeries &gs, const Reg
     const int ms = R.fb_ms[c];
     if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
     return v;
+}
+
+// input element c of phase column col as the state update of training sees it: tiled + standardised, then noised
+__device__ __forceinline__ double train_input(const GlobalSeries &gs, const TrainRegionDev &t, int col, int c)
+{
+    double v = series_input(gs, t.R, col, c);
+    if (gs.noisemag != 0.0) {
+        const double g = counter_gauss(gs.seed, t.region, gs.first + gs.stride * col, c);
+        v = noised_value(gs, t.R, t.region, t.precip_off, t.precip_len, col, c, v, g);
+    }
+    return v;
+}
+
+// inspection kernel for the tests: clean / gaussian / noised value of every input element of one region and column
+__global__ void k_train_noise_sample(const TrainRegionDev *__restrict__ T, int wave_index, int col, GlobalSeries gs,
+                                     double *__restrict__ clean, double *__restrict__ gauss, double *__restrict__ noisy)
+{
+    const TrainRegionDev &t = T[wave_index];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < t.R.D; c += gridDim.x * blockDim.x) {
+        clean[c] = series_input(gs, t.R, col, c);
+        gauss[c] = counter_gauss(gs.seed, t.region, gs.first + gs.stride * col, c);
+        noisy[c] = train_input(gs, t, col, c);
+    }
 }
 
 // one reservoir step for every region of the wave: reads input column in_col, writes the new state to the
@@ -76,11 +142,11 @@ __global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity,
     double tw;
     if (R.win_mode == 0) {
         const int wc = __ldg(R.wcol + row);
-        tw = __dmul_rn(__ldg(R.winc + row), gs.G ? series_input(gs, R, in_col, wc) : u[wc]);
+        tw = __dmul_rn(__ldg(R.winc + row), gs.G ? train_input(gs, t, in_col, wc) : u[wc]);
     } else {
         tw = 0.0;
         for (int i = 0; i < R.D; ++i)
-            tw = fma(R.win_dense[(size_t)i * n + row], gs.G ? series_input(gs, R, in_col, i) : u[i], tw);
+            tw = fma(R.win_dense[(size_t)i * n + row], gs.G ? train_input(gs, t, in_col, i) : u[i], tw);
     }
     const double xt = tanh(__dadd_rn(acc, tw));
     const double xv = __dadd_rn(__dmul_rn(1.0 - R.leak, xo[row]), __dmul_rn(R.leak, xt));
@@ -506,6 +572,8 @@ struct TrainGlobal {
     double *d_G = nullptr, *d_F = nullptr;
     int ncols_total = 0;
     bool conditioned = false;
+    double noisemag = 0.0, precip_eps = 0.001;   // sml_train_set_noise
+    unsigned long long seed = 0;
 };
 
 inline void train_release(TrainState &t, TrainPool *pool = nullptr)

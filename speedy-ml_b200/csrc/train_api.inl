@@ -74,6 +74,13 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         tr.region = regions[i];
         TrainRegionDev &d = tr.dev;
         d.R = K.regs[li].dev;
+        d.region = regions[i];
+        d.precip_off = -1;
+        d.precip_len = 0;
+        if (kind == SML_ATMO && K.regs[li].sizes.precip_off >= 0) {
+            d.precip_off = K.regs[li].sizes.precip_off;
+            d.precip_len = K.regs[li].sizes.logp_off > 0 ? K.regs[li].sizes.precip_off - K.regs[li].sizes.logp_off : 0;  // = ixy
+        }
         const int N = d.R.n + d.R.S;
         d.ld = (N + d.R.P + 15) / 16 * 16;
         T.ld_max = std::max(T.ld_max, d.ld);
@@ -292,6 +299,54 @@ int sml_train_trim(sml_engine *h)
     return 0;
 }
 
+// multiplicative Gaussian input noise of the state generation when feeding from the resident series
+// (gaussian_noise_1d_function / _precip, src/mod_utilities.f90:1387-1464): u*(1 + noisemag*g), precip noised in linear
+// space.  noisemag = 0 switches it off (parity runs).  The generator is counter-based (train.cuh), keyed by seed.
+int sml_train_set_noise(sml_engine *h, double noisemag, unsigned long long seed, double precip_epsilon)
+{
+    if (!h) return -1;
+    if (noisemag < 0.0 || !(precip_epsilon > 0.0)) FAIL(h, "sml_train_set_noise: bad arguments");
+    h->train_global.noisemag = noisemag;
+    h->train_global.seed = seed;
+    h->train_global.precip_eps = precip_epsilon;
+    return 0;
+}
+
+// what the state update would read for one region of the current wave at phase column col: the standardised input
+// vector, the N(0,1) draws and the noised vector (test / inspection hook)
+int sml_train_noise_sample(sml_engine *h, int region, int first_col, int stride, int col, double *clean, double *gauss,
+                           double *noisy)
+{
+    if (!h) return -1;
+    TrainState &T = h->train;
+    TrainGlobal &TG = h->train_global;
+    if (!T.active || !TG.d_G) FAIL(h, "sml_train_noise_sample needs an active wave and a resident series");
+    int wi = -1;
+    for (size_t i = 0; i < T.regs.size(); ++i)
+        if (T.regs[i].region == region) wi = (int)i;
+    if (wi < 0) FAIL(h, "region %d is not in the training wave", region);
+    if (first_col < 0 || stride < 1 || col < 0 || first_col + (long long)stride * col >= TG.ncols_total) FAIL(h, "column out of range");
+    CK(h, cudaSetDevice(h->p.device));
+    const int D = T.regs[wi].dev.R.D;
+    std::vector<TrainRegionDev> devs(T.regs.size());
+    for (size_t i = 0; i < T.regs.size(); ++i) devs[i] = T.regs[i].dev;
+    CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * devs.size(), cudaMemcpyHostToDevice, h->stream));
+    double *d = nullptr;
+    CK(h, cudaMalloc(&d, sizeof(double) * 3 * D));
+    GlobalSeries gs;
+    gs.G = TG.d_G; gs.F = TG.d_F; gs.g_len = G_TOTAL; gs.f_len = F_TOTAL; gs.first = first_col; gs.stride = stride;
+    gs.noisemag = TG.noisemag; gs.precip_eps = TG.precip_eps; gs.seed = TG.seed;
+    k_train_noise_sample<<<(D + 127) / 128, 128, 0, h->stream>>>(T.d_regs, wi, col, gs, d, d + D, d + 2 * D);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(clean, d, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(gauss, d + D, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(noisy, d + 2 * D, sizeof(double) * D, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    return 0;
+}
+
 // get_training_data's conditioning (unit conversion, floors, precip accumulation + log transform) applied in place to the
 // resident RAW series; call once, before sml_conditioning_stats / sml_train_feed_global
 int sml_condition_series(sml_engine *h, int period, double precip_epsilon)
@@ -397,6 +452,7 @@ int sml_train_feed_global(sml_engine *h, int first_col, int stride, int ncols, i
     gs.G = TG.d_G; gs.F = TG.d_F;
     gs.g_len = G_TOTAL; gs.f_len = F_TOTAL;
     gs.first = first_col; gs.stride = stride;
+    gs.noisemag = TG.noisemag; gs.precip_eps = TG.precip_eps; gs.seed = TG.seed;
     return train_run_phase(h, ncols, discard_cols, gs);
 }
 

@@ -104,6 +104,8 @@ _SIGNATURES = {
     "sml_train_global_series": ([C.c_void_p, _dp, _dp, C.c_int], C.c_int),
     "sml_train_feed_global": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_train_global_release": ([C.c_void_p], C.c_int),
+    "sml_train_set_noise": ([C.c_void_p, C.c_double, C.c_uint64, C.c_double], C.c_int),
+    "sml_train_noise_sample": ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp], C.c_int),
     "sml_condition_series": ([C.c_void_p, C.c_int, C.c_double], C.c_int),
     "sml_conditioning_stats": ([C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip], C.c_int),
     "sml_train_solve": ([C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, _ip], C.c_int),
@@ -620,6 +622,17 @@ class Engine:
 
     def train_feed_global(self, first_col, stride, ncols, discard_cols):
         self._ck(self.lib.sml_train_feed_global(self.h, first_col, stride, ncols, discard_cols))
+
+    def train_set_noise(self, noisemag, seed=0, precip_epsilon=0.001):
+        """input noise of sml_train_feed_global: u*(1 + noisemag*N(0,1)), precip in linear space; 0 = off"""
+        self._ck(self.lib.sml_train_set_noise(self.h, float(noisemag), int(seed), float(precip_epsilon)))
+
+    def train_noise_sample(self, region, first_col, stride, col):
+        """-> (clean, gauss, noisy) input vectors [D] of one region of the current wave at phase column col"""
+        D = self.dims[(self._train_kind, region)]["D"]
+        a, b, c = np.zeros(D), np.zeros(D), np.zeros(D)
+        self._ck(self.lib.sml_train_noise_sample(self.h, region, first_col, stride, col, _d(a), _d(b), _d(c)))
+        return a, b, c
 
     def condition_series(self, period=6, precip_epsilon=0.001):
         """get_training_data's unit conversion, floors and precip accumulation + log transform, in place on the device"""

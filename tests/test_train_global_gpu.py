@@ -150,3 +150,68 @@ def test_condition_raw_series_on_device():
         assert rel_inf(mean[i], m) < 1e-12 and rel_inf(std[i], s) < 1e-11
     assert pc.min() >= 0.0 and w4c[3].min() >= 0.000001 and sstc.min() >= 272.0
     eng.close()
+
+
+def test_device_input_noise_for_global_feed():
+    """u*(1 + noisemag*g) with precip noised in linear space (gaussian_noise_1d_function_precip,
+    src/mod_utilities.f90:1410-1464): the arithmetic is checked exactly against the NumPy restatement given the engine's
+    own N(0,1) draws; the draws are checked statistically and for reproducibility (counter-based generator)."""
+    from helpers import on
+    E = importlib.import_module("speedy-ml_b200.engine")
+    regions = [0, 1, 2, 3]
+    ws = {r: region_weights(1152, r, m=450, with_dense_win=False) for r in regions}
+    eng = E.Engine(number_of_regions=1152, irank=0, numprocs=288)
+    for r in regions:
+        w = ws[r]
+        eng.region_upload(r, w["rows"], w["cols"], w["vals"], None, w["mean"], w["std"], win_compact=w["winc"],
+                          win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"], S=w["S"], P=w["P"])
+    eng.finalize()
+    lay = E.global_layout()
+    F0 = initial_grids()
+    rng = np.random.default_rng(41)
+    T = 48
+    G = np.zeros((lay["g_total"], T), order="F")
+    for t in range(T):
+        w4d = F0["clim4d"] * (1.0 + 0.02 * rng.standard_normal(F0["clim4d"].shape))
+        G[:, t] = np.concatenate([w4d.ravel(order="F"), (F0["clim2d"] + 0.01 * rng.standard_normal((96, 48))).ravel(order="F"),
+                                  np.log1p(np.abs(rng.standard_normal(96 * 48))), np.maximum(F0["base_sst"], 272.0).ravel(order="F"),
+                                  np.abs(F0["tisr"]).ravel(order="F")])
+    Fz = np.asfortranarray(np.tile(G[:lay["f_total"], :1], (1, T)))
+    eng.train_global_series(G, Fz)
+    bs = 6
+    eng.train_begin(regions, bs)
+    eng.train_set_noise(0.2, seed=7, precip_epsilon=0.001)
+    draws = []
+    for r in regions:
+        ca = oc.Region(1152, r, sst_bool_input=ws[r]["sst_bool_input"])
+        for col in (0, 5, 17):
+            clean, g, noisy = eng.train_noise_sample(r, 1, 2, col)
+            clean2, g2, noisy2 = eng.train_noise_sample(r, 1, 2, col)
+            assert np.array_equal(g, g2) and np.array_equal(noisy, noisy2)          # reproducible
+            pi = ca.g.precip_mean_std_idx - 1
+            want = on.gaussian_noise_1d_function_precip(clean, g, 0.2, ca.g.precip_start, ca.g.precip_end,
+                                                        ws[r]["mean"][pi], ws[r]["std"][pi], 0.001)
+            assert rel_inf(noisy, want) < 1e-13
+            draws.append(g)
+    g_all = np.concatenate(draws)
+    assert len(np.unique(g_all)) == g_all.size                                   # no repeated draws across regions / columns
+    for r in regions:                                                            # more samples for the moments
+        for col in range(20):
+            draws.append(eng.train_noise_sample(r, 0, 1, col)[1])
+    g_all = np.concatenate(draws)
+    assert abs(g_all.mean()) < 0.02 and abs(g_all.var() - 1.0) < 0.03 and np.abs(g_all).max() < 6.5
+    # a noisy phase changes the Gram, reproducibly; noise off restores the clean one
+    eng.train_feed_global(1, 2, 20, 2)
+    noisy_gram = eng.train_gram_get(1)[0]
+    eng.train_end()
+    eng.train_begin(regions, bs)
+    eng.train_feed_global(1, 2, 20, 2)
+    assert np.array_equal(eng.train_gram_get(1)[0], noisy_gram)
+    eng.train_end()
+    eng.train_set_noise(0.0)
+    eng.train_begin(regions, bs)
+    eng.train_feed_global(1, 2, 20, 2)
+    clean_gram = eng.train_gram_get(1)[0]
+    eng.train_end()
+    assert rel_inf(noisy_gram, clean_gram) > 1e-4
+    eng.close()
