@@ -17,7 +17,7 @@ LIB = os.path.join(LIB_DIR, "libspeedyml_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-lcusolver", "-lcublas",
+    "-Xcompiler", "-fPIC", "-shared",
 ]
 
 
@@ -69,9 +69,8 @@ def build_host_driver(force: bool = False) -> str:
         return HOST_DRIVER
     build()
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cuda_lib = "/usr/local/cuda/lib64"
     cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-o", HOST_DRIVER, srcs[0], "-L" + LIB_DIR, "-lspeedyml_b200",
-           "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + cuda_lib, "-L" + cuda_lib]
+           "-Wl,-rpath,$ORIGIN"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

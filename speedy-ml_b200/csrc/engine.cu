@@ -15,6 +15,7 @@
 #include "resdomain.hpp"
 #include "train.cuh"
 #include "chol.cuh"
+#include "lu.cuh"
 #include "genres.cuh"
 #include "ncfile.hpp"
 
@@ -258,7 +259,6 @@ int sml_destroy(sml_engine *h)
     train_release(h->train);
     h->train_pool.drop_all();
     cudaFree(h->train_global.d_G); cudaFree(h->train_global.d_F);
-    if (h->train.solver) cusolverDnDestroy(h->train.solver);
     for (int k = 0; k < 2; ++k) free_kind(h->kinds[k]);
     cudaFree(h->d_G); cudaFree(h->d_F); cudaFree(h->d_gathered); cudaFree(h->d_base_sst); cudaFree(h->d_mask);
     cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);

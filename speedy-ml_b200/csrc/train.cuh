@@ -10,7 +10,6 @@
 #pragma once
 #include "kernels.cuh"
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 #include <map>
 #include <vector>
 
@@ -435,7 +434,6 @@ struct TrainState {
     int ld_max = 0, n_max = 0, ks = 1024;
     double *d_series_td = nullptr, *d_series_im = nullptr;
     size_t series_td_cap = 0, series_im_cap = 0;
-    cusolverDnHandle_t solver = nullptr;
     double gram_flops_useful = 0.0;   // N(N+1)K + 2PNK summed over feeds
     double gram_ms = 0.0;             // CUDA-event time of the Gram kernels
     double stategen_ms = 0.0;

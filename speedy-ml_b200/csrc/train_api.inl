@@ -10,39 +10,45 @@
 
 namespace {
 
-int solver_handle(sml_engine *h)
-{
-    if (!h->train.solver) {
-        if (cusolverDnCreate(&h->train.solver) != CUSOLVER_STATUS_SUCCESS) FAIL(h, "cusolverDnCreate failed");
-    }
-    if (cusolverDnSetStream(h->train.solver, h->stream) != CUSOLVER_STATUS_SUCCESS) FAIL(h, "cusolverDnSetStream failed");
-    return 0;
-}
-
-// LU with partial pivoting + solve, the dgesv the reference calls (src/mod_linalg.f90:145); A, B on device
+// LU with partial pivoting + solve, the dgesv the reference calls (src/mod_linalg.f90:145); A, B on device (lu.cuh)
 int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n, int nrhs, int *info_out)
 {
-    if (solver_handle(h)) return -1;
-    int lwork = 0;
-    if (cusolverDnDgetrf_bufferSize(h->train.solver, n, n, dA, lda, &lwork) != CUSOLVER_STATUS_SUCCESS)
-        FAIL(h, "cusolverDnDgetrf_bufferSize failed");
-    double *work = nullptr;
     int *ipiv = nullptr, *dinfo = nullptr;
-    CK(h, cudaMalloc(&work, sizeof(double) * (size_t)std::max(lwork, 1)));
     CK(h, cudaMalloc(&ipiv, sizeof(int) * (size_t)std::max(n, 1)));
     CK(h, cudaMalloc(&dinfo, sizeof(int)));
-    int info = 0;
-    cusolverStatus_t st = cusolverDnDgetrf(h->train.solver, n, n, dA, lda, work, ipiv, dinfo);
-    if (st == CUSOLVER_STATUS_SUCCESS) {
-        cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-        cudaStreamSynchronize(h->stream);
-        if (info == 0) {
-            st = cusolverDnDgetrs(h->train.solver, CUBLAS_OP_N, n, nrhs, dA, lda, ipiv, dB, ldb, dinfo);
-            cudaStreamSynchronize(h->stream);
+    CK(h, cudaMemsetAsync(dinfo, 0, sizeof(int), h->stream));
+    for (int j0 = 0; j0 < n; j0 += LU_NB) {
+        const int nb = std::min(LU_NB, n - j0);
+        k_lu_panel<<<1, 1024, 0, h->stream>>>(dA, lda, n, j0, nb, ipiv, dinfo);
+        if (j0 > 0) k_lu_laswp<<<(j0 + 127) / 128, 128, 0, h->stream>>>(dA, lda, 0, j0, ipiv, j0, nb);
+        const int rest = n - j0 - nb;
+        if (rest > 0) {
+            k_lu_laswp<<<(rest + 127) / 128, 128, 0, h->stream>>>(dA, lda, j0 + nb, n, ipiv, j0, nb);
+            k_lu_trsm<<<(rest + 127) / 128, 128, 0, h->stream>>>(dA, lda, n, j0, nb);
+            k_lu_gemm<<<dim3((rest + 63) / 64, (rest + 63) / 64), 256, 0, h->stream>>>(dA, lda, n, j0, nb);
         }
+        h->launches += rest > 0 ? 5 : 2;
     }
-    cudaFree(work); cudaFree(ipiv); cudaFree(dinfo);
-    if (st != CUSOLVER_STATUS_SUCCESS) FAIL(h, "cusolver getrf/getrs failed (status %d)", (int)st);
+    CK(h, cudaGetLastError());
+    int info = 0;
+    CK(h, cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (info == 0 && nrhs > 0) {
+        // dgetrs: P applied to B, then L, then U
+        for (int j0 = 0; j0 < n; j0 += LU_NB)
+            k_lu_laswp<<<(nrhs + 127) / 128, 128, 0, h->stream>>>(dB, ldb, 0, nrhs, ipiv, j0, std::min(LU_NB, n - j0));
+        const size_t smem = sizeof(double) * (size_t)n;
+        if (smem > 200 * 1024) {
+            cudaFree(ipiv); cudaFree(dinfo);
+            FAIL(h, "mldivide: n = %d exceeds the solve kernel's shared-memory vector", n);
+        }
+        CK(h, cudaFuncSetAttribute(k_lu_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_lu_solve<<<nrhs, 1024, smem, h->stream>>>(dA, lda, n, dB, ldb);
+        h->launches += (n + LU_NB - 1) / LU_NB + 1;
+        CK(h, cudaGetLastError());
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(ipiv); cudaFree(dinfo);
     *info_out = info;
     return 0;
 }
@@ -59,9 +65,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     if (T.active) FAIL(h, "sml_train_begin while a training wave is active (call sml_train_end)");
     if (nregions <= 0 || batch_size < 2) FAIL(h, "bad training wave (nregions %d, batch_size %d)", nregions, batch_size);
     KindState &K = h->kinds[kind];
-    cusolverDnHandle_t keep_solver = T.solver;
     T = TrainState{};
-    T.solver = keep_solver;
     T.kind = kind;
     T.batch_size = batch_size;
     if (const char *s = getenv("SML_TRAIN_SLAB")) T.ks = std::max(16, atoi(s) / 16 * 16);
@@ -629,9 +633,7 @@ int sml_train_end(sml_engine *h)
     if (!h) return -1;
     CK(h, cudaSetDevice(h->p.device));
     cudaStreamSynchronize(h->stream);
-    cusolverDnHandle_t keep = h->train.solver;
     train_release(h->train, &h->train_pool);  // the next wave reuses the blocks
-    h->train.solver = keep;
     return 0;
 }
 

@@ -10,7 +10,7 @@
 !> STATUS: source only.  The image this engine is developed in has no Fortran compiler (gcc lacks f951) and no
 !> MPI/MKL/NetCDF, so this file has never been compiled; the same C entry points are exercised from Python
 !> (speedy-ml_b200/engine.py) by tests/.  Build on a host with the reference toolchain:
-!>     mpif90 -c speedyml_gpu.f90 ; link imp.exe with -lspeedyml_b200 -lcudart -lcusolver
+!>     mpif90 -c speedyml_gpu.f90 ; link imp.exe with -lspeedyml_b200
 !>
 !> Execution model: the device holds every local region's weights and state.  predict() enqueues nothing per
 !> region; the first predict call of a hybrid step launches ONE batched kernel for all local regions, later
