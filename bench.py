@@ -243,6 +243,7 @@ def train_leg(E, torch, nreg=16, cols=2000, discard=40, batch=98):
     rng = np.random.default_rng(1)
     tds = [syn.ar1_series(ws[r]["D"], cols, rng) for r in regions]
     ims = [np.asfortranarray(rng.standard_normal((ws[r]["S"], cols))) for r in regions]
+    eng.train_set_overlap(False)               # serial schedule: the Gram kernel is timed alone
     eng.train_begin(regions, batch)
     eng.train_feed(tds, ims, discard)          # warm-up phase (also the second of two accumulated phases)
     st0 = eng.train_stats()
@@ -271,6 +272,7 @@ def train_leg(E, torch, nreg=16, cols=2000, discard=40, batch=98):
     return {"metric": "training Gram FP64 TFLOP/s", "value": tf, "unit": "TFLOP/s",
             "workload": f"ridge training, {nreg} regions x 1 phase x {cols} columns, m=6000 (N=5892..6292)",
             "flops_counted": "useful: N(N+1)K + 2PNK (symmetric half + Y*R^T)",
+            "schedule": "serial (sml_train_set_overlap(0)): the Gram kernel timed alone",
             "gram_ms": gram_ms, "stategen_ms": st["stategen_ms"] / 2, "solve_ms_per_region": st["solve_ms"] / nreg,
             "solve_info_max": int(max(info)),
             "roofline": {"bound": "tensor", "kernel": "k_syrk_dmma (FP64 DMMA)", "achieved": tf, "peak": dmma_peak,

@@ -300,6 +300,12 @@ int sml_train_solver_stats(sml_engine *h, int *by_cholesky);
 int sml_train_gram_get(sml_engine *h, int region, double *states_x_states_aug,
                        double *states_x_trainingdata_aug);
 int sml_train_end(sml_engine *h);
+/* scheduling of a wave's feeds: on = 1 (default; SML_TRAIN_OVERLAP=0 in the environment turns it off) double-buffers
+ * the state slab and runs the Gram of one slab on its own stream while the state generation -- the sequential part,
+ * reservoir_layer_chunking_hybrid's time loop -- fills the other, across phases too; sml_train_solve / _gram_get /
+ * _stats / _end wait for both.  on = 0 is the serial schedule (each kernel timed alone).  Same arithmetic in the same
+ * order either way: the accumulators are bit-identical.  Takes effect at the next sml_train_begin. */
+int sml_train_set_overlap(sml_engine *h, int on);
 /* sml_train_end keeps the wave's device blocks for the next sml_train_begin (allocating ~350 MB per region anew for
  * every wave costs more than the solve); sml_train_trim returns them to the allocator */
 int sml_train_trim(sml_engine *h);
@@ -307,6 +313,14 @@ int sml_train_trim(sml_engine *h);
  * the Gram kernels, the state generation and the solves of the current wave */
 int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms,
                     double *solve_ms);
+
+/* rolling_average_over_a_period_2d(grid, period) (src/mod_utilities.f90:1773-1815), the time smoothing
+ * get_training_data_from_atmo / get_prediction_data_from_atmo apply to the atmosphere rows of a slab-ocean reservoir's
+ * input series (src/mod_slab_ocean_reservoir.f90:398, :452).  In place on a caller-owned host array: grid(i,t) at
+ * grid[ld*t + i], i < nrows, t < t_len.  As written in the reference: sum(copy(i,1:t))/t while t-period < 1, else
+ * sum(copy(i,t-period:t))/period (period+1 values), the latter kept only when |sum| > 1e-7 (keep_small = 1; 0 gives the
+ * 3-D variant :1731-1771, which has no such test).  Windows are summed first to last. */
+int sml_rolling_average_2d(sml_engine *h, double *grid, int ld, int nrows, int t_len, int period, int keep_small);
 
 /* mldivide (src/mod_linalg.f90:109-151): solves A X = B in place of B; A(n,n) lda, B(n,nrhs) ldb.
  * returns dgesv's info (>0: singular, B is not the solution) */

@@ -611,6 +611,26 @@ def total_precip_over_a_period(precip, period):
     return out
 
 
+def rolling_average_over_a_period_2d(grid, period, keep_small=True):
+    """src/mod_utilities.f90:1773-1815 (keep_small=False: the 3-D variant :1731-1771 with the leading axes merged).
+    grid (rows, T); returns a copy.  As written: sum(copy(i,1:t))/t while t-period < 1, else sum(copy(i,t-period:t))/period
+    -- period+1 values divided by period -- kept only when |sum| > 1e-7.  (The worked example in the subroutine's own
+    comment assumes a window of `period` values and does not match the code; the code is what runs.)"""
+    out = np.array(grid, dtype=np.float64, copy=True)
+    T = grid.shape[-1]
+    for t in range(1, T + 1):
+        lo = 1 if t - period < 1 else t - period
+        acc = np.zeros(grid.shape[:-1])
+        for k in range(lo, t + 1):          # Fortran sum over the slice, first to last
+            acc = acc + grid[..., k - 1]
+        if t - period < 1:
+            out[..., t - 1] = acc / t
+        else:
+            avg = acc / period
+            out[..., t - 1] = np.where(np.abs(acc) > 0.0000001, avg, grid[..., t - 1]) if keep_small else avg
+    return out
+
+
 def condition_raw_series(w4d_t, tisr_t, precip_t, sst_t, period, eps):
     """get_training_data's conditioning (src/mod_reservoir.f90:362-395) on raw series (time last); returns copies"""
     w4d = w4d_t.copy()

@@ -66,7 +66,8 @@ struct KindState {
     double *d_fb = nullptr, *d_lm = nullptr, *d_out = nullptr, *d_partials = nullptr, *d_temp = nullptr;
     long long *d_fb_offs = nullptr;
     long long x_total = 0, fb_total = 0, lm_total = 0;
-    int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0, chunk_rows = 0;
+    int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0, chunk_rows = 0, D_max = 0;
+    int sx_threads = 0, sx_threads_split = 0;   // block size of k_update_sx chosen for this model at that row split
     int *d_order = nullptr;  // launch order of the items: largest first
     int *d_one_region = nullptr;  // region index for one region's synchronize
     int one_region = -1;
@@ -117,6 +118,9 @@ struct sml_engine {
     TrainState train;
     TrainGlobal train_global;
     TrainPool train_pool;
+    int num_sms = 148;
+    cudaStream_t train_gram_stream = nullptr;   // the Gram kernels' stream when state generation overlaps them
+    int train_overlap = -1;                     // -1: SML_TRAIN_OVERLAP decides (default on), 0 / 1: sml_train_set_overlap
     // overlapped step: the state update and the W_out[:, S:]*x~ partials of the NEXT
     // predict run while the host model works on this step's grids; the S model columns are added when its
     // forecast arrives
@@ -235,12 +239,16 @@ int sml_create(sml_engine **out, const sml_params *p)
         return -1;
     }
     h->stream = h->own_stream;
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess || h->num_sms < 1) h->num_sms = 148;
     h->local_ids = regions_of_rank(p->irank, p->numprocs, p->number_of_regions);
     for (size_t i = 0; i < h->local_ids.size(); ++i) h->local_index[h->local_ids[i]] = (int)i;
     for (int k = 0; k < 2; ++k) h->kinds[k].regs.resize(h->local_ids.size());
     *out = h;
     return 0;
 }
+
+// which update-only kernel sml_synchronize launches when SML_UPDATE_KERNEL is not set (profiles/round1_summary.md section 3)
+constexpr bool SML_UPDATE_SX_DEFAULT = true;
 
 static void free_kind(KindState &K)
 {
@@ -267,6 +275,7 @@ int sml_destroy(sml_engine *h)
     cudaFree(h->d_xchg); cudaFree(h->d_done); cudaFree(h->d_peer_err); cudaFree(h->d_vp); cudaFree(h->d_vml);
     cudaFreeHost(h->h_pin_G); cudaFreeHost(h->h_pin_F); cudaFreeHost(h->h_pin_tisr);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->train_gram_stream) cudaStreamDestroy(h->train_gram_stream);
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
     if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
     if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
@@ -648,6 +657,7 @@ static int finalize_kind(sml_engine *h, int kind)
         lo += (d.S + 31) / 32 * 32;
         S_max = std::max(S_max, d.S);
         K.n_max = std::max(K.n_max, d.n);
+        K.D_max = std::max(K.D_max, d.D);
         const int nch = (d.n + chunk_rows - 1) / chunk_rows;
         const int rows_per = (d.n + nch - 1) / nch;
         d.item0 = (int)K.items.size();
@@ -902,7 +912,7 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
     if (!do_readout) {
         // update-only step (synchronize): the dedicated latency-tolerant kernel, all regions or one region's slice
         // rows per thread: measured 0.200 / 0.206 / 0.151 ms for 1 / 2 / 4 at the bench config (profiles/round1_summary.md)
-        static const int rpt = getenv("SML_UPDATE_RPT") ? atoi(getenv("SML_UPDATE_RPT")) : 4;  // A/B switch
+        const int rpt = getenv("SML_UPDATE_RPT") ? atoi(getenv("SML_UPDATE_RPT")) : 4;  // A/B switch
         const int RPT = (rpt == 1 || rpt == 2 || rpt == 8) ? rpt : 4;
         const bool all = d_items == K.d_items && nitems == K.nitems;
         int nreg = (int)K.regs.size();
@@ -917,6 +927,53 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
             }
             list = K.d_one_region;
             nreg = 1;
+        }
+        // SML_UPDATE_KERNEL=sx: state vector staged in shared memory (k_update_sx); =global: gathers from L2 (k_update)
+        const char *uk = getenv("SML_UPDATE_KERNEL");
+        const int xs_cap = (K.n_max + 1) & ~1;
+        const size_t sx_smem = sizeof(double) * ((size_t)xs_cap + ((K.D_max + 1) & ~1)) + 16;
+        const bool use_sx = (uk ? std::string(uk) == "sx" : SML_UPDATE_SX_DEFAULT) && sx_smem <= 110 * 1024;
+        if (use_sx) {
+            // about one wave of 2 CTAs per SM when there are few regions (each split stages the whole x: L2 hits after
+            // the first); measured best: 1 split at 1152 regions, 2 at 144 (tools/ab_update.py)
+            int nsplit = getenv("SML_UPDATE_SPLIT") ? atoi(getenv("SML_UPDATE_SPLIT")) : (2 * h->num_sms + nreg / 2) / nreg;
+            nsplit = std::max(1, std::min(nsplit, 16));
+            const int sxr = getenv("SML_UPDATE_RPT") ? rpt : 2;   // rows per thread per sweep: 2 measured best (64 registers)
+            const int SXR = (sxr == 1 || sxr == 4) ? sxr : 2;
+            // block size: the multiple of 32 in [384, 512] that leaves the fewest idle row slots in the last sweep
+            int nt = getenv("SML_UPDATE_THREADS") ? atoi(getenv("SML_UPDATE_THREADS")) / 32 * 32 : 0;
+            if ((nt < 64 || nt > UPD_SX_THREADS) && K.sx_threads && K.sx_threads_split == nsplit * 8 + SXR) nt = K.sx_threads;
+            if (nt < 64 || nt > UPD_SX_THREADS) {
+                long long best = -1;
+                for (int t = UPD_SX_THREADS; t >= 384; t -= 32) {
+                    long long slots = 0;
+                    for (auto &r : K.regs) {
+                        if (!r.uploaded) continue;
+                        const int per = (((r.dev.n + nsplit - 1) / nsplit) + 31) & ~31;
+                        for (int r0 = 0; r0 < r.dev.n; r0 += per) {
+                            const int rows = std::min(per, r.dev.n - r0);
+                            slots += (long long)((rows + t * SXR - 1) / (t * SXR)) * t * SXR;
+                        }
+                    }
+                    if (best < 0 || slots < best) { best = slots; nt = t; }
+                }
+                K.sx_threads = nt;
+                K.sx_threads_split = nsplit * 8 + SXR;
+            }
+            dim3 grid((unsigned)nsplit, (unsigned)nreg);
+            if (SXR == 2) {
+                CK(h, cudaFuncSetAttribute(k_update_sx<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx_smem));
+                k_update_sx<2><<<grid, nt, sx_smem, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp, nsplit, xs_cap);
+            } else if (SXR == 1) {
+                CK(h, cudaFuncSetAttribute(k_update_sx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx_smem));
+                k_update_sx<1><<<grid, nt, sx_smem, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp, nsplit, xs_cap);
+            } else {
+                CK(h, cudaFuncSetAttribute(k_update_sx<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx_smem));
+                k_update_sx<4><<<grid, nt, sx_smem, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp, nsplit, xs_cap);
+            }
+            h->launches++;
+            CK(h, cudaGetLastError());
+            return 0;
         }
         dim3 grid((K.n_max + 256 * RPT - 1) / (256 * RPT), (unsigned)nreg);
         if (RPT == 1)

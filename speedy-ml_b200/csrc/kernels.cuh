@@ -360,6 +360,108 @@ k_update(const RegionDev *__restrict__ regs, const int *__restrict__ region_list
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_update_sx: the same update with the region's state vector (and input vector) staged in shared memory, so that
+// the x gathers of the SpMV -- random within the region's 46 KB vector -- are shared-memory reads instead of L2
+// round trips and only the coalesced ELL / W_in streams go to global memory.  One CTA per (region, row split), up to
+// 512 threads (the launch picks the multiple of 32 that divides the rows most evenly), 2 CTAs per SM, n*8 + D*8 bytes of
+// dynamic shared memory.  x arrives by one TMA bulk copy (the x pool is padded to 256 B per region) while every thread
+// already has its first ELL group in flight; RPT rows per thread per sweep.
+// Accumulation order per row is the entry order, as in update_row.   grid (nsplit, regions)
+// Measured (tools/ab_update.py, 1152 regions, m = 6000): 0.759 of the HBM roof at degree 6, 0.893 at degree 24,
+// against 0.722 / 0.778 for k_update<4>; 144 regions (one of 8 ranks): 0.638 against 0.461.
+// ---------------------------------------------------------------------------------------------
+constexpr int UPD_SX_THREADS = 512;
+template <int RPT>
+__global__ void __launch_bounds__(UPD_SX_THREADS, 2)
+k_update_sx(const RegionDev *__restrict__ regs, const int *__restrict__ region_list, const double *__restrict__ x_old,
+            double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
+            const double *__restrict__ temp_pool, int nsplit, int xs_cap)
+{
+    extern __shared__ __align__(128) double sx_smem[];
+    const int reg = region_list ? region_list[blockIdx.y] : (int)blockIdx.y;
+    const RegionDev &R = regs[reg];
+    const int n = R.n, D = R.D, W = R.ell_w;
+    const int per = (((n + nsplit - 1) / nsplit) + 31) & ~31;
+    const int r0 = blockIdx.x * per, r1 = min(n, r0 + per);
+    if (r0 >= n) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double *__restrict__ xo = x_old + R.x_off;
+    const double *__restrict__ u = u_pool + u_offs[reg] + (long long)u_t * D;
+    double *xs = sx_smem, *us = sx_smem + xs_cap;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(us + ((D + 1) & ~1));
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const uint32_t bytes = (uint32_t)((n + 1) & ~1) * 8u;   // inside the region's padded slot of the x pool
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(xs, xo, bytes, bar);
+    }
+    const bool compact = R.win_mode == 0;
+    if (compact)
+        for (int i = tid; i < D; i += nt) us[i] = u[i];
+    __syncthreads();   // the barrier is initialised and u is staged; x may still be in flight
+    const int *__restrict__ ecol = R.ell_col;
+    const double *__restrict__ eval = R.ell_val;
+    double *__restrict__ xn = x_new + R.x_off;
+    const double leak = R.leak;
+    bool x_ready = false;
+    for (int base = r0 + tid; base < r1; base += nt * RPT) {
+        int row[RPT];
+        bool ok[RPT];
+        double acc[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int r = base + i * nt;
+            ok[i] = r < r1;
+            row[i] = ok[i] ? r : base;
+            acc[i] = 0.0;
+        }
+        double wv[RPT];
+        int wc[RPT];
+        if (compact) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                wv[i] = __ldg(R.winc + row[i]);
+                wc[i] = __ldg(R.wcol + row[i]);
+            }
+        }
+        for (int s = 0; s < W; s += 3) {
+            int c[RPT][3];
+            double v[RPT][3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const bool in = s + j < W;
+                    c[i][j] = in ? __ldg(ecol + (size_t)(s + j) * n + row[i]) : 0;
+                    v[i][j] = in ? __ldg(eval + (size_t)(s + j) * n + row[i]) : 0.0;
+                }
+            if (!x_ready) {   // first group of the first sweep: its loads are in flight while x lands
+                mbar_wait(bar, 0);
+                x_ready = true;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int i = 0; i < RPT; ++i)
+                    if (s + j < W) acc[i] = fma(v[i][j], xs[c[i][j]], acc[i]);
+        }
+        if (!x_ready) {   // W == 0
+            mbar_wait(bar, 0);
+            x_ready = true;
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const double t = compact ? __dmul_rn(wv[i], us[wc[i]]) : temp_pool[R.x_off + row[i]];
+            const double xt = tanh(__dadd_rn(acc[i], t));
+            const double xv2 = __dadd_rn(__dmul_rn(1.0 - leak, xs[row[i]]), __dmul_rn(leak, xt));
+            if (ok[i]) xn[row[i]] = xv2;
+        }
+    }
+}
+
 // dense W_in fallback: temp = matmul(win, u) for regions with win_mode == 1 (src/mod_reservoir.f90:1445).
 // grid: (ceil(n_max/256), nregions)
 __global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__restrict__ u_pool,

@@ -6,12 +6,13 @@
 // pivot is not positive -- with dgesv's semantics: row interchanges (first maximal |a| in the column, like idamax),
 // unit-lower L and U stored over A, info = index of the first exactly-zero pivot (then B is not touched).
 // Right-looking, panel width 32:
-//   k_lu_panel  one CTA factorises the panel columns over all remaining rows (pivot search, swap inside the panel,
-//               scale, rank-1 updates inside the panel) and records ipiv;
+//   k_lu_panel  a cooperative launch factorises the panel: its rows are split over the CTAs (each block in shared
+//               memory), one grid barrier per column carries the pivot candidates and the two interchanged rows;
 //   k_lu_laswp  applies the panel's interchanges to the columns left and right of it;
 //   k_lu_trsm   U12 = L11^-1 A12 (unit lower, thread per column);
 //   k_lu_gemm   A22 -= L21 U12, 64 x 64 tiles, K = 32 (FP64 FMA; this is the fallback, the DMMA path is chol.cuh).
-// Solve: interchanges on B, forward substitution (unit L), back substitution (U), one CTA per right-hand side.
+// Solve: interchanges on B, forward substitution (unit L), back substitution (U), one CTA per right-hand side,
+// blocked by the panel width.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -19,23 +20,71 @@ namespace sml {
 
 constexpr int LU_NB = 32;
 
-__global__ void __launch_bounds__(1024, 1)
-k_lu_panel(double *__restrict__ A, int lda, int n, int j0, int nb, int *__restrict__ ipiv, int *__restrict__ info)
+// ---------------------------------------------------------------------------------------------
+// k_lu_panel: the panel's rows are split over the CTAs of one cooperative launch (all co-resident), each keeping its
+// row block of the panel in shared memory.  Per column ONE grid barrier: before it every CTA publishes its local pivot
+// candidate (|a|, row index) together with that row's nb panel values, and the owner of row j publishes row j; after
+// it every CTA derives the same pivot (largest |a|, first index on ties -- idamax), has both rows of the interchange,
+// and scales / rank-1-updates its own rows.  The exchange buffers are double-buffered by column parity (a fast CTA
+// may publish column j+1 while a slow one still reads column j).
+//   xch layout per parity: cand_val[G] | cand_row[G][LU_NB] | jrow[LU_NB] (doubles), cand_idx[G] (ints) behind them.
+// ---------------------------------------------------------------------------------------------
+constexpr int LU_PANEL_THREADS = 256;
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
 {
-    __shared__ double s_val[32];
-    __shared__ int s_idx[32];
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs of the (cooperative) launch; *ctr counts arrivals monotonically, target = G * (barriers passed + 1)
+__device__ __forceinline__ void lu_grid_barrier(unsigned *ctr, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_gpu_u32(ctr) < target) {
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LU_PANEL_THREADS, 1)
+k_lu_panel(double *__restrict__ A, int lda, int n, int j0, int nb, int rows_per, int *__restrict__ ipiv, int *__restrict__ info,
+           double *__restrict__ xch, unsigned *__restrict__ ctr, unsigned ctr_base)
+{
+    extern __shared__ double pan[];           // [nb][rows_per + 1]: this CTA's rows of the panel, column-major
+    __shared__ double s_val[LU_PANEL_THREADS / 32];
+    __shared__ int s_idx[LU_PANEL_THREADS / 32];
+    __shared__ double s_prow[LU_NB], s_jrow[LU_NB];
     __shared__ int s_piv;
-    __shared__ double s_pivval;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ldp = rows_per + 1;
+    const int g0 = j0 + cta * rows_per;                      // first global row of this CTA
+    const int nr = max(0, min(rows_per, n - g0));            // rows held
+    for (int e = tid; e < nr * nb; e += LU_PANEL_THREADS) {
+        const int c = e / nr, i = e % nr;
+        pan[c * ldp + i] = A[(size_t)lda * (j0 + c) + g0 + i];
+    }
+    __syncthreads();
+    const size_t xstride = (size_t)G + (size_t)G * LU_NB + LU_NB + (G + 1) / 2;   // doubles per parity
     for (int jj = 0; jj < nb; ++jj) {
         const int j = j0 + jj;
-        double *col = A + (size_t)lda * j;
-        // pivot: first index of the largest |a| in rows j..n-1
+        double *xb = xch + (size_t)(jj & 1) * xstride;
+        double *cand_val = xb, *cand_row = xb + G, *jrow = cand_row + (size_t)G * LU_NB;
+        int *cand_idx = reinterpret_cast<int *>(jrow + LU_NB);
+        // ---- local candidate over rows >= j
         double best = -1.0;
         int bi = n;
-        for (int i = j + tid; i < n; i += nt) {
+        const double *col = pan + jj * ldp;
+        for (int i = tid; i < nr; i += LU_PANEL_THREADS) {
+            const int gi = g0 + i;
+            if (gi < j) continue;
             const double v = fabs(col[i]);
-            if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+            if (v > best || (v == best && gi < bi)) { best = v; bi = gi; }
         }
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_down_sync(0xffffffffu, best, o);
@@ -45,46 +94,86 @@ k_lu_panel(double *__restrict__ A, int lda, int n, int j0, int nb, int *__restri
         if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
         __syncthreads();
         if (warp == 0) {
-            best = (lane < nt / 32) ? s_val[lane] : -1.0;
-            bi = (lane < nt / 32) ? s_idx[lane] : n;
+            best = (lane < LU_PANEL_THREADS / 32) ? s_val[lane] : -1.0;
+            bi = (lane < LU_PANEL_THREADS / 32) ? s_idx[lane] : n;
             for (int o = 16; o > 0; o >>= 1) {
                 const double ov = __shfl_down_sync(0xffffffffu, best, o);
                 const int oi = __shfl_down_sync(0xffffffffu, bi, o);
                 if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
             }
             if (lane == 0) {
-                if (bi >= n) bi = j;   // a column of NaNs: keep the diagonal (the NaNs propagate, as in LAPACK)
+                cand_val[cta] = best;
+                cand_idx[cta] = bi;
                 s_piv = bi;
-                s_pivval = col[bi];
-                ipiv[j] = bi;
-                if (col[bi] == 0.0 && *info == 0) *info = j + 1;   // exactly singular: U(j,j) = 0 (dgetf2)
             }
+        }
+        __syncthreads();
+        {
+            const int lb = s_piv;   // local best row (n if this CTA has no row >= j)
+            if (tid < nb && lb < n) cand_row[(size_t)cta * LU_NB + tid] = pan[tid * ldp + (lb - g0)];
+            if (tid < nb && j >= g0 && j < g0 + nr) jrow[tid] = pan[tid * ldp + (j - g0)];
+        }
+        lu_grid_barrier(ctr, ctr_base + (unsigned)G * (unsigned)(jj + 1));
+        // ---- global pivot, identical in every CTA
+        if (warp == 0) {
+            best = -1.0;
+            bi = n;
+            int bc = 0;
+            for (int c = lane; c < G; c += 32) {
+                const double v = __ldcg(cand_val + c);   // exchange buffers: L2 reads, never a stale L1 line
+                const int ci = __ldcg(cand_idx + c);
+                if (v > best || (v == best && ci < bi)) { best = v; bi = ci; bc = c; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                const int oc = __shfl_down_sync(0xffffffffu, bc, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; bc = oc; }
+            }
+            bi = __shfl_sync(0xffffffffu, bi, 0);
+            bc = __shfl_sync(0xffffffffu, bc, 0);
+            if (bi >= n) {   // a column of NaNs: keep the diagonal (the NaNs propagate, as in LAPACK)
+                bi = j;
+                bc = (j - j0) / rows_per;
+            }
+            if (lane < nb) {
+                s_prow[lane] = (bi == j) ? __ldcg(jrow + lane) : __ldcg(cand_row + (size_t)bc * LU_NB + lane);
+                s_jrow[lane] = __ldcg(jrow + lane);
+            }
+            if (lane == 0) s_piv = bi;
         }
         __syncthreads();
         const int p = s_piv;
-        const double piv = s_pivval;
-        // interchange inside the panel
+        const double piv = s_prow[jj];
+        if (cta == 0 && tid == 0) {
+            ipiv[j] = p;
+            if (piv == 0.0 && *info == 0) *info = j + 1;   // exactly singular: U(j,j) = 0 (dgetf2)
+        }
+        // ---- interchange inside the panel (rows j and p), then scale and rank-1 update of the local rows
         if (p != j && tid < nb) {
-            double *c = A + (size_t)lda * (j0 + tid);
-            const double t = c[j];
-            c[j] = c[p];
-            c[p] = t;
+            if (j >= g0 && j < g0 + nr) pan[tid * ldp + (j - g0)] = s_prow[tid];
+            if (p >= g0 && p < g0 + nr) pan[tid * ldp + (p - g0)] = s_jrow[tid];
         }
         __syncthreads();
+        const int i_lo = max(0, j + 1 - g0);   // local rows strictly below the diagonal
         if (piv != 0.0) {
-            for (int i = j + 1 + tid; i < n; i += nt) col[i] = col[i] / piv;
+            double *cj = pan + jj * ldp;
+            for (int i = i_lo + tid; i < nr; i += LU_PANEL_THREADS) cj[i] = cj[i] / piv;
         }
         __syncthreads();
-        // rank-1 update of the remaining panel columns
-        const int rem = nb - jj - 1;
-        if (rem > 0) {
-            const int rows = n - j - 1;
-            for (long long e = tid; e < (long long)rows * rem; e += nt) {
-                const int i = j + 1 + (int)(e % rows), c = j + 1 + (int)(e / rows);
-                A[(size_t)lda * c + i] -= col[i] * A[(size_t)lda * c + j];
+        const int rem = nb - jj - 1, rows = nr - i_lo;
+        if (rem > 0 && rows > 0) {
+            const double *cj = pan + jj * ldp;
+            for (int e = tid; e < rows * rem; e += LU_PANEL_THREADS) {
+                const int i = i_lo + e % rows, c = jj + 1 + e / rows;
+                pan[c * ldp + i] -= cj[i] * s_prow[c];
             }
         }
         __syncthreads();
+    }
+    for (int e = tid; e < nr * nb; e += LU_PANEL_THREADS) {
+        const int c = e / nr, i = e % nr;
+        A[(size_t)lda * (j0 + c) + g0 + i] = pan[c * ldp + i];
     }
 }
 
@@ -163,27 +252,62 @@ k_lu_gemm(double *__restrict__ A, int lda, int n, int j0, int nb)
             if (r0 + ti + i < n && c0 + tc + c < n) A[(size_t)lda * (c0 + tc + c) + r0 + ti + i] -= acc[i][c];
 }
 
-// L y = b (unit lower) then U x = y for one right-hand side per CTA; x lives in shared memory
+// L y = b (unit lower) then U x = y for one right-hand side per CTA; x lives in shared memory.  Blocked by LU_NB
+// columns: the diagonal block is solved by one warp from a shared-memory copy, then all threads apply the block's LU_NB
+// columns to the rest of x -- two block barriers per LU_NB columns instead of one per column.  Each x(i) receives its
+// updates in the order of the column-by-column substitution (j ascending for L, descending for U).
 __global__ void __launch_bounds__(1024, 1)
 k_lu_solve(const double *__restrict__ A, int lda, int n, double *__restrict__ B, int ldb)
 {
     extern __shared__ double xs[];
+    __shared__ double blk[LU_NB][LU_NB + 1];   // blk[i][k] = A(jb + i, jb + k)
     double *b = B + (size_t)ldb * blockIdx.x;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += nt) xs[i] = b[i];
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        const double xj = xs[j];
-        const double *col = A + (size_t)lda * j;
-        for (int i = j + 1 + tid; i < n; i += nt) xs[i] = fma(-col[i], xj, xs[i]);
+    // ---- forward: unit lower triangle
+    for (int jb = 0; jb < n; jb += LU_NB) {
+        const int nb = min(LU_NB, n - jb);
+        for (int e = tid; e < nb * nb; e += nt) blk[e % nb][e / nb] = A[(size_t)lda * (jb + e / nb) + jb + e % nb];
+        __syncthreads();
+        if (warp == 0) {
+            double x = (lane < nb) ? xs[jb + lane] : 0.0;
+            for (int k = 0; k < nb; ++k) {
+                const double xk = __shfl_sync(0xffffffffu, x, k);
+                if (lane > k && lane < nb) x = fma(-blk[lane][k], xk, x);
+            }
+            if (lane < nb) xs[jb + lane] = x;
+        }
+        __syncthreads();
+        for (int i = jb + nb + tid; i < n; i += nt) {
+            double acc = xs[i];
+            const double *row = A + (size_t)lda * jb + i;
+            for (int k = 0; k < nb; ++k) acc = fma(-row[(size_t)lda * k], xs[jb + k], acc);
+            xs[i] = acc;
+        }
         __syncthreads();
     }
-    for (int j = n - 1; j >= 0; --j) {
-        const double *col = A + (size_t)lda * j;
-        if (tid == 0) xs[j] = xs[j] / col[j];
+    // ---- backward: upper triangle with its diagonal
+    for (int jb = ((n - 1) / LU_NB) * LU_NB; jb >= 0; jb -= LU_NB) {
+        const int nb = min(LU_NB, n - jb);
+        for (int e = tid; e < nb * nb; e += nt) blk[e % nb][e / nb] = A[(size_t)lda * (jb + e / nb) + jb + e % nb];
         __syncthreads();
-        const double xj = xs[j];
-        for (int i = tid; i < j; i += nt) xs[i] = fma(-col[i], xj, xs[i]);
+        if (warp == 0) {
+            double x = (lane < nb) ? xs[jb + lane] : 0.0;
+            for (int k = nb - 1; k >= 0; --k) {
+                if (lane == k) x = x / blk[k][k];
+                const double xk = __shfl_sync(0xffffffffu, x, k);
+                if (lane < k) x = fma(-blk[lane][k], xk, x);
+            }
+            if (lane < nb) xs[jb + lane] = x;
+        }
+        __syncthreads();
+        for (int i = tid; i < jb; i += nt) {
+            double acc = xs[i];
+            const double *row = A + (size_t)lda * jb + i;
+            for (int k = nb - 1; k >= 0; --k) acc = fma(-row[(size_t)lda * k], xs[jb + k], acc);
+            xs[i] = acc;
+        }
         __syncthreads();
     }
     for (int i = tid; i < n; i += nt) b[i] = xs[i];

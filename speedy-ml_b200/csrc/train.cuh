@@ -17,7 +17,7 @@ namespace sml {
 
 struct TrainRegionDev {
     RegionDev R;              // the reservoir's weights (ELL adjacency, W_in, ...)
-    double *slab;             // [ld][KS] column-major
+    double *slab;             // [ld][KS] column-major ([ld][2*KS], two buffers, in overlap mode)
     double *gram;             // [ld][ld] column-major, lower triangle accumulated
     double *xa, *xb;          // training state ping-pong [n]
     const double *td;         // [D][ncols] this phase's (pre-noised) input series
@@ -165,13 +165,15 @@ __global__ void k_train_store_state(const TrainRegionDev *__restrict__ T, int pa
 
 // imperfect-model rows and target rows of slab columns [0, ncols): series column = first_series_col + c.
 // chunking_matmul :1668 (imperfect), tile_full_input_to_target_data2d src/res_domain.f90:602-651 (target).
-// Columns [ncols, kpad) are zeroed entirely (K padding of the tensor-core kernel).  grid (kpad, nwave)
-__global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_series_col, int ncols, int kpad, GlobalSeries gs)
+// Columns [ncols, kpad) are zeroed entirely (K padding of the tensor-core kernel).  col_base selects the slab
+// buffer (0 or ks: the slab is double-buffered when state generation overlaps the Gram).  grid (kpad, nwave)
+__global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_series_col, int ncols, int kpad, int col_base,
+                             GlobalSeries gs)
 {
     const TrainRegionDev &t = T[blockIdx.y];
     const RegionDev &R = t.R;
     const int c = blockIdx.x;
-    double *col = t.slab + (size_t)t.ld * c;
+    double *col = t.slab + (size_t)t.ld * (col_base + c);
     const int N = R.S + R.n;
     if (c >= ncols) {
         for (int i = threadIdx.x; i < t.ld; i += blockDim.x) col[i] = 0.0;
@@ -226,7 +228,7 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
 // issue bubbles).  Launch with (WM*WN + 1) * 32 threads.
 template <int WM, int WN>
 __global__ void __launch_bounds__((WM * WN + 1) * 32, 1)
-k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles, int kpad)
+k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles, int kpad, int col_base)
 {
     constexpr int NCW = WM * WN;               // consumer warps
     constexpr int TR = SY_BM / WM, TC = SY_BM / WN;   // warp sub-tile
@@ -265,7 +267,7 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
                 mbar_expect_tx(&full[s], bytes);
                 double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
                 double *sB = sA + SY_BK * SY_LDS;
-                const double *src = t.slab + (size_t)ld * (kc * SY_BK);
+                const double *src = t.slab + (size_t)ld * (col_base + kc * SY_BK);
                 for (int kk = 0; kk < SY_BK; ++kk) {
                     tma_load_1d(sA + kk * SY_LDS, src + (size_t)ld * kk + i0, rowsA * 8u, &full[s]);
                     if (!diag) tma_load_1d(sB + kk * SY_LDS, src + (size_t)ld * kk + j0, rowsB * 8u, &full[s]);
@@ -439,6 +441,13 @@ struct TrainState {
     double stategen_ms = 0.0;
     double solve_ms = 0.0;
     int solved_by_cholesky = 0;
+    // overlap mode: the Gram of slab buffer b runs on its own stream while the state generation fills buffer b^1
+    bool overlap = false;
+    unsigned slab_seq = 0;                    // slabs produced so far in this wave; buffer = slab_seq & 1
+    cudaEvent_t ev_gram[2] = {nullptr, nullptr};   // end of the last Gram that read buffer b (owned by spans)
+    struct Span { cudaEvent_t a, b; int what; };   // what: 0 state generation, 1 Gram; resolved at the next sync point
+    std::vector<Span> spans;
+    std::vector<TrainRegionDev> uploaded;     // what d_regs holds (re-uploaded only when it changes)
 };
 
 // Per-region standardisation constants from the resident global series (get_training_data, src/mod_reservoir.f90:
@@ -565,6 +574,29 @@ __global__ void k_condition_series(double *__restrict__ Gs, long long g_len, int
     }
 }
 
+// rolling_average_over_a_period_2d (src/mod_utilities.f90:1773-1815), which get_training_data_from_atmo applies to the
+// atmosphere rows of every slab-ocean reservoir's training series (src/mod_slab_ocean_reservoir.f90:398, :452):
+//   t - period < 1 (1-based):  out(i,t) = sum(copy(i,1:t)) / t
+//   else                    :  out(i,t) = sum(copy(i,t-period:t)) / period   -- period+1 values over period, as written --
+//                              kept only if |sum| > 1e-7 (keep_small: the 2-D variant; the 3-D variant :1731 has no test)
+// Every window is summed first to last like the Fortran intrinsic (no sliding update: that would change the rounding).
+// src, dst: [t_len][nrows] column-major copies (row fastest).   grid (t_len, ceil(nrows/128))
+__global__ void k_rolling_average(const double *__restrict__ src, double *__restrict__ dst, int nrows, int t_len, int period,
+                                  int keep_small)
+{
+    const int t = blockIdx.x, i = blockIdx.y * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const bool head = (t + 1) - period < 1;
+    const int lo = head ? 0 : t - period;
+    double s = 0.0;
+    for (int k = lo; k <= t; ++k) s = __dadd_rn(s, src[(size_t)nrows * k + i]);
+    double out;
+    if (head) out = s / (double)(t + 1);
+    else if (keep_small && !(fabs(s) > 0.0000001)) out = src[(size_t)nrows * t + i];
+    else out = s / (double)period;
+    dst[(size_t)nrows * t + i] = out;
+}
+
 // global training series, kept across waves (sml_train_global_series / sml_train_global_release)
 struct TrainGlobal {
     double *d_G = nullptr, *d_F = nullptr;
@@ -582,6 +614,11 @@ inline void train_release(TrainState &t, TrainPool *pool = nullptr)
             else cudaFree(a.first);
         }
     t.regs.clear();
+    for (auto &sp : t.spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    t.spans.clear();
+    t.ev_gram[0] = t.ev_gram[1] = nullptr;
+    t.uploaded.clear();
+    t.slab_seq = 0;
     cudaFree(t.d_regs); t.d_regs = nullptr;
     cudaFree(t.d_tiles); t.d_tiles = nullptr;
     cudaFree(t.d_series_td); t.d_series_td = nullptr; t.series_td_cap = 0;

@@ -14,12 +14,40 @@ namespace {
 int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n, int nrhs, int *info_out)
 {
     int *ipiv = nullptr, *dinfo = nullptr;
+    unsigned *ctr = nullptr;
+    double *xch = nullptr;
+    // CTAs of the cooperative panel launch: one per SM at most (SML_LU_GMAX lowers it: test hook for the many-rows-per-CTA path)
+    const int Gmax = std::max(1, getenv("SML_LU_GMAX") ? std::min(atoi(getenv("SML_LU_GMAX")), h->num_sms) : h->num_sms);
+    const size_t xstride = (size_t)Gmax + (size_t)Gmax * LU_NB + LU_NB + (Gmax + 1) / 2;
     CK(h, cudaMalloc(&ipiv, sizeof(int) * (size_t)std::max(n, 1)));
-    CK(h, cudaMalloc(&dinfo, sizeof(int)));
-    CK(h, cudaMemsetAsync(dinfo, 0, sizeof(int), h->stream));
+    CK(h, cudaMalloc(&dinfo, 2 * sizeof(int)));
+    CK(h, cudaMalloc(&xch, sizeof(double) * 2 * xstride));
+    CK(h, cudaMemsetAsync(dinfo, 0, 2 * sizeof(int), h->stream));
+    ctr = reinterpret_cast<unsigned *>(dinfo + 1);
+    auto cleanup = [&]() { cudaFree(ipiv); cudaFree(dinfo); cudaFree(xch); };
+    // SML_LU_TIMING=1: CUDA-event split of the factorisation (panel / interchanges + trsm + gemm) and the solve on stderr
+    const bool timing = getenv("SML_LU_TIMING") && atoi(getenv("SML_LU_TIMING")) != 0;
+    float t_panel = 0.f, t_trail = 0.f, t_solve = 0.f;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing) for (auto &e : ev) cudaEventCreate(&e);
+    unsigned ctr_base = 0;
     for (int j0 = 0; j0 < n; j0 += LU_NB) {
         const int nb = std::min(LU_NB, n - j0);
-        k_lu_panel<<<1, 1024, 0, h->stream>>>(dA, lda, n, j0, nb, ipiv, dinfo);
+        const int rows = n - j0;
+        int rows_per = std::max(64, (rows + Gmax - 1) / Gmax);
+        int G = (rows + rows_per - 1) / rows_per;
+        const size_t smem = sizeof(double) * (size_t)nb * (rows_per + 1);
+        if (smem > 200 * 1024) { cleanup(); FAIL(h, "mldivide: n = %d is too large for the panel kernel", n); }
+        if (smem > 48 * 1024) CK(h, cudaFuncSetAttribute(k_lu_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (timing) cudaEventRecord(ev[0], h->stream);
+        {
+            double *A_ = dA; int lda_ = lda, n_ = n, j0_ = j0, nb_ = nb, rp_ = rows_per;
+            void *args[] = {&A_, &lda_, &n_, &j0_, &nb_, &rp_, &ipiv, &dinfo, &xch, &ctr, &ctr_base};
+            cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_lu_panel, dim3(G), dim3(LU_PANEL_THREADS), args, smem, h->stream);
+            if (e != cudaSuccess) { cleanup(); FAIL(h, "mldivide: cooperative panel launch failed: %s", cudaGetErrorString(e)); }
+        }
+        ctr_base += (unsigned)G * (unsigned)nb;
+        if (timing) cudaEventRecord(ev[1], h->stream);
         if (j0 > 0) k_lu_laswp<<<(j0 + 127) / 128, 128, 0, h->stream>>>(dA, lda, 0, j0, ipiv, j0, nb);
         const int rest = n - j0 - nb;
         if (rest > 0) {
@@ -28,27 +56,43 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
             k_lu_gemm<<<dim3((rest + 63) / 64, (rest + 63) / 64), 256, 0, h->stream>>>(dA, lda, n, j0, nb);
         }
         h->launches += rest > 0 ? 5 : 2;
+        if (timing) {
+            cudaEventRecord(ev[2], h->stream);
+            cudaEventSynchronize(ev[2]);
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, ev[0], ev[1]);
+            cudaEventElapsedTime(&b, ev[1], ev[2]);
+            t_panel += a;
+            t_trail += b;
+        }
     }
-    CK(h, cudaGetLastError());
+    if (cudaGetLastError() != cudaSuccess) { cleanup(); FAIL(h, "mldivide: factorisation launch failed"); }
     int info = 0;
     CK(h, cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (info == 0 && nrhs > 0) {
         // dgetrs: P applied to B, then L, then U
+        if (timing) cudaEventRecord(ev[0], h->stream);
         for (int j0 = 0; j0 < n; j0 += LU_NB)
             k_lu_laswp<<<(nrhs + 127) / 128, 128, 0, h->stream>>>(dB, ldb, 0, nrhs, ipiv, j0, std::min(LU_NB, n - j0));
         const size_t smem = sizeof(double) * (size_t)n;
         if (smem > 200 * 1024) {
-            cudaFree(ipiv); cudaFree(dinfo);
+            cleanup();
             FAIL(h, "mldivide: n = %d exceeds the solve kernel's shared-memory vector", n);
         }
         CK(h, cudaFuncSetAttribute(k_lu_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_lu_solve<<<nrhs, 1024, smem, h->stream>>>(dA, lda, n, dB, ldb);
         h->launches += (n + LU_NB - 1) / LU_NB + 1;
+        if (timing) cudaEventRecord(ev[1], h->stream);
         CK(h, cudaGetLastError());
         CK(h, cudaStreamSynchronize(h->stream));
+        if (timing) cudaEventElapsedTime(&t_solve, ev[0], ev[1]);
     }
-    cudaFree(ipiv); cudaFree(dinfo);
+    if (timing) {
+        fprintf(stderr, "[sml lu] n=%d nrhs=%d panel %.3f ms, interchanges+trsm+gemm %.3f ms, solve %.3f ms\n", n, nrhs, t_panel, t_trail, t_solve);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    cleanup();
     *info_out = info;
     return 0;
 }
@@ -69,6 +113,19 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     T.kind = kind;
     T.batch_size = batch_size;
     if (const char *s = getenv("SML_TRAIN_SLAB")) T.ks = std::max(16, atoi(s) / 16 * 16);
+    {
+        int ov = h->train_overlap;
+        if (ov < 0) {
+            const char *e = getenv("SML_TRAIN_OVERLAP");
+            ov = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        T.overlap = ov != 0;
+        if (T.overlap && !h->train_gram_stream) {
+            int lo = 0, hi = 0;   // lowest priority: the small state-generation launches must not queue behind Gram CTAs
+            CK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(h, cudaStreamCreateWithPriority(&h->train_gram_stream, cudaStreamNonBlocking, lo));
+        }
+    }
     std::vector<TrainRegionDev> devs;
     for (int i = 0; i < nregions; ++i) {
         int li;
@@ -112,7 +169,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         bool bad = false;
         bad = bad || alloc((size_t)d.ld * d.ld * 8, &p); d.gram = (double *)p;
         if (!bad) cudaMemsetAsync(d.gram, 0, (size_t)d.ld * d.ld * 8, h->stream);
-        bad = bad || alloc((size_t)d.ld * T.ks * 8, &p); d.slab = (double *)p;
+        bad = bad || alloc((size_t)d.ld * T.ks * 8 * (T.overlap ? 2 : 1), &p); d.slab = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xa = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xb = (double *)p;
         bad = bad || alloc((size_t)((N + CH_NB - 1) / CH_NB) * CH_LINV * 8, &p); d.linv = (double *)p;
@@ -149,8 +206,30 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     return 0;
 }
 
+// wait for everything the training wave has in flight (both streams) and fold the recorded event spans into the timers
+static int train_sync(sml_engine *h)
+{
+    TrainState &T = h->train;
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (h->train_gram_stream) CK(h, cudaStreamSynchronize(h->train_gram_stream));
+    for (auto &sp : T.spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        (sp.what ? T.gram_ms : T.stategen_ms) += ms;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    T.spans.clear();
+    T.ev_gram[0] = T.ev_gram[1] = nullptr;
+    return 0;
+}
+
 // state generation + Gram accumulation of one phase for the wave; inputs come either from the per-region series
-// already placed in T.regs[i].dev.td / im, or from the device-resident global series gs
+// already placed in T.regs[i].dev.td / im, or from the device-resident global series gs.
+// Overlap mode (default): the slab is double-buffered and the Gram of buffer b runs on its own low-priority stream
+// while the state generation -- a chain of small latency-bound launches -- fills buffer b^1, also across phase
+// boundaries (the call returns with the last Gram still in flight; train_sync at solve / gram_get / stats / end).
+// The arithmetic and its order are those of the serial schedule, so the accumulators are bit-identical.
 static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const GlobalSeries &gs)
 {
     TrainState &T = h->train;
@@ -161,64 +240,87 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
         CK(h, cudaMemsetAsync(d.xa, 0, (size_t)d.R.n * 8, h->stream));  // x = 0 at the start of every phase (:1091)
         devs[i] = d;
     }
-    CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * nw, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
+    if (T.uploaded.size() != devs.size() || memcmp(T.uploaded.data(), devs.data(), sizeof(TrainRegionDev) * nw) != 0) {
+        if (train_sync(h)) return -1;   // a Gram still in flight reads d_regs
+        CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * nw, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        T.uploaded = devs;
+    }
+    cudaStream_t S = h->stream;
+    cudaStream_t GS = T.overlap ? h->train_gram_stream : h->stream;
 
-    cudaEvent_t e0, e1, e2;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
     const dim3 ugrid((T.n_max + 255) / 256, nw);
     int parity = 0;
+    cudaEvent_t d0 = nullptr, d1 = nullptr;
+    if (discard_cols > 0) {
+        cudaEventCreate(&d0); cudaEventCreate(&d1);
+        CK(h, cudaEventRecord(d0, S));
+    }
     // discard loop (:1093-1106)
     for (int i = 0; i < discard_cols; ++i) {
-        k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, i, -1, -1, gs);
+        k_train_update<<<ugrid, 256, 0, S>>>(T.d_regs, parity, i, -1, -1, gs);
         parity ^= 1;
         h->launches++;
+    }
+    if (discard_cols > 0) {
+        CK(h, cudaEventRecord(d1, S));
+        T.spans.push_back({d0, d1, 0});
     }
     const int TL = ncols - discard_cols;
     const int bs = T.batch_size;
     const int kept = (TL / bs) * bs;  // states 1..kept enter the Gram
     // state s (1-based) pairs with series column discard+s (1-based) = discard+s-1 (0-based); it is produced
     // from state s-1 with input column discard+s-1 (1-based) = discard+s-2 (0-based)
+    int prev_base = 0;
     for (int s0 = 0; s0 < kept; s0 += T.ks) {
         const int nc = std::min(T.ks, kept - s0);
         const int kpad = (nc + SY_BK - 1) / SY_BK * SY_BK;
-        CK(h, cudaEventRecord(e0, h->stream));
+        const int buf = T.overlap ? (int)(T.slab_seq & 1u) : 0;
+        const int base = buf * T.ks;   // first slab column of this buffer
+        T.slab_seq++;
+        cudaEvent_t e0, e1, g0, g1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&g0); cudaEventCreate(&g1);
+        if (T.overlap && T.ev_gram[buf]) CK(h, cudaStreamWaitEvent(S, T.ev_gram[buf], 0));  // the Gram that read this buffer
+        CK(h, cudaEventRecord(e0, S));
         for (int c = 0; c < nc; ++c) {
             const int s = s0 + c;  // 0-based state index
             if (s == 0) {
-                k_train_store_state<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, 0);
+                k_train_store_state<<<ugrid, 256, 0, S>>>(T.d_regs, parity, base);
             } else {
                 // ML-only paths restart every batch from the squared copy (SpMV operand only)
                 // (at a slab boundary the previous slab was full, its last column is still intact)
                 int gather = -1;
-                if (!T.hybrid && (s % bs) == 0) gather = (c > 0) ? c - 1 : T.ks - 1;
-                k_train_update<<<ugrid, 256, 0, h->stream>>>(T.d_regs, parity, discard_cols + s - 1, c, gather, gs);
+                if (!T.hybrid && (s % bs) == 0) gather = (c > 0) ? base + c - 1 : prev_base + T.ks - 1;
+                k_train_update<<<ugrid, 256, 0, S>>>(T.d_regs, parity, discard_cols + s - 1, base + c, gather, gs);
                 parity ^= 1;
             }
             h->launches++;
         }
-        k_train_fill<<<dim3(kpad, nw), 128, 0, h->stream>>>(T.d_regs, discard_cols + s0, nc, kpad, gs);
+        k_train_fill<<<dim3(kpad, nw), 128, 0, S>>>(T.d_regs, discard_cols + s0, nc, kpad, base, gs);
         h->launches++;
-        CK(h, cudaEventRecord(e1, h->stream));
+        CK(h, cudaEventRecord(e1, S));
+        T.spans.push_back({e0, e1, 0});
+        if (T.overlap) CK(h, cudaStreamWaitEvent(GS, e1, 0));
+        CK(h, cudaEventRecord(g0, GS));
         // warp layout of the Gram kernel: A/B switch SML_SYRK_WARPS=16 -> 4 x 4 warps of 32 x 32, default 2 x 4 of 64 x 32
         static const bool w16 = getenv("SML_SYRK_WARPS") && atoi(getenv("SML_SYRK_WARPS")) == 16;
-        if (w16) k_syrk_dmma<4, 4><<<dim3(T.ntiles, nw), 17 * 32, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
-        else k_syrk_dmma<2, 4><<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, h->stream>>>(T.d_regs, T.d_tiles, kpad);
+        if (w16) k_syrk_dmma<4, 4><<<dim3(T.ntiles, nw), 17 * 32, SY_SMEM, GS>>>(T.d_regs, T.d_tiles, kpad, base);
+        else k_syrk_dmma<2, 4><<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, GS>>>(T.d_regs, T.d_tiles, kpad, base);
         h->launches++;
-        CK(h, cudaEventRecord(e2, h->stream));
+        CK(h, cudaEventRecord(g1, GS));
+        T.spans.push_back({g0, g1, 1});
+        T.ev_gram[buf] = g1;
         CK(h, cudaGetLastError());
-        CK(h, cudaEventSynchronize(e2));
-        float a = 0.f, b = 0.f;
-        cudaEventElapsedTime(&a, e0, e1);
-        cudaEventElapsedTime(&b, e1, e2);
-        T.stategen_ms += a;
-        T.gram_ms += b;
+        prev_base = base;
         for (auto &r : T.regs) {
             const double N = r.dev.R.n + r.dev.R.S, P = r.dev.R.P;
             T.gram_flops_useful += (N * (N + 1.0) + 2.0 * P * N) * nc;
         }
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (!T.overlap) return train_sync(h);
+    // the host series of sml_train_feed may be reused by the caller as soon as the call returns, and the next call
+    // overwrites the device copy: the state-generation stream has consumed both once it is idle
+    CK(h, cudaStreamSynchronize(S));
     return 0;
 }
 
@@ -334,7 +436,9 @@ int sml_train_noise_sample(sml_engine *h, int region, int first_col, int stride,
     const int D = T.regs[wi].dev.R.D;
     std::vector<TrainRegionDev> devs(T.regs.size());
     for (size_t i = 0; i < T.regs.size(); ++i) devs[i] = T.regs[i].dev;
+    if (train_sync(h)) return -1;
     CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * devs.size(), cudaMemcpyHostToDevice, h->stream));
+    T.uploaded = devs;
     double *d = nullptr;
     CK(h, cudaMalloc(&d, sizeof(double) * 3 * D));
     GlobalSeries gs;
@@ -429,6 +533,32 @@ int sml_conditioning_stats(sml_engine *h, int first_col, int stride, int ncols, 
     return L;
 }
 
+// rolling_average_over_a_period_2d(grid, period) on a caller-owned host array, in place: grid(i, t) at grid[ld*t + i],
+// i < nrows (pass the address of the first averaged row: trainingdata(grid%atmo3d_start, 1), ld = reservoir_numinputs)
+int sml_rolling_average_2d(sml_engine *h, double *grid, int ld, int nrows, int t_len, int period, int keep_small)
+{
+    if (!h) return -1;
+    if (!grid || nrows < 1 || t_len < 1 || ld < nrows || period < 1) FAIL(h, "sml_rolling_average_2d: bad arguments");
+    CK(h, cudaSetDevice(h->p.device));
+    double *d = nullptr;
+    const size_t cnt = (size_t)nrows * t_len;
+    CK(h, cudaMalloc(&d, sizeof(double) * 2 * cnt));
+    cudaError_t e = cudaMemcpy2DAsync(d, sizeof(double) * nrows, grid, sizeof(double) * ld, sizeof(double) * nrows, t_len,
+                                      cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_rolling_average<<<dim3(t_len, (nrows + 127) / 128), 128, 0, h->stream>>>(d, d + cnt, nrows, t_len, period, keep_small);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(grid, sizeof(double) * ld, d + cnt, sizeof(double) * nrows, sizeof(double) * nrows, t_len,
+                              cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) FAIL(h, "sml_rolling_average_2d: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 int sml_train_global_release(sml_engine *h)
 {
     if (!h) return -1;
@@ -472,6 +602,7 @@ int sml_train_solve(sml_engine *h, double beta_res, double beta_model, int using
     // SML_SOLVER=lu forces dgesv-style LU with partial pivoting for every region (the fallback path)
     const char *solver_env = getenv("SML_SOLVER");
     const bool force_lu = solver_env && std::string(solver_env) == "lu";
+    if (train_sync(h)) return -1;   // the last Gram may still be running on its own stream
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     CK(h, cudaEventRecord(e0, h->stream));
@@ -600,6 +731,7 @@ int sml_train_gram_get(sml_engine *h, int region, double *sxs, double *sxt)
     if (!h) return -1;
     TrainState &T = h->train;
     if (!T.active) FAIL(h, "no active training wave");
+    if (train_sync(h)) return -1;
     for (auto &r : T.regs) {
         if (r.region != region) continue;
         const TrainRegionDev &d = r.dev;
@@ -621,6 +753,7 @@ int sml_train_gram_get(sml_engine *h, int region, double *sxs, double *sxt)
 int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms, double *solve_ms)
 {
     if (!h) return -1;
+    if (h->train.active && train_sync(h)) return -1;
     *gram_flops_useful = h->train.gram_flops_useful;
     *gram_ms = h->train.gram_ms;
     *stategen_ms = h->train.stategen_ms;
@@ -628,11 +761,20 @@ int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, d
     return 0;
 }
 
+// 1: state generation overlaps the Gram of the previous slab (default), 0: serial schedule (kernel timing runs);
+// takes effect at the next sml_train_begin
+int sml_train_set_overlap(sml_engine *h, int on)
+{
+    if (!h) return -1;
+    h->train_overlap = on ? 1 : 0;
+    return 0;
+}
+
 int sml_train_end(sml_engine *h)
 {
     if (!h) return -1;
     CK(h, cudaSetDevice(h->p.device));
-    cudaStreamSynchronize(h->stream);
+    if (train_sync(h)) return -1;
     train_release(h->train, &h->train_pool);  // the next wave reuses the blocks
     return 0;
 }

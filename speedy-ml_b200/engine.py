@@ -113,7 +113,9 @@ _SIGNATURES = {
     "sml_train_gram_get": ([C.c_void_p, C.c_int, _dp, _dp], C.c_int),
     "sml_train_end": ([C.c_void_p], C.c_int),
     "sml_train_trim": ([C.c_void_p], C.c_int),
+    "sml_train_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_stats": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
+    "sml_rolling_average_2d": ([C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_profile": ([C.c_void_p, C.c_int], C.c_int),
     "sml_kernel_times": ([C.c_void_p, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
@@ -680,9 +682,23 @@ class Engine:
     def train_end(self):
         self._ck(self.lib.sml_train_end(self.h))
 
+    def train_set_overlap(self, on: bool):
+        """state generation overlapping the previous slab's Gram (default on); applies from the next train_begin"""
+        self._ck(self.lib.sml_train_set_overlap(self.h, 1 if on else 0))
+
     def train_trim(self):
         """return the device blocks kept from finished waves to the allocator"""
         self._ck(self.lib.sml_train_trim(self.h))
+
+    # -- rolling_average_over_a_period_2d(grid, period)   mod_utilities.f90:1773
+    def rolling_average_over_a_period_2d(self, grid, period, row0=0, nrows=None, keep_small=True):
+        """in place on rows [row0, row0+nrows) of the Fortran-ordered (rows, time) array grid"""
+        assert grid.dtype == np.float64 and grid.flags["F_CONTIGUOUS"] and grid.ndim == 2
+        nrows = grid.shape[0] - row0 if nrows is None else nrows
+        assert 0 <= row0 and row0 + nrows <= grid.shape[0]
+        ptr = C.cast(grid.ctypes.data + 8 * row0, _dp)
+        self._ck(self.lib.sml_rolling_average_2d(self.h, ptr, grid.shape[0], nrows, grid.shape[1], period, int(keep_small)))
+        return grid
 
     # -- mldivide(A, B)   mod_linalg.f90:109
     def mldivide(self, A, B):

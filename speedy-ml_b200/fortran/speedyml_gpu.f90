@@ -25,6 +25,7 @@ module speedyml_gpu
   public :: mklsparse, synchronize, predict, predict_ml, predict_slab_ml, sendrecievegrid
   public :: gpu_train_begin, gpu_train_phase, gpu_fit_chunk, gpu_train_end, mldivide
   public :: gen_res, read_trained_res, gpu_train_global_series, gpu_train_phase_global, gpu_set_overlap, gpu_set_tisr
+  public :: rolling_average_over_a_period_2d
 
   integer(c_int), parameter :: SML_ATMO = 0, SML_OCEAN = 1, SML_ALL_REGIONS = -1
 
@@ -221,6 +222,13 @@ module speedyml_gpu
        type(c_ptr), value :: h
        real(c_double), intent(inout) :: A(*), B(*)
        integer(c_int), value :: lda, ldb, n, nrhs
+     end function
+     integer(c_int) function sml_rolling_average_2d(h, grid, ld, nrows, t_len, period, keep_small) &
+          bind(C, name='sml_rolling_average_2d')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(inout) :: grid(*)
+       integer(c_int), value :: ld, nrows, t_len, period, keep_small
      end function
   end interface
 
@@ -549,6 +557,16 @@ contains
        print *, 'something went wrong with dgesv info = ', info
        print *, 'B is not the solution'
     end if
+  end subroutine
+
+  !> rolling_average_over_a_period_2d(grid,period), src/mod_utilities.f90:1773-1815 (called on a row section of
+  !> reservoir%trainingdata, src/mod_slab_ocean_reservoir.f90:398,452: a non-contiguous actual is copied in/out by
+  !> the compiler, so the dummy is contiguous here)
+  subroutine rolling_average_over_a_period_2d(grid, period)
+    real(kind=dp), intent(inout), contiguous :: grid(:,:)
+    integer, intent(in) :: period
+    call ck(sml_rolling_average_2d(h, grid, size(grid, 1), size(grid, 1), size(grid, 2), period, 1), &
+            'sml_rolling_average_2d')
   end subroutine
 
 end module speedyml_gpu

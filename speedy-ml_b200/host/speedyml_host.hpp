@@ -246,6 +246,14 @@ public:
         return info;
     }
 
+    // rolling_average_over_a_period_2d(grid(row0:row0+nrows-1, :), period), src/mod_utilities.f90:1773; grid is
+    // (ld, t_len) column-major
+    void rolling_average_over_a_period_2d(std::vector<dp> &grid, int ld, int t_len, int period, int row0 = 0, int nrows = -1)
+    {
+        if (nrows < 0) nrows = ld - row0;
+        ck(sml_rolling_average_2d(h_, grid.data() + row0, ld, nrows, t_len, period, 1), "sml_rolling_average_2d");
+    }
+
     void state_get(const reservoir_type &r, std::vector<dp> &x, int kind = ATMO)
     {
         x.resize(r.n);

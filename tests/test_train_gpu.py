@@ -153,7 +153,7 @@ def test_wave_of_regions_with_different_shapes_and_slab_boundaries(E, monkeypatc
     eng.close()
 
 
-def test_mldivide_matches_dgesv(E):
+def test_mldivide_matches_dgesv(E, monkeypatch):
     eng = E.Engine(number_of_regions=1152, irank=0, numprocs=1152)
     rng = np.random.default_rng(0)
     for n, k in ((1, 1), (7, 3), (333, 136), (1200, 40)):
@@ -164,6 +164,28 @@ def test_mldivide_matches_dgesv(E):
         assert info == 0 and infol == 0
         assert rel_inf(X, Xl) < 1e-10
         assert _residual(A, X, B) < 1e-14
+    # no diagonal dominance: every column needs its interchange, pivots come from any CTA of the panel launch
+    for n, k, gmax in ((500, 5, None), (777, 3, 3), (130, 2, 1)):
+        if gmax is None:
+            monkeypatch.delenv("SML_LU_GMAX", raising=False)
+        else:
+            monkeypatch.setenv("SML_LU_GMAX", str(gmax))     # few CTAs: many rows per CTA
+        A = rng.standard_normal((n, n))
+        A[:, 7] = np.sign(A[:, 7])                            # ties in |a|: the first maximal row must win (idamax)
+        B = rng.standard_normal((n, k))
+        X, info = eng.mldivide(A, B)
+        _, _, Xl, infol = lapack.dgesv(A, B)
+        assert info == 0 and infol == 0
+        assert rel_inf(X, Xl) < 1e-8
+        assert _residual(A, X, B) < 1e-13
+    monkeypatch.delenv("SML_LU_GMAX", raising=False)
+    # a permutation matrix: pure interchanges
+    perm = rng.permutation(200)
+    A = np.zeros((200, 200))
+    A[np.arange(200), perm] = 2.0
+    B = rng.standard_normal((200, 4))
+    X, info = eng.mldivide(A, B)
+    assert info == 0 and np.allclose(A @ X, B, rtol=0, atol=1e-14)
     # singular: LAPACK info > 0, B is not the solution (src/mod_linalg.f90:147-150 prints and continues)
     A = np.array([[1.0, 2.0], [2.0, 4.0]])
     _, info = eng.mldivide(A, np.ones((2, 1)))
@@ -248,3 +270,37 @@ def test_solver_wave_mixed_shapes(E):
         assert _residual(A.T, eng.wout_get(r).T, B.T) < 1e-13
     eng.train_end()
     eng.close()
+
+
+@pytest.mark.parametrize("ml_only", [False, True])
+def test_overlapped_schedule_is_bit_identical(E, monkeypatch, ml_only):
+    """sml_train_set_overlap: state generation of slab k+1 runs while the Gram of slab k is accumulated on its own
+    stream (double-buffered slab), across phases too.  Same arithmetic in the same order: the accumulators of the
+    overlapped and the serial schedule must agree bit for bit -- and with the oracle.  The slab is shrunk to 32
+    columns so that a phase spans many slabs; batch 16 puts the ML-only restart (which reads the previous slab's last
+    column, src/mod_reservoir.f90:1034) on every second slab boundary."""
+    monkeypatch.setenv("SML_TRAIN_SLAB", "32")
+    region, bs, discard = 555, 16, 4
+    w = region_weights(1152, region, m=450, ml_only=ml_only)
+    phases = [_series(w, discard + 11 * bs + 5, 300 + p) for p in range(3)]
+    rc = c_region(w)
+    rc.train_init(bs)
+    for td, im in phases:
+        rc.train_phase(td, im, discard)
+    grams = []
+    for on in (True, False):
+        eng = single_region_engine(E, w)
+        eng.train_set_overlap(on)
+        eng.train_begin([region], bs)
+        for td, im in phases:
+            eng.train_feed([td], [im] if im is not None else None, discard)
+        grams.append(eng.train_gram_get(region))
+        st = eng.train_stats()
+        assert st["gram_ms"] > 0.0 and st["stategen_ms"] > 0.0
+        assert eng.train_solve(1e-2, 1.0, True, 0.0)[0] == 0 if not ml_only else eng.train_solve(1e-2)[0] == 0
+        eng.train_end()
+        eng.close()
+    assert np.array_equal(grams[0][0], grams[1][0])
+    assert np.array_equal(grams[0][1], grams[1][1])
+    assert rel_inf(grams[0][0], rc.sxs) < 1e-12
+    assert rel_inf(grams[0][1], rc.sxt) < 1e-12

@@ -46,6 +46,10 @@ def main():
     ap.add_argument("--batch", type=int, default=98)
     ap.add_argument("--solve", action="store_true")
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="default schedule of the engine (state generation overlaps the previous slab's Gram); "
+                         "off here so that every kernel is timed alone")
+    ap.add_argument("--phases", type=int, default=1)
     args = ap.parse_args()
     E = importlib.import_module("speedy-ml_b200.engine")
     syn = importlib.import_module("speedy-ml_b200.synthetic")
@@ -62,15 +66,18 @@ def main():
     rng = np.random.default_rng(1)
     tds = [syn.ar1_series(ws[r]["D"], args.cols, rng) for r in regions]
     ims = [np.asfortranarray(rng.standard_normal((ws[r]["S"], args.cols))) for r in regions]
+    eng.train_set_overlap(args.overlap)
     eng.train_begin(regions, args.batch)
     t0 = time.perf_counter()
-    eng.train_feed(tds, ims, args.discard)
+    for _ in range(args.phases):
+        eng.train_feed(tds, ims, args.discard)
+    st = eng.train_stats()                      # waits for both streams
     wall_feed = time.perf_counter() - t0
-    st = eng.train_stats()
-    out = {"workload": f"ridge training, {nreg} regions x 1 phase x {args.cols} columns, m=6000",
+    out = {"workload": f"ridge training, {nreg} regions x {args.phases} phase(s) x {args.cols} columns, m=6000",
            "gram_tflops_useful": st["gram_flops_useful"] / (st["gram_ms"] * 1e-3) / 1e12,
            "gram_ms": st["gram_ms"], "stategen_ms": st["stategen_ms"], "feed_wall_s": wall_feed,
-           "kept_columns": (args.cols - args.discard) // args.batch * args.batch}
+           "kept_columns": (args.cols - args.discard) // args.batch * args.batch, "phases": args.phases,
+           "schedule": "overlap" if args.overlap else "serial"}
     if args.solve:
         info = eng.train_solve(1e-3, 1.0, True, 0.0)
         st = eng.train_stats()
