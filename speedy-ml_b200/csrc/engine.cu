@@ -67,7 +67,6 @@ struct KindState {
     long long *d_fb_offs = nullptr;
     long long x_total = 0, fb_total = 0, lm_total = 0;
     int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0, chunk_rows = 0, D_max = 0;
-    int sx_threads = 0, sx_threads_split = 0;   // block size of k_update_sx chosen for this model at that row split
     int *d_order = nullptr;  // launch order of the items: largest first
     int *d_one_region = nullptr;  // region index for one region's synchronize
     int one_region = -1;
@@ -940,26 +939,10 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
             nsplit = std::max(1, std::min(nsplit, 16));
             const int sxr = getenv("SML_UPDATE_RPT") ? rpt : 2;   // rows per thread per sweep: 2 measured best (64 registers)
             const int SXR = (sxr == 1 || sxr == 4) ? sxr : 2;
-            // block size: the multiple of 32 in [384, 512] that leaves the fewest idle row slots in the last sweep
-            int nt = getenv("SML_UPDATE_THREADS") ? atoi(getenv("SML_UPDATE_THREADS")) / 32 * 32 : 0;
-            if ((nt < 64 || nt > UPD_SX_THREADS) && K.sx_threads && K.sx_threads_split == nsplit * 8 + SXR) nt = K.sx_threads;
-            if (nt < 64 || nt > UPD_SX_THREADS) {
-                long long best = -1;
-                for (int t = UPD_SX_THREADS; t >= 384; t -= 32) {
-                    long long slots = 0;
-                    for (auto &r : K.regs) {
-                        if (!r.uploaded) continue;
-                        const int per = (((r.dev.n + nsplit - 1) / nsplit) + 31) & ~31;
-                        for (int r0 = 0; r0 < r.dev.n; r0 += per) {
-                            const int rows = std::min(per, r.dev.n - r0);
-                            slots += (long long)((rows + t * SXR - 1) / (t * SXR)) * t * SXR;
-                        }
-                    }
-                    if (best < 0 || slots < best) { best = slots; nt = t; }
-                }
-                K.sx_threads = nt;
-                K.sx_threads_split = nsplit * 8 + SXR;
-            }
+            // block size: 512 measured best (0.796 of the roof against 0.781 / 0.776 / 0.706 for 480 / 448 / 384 threads,
+            // although 480 divides the 5760 rows evenly); SML_UPDATE_THREADS is the A/B switch
+            int nt = getenv("SML_UPDATE_THREADS") ? atoi(getenv("SML_UPDATE_THREADS")) / 32 * 32 : UPD_SX_THREADS;
+            if (nt < 64 || nt > UPD_SX_THREADS) nt = UPD_SX_THREADS;
             dim3 grid((unsigned)nsplit, (unsigned)nreg);
             if (SXR == 2) {
                 CK(h, cudaFuncSetAttribute(k_update_sx<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sx_smem));

@@ -363,13 +363,12 @@ k_update(const RegionDev *__restrict__ regs, const int *__restrict__ region_list
 // ---------------------------------------------------------------------------------------------
 // k_update_sx: the same update with the region's state vector (and input vector) staged in shared memory, so that
 // the x gathers of the SpMV -- random within the region's 46 KB vector -- are shared-memory reads instead of L2
-// round trips and only the coalesced ELL / W_in streams go to global memory.  One CTA per (region, row split), up to
-// 512 threads (the launch picks the multiple of 32 that divides the rows most evenly), 2 CTAs per SM, n*8 + D*8 bytes of
-// dynamic shared memory.  x arrives by one TMA bulk copy (the x pool is padded to 256 B per region) while every thread
+// round trips and only the coalesced ELL / W_in streams go to global memory.  One CTA per (region, row split), 512
+// threads, 2 CTAs per SM (64 registers), n*8 + D*8 bytes of dynamic shared memory.  x arrives by one TMA bulk copy (the x pool is padded to 256 B per region) while every thread
 // already has its first ELL group in flight; RPT rows per thread per sweep.
 // Accumulation order per row is the entry order, as in update_row.   grid (nsplit, regions)
-// Measured (tools/ab_update.py, 1152 regions, m = 6000): 0.759 of the HBM roof at degree 6, 0.893 at degree 24,
-// against 0.722 / 0.778 for k_update<4>; 144 regions (one of 8 ranks): 0.638 against 0.461.
+// Measured (tools/ab_update.py, 1152 regions, m = 6000): 0.796 of the HBM roof at degree 6, 0.917 at degree 24,
+// against 0.723 / 0.778 for k_update<4>; 144 regions (one of 8 ranks, 2 row splits): 0.60 against 0.47.
 // ---------------------------------------------------------------------------------------------
 constexpr int UPD_SX_THREADS = 512;
 template <int RPT>

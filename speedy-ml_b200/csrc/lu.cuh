@@ -10,7 +10,7 @@
 //               memory), one grid barrier per column carries the pivot candidates and the two interchanged rows;
 //   k_lu_laswp  applies the panel's interchanges to the columns left and right of it;
 //   k_lu_trsm   U12 = L11^-1 A12 (unit lower, thread per column);
-//   k_lu_gemm   A22 -= L21 U12, 64 x 64 tiles, K = 32 (FP64 FMA; this is the fallback, the DMMA path is chol.cuh).
+//   k_lu_gemm   A22 -= L21 U12 on the FP64 tensor cores (DMMA), 128 x 64 tiles, K = 32.
 // Solve: interchanges on B, forward substitution (unit L), back substitution (U), one CTA per right-hand side,
 // blocked by the panel width.
 #pragma once
@@ -28,6 +28,9 @@ constexpr int LU_NB = 32;
 // and scales / rank-1-updates its own rows.  The exchange buffers are double-buffered by column parity (a fast CTA
 // may publish column j+1 while a slow one still reads column j).
 //   xch layout per parity: cand_val[G] | cand_row[G][LU_NB] | jrow[LU_NB] (doubles), cand_idx[G] (ints) behind them.
+// Measured at n = 5892: 22.8 ms for the 184 panels (3.8 us per column).  A variant with two block barriers per column
+// (only warp 0 publishes and waits at the grid barrier; interchange, scaling and the rank-1 update folded into one pass
+// that also yields the next column's candidates) measured 38.4 ms and was dropped.
 // ---------------------------------------------------------------------------------------------
 constexpr int LU_PANEL_THREADS = 256;
 
@@ -177,20 +180,47 @@ k_lu_panel(double *__restrict__ A, int lda, int n, int j0, int nb, int rows_per,
     }
 }
 
-// interchanges of panel [j0, j0+nb) applied to columns [c_lo, c_hi) of M (leading dimension ldm), thread per column
-__global__ void k_lu_laswp(double *__restrict__ M, int ldm, int c_lo, int c_hi, const int *__restrict__ ipiv, int j0, int nb)
+// interchanges of panel [j0, j0+nb) applied to columns [c_lo, c_hi) of M (leading dimension ldm), thread per column.
+// The nb sequential row swaps touch at most 2 nb rows and compose to one permutation that is the same for every
+// column: thread 0 of each CTA derives it once (row r receives the element that was in row src[r]); every thread
+// then issues all its loads, then all its stores -- two dependent memory phases instead of nb.
+__global__ void __launch_bounds__(128)
+k_lu_laswp(double *__restrict__ M, int ldm, int c_lo, int c_hi, const int *__restrict__ ipiv, int j0, int nb)
 {
+    __shared__ int s_row[2 * LU_NB], s_src[2 * LU_NB], s_ip[LU_NB];
+    __shared__ int s_cnt;
+    if (threadIdx.x < nb) s_ip[threadIdx.x] = ipiv[j0 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int cnt = 0;
+        for (int jj = 0; jj < nb; ++jj) {
+            const int j = j0 + jj, p = s_ip[jj];
+            if (p == j) continue;
+            int aj = -1, ap = -1;
+            for (int e = 0; e < cnt; ++e) {
+                if (s_row[e] == j) aj = e;
+                if (s_row[e] == p) ap = e;
+            }
+            if (aj < 0) { aj = cnt; s_row[cnt] = j; s_src[cnt] = j; ++cnt; }
+            if (ap < 0) { ap = cnt; s_row[cnt] = p; s_src[cnt] = p; ++cnt; }
+            const int t = s_src[aj];
+            s_src[aj] = s_src[ap];
+            s_src[ap] = t;
+        }
+        s_cnt = cnt;
+    }
+    __syncthreads();
     const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c_hi) return;
     double *col = M + (size_t)ldm * c;
-    for (int jj = 0; jj < nb; ++jj) {
-        const int j = j0 + jj, p = ipiv[j];
-        if (p != j) {
-            const double t = col[j];
-            col[j] = col[p];
-            col[p] = t;
-        }
-    }
+    const int cnt = s_cnt;
+    double v[2 * LU_NB];
+#pragma unroll
+    for (int e = 0; e < 2 * LU_NB; ++e)
+        if (e < cnt) v[e] = col[s_src[e]];
+#pragma unroll
+    for (int e = 0; e < 2 * LU_NB; ++e)
+        if (e < cnt) col[s_row[e]] = v[e];
 }
 
 // U12 = L11^-1 A12 for the columns right of the panel: unit-lower forward substitution, thread per column
@@ -215,9 +245,87 @@ __global__ void k_lu_trsm(double *__restrict__ A, int lda, int n, int j0, int nb
         if (i < nb) col[i] = x[i];
 }
 
-// A22 -= L21 * U12 : CTA tile 64 x 64, 256 threads x (4 x 4), K = nb <= 32
-__global__ void __launch_bounds__(256)
+// A22 -= L21 * U12 on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA): CTA tile 128 x 64, 4 warps (2 x 2) of 64 x 32 =
+// 8 x 4 DMMA tiles, K = nb <= 32 zero-padded to 32.  L21 is staged k-major (rows contiguous, as it lies in memory), U12
+// transposed into the same form; the accumulators start from A22 (loaded first, in flight while the operands are
+// staged) and the L operand is negated, so the tile leaves as A22 - L21 U12 with one read and one write of A22.  128 threads x 164 registers: 3 CTAs per SM cover each other's load / store phases.
+constexpr int LG_BM = 128, LG_BN = 64, LG_LDL = 132, LG_LDU = 68;
+constexpr size_t LG_SMEM = sizeof(double) * (size_t)LU_NB * (LG_LDL + LG_LDU);
+
+__device__ __forceinline__ void lu_dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128, 3)
 k_lu_gemm(double *__restrict__ A, int lda, int n, int j0, int nb)
+{
+    extern __shared__ __align__(16) double lg_smem[];
+    double *sL = lg_smem;                    // [LU_NB][LG_LDL]: sL[k][i] = -L21(r0 + i, k)
+    double *sU = lg_smem + LU_NB * LG_LDL;   // [LU_NB][LG_LDU]: sU[k][c] =  U12(k, c0 + c)
+    const int r0 = j0 + nb + blockIdx.x * LG_BM, c0 = j0 + nb + blockIdx.y * LG_BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < LU_NB * LG_BM; e += 128) {
+        const int k = e / LG_BM, i = e % LG_BM;
+        sL[k * LG_LDL + i] = (k < nb && r0 + i < n) ? -A[(size_t)lda * (j0 + k) + r0 + i] : 0.0;
+    }
+    for (int e = tid; e < LU_NB * LG_BN; e += 128) {
+        const int c = e / LU_NB, k = e % LU_NB;
+        sU[k * LG_LDU + c] = (k < nb && c0 + c < n) ? A[(size_t)lda * (c0 + c) + j0 + k] : 0.0;
+    }
+    const int wm = warp >> 1, wn = warp & 1;
+    const int g = lane >> 2, q = lane & 3;
+    // accumulators <- A22 tile, issued before the barrier so that these loads fly while the operand tiles are staged
+    // (thread holds C[g][2q], C[g][2q+1] of every 8 x 8 tile)
+    double acc[8][4][2];
+    const int ib = r0 + wm * 64 + g;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int c = c0 + wn * 32 + b * 8 + 2 * q;
+        const double *col0 = A + (size_t)lda * c + ib, *col1 = col0 + lda;
+        const bool ok0 = c < n, ok1 = c + 1 < n;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const bool okr = ib + a * 8 < n;
+            acc[a][b][0] = (okr && ok0) ? col0[a * 8] : 0.0;
+            acc[a][b][1] = (okr && ok1) ? col1[a * 8] : 0.0;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < LU_NB; k4 += 4) {
+        double af[8], bf[4];
+        const double *pa = sL + (k4 + q) * LG_LDL + wm * 64 + g;
+        const double *pb = sU + (k4 + q) * LG_LDU + wn * 32 + g;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) af[a] = pa[a * 8];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = pb[b * 8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) lu_dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int c = c0 + wn * 32 + b * 8 + 2 * q;
+        double *col0 = A + (size_t)lda * c + ib, *col1 = col0 + lda;
+        const bool ok0 = c < n, ok1 = c + 1 < n;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            if (ib + a * 8 < n) {
+                if (ok0) col0[a * 8] = acc[a][b][0];
+                if (ok1) col1[a * 8] = acc[a][b][1];
+            }
+        }
+    }
+}
+
+// A22 -= L21 * U12 with plain FP64 FMAs: CTA tile 64 x 64, 256 threads x (4 x 4), K = nb <= 32 (SML_LU_GEMM=fma; A/B)
+__global__ void __launch_bounds__(256)
+k_lu_gemm_fma(double *__restrict__ A, int lda, int n, int j0, int nb)
 {
     __shared__ double sL[LU_NB][64 + 1];   // L21 tile: [k][row]
     __shared__ double sU[LU_NB][64 + 1];   // U12 tile: [k][col]
@@ -251,6 +359,7 @@ k_lu_gemm(double *__restrict__ A, int lda, int n, int j0, int nb)
         for (int i = 0; i < 4; ++i)
             if (r0 + ti + i < n && c0 + tc + c < n) A[(size_t)lda * (c0 + tc + c) + r0 + ti + i] -= acc[i][c];
 }
+
 
 // L y = b (unit lower) then U x = y for one right-hand side per CTA; x lives in shared memory.  Blocked by LU_NB
 // columns: the diagonal block is solved by one warp from a shared-memory copy, then all threads apply the block's LU_NB

@@ -31,6 +31,8 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (timing) for (auto &e : ev) cudaEventCreate(&e);
     unsigned ctr_base = 0;
+    const bool gemm_fma = getenv("SML_LU_GEMM") && std::string(getenv("SML_LU_GEMM")) == "fma";   // A/B switch
+    CK(h, cudaFuncSetAttribute(k_lu_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_SMEM));
     for (int j0 = 0; j0 < n; j0 += LU_NB) {
         const int nb = std::min(LU_NB, n - j0);
         const int rows = n - j0;
@@ -53,7 +55,8 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
         if (rest > 0) {
             k_lu_laswp<<<(rest + 127) / 128, 128, 0, h->stream>>>(dA, lda, j0 + nb, n, ipiv, j0, nb);
             k_lu_trsm<<<(rest + 127) / 128, 128, 0, h->stream>>>(dA, lda, n, j0, nb);
-            k_lu_gemm<<<dim3((rest + 63) / 64, (rest + 63) / 64), 256, 0, h->stream>>>(dA, lda, n, j0, nb);
+            if (gemm_fma) k_lu_gemm_fma<<<dim3((rest + 63) / 64, (rest + 63) / 64), 256, 0, h->stream>>>(dA, lda, n, j0, nb);
+            else k_lu_gemm<<<dim3((rest + LG_BM - 1) / LG_BM, (rest + LG_BN - 1) / LG_BN), 128, LG_SMEM, h->stream>>>(dA, lda, n, j0, nb);
         }
         h->launches += rest > 0 ? 5 : 2;
         if (timing) {
