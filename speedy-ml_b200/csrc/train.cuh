@@ -209,6 +209,8 @@ constexpr int SY_CONS_WARPS = 8;
 constexpr int SY_THREADS = (SY_CONS_WARPS + 1) * 32;
 constexpr int SY_STAGE_DOUBLES = 2 * SY_BK * SY_LDS;
 constexpr size_t SY_SMEM = (size_t)SY_STAGES * SY_STAGE_DOUBLES * 8 + 2 * SY_STAGES * 8;
+constexpr int SY_STAGES_DEEP = 6;   // A/B: SML_SYRK_STAGES=6 (203 KB of shared memory)
+constexpr size_t SY_SMEM_DEEP = (size_t)SY_STAGES_DEEP * SY_STAGE_DOUBLES * 8 + 2 * SY_STAGES_DEEP * 8;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
@@ -226,7 +228,7 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
 // WM x WN consumer warps, each owning a (128/WM) x (128/WN) sub-tile; <2,4> = 8 warps with 64 accumulators per thread
 // (fewest shared-memory loads per DMMA), <4,4> = 16 warps with 32 (more warps per scheduler to cover the DMMA
 // issue bubbles).  Launch with (WM*WN + 1) * 32 threads.
-template <int WM, int WN>
+template <int WM, int WN, int ST = SY_STAGES>
 __global__ void __launch_bounds__((WM * WN + 1) * 32, 1)
 k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles, int kpad, int col_base)
 {
@@ -235,8 +237,8 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
     constexpr int TA = TR / 8, TB = TC / 8;    // 8 x 8 DMMA tiles per warp
     extern __shared__ __align__(128) unsigned char sy_smem[];
     double *stage0 = reinterpret_cast<double *>(sy_smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(sy_smem + (size_t)SY_STAGES * SY_STAGE_DOUBLES * 8);
-    uint64_t *empty = full + SY_STAGES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sy_smem + (size_t)ST * SY_STAGE_DOUBLES * 8);
+    uint64_t *empty = full + ST;
 
     const TrainRegionDev &t = T[blockIdx.y];
     const int2 tile = tiles[blockIdx.x];
@@ -249,7 +251,7 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < SY_STAGES; ++s) {
+        for (int s = 0; s < ST; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], NCW);
         }
@@ -262,8 +264,8 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)SY_BK * (rowsA + (diag ? 0 : rowsB)) * 8u;
             for (int kc = 0; kc < nchunks; ++kc) {
-                const int s = kc % SY_STAGES;
-                mbar_wait(&empty[s], ((kc / SY_STAGES) & 1) ^ 1);
+                const int s = kc % ST;
+                mbar_wait(&empty[s], ((kc / ST) & 1) ^ 1);
                 mbar_expect_tx(&full[s], bytes);
                 double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
                 double *sB = sA + SY_BK * SY_LDS;
@@ -289,8 +291,8 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
         for (int b = 0; b < TB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     for (int kc = 0; kc < nchunks; ++kc) {
-        const int s = kc % SY_STAGES;
-        mbar_wait(&full[s], (kc / SY_STAGES) & 1);
+        const int s = kc % ST;
+        mbar_wait(&full[s], (kc / ST) & 1);
         const double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
         const double *sB = diag ? sA : sA + SY_BK * SY_LDS;
         if (ma == TA && nb == TB) {

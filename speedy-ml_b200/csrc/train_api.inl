@@ -202,6 +202,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     CK(h, cudaMemcpy(T.d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
     CK(h, cudaFuncSetAttribute(k_syrk_dmma<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     CK(h, cudaFuncSetAttribute(k_syrk_dmma<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+    CK(h, cudaFuncSetAttribute(k_syrk_dmma<2, 4, SY_STAGES_DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM_DEEP));
     CK(h, cudaFuncSetAttribute(k_chol_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     CK(h, cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_DIAG_SMEM));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -307,7 +308,9 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
         CK(h, cudaEventRecord(g0, GS));
         // warp layout of the Gram kernel: A/B switch SML_SYRK_WARPS=16 -> 4 x 4 warps of 32 x 32, default 2 x 4 of 64 x 32
         static const bool w16 = getenv("SML_SYRK_WARPS") && atoi(getenv("SML_SYRK_WARPS")) == 16;
-        if (w16) k_syrk_dmma<4, 4><<<dim3(T.ntiles, nw), 17 * 32, SY_SMEM, GS>>>(T.d_regs, T.d_tiles, kpad, base);
+        const bool deep = getenv("SML_SYRK_STAGES") && atoi(getenv("SML_SYRK_STAGES")) == SY_STAGES_DEEP;   // A/B switch
+        if (deep) k_syrk_dmma<2, 4, SY_STAGES_DEEP><<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM_DEEP, GS>>>(T.d_regs, T.d_tiles, kpad, base);
+        else if (w16) k_syrk_dmma<4, 4><<<dim3(T.ntiles, nw), 17 * 32, SY_SMEM, GS>>>(T.d_regs, T.d_tiles, kpad, base);
         else k_syrk_dmma<2, 4><<<dim3(T.ntiles, nw), SY_THREADS, SY_SMEM, GS>>>(T.d_regs, T.d_tiles, kpad, base);
         h->launches++;
         CK(h, cudaEventRecord(g1, GS));
