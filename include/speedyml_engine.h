@@ -300,11 +300,13 @@ int sml_train_solver_stats(sml_engine *h, int *by_cholesky);
 int sml_train_gram_get(sml_engine *h, int region, double *states_x_states_aug,
                        double *states_x_trainingdata_aug);
 int sml_train_end(sml_engine *h);
-/* scheduling of a wave's feeds: on = 1 (default; SML_TRAIN_OVERLAP=0 in the environment turns it off) double-buffers
- * the state slab and runs the Gram of one slab on its own stream while the state generation -- the sequential part,
- * reservoir_layer_chunking_hybrid's time loop -- fills the other, across phases too; sml_train_solve / _gram_get /
- * _stats / _end wait for both.  on = 0 is the serial schedule (each kernel timed alone).  Same arithmetic in the same
- * order either way: the accumulators are bit-identical.  Takes effect at the next sml_train_begin. */
+/* scheduling of a wave's feeds: on = 0 (default) is the serial schedule -- per slab, state generation then Gram.
+ * on = 1 (or SML_TRAIN_OVERLAP=1 in the environment) double-buffers the state slab and runs the Gram of one slab on its
+ * own stream while the state generation -- the sequential part, reservoir_layer_chunking_hybrid's time loop -- fills
+ * the other, across phases too; sml_train_solve / _gram_get / _stats / _end wait for both.  Same arithmetic in the same
+ * order either way: the accumulators are bit-identical.  Measured: it pays for small waves (96 regions: 6.5 -> 5.5 s)
+ * and not at full wave size (192 regions: 24.2 vs 23.6 s: the latency-bound state generation gets a quarter of its
+ * threads beside a resident Gram CTA and slows the Gram by 9 %).  Takes effect at the next sml_train_begin. */
 int sml_train_set_overlap(sml_engine *h, int on);
 /* sml_train_end keeps the wave's device blocks for the next sml_train_begin (allocating ~350 MB per region anew for
  * every wave costs more than the solve); sml_train_trim returns them to the allocator */

@@ -119,7 +119,7 @@ struct sml_engine {
     TrainPool train_pool;
     int num_sms = 148;
     cudaStream_t train_gram_stream = nullptr;   // the Gram kernels' stream when state generation overlaps them
-    int train_overlap = -1;                     // -1: SML_TRAIN_OVERLAP decides (default on), 0 / 1: sml_train_set_overlap
+    int train_overlap = -1;                     // -1: SML_TRAIN_OVERLAP decides (default off), 0 / 1: sml_train_set_overlap
     // overlapped step: the state update and the W_out[:, S:]*x~ partials of the NEXT
     // predict run while the host model works on this step's grids; the S model columns are added when its
     // forecast arrives

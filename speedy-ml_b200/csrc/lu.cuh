@@ -182,32 +182,48 @@ k_lu_panel(double *__restrict__ A, int lda, int n, int j0, int nb, int rows_per,
 
 // interchanges of panel [j0, j0+nb) applied to columns [c_lo, c_hi) of M (leading dimension ldm), thread per column.
 // The nb sequential row swaps touch at most 2 nb rows and compose to one permutation that is the same for every
-// column: thread 0 of each CTA derives it once (row r receives the element that was in row src[r]); every thread
+// column: warp 0 of each CTA derives it once (row r receives the element that was in row src[r]); every thread
 // then issues all its loads, then all its stores -- two dependent memory phases instead of nb.
 __global__ void __launch_bounds__(128)
 k_lu_laswp(double *__restrict__ M, int ldm, int c_lo, int c_hi, const int *__restrict__ ipiv, int j0, int nb)
 {
-    __shared__ int s_row[2 * LU_NB], s_src[2 * LU_NB], s_ip[LU_NB];
+    // entries 0..nb-1 are the panel's own rows j0..j0+nb-1 (direct index); pivot rows below the panel get entries
+    // nb.. as they appear -- warp 0 looks them up with one ballot per interchange
+    __shared__ int s_row[2 * LU_NB], s_src[2 * LU_NB];
     __shared__ int s_cnt;
-    if (threadIdx.x < nb) s_ip[threadIdx.x] = ipiv[j0 + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int cnt = 0;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int myp = (lane < nb) ? ipiv[j0 + lane] : 0;
+        if (lane < nb) { s_row[lane] = j0 + lane; s_src[lane] = j0 + lane; }
+        int orow = -1;   // the row held by entry nb + lane
+        int ocnt = 0;
+        __syncwarp();
         for (int jj = 0; jj < nb; ++jj) {
-            const int j = j0 + jj, p = s_ip[jj];
-            if (p == j) continue;
-            int aj = -1, ap = -1;
-            for (int e = 0; e < cnt; ++e) {
-                if (s_row[e] == j) aj = e;
-                if (s_row[e] == p) ap = e;
+            const int p = __shfl_sync(0xffffffffu, myp, jj);
+            if (p == j0 + jj) continue;
+            int ap;
+            if (p < j0 + nb) {
+                ap = p - j0;
+            } else {
+                const unsigned m = __ballot_sync(0xffffffffu, orow == p);
+                if (m) {
+                    ap = nb + __ffs(m) - 1;
+                } else {
+                    ap = nb + ocnt;
+                    if (lane == ocnt) orow = p;
+                    if (lane == 0) { s_row[ap] = p; s_src[ap] = p; }
+                    ++ocnt;
+                }
             }
-            if (aj < 0) { aj = cnt; s_row[cnt] = j; s_src[cnt] = j; ++cnt; }
-            if (ap < 0) { ap = cnt; s_row[cnt] = p; s_src[cnt] = p; ++cnt; }
-            const int t = s_src[aj];
-            s_src[aj] = s_src[ap];
-            s_src[ap] = t;
+            __syncwarp();
+            if (lane == 0) {
+                const int t = s_src[jj];
+                s_src[jj] = s_src[ap];
+                s_src[ap] = t;
+            }
+            __syncwarp();
         }
-        s_cnt = cnt;
+        if (lane == 0) s_cnt = nb + ocnt;
     }
     __syncthreads();
     const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;

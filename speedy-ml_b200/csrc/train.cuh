@@ -153,6 +153,118 @@ __global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity,
     if (out_col >= 0) t.slab[(size_t)t.ld * out_col + R.S + row] = (row & 1) ? __dmul_rn(xv, xv) : xv;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_train_stategen: the time loop of reservoir_layer_chunking_hybrid/_ml (src/mod_reservoir.f90:963-1175) INSIDE the
+// kernel -- one CTA per region of the wave keeps the region's state vector in shared memory and advances it nsteps
+// time steps, two block barriers per step, instead of one launch per time step over the whole wave (k_train_update).
+// Per step: (a) the step's input vector is staged in shared memory (tiled + standardised + noised on the fly from the
+// resident global series, or read from the per-region series; each input element is evaluated once, not once per
+// row), (b) every thread computes its rows -- ELL slots streamed from global memory (L2-resident across steps), the x
+// gathers from shared memory -- and parks the new values in the region's scratch vector xb, writing x~ into the slab
+// column when the state is kept, (c) after a barrier each thread moves its own rows from xb into the shared vector.
+// The state lives in xa between launches.  Arithmetic and order per row are those of k_train_update, so the states
+// are bit-identical.  The ML-only restart (SpMV operand = the squared copy states(:,batch_size), :1034; slab ocean
+// :933) is evaluated from the shared vector: the squared copy of the previous state is x~(x).
+//   c_first..c_end-1 : slab-column range produced by this launch (state index s = s0 + c, input column discard+s-1);
+//                      store_first: column c_first-1... see train_run_phase; out_base < 0: discard steps, nothing kept.
+// grid (nwave); block 256 (fits beside a resident Gram CTA: 64 registers) or 512.
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_MAX_THREADS = 512;
+__global__ void __launch_bounds__(SG_MAX_THREADS, 2)
+k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, int out_col0, int store_first,
+                 int s_first, int restart_period, int xs_cap, GlobalSeries gs)
+{
+    extern __shared__ __align__(16) double sg_smem[];
+    const TrainRegionDev &t = T[blockIdx.x];
+    const RegionDev &R = t.R;
+    const int n = R.n, D = R.D, W = R.ell_w, S = R.S;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double *xs = sg_smem, *us = sg_smem + xs_cap;
+    double *__restrict__ xa = t.xa, *__restrict__ xb = t.xb;
+    for (int i = tid; i < n; i += nt) xs[i] = xa[i];
+    __syncthreads();
+    if (store_first) {   // states(:,1) = x after the discard loop: no update, only the x~ copy
+        double *col = t.slab + (size_t)t.ld * (out_col0 - 1) + S;
+        for (int i = tid; i < n; i += nt) {
+            const double xv = xs[i];
+            col[i] = (i & 1) ? __dmul_rn(xv, xv) : xv;
+        }
+    }
+    const int *__restrict__ ecol = R.ell_col;
+    const double *__restrict__ eval = R.ell_val;
+    const bool compact = R.win_mode == 0;
+    const double leak = R.leak;
+    for (int k = 0; k < nsteps; ++k) {
+        const int in_col = in_col0 + k;
+        // (a) this step's input vector
+        if (gs.G) {
+            for (int i = tid; i < D; i += nt) us[i] = train_input(gs, t, in_col, i);
+        } else {
+            const double *u = t.td + (size_t)D * in_col;
+            for (int i = tid; i < D; i += nt) us[i] = u[i];
+        }
+        __syncthreads();
+        // (b) rows of this thread
+        const bool restart = restart_period > 0 && ((s_first + k) % restart_period) == 0;
+        double *slabcol = (out_col0 >= 0) ? t.slab + (size_t)t.ld * (out_col0 + k) + S : nullptr;
+        for (int base = tid; base < n; base += 2 * nt) {
+            const int r0 = base, r1 = base + nt;
+            const bool ok1 = r1 < n;
+            const int q1 = ok1 ? r1 : r0;
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int s = 0; s < W; s += 3) {
+                int c0[3], c1[3];
+                double v0[3], v1[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const bool in = s + j < W;
+                    c0[j] = in ? __ldg(ecol + (size_t)(s + j) * n + r0) : 0;
+                    v0[j] = in ? __ldg(eval + (size_t)(s + j) * n + r0) : 0.0;
+                    c1[j] = in ? __ldg(ecol + (size_t)(s + j) * n + q1) : 0;
+                    v1[j] = in ? __ldg(eval + (size_t)(s + j) * n + q1) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (s + j < W) {
+                        double g0 = xs[c0[j]], g1 = xs[c1[j]];
+                        if (restart) {
+                            if (c0[j] & 1) g0 = __dmul_rn(g0, g0);
+                            if (c1[j] & 1) g1 = __dmul_rn(g1, g1);
+                        }
+                        acc0 = fma(v0[j], g0, acc0);
+                        acc1 = fma(v1[j], g1, acc1);
+                    }
+                }
+            }
+            double tw0, tw1;
+            if (compact) {
+                tw0 = __dmul_rn(__ldg(R.winc + r0), us[__ldg(R.wcol + r0)]);
+                tw1 = __dmul_rn(__ldg(R.winc + q1), us[__ldg(R.wcol + q1)]);
+            } else {
+                tw0 = tw1 = 0.0;
+                for (int i = 0; i < D; ++i) {
+                    tw0 = fma(R.win_dense[(size_t)i * n + r0], us[i], tw0);
+                    tw1 = fma(R.win_dense[(size_t)i * n + q1], us[i], tw1);
+                }
+            }
+            const double xv0 = __dadd_rn(__dmul_rn(1.0 - leak, xs[r0]), __dmul_rn(leak, tanh(__dadd_rn(acc0, tw0))));
+            const double xv1 = __dadd_rn(__dmul_rn(1.0 - leak, xs[q1]), __dmul_rn(leak, tanh(__dadd_rn(acc1, tw1))));
+            xb[r0] = xv0;
+            if (slabcol) slabcol[r0] = (r0 & 1) ? __dmul_rn(xv0, xv0) : xv0;
+            if (ok1) {
+                xb[r1] = xv1;
+                if (slabcol) slabcol[r1] = (r1 & 1) ? __dmul_rn(xv1, xv1) : xv1;
+            }
+        }
+        __syncthreads();   // every gather of the old state is done
+        // (c) own rows: xb -> shared (written by this very thread above)
+        for (int i = tid; i < n; i += nt) xs[i] = xb[i];
+        // the next step's barrier after (a) orders these writes before the next gathers
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) xa[i] = xs[i];
+}
+
 // copy the current state (no update) into slab column out_col: states(:,1) = x after the discard loop
 __global__ void k_train_store_state(const TrainRegionDev *__restrict__ T, int parity, int out_col)
 {
@@ -435,7 +547,7 @@ struct TrainState {
     TrainRegionDev *d_regs = nullptr;
     int2 *d_tiles = nullptr;
     int ntiles = 0;
-    int ld_max = 0, n_max = 0, ks = 1024;
+    int ld_max = 0, n_max = 0, D_max = 0, ks = 1024;
     double *d_series_td = nullptr, *d_series_im = nullptr;
     size_t series_td_cap = 0, series_im_cap = 0;
     double gram_flops_useful = 0.0;   // N(N+1)K + 2PNK summed over feeds
@@ -445,6 +557,7 @@ struct TrainState {
     int solved_by_cholesky = 0;
     // overlap mode: the Gram of slab buffer b runs on its own stream while the state generation fills buffer b^1
     bool overlap = false;
+    bool per_step_launches = false;           // SML_TRAIN_STATEGEN=steps: k_train_update per time step (A/B) instead of k_train_stategen
     unsigned slab_seq = 0;                    // slabs produced so far in this wave; buffer = slab_seq & 1
     cudaEvent_t ev_gram[2] = {nullptr, nullptr};   // end of the last Gram that read buffer b (owned by spans)
     struct Span { cudaEvent_t a, b; int what; };   // what: 0 state generation, 1 Gram; resolved at the next sync point

@@ -120,9 +120,11 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         int ov = h->train_overlap;
         if (ov < 0) {
             const char *e = getenv("SML_TRAIN_OVERLAP");
-            ov = (e && atoi(e) == 0) ? 0 : 1;
+            ov = (e && atoi(e) != 0) ? 1 : 0;   // off unless asked for: at full wave size it does not pay
         }
         T.overlap = ov != 0;
+        const char *sg = getenv("SML_TRAIN_STATEGEN");
+        T.per_step_launches = sg && std::string(sg) == "steps";
         if (T.overlap && !h->train_gram_stream) {
             int lo = 0, hi = 0;   // lowest priority: the small state-generation launches must not queue behind Gram CTAs
             CK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -149,6 +151,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         d.ld = (N + d.R.P + 15) / 16 * 16;
         T.ld_max = std::max(T.ld_max, d.ld);
         T.n_max = std::max(T.n_max, d.R.n);
+        T.D_max = std::max(T.D_max, d.R.D);
         T.hybrid = d.R.S > 0;
         auto alloc = [&](size_t bytes, void **p) -> int {
             if ((*p = h->train_pool.take(bytes)) != nullptr) {  // a block of a finished wave
@@ -230,7 +233,7 @@ static int train_sync(sml_engine *h)
 
 // state generation + Gram accumulation of one phase for the wave; inputs come either from the per-region series
 // already placed in T.regs[i].dev.td / im, or from the device-resident global series gs.
-// Overlap mode (default): the slab is double-buffered and the Gram of buffer b runs on its own low-priority stream
+// Overlap mode (sml_train_set_overlap(1) / SML_TRAIN_OVERLAP=1; off by default): the slab is double-buffered and the Gram of buffer b runs on its own low-priority stream
 // while the state generation -- a chain of small latency-bound launches -- fills buffer b^1, also across phase
 // boundaries (the call returns with the last Gram still in flight; train_sync at solve / gram_get / stats / end).
 // The arithmetic and its order are those of the serial schedule, so the accumulators are bit-identical.
@@ -260,7 +263,21 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
         cudaEventCreate(&d0); cudaEventCreate(&d1);
         CK(h, cudaEventRecord(d0, S));
     }
+    // the time loop runs inside k_train_stategen (one CTA per region, state in shared memory); 256 threads fit beside
+    // a resident Gram CTA (64 registers x 256 of the 17 K the Gram leaves per SM), 512 are faster when it runs alone
+    const int sg_xs_cap = (T.n_max + 1) & ~1;
+    const size_t sg_smem = sizeof(double) * ((size_t)sg_xs_cap + ((T.D_max + 1) & ~1));
+    const bool persistent = !T.per_step_launches && sg_smem <= 90 * 1024;
+    const int sg_threads = getenv("SML_TRAIN_SG_THREADS") ? std::max(64, std::min(SG_MAX_THREADS, atoi(getenv("SML_TRAIN_SG_THREADS")) / 32 * 32))
+                                                           : (T.overlap ? 256 : SG_MAX_THREADS);
+    if (persistent) CK(h, cudaFuncSetAttribute(k_train_stategen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
     // discard loop (:1093-1106)
+    if (persistent) {
+        if (discard_cols > 0) {
+            k_train_stategen<<<nw, sg_threads, sg_smem, S>>>(T.d_regs, 0, discard_cols, -1, 0, 0, 0, sg_xs_cap, gs);
+            h->launches++;
+        }
+    } else
     for (int i = 0; i < discard_cols; ++i) {
         k_train_update<<<ugrid, 256, 0, S>>>(T.d_regs, parity, i, -1, -1, gs);
         parity ^= 1;
@@ -286,6 +303,14 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
         cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&g0); cudaEventCreate(&g1);
         if (T.overlap && T.ev_gram[buf]) CK(h, cudaStreamWaitEvent(S, T.ev_gram[buf], 0));  // the Gram that read this buffer
         CK(h, cudaEventRecord(e0, S));
+        if (persistent) {
+            // columns base .. base+nc-1 hold states s0 .. s0+nc-1; state 0 is the stored x after the discard loop, state s > 0
+            // is produced from input column discard+s-1; the ML-only paths restart every batch from the squared copy
+            const int first = (s0 == 0) ? 1 : 0;
+            k_train_stategen<<<nw, sg_threads, sg_smem, S>>>(T.d_regs, discard_cols + s0 + first - 1, nc - first, base + first, first,
+                                                             s0 + first, T.hybrid ? 0 : bs, sg_xs_cap, gs);
+            h->launches++;
+        } else
         for (int c = 0; c < nc; ++c) {
             const int s = s0 + c;  // 0-based state index
             if (s == 0) {
@@ -767,8 +792,8 @@ int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, d
     return 0;
 }
 
-// 1: state generation overlaps the Gram of the previous slab (default), 0: serial schedule (kernel timing runs);
-// takes effect at the next sml_train_begin
+// 1: state generation overlaps the Gram of the previous slab, 0: serial schedule (default); takes effect at the next
+// sml_train_begin
 int sml_train_set_overlap(sml_engine *h, int on)
 {
     if (!h) return -1;

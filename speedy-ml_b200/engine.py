@@ -683,7 +683,7 @@ class Engine:
         self._ck(self.lib.sml_train_end(self.h))
 
     def train_set_overlap(self, on: bool):
-        """state generation overlapping the previous slab's Gram (default on); applies from the next train_begin"""
+        """state generation overlapping the previous slab's Gram (default off); applies from the next train_begin"""
         self._ck(self.lib.sml_train_set_overlap(self.h, 1 if on else 0))
 
     def train_trim(self):

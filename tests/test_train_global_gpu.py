@@ -152,7 +152,7 @@ def test_condition_raw_series_on_device():
     eng.close()
 
 
-def test_device_input_noise_for_global_feed():
+def test_device_input_noise_for_global_feed(monkeypatch):
     """u*(1 + noisemag*g) with precip noised in linear space (gaussian_noise_1d_function_precip,
     src/mod_utilities.f90:1410-1464): the arithmetic is checked exactly against the NumPy restatement given the engine's
     own N(0,1) draws; the draws are checked statistically and for reproducibility (counter-based generator)."""
@@ -208,6 +208,13 @@ def test_device_input_noise_for_global_feed():
     eng.train_feed_global(1, 2, 20, 2)
     assert np.array_equal(eng.train_gram_get(1)[0], noisy_gram)
     eng.train_end()
+    # the per-time-step launches (k_train_update) and the in-kernel time loop (k_train_stategen) see the same noised inputs
+    monkeypatch.setenv("SML_TRAIN_STATEGEN", "steps")
+    eng.train_begin(regions, bs)
+    eng.train_feed_global(1, 2, 20, 2)
+    assert np.array_equal(eng.train_gram_get(1)[0], noisy_gram)
+    eng.train_end()
+    monkeypatch.delenv("SML_TRAIN_STATEGEN", raising=False)
     eng.train_set_noise(0.0)
     eng.train_begin(regions, bs)
     eng.train_feed_global(1, 2, 20, 2)

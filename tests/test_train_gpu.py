@@ -288,7 +288,13 @@ def test_overlapped_schedule_is_bit_identical(E, monkeypatch, ml_only):
     for td, im in phases:
         rc.train_phase(td, im, discard)
     grams = []
-    for on in (True, False):
+    # (overlap, state generation): the time loop inside one kernel per slab (k_train_stategen, default) or one launch per
+    # time step (k_train_update, SML_TRAIN_STATEGEN=steps)
+    for on, stategen in ((True, None), (False, None), (True, "steps"), (False, "steps")):
+        if stategen:
+            monkeypatch.setenv("SML_TRAIN_STATEGEN", stategen)
+        else:
+            monkeypatch.delenv("SML_TRAIN_STATEGEN", raising=False)
         eng = single_region_engine(E, w)
         eng.train_set_overlap(on)
         eng.train_begin([region], bs)
@@ -300,6 +306,10 @@ def test_overlapped_schedule_is_bit_identical(E, monkeypatch, ml_only):
         assert eng.train_solve(1e-2, 1.0, True, 0.0)[0] == 0 if not ml_only else eng.train_solve(1e-2)[0] == 0
         eng.train_end()
         eng.close()
+    monkeypatch.delenv("SML_TRAIN_STATEGEN", raising=False)
+    for g in grams[1:]:
+        assert np.array_equal(grams[0][0], g[0])
+        assert np.array_equal(grams[0][1], g[1])
     assert np.array_equal(grams[0][0], grams[1][0])
     assert np.array_equal(grams[0][1], grams[1][1])
     assert rel_inf(grams[0][0], rc.sxs) < 1e-12

@@ -33,7 +33,8 @@ def main():
     ap.add_argument("--batch", type=int, default=98)
     ap.add_argument("--global-series", action="store_true",
                     help="feed from the device-resident global series (sml_train_global_series) instead of per-region series")
-    ap.add_argument("--no-overlap", action="store_true", help="serial schedule (state generation, then Gram, per slab)")
+    ap.add_argument("--overlap", action="store_true", help="state generation overlaps the previous slab's Gram (default: serial schedule)")
+    ap.add_argument("--no-overlap", action="store_true", help="(default) serial schedule: state generation, then Gram, per slab")
     args = ap.parse_args()
     E = importlib.import_module("speedy-ml_b200.engine")
     syn = importlib.import_module("speedy-ml_b200.synthetic")
@@ -48,7 +49,7 @@ def main():
                               S=w["S"], P=w["P"])
             dims[w["region"]] = (w["D"], w["S"], w["n"], w["P"])
     eng.finalize()
-    eng.train_set_overlap(not args.no_overlap)
+    eng.train_set_overlap(args.overlap and not args.no_overlap)
     setup = time.perf_counter() - t0
     rng = np.random.default_rng(3)
     up_s = 0.0
@@ -100,7 +101,7 @@ def main():
            "gram_tflops_useful": tot["gram_flops_useful"] / (tot["gram_ms"] * 1e-3) / 1e12,
            "solve_ms_per_region": tot["solve_ms"] / len(regions), "solved_by_cholesky": by_chol, "dgesv_info_nonzero": bad,
            "wout_finite": bool(np.isfinite(w).all()), "setup_s": round(setup, 1),
-           "schedule": "serial" if args.no_overlap else "state generation overlaps the previous slab's Gram (stategen_s and gram_s overlap in time)",
+           "schedule": "state generation overlaps the previous slab's Gram (stategen_s and gram_s overlap in time)" if (args.overlap and not args.no_overlap) else "serial",
            "feed": "device-resident global series" if args.global_series else "per-region host series",
            "global_series_upload_s": up_s}
     print(json.dumps(out))
