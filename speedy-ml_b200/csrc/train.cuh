@@ -170,7 +170,10 @@ __global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity,
 // grid (nwave); block 256 (fits beside a resident Gram CTA: 64 registers) or 512.
 // ---------------------------------------------------------------------------------------------
 constexpr int SG_MAX_THREADS = 512;
-__global__ void __launch_bounds__(SG_MAX_THREADS, 2)
+// G: ELL slots fetched per group for the thread's two rows (4*G loads in flight); <3, 512>: 64 registers, fits beside a
+// resident Gram CTA at 256 threads; <6, 384>: up to 85 registers, twice the loads in flight when the kernel runs alone
+template <int G, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
 k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, int out_col0, int store_first,
                  int s_first, int restart_period, int xs_cap, GlobalSeries gs)
 {
@@ -212,11 +215,11 @@ k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, 
             const bool ok1 = r1 < n;
             const int q1 = ok1 ? r1 : r0;
             double acc0 = 0.0, acc1 = 0.0;
-            for (int s = 0; s < W; s += 3) {
-                int c0[3], c1[3];
-                double v0[3], v1[3];
+            for (int s = 0; s < W; s += G) {
+                int c0[G], c1[G];
+                double v0[G], v1[G];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < G; ++j) {
                     const bool in = s + j < W;
                     c0[j] = in ? __ldg(ecol + (size_t)(s + j) * n + r0) : 0;
                     v0[j] = in ? __ldg(eval + (size_t)(s + j) * n + r0) : 0.0;
@@ -224,7 +227,7 @@ k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, 
                     v1[j] = in ? __ldg(eval + (size_t)(s + j) * n + q1) : 0.0;
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < G; ++j) {
                     if (s + j < W) {
                         double g0 = xs[c0[j]], g1 = xs[c1[j]];
                         if (restart) {
@@ -557,7 +560,7 @@ struct TrainState {
     int solved_by_cholesky = 0;
     // overlap mode: the Gram of slab buffer b runs on its own stream while the state generation fills buffer b^1
     bool overlap = false;
-    bool per_step_launches = false;           // SML_TRAIN_STATEGEN=steps: k_train_update per time step (A/B) instead of k_train_stategen
+    int stategen_route = 0;                   // SML_TRAIN_STATEGEN: 0 auto (by wave size), 1 'steps' (k_train_update per time step), 2 'kernel' (k_train_stategen)
     unsigned slab_seq = 0;                    // slabs produced so far in this wave; buffer = slab_seq & 1
     cudaEvent_t ev_gram[2] = {nullptr, nullptr};   // end of the last Gram that read buffer b (owned by spans)
     struct Span { cudaEvent_t a, b; int what; };   // what: 0 state generation, 1 Gram; resolved at the next sync point

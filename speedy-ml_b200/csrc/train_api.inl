@@ -10,6 +10,10 @@
 
 namespace {
 
+// state generation alone on the SMs (serial schedule): the <6, 384> instantiation of k_train_stategen unless measured otherwise
+constexpr bool SG_WIDE_DEFAULT = false;
+constexpr int SG_MIN_WAVE = 64;   // smallest wave for which the in-kernel time loop is the default route
+
 // LU with partial pivoting + solve, the dgesv the reference calls (src/mod_linalg.f90:145); A, B on device (lu.cuh)
 int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n, int nrhs, int *info_out)
 {
@@ -124,7 +128,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         }
         T.overlap = ov != 0;
         const char *sg = getenv("SML_TRAIN_STATEGEN");
-        T.per_step_launches = sg && std::string(sg) == "steps";
+        T.stategen_route = !sg ? 0 : (std::string(sg) == "steps" ? 1 : (std::string(sg) == "kernel" ? 2 : 0));
         if (T.overlap && !h->train_gram_stream) {
             int lo = 0, hi = 0;   // lowest priority: the small state-generation launches must not queue behind Gram CTAs
             CK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -267,16 +271,30 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
     // a resident Gram CTA (64 registers x 256 of the 17 K the Gram leaves per SM), 512 are faster when it runs alone
     const int sg_xs_cap = (T.n_max + 1) & ~1;
     const size_t sg_smem = sizeof(double) * ((size_t)sg_xs_cap + ((T.D_max + 1) & ~1));
-    const bool persistent = !T.per_step_launches && sg_smem <= 90 * 1024;
-    const int sg_threads = getenv("SML_TRAIN_SG_THREADS") ? std::max(64, std::min(SG_MAX_THREADS, atoi(getenv("SML_TRAIN_SG_THREADS")) / 32 * 32))
-                                                           : (T.overlap ? 256 : SG_MAX_THREADS);
-    if (persistent) CK(h, cudaFuncSetAttribute(k_train_stategen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
+    // one CTA per region: pays once the wave fills the machine (32 us per step at 192 regions against 42-48 us for the
+    // per-step launches; 18 us against 7.5 us at 16 regions, where the per-step launches spread the rows over all SMs)
+    const bool persistent = sg_smem <= 90 * 1024 && (T.stategen_route == 2 || (T.stategen_route == 0 && nw >= SG_MIN_WAVE));
+    // serial schedule, A/B: SML_TRAIN_SG_GROUP=6 -> 6 ELL slots per group and 384 threads (more loads in flight per thread)
+    const bool sg_wide = !T.overlap && (getenv("SML_TRAIN_SG_GROUP") ? atoi(getenv("SML_TRAIN_SG_GROUP")) == 6 : SG_WIDE_DEFAULT);
+    const int sg_cap = sg_wide ? 384 : SG_MAX_THREADS;
+    const int sg_threads = getenv("SML_TRAIN_SG_THREADS") ? std::max(64, std::min(sg_cap, atoi(getenv("SML_TRAIN_SG_THREADS")) / 32 * 32))
+                                                           : (T.overlap ? 256 : sg_cap);
+    auto launch_stategen = [&](int in_col0, int nsteps, int out_col0, int store_first, int s_first, int restart_period) {
+        if (sg_wide)
+            k_train_stategen<6, 384><<<nw, sg_threads, sg_smem, S>>>(T.d_regs, in_col0, nsteps, out_col0, store_first, s_first,
+                                                                      restart_period, sg_xs_cap, gs);
+        else
+            k_train_stategen<3, SG_MAX_THREADS><<<nw, sg_threads, sg_smem, S>>>(T.d_regs, in_col0, nsteps, out_col0, store_first, s_first,
+                                                                                 restart_period, sg_xs_cap, gs);
+        h->launches++;
+    };
+    if (persistent) {
+        CK(h, cudaFuncSetAttribute(k_train_stategen<3, SG_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
+        CK(h, cudaFuncSetAttribute(k_train_stategen<6, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
+    }
     // discard loop (:1093-1106)
     if (persistent) {
-        if (discard_cols > 0) {
-            k_train_stategen<<<nw, sg_threads, sg_smem, S>>>(T.d_regs, 0, discard_cols, -1, 0, 0, 0, sg_xs_cap, gs);
-            h->launches++;
-        }
+        if (discard_cols > 0) launch_stategen(0, discard_cols, -1, 0, 0, 0);
     } else
     for (int i = 0; i < discard_cols; ++i) {
         k_train_update<<<ugrid, 256, 0, S>>>(T.d_regs, parity, i, -1, -1, gs);
@@ -307,9 +325,7 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
             // columns base .. base+nc-1 hold states s0 .. s0+nc-1; state 0 is the stored x after the discard loop, state s > 0
             // is produced from input column discard+s-1; the ML-only paths restart every batch from the squared copy
             const int first = (s0 == 0) ? 1 : 0;
-            k_train_stategen<<<nw, sg_threads, sg_smem, S>>>(T.d_regs, discard_cols + s0 + first - 1, nc - first, base + first, first,
-                                                             s0 + first, T.hybrid ? 0 : bs, sg_xs_cap, gs);
-            h->launches++;
+            launch_stategen(discard_cols + s0 + first - 1, nc - first, base + first, first, s0 + first, T.hybrid ? 0 : bs);
         } else
         for (int c = 0; c < nc; ++c) {
             const int s = s0 + c;  // 0-based state index

@@ -288,9 +288,15 @@ def test_overlapped_schedule_is_bit_identical(E, monkeypatch, ml_only):
     for td, im in phases:
         rc.train_phase(td, im, discard)
     grams = []
-    # (overlap, state generation): the time loop inside one kernel per slab (k_train_stategen, default) or one launch per
-    # time step (k_train_update, SML_TRAIN_STATEGEN=steps)
-    for on, stategen in ((True, None), (False, None), (True, "steps"), (False, "steps")):
+    # (overlap, state generation): the time loop inside one kernel per slab (k_train_stategen: the default for waves of
+    # 64 regions and more, SML_TRAIN_STATEGEN=kernel forces it) or one launch per time step (k_train_update, =steps);
+    # SML_TRAIN_SG_GROUP=6 selects the wide instantiation of the in-kernel loop
+    for on, stategen, group in ((True, "kernel", None), (False, "kernel", None), (False, "kernel", "6"), (True, "steps", None),
+                                (False, "steps", None), (False, None, None)):
+        if group:
+            monkeypatch.setenv("SML_TRAIN_SG_GROUP", group)
+        else:
+            monkeypatch.delenv("SML_TRAIN_SG_GROUP", raising=False)
         if stategen:
             monkeypatch.setenv("SML_TRAIN_STATEGEN", stategen)
         else:
@@ -312,5 +318,33 @@ def test_overlapped_schedule_is_bit_identical(E, monkeypatch, ml_only):
         assert np.array_equal(grams[0][1], g[1])
     assert np.array_equal(grams[0][0], grams[1][0])
     assert np.array_equal(grams[0][1], grams[1][1])
+    assert rel_inf(grams[0][0], rc.sxs) < 1e-12
+    assert rel_inf(grams[0][1], rc.sxt) < 1e-12
+
+
+def test_training_with_dense_win_on_both_state_generation_routes(E, monkeypatch):
+    """A W_in that is not one-non-zero-per-row takes the dense matmul(win, u) branch (src/mod_reservoir.f90:1113) in
+    training too; both state-generation routes must agree bit for bit with each other and with the oracle to 1e-12."""
+    region, bs, discard = 555, 6, 3
+    w = region_weights(1152, region, m=450)
+    rng = np.random.default_rng(8)
+    win = w["win"].copy(order="F")
+    win[::5, 2] += rng.standard_normal(win[::5, 2].shape)
+    win[7, :] = rng.standard_normal(w["D"])
+    w["win"] = win
+    td, im = _series(w, discard + 4 * bs + 2, 21)
+    rc = c_region(w)
+    rc.train_init(bs)
+    rc.train_phase(td, im, discard)
+    grams = []
+    for route in ("kernel", "steps"):
+        monkeypatch.setenv("SML_TRAIN_STATEGEN", route)
+        eng = single_region_engine(E, w)
+        eng.train_begin([region], bs)
+        eng.train_feed([td], [im], discard)
+        grams.append(eng.train_gram_get(region))
+        eng.train_end()
+        eng.close()
+    assert np.array_equal(grams[0][0], grams[1][0]) and np.array_equal(grams[0][1], grams[1][1])
     assert rel_inf(grams[0][0], rc.sxs) < 1e-12
     assert rel_inf(grams[0][1], rc.sxt) < 1e-12
