@@ -226,6 +226,27 @@ def run_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------ update-only leg
+def update_leg(eng, E, regions, peak, peak_src, steps=40):
+    """The state update alone (synchronize / spin-up, src/mod_reservoir.f90:1354-1381): all regions driven by a
+    synthetic input series for `steps` steps, CUDA events around every launch inside the engine (sml_sync_times);
+    algorithmic bytes = the update part of DESIGN.md section 4.1.  Runs after the timed region; the model state it
+    leaves is not used again."""
+    rng = np.random.default_rng(5)
+    inputs = [np.asfortranarray(rng.standard_normal((eng.dims[(E.ATMO, r)]["D"], steps))) for r in regions]
+    eng.synchronize_all(inputs, 3)
+    eng.profile(True)
+    eng.synchronize_all(inputs, steps)
+    ms, n = eng.sync_times()
+    eng.profile(False)
+    ms /= max(1, n)
+    nbytes = eng.update_algorithmic_bytes()
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_update_sx<2> (state update alone: synchronize)", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(nbytes),
+            "kernel_ms_per_launch": ms, "launches_timed": int(n)}
+
+
 # ------------------------------------------------------------------------------------------ training leg
 def train_leg(E, torch, nreg=16, cols=2000, discard=40, batch=98):
     """BASELINE's second metric: training Gram FP64 TFLOP/s on USEFUL flops N(N+1)K + 2PNK (configs[2]), one
@@ -452,6 +473,8 @@ def run_gpu(args):
             "clocks": clocks,
             "wall_ms_per_step": dev_wall / args.steps,
         }
+        if world == 1 and eng_world == 1:
+            line["update_roofline"] = update_leg(eng, E, my_regions, peak, peak_src)
         if world == 1 and not args.no_cpu_baseline:
             _, info, _ = cpu_oracle_run(args.cpu_seconds, os.cpu_count() or 1)
             line["cpu_baseline"] = info

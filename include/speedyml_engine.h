@@ -338,6 +338,8 @@ int sml_step_chunk_rows(const sml_engine *h, int kind); /* rows per CTA the step
 int64_t sml_kernel_launch_count(const sml_engine *h);
 /* algorithmic bytes one sml_predict(kind) moves */
 int64_t sml_predict_algorithmic_bytes(const sml_engine *h, int kind);
+/* the state-update part of it: what one step of sml_synchronize(kind, all regions) moves */
+int64_t sml_update_algorithmic_bytes(const sml_engine *h, int kind);
 
 #ifdef __cplusplus
 }

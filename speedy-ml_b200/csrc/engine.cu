@@ -72,7 +72,7 @@ struct KindState {
     int one_region = -1;
     size_t smem_bytes = 0;
     bool any_dense = false;
-    int64_t alg_bytes = 0;
+    int64_t alg_bytes = 0, alg_bytes_update = 0;
     // synchronize input staging
     double *d_in = nullptr;
     size_t d_in_cap = 0;
@@ -640,6 +640,7 @@ static int finalize_kind(sml_engine *h, int kind)
     int S_max = 0, max_rows = 0;
     K.items.clear();
     K.alg_bytes = 0;
+    K.alg_bytes_update = 0;
     std::vector<long long> fb_offs(nloc, 0);
     for (int i = 0; i < nloc; ++i) {
         HostRegion &hr = K.regs[i];
@@ -674,6 +675,7 @@ static int finalize_kind(sml_engine *h, int kind)
         d.nitems = (int)K.items.size() - d.item0;
         // algorithmic bytes per region-step: ELL adjacency + x read + x write +
         // compact W_in + feedback + W_out + local_model + outvec + mean/std
+        K.alg_bytes_update += (int64_t)d.ell_w * d.n * 12 + 8LL * d.n * 2 + 12LL * d.n + 8LL * d.D;   // the synchronize step
         K.alg_bytes += (int64_t)d.ell_w * d.n * 12 + 8LL * d.n * 2 + 12LL * d.n + 8LL * d.D +
                        8LL * d.P * ((int64_t)d.n + d.S) + 8LL * d.S + 8LL * d.P + 16LL * d.L;
     }
@@ -1654,6 +1656,12 @@ int64_t sml_predict_algorithmic_bytes(const sml_engine *h, int kind)
 {
     if (!h || kind < 0 || kind > 1) return 0;
     return h->kinds[kind].alg_bytes;
+}
+
+int64_t sml_update_algorithmic_bytes(const sml_engine *h, int kind)
+{
+    if (!h || kind < 0 || kind > 1) return -1;
+    return h->kinds[kind].alg_bytes_update;
 }
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 // Solve: interchanges on B, forward substitution (unit L), back substitution (U), one CTA per right-hand side,
 // blocked by the panel width.
 #pragma once
+#include "train.cuh"   // dmma884
 #include <cuda_runtime.h>
 
 namespace sml {
@@ -268,13 +269,6 @@ __global__ void k_lu_trsm(double *__restrict__ A, int lda, int n, int j0, int nb
 constexpr int LG_BM = 128, LG_BN = 64, LG_LDL = 132, LG_LDU = 68;
 constexpr size_t LG_SMEM = sizeof(double) * (size_t)LU_NB * (LG_LDL + LG_LDU);
 
-__device__ __forceinline__ void lu_dmma884(double &c0, double &c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 __global__ void __launch_bounds__(128, 3)
 k_lu_gemm(double *__restrict__ A, int lda, int n, int j0, int nb)
 {
@@ -322,7 +316,7 @@ k_lu_gemm(double *__restrict__ A, int lda, int n, int j0, int nb)
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) lu_dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
 #pragma unroll
     for (int b = 0; b < 4; ++b) {

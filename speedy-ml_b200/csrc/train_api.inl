@@ -10,25 +10,30 @@
 
 namespace {
 
-// state generation alone on the SMs (serial schedule): the <6, 384> instantiation of k_train_stategen unless measured otherwise
-constexpr bool SG_WIDE_DEFAULT = false;
+// state generation alone on the SMs (serial schedule): whether the <6, 384> instantiation of k_train_stategen is used
+constexpr bool SG_WIDE_DEFAULT = false;   // measured slower (0.91 vs 0.76 s for 384 regions)
 constexpr int SG_MIN_WAVE = 64;   // smallest wave for which the in-kernel time loop is the default route
+
+// device buffer freed on every exit path of its scope
+struct ScopedDev {
+    void *p = nullptr;
+    ~ScopedDev() { cudaFree(p); }
+};
 
 // LU with partial pivoting + solve, the dgesv the reference calls (src/mod_linalg.f90:145); A, B on device (lu.cuh)
 int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n, int nrhs, int *info_out)
 {
-    int *ipiv = nullptr, *dinfo = nullptr;
-    unsigned *ctr = nullptr;
-    double *xch = nullptr;
+    ScopedDev b_ipiv, b_info, b_xch;
     // CTAs of the cooperative panel launch: one per SM at most (SML_LU_GMAX lowers it: test hook for the many-rows-per-CTA path)
     const int Gmax = std::max(1, getenv("SML_LU_GMAX") ? std::min(atoi(getenv("SML_LU_GMAX")), h->num_sms) : h->num_sms);
     const size_t xstride = (size_t)Gmax + (size_t)Gmax * LU_NB + LU_NB + (Gmax + 1) / 2;
-    CK(h, cudaMalloc(&ipiv, sizeof(int) * (size_t)std::max(n, 1)));
-    CK(h, cudaMalloc(&dinfo, 2 * sizeof(int)));
-    CK(h, cudaMalloc(&xch, sizeof(double) * 2 * xstride));
+    CK(h, cudaMalloc(&b_ipiv.p, sizeof(int) * (size_t)std::max(n, 1)));
+    CK(h, cudaMalloc(&b_info.p, 2 * sizeof(int)));
+    CK(h, cudaMalloc(&b_xch.p, sizeof(double) * 2 * xstride));
+    int *ipiv = static_cast<int *>(b_ipiv.p), *dinfo = static_cast<int *>(b_info.p);
+    double *xch = static_cast<double *>(b_xch.p);
     CK(h, cudaMemsetAsync(dinfo, 0, 2 * sizeof(int), h->stream));
-    ctr = reinterpret_cast<unsigned *>(dinfo + 1);
-    auto cleanup = [&]() { cudaFree(ipiv); cudaFree(dinfo); cudaFree(xch); };
+    unsigned *ctr = reinterpret_cast<unsigned *>(dinfo + 1);
     // SML_LU_TIMING=1: CUDA-event split of the factorisation (panel / interchanges + trsm + gemm) and the solve on stderr
     const bool timing = getenv("SML_LU_TIMING") && atoi(getenv("SML_LU_TIMING")) != 0;
     float t_panel = 0.f, t_trail = 0.f, t_solve = 0.f;
@@ -43,14 +48,14 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
         int rows_per = std::max(64, (rows + Gmax - 1) / Gmax);
         int G = (rows + rows_per - 1) / rows_per;
         const size_t smem = sizeof(double) * (size_t)nb * (rows_per + 1);
-        if (smem > 200 * 1024) { cleanup(); FAIL(h, "mldivide: n = %d is too large for the panel kernel", n); }
+        if (smem > 200 * 1024) { FAIL(h, "mldivide: n = %d is too large for the panel kernel", n); }
         if (smem > 48 * 1024) CK(h, cudaFuncSetAttribute(k_lu_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (timing) cudaEventRecord(ev[0], h->stream);
         {
             double *A_ = dA; int lda_ = lda, n_ = n, j0_ = j0, nb_ = nb, rp_ = rows_per;
             void *args[] = {&A_, &lda_, &n_, &j0_, &nb_, &rp_, &ipiv, &dinfo, &xch, &ctr, &ctr_base};
             cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_lu_panel, dim3(G), dim3(LU_PANEL_THREADS), args, smem, h->stream);
-            if (e != cudaSuccess) { cleanup(); FAIL(h, "mldivide: cooperative panel launch failed: %s", cudaGetErrorString(e)); }
+            if (e != cudaSuccess) { FAIL(h, "mldivide: cooperative panel launch failed: %s", cudaGetErrorString(e)); }
         }
         ctr_base += (unsigned)G * (unsigned)nb;
         if (timing) cudaEventRecord(ev[1], h->stream);
@@ -73,7 +78,7 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
             t_trail += b;
         }
     }
-    if (cudaGetLastError() != cudaSuccess) { cleanup(); FAIL(h, "mldivide: factorisation launch failed"); }
+    if (cudaGetLastError() != cudaSuccess) { FAIL(h, "mldivide: factorisation launch failed"); }
     int info = 0;
     CK(h, cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -84,7 +89,6 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
             k_lu_laswp<<<(nrhs + 127) / 128, 128, 0, h->stream>>>(dB, ldb, 0, nrhs, ipiv, j0, std::min(LU_NB, n - j0));
         const size_t smem = sizeof(double) * (size_t)n;
         if (smem > 200 * 1024) {
-            cleanup();
             FAIL(h, "mldivide: n = %d exceeds the solve kernel's shared-memory vector", n);
         }
         CK(h, cudaFuncSetAttribute(k_lu_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -99,7 +103,6 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
         fprintf(stderr, "[sml lu] n=%d nrhs=%d panel %.3f ms, interchanges+trsm+gemm %.3f ms, solve %.3f ms\n", n, nrhs, t_panel, t_trail, t_solve);
         for (auto &e : ev) cudaEventDestroy(e);
     }
-    cleanup();
     *info_out = info;
     return 0;
 }

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "sml_step_chunk_rows": ([C.c_void_p, C.c_int], C.c_int),
     "sml_kernel_launch_count": ([C.c_void_p], C.c_int64),
     "sml_predict_algorithmic_bytes": ([C.c_void_p, C.c_int], C.c_int64),
+    "sml_update_algorithmic_bytes": ([C.c_void_p, C.c_int], C.c_int64),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -742,3 +743,6 @@ class Engine:
 
     def predict_algorithmic_bytes(self, kind=ATMO):
         return int(self.lib.sml_predict_algorithmic_bytes(self.h, kind))
+
+    def update_algorithmic_bytes(self, kind=ATMO):
+        return int(self.lib.sml_update_algorithmic_bytes(self.h, kind))
