@@ -78,21 +78,31 @@ def main():
     by_chol = 0
     bad = 0
     t0 = time.perf_counter()
+    host = dict(begin_s=0.0, feed_s=0.0, solve_s=0.0, end_s=0.0)   # wall clock of the calls, per kind
     for i0 in range(0, len(regions), args.wave):
         wave = regions[i0:i0 + args.wave]
+        ta = time.perf_counter()
         eng.train_begin(wave, args.batch)
+        tb = time.perf_counter()
         for ph, (td, im) in enumerate(phases):
             if args.global_series:
                 eng.train_feed_global(ph, 1, args.cols, args.discard)
             else:
                 eng.train_feed([td[:dims[r][0]] for r in wave], [im[:dims[r][1]] for r in wave], args.discard)
+        tc = time.perf_counter()
         info = eng.train_solve(1e-3, 1.0, True, 0.0)
+        td_ = time.perf_counter()
         bad += int(np.count_nonzero(info))
         by_chol += eng.train_solver_stats()
         st = eng.train_stats()
         for k in tot:
             tot[k] += st[k]
         eng.train_end()
+        te = time.perf_counter()
+        host["begin_s"] += tb - ta
+        host["feed_s"] += tc - tb
+        host["solve_s"] += td_ - tc
+        host["end_s"] += te - td_
     wall = time.perf_counter() - t0
     w = eng.wout_get(regions[-1])
     out = {"workload": f"ridge training of {len(regions)} W_out (m=6000), {args.phases} phases x {args.cols} columns, "
@@ -102,6 +112,7 @@ def main():
            "solve_ms_per_region": tot["solve_ms"] / len(regions), "solved_by_cholesky": by_chol, "dgesv_info_nonzero": bad,
            "wout_finite": bool(np.isfinite(w).all()), "setup_s": round(setup, 1),
            "schedule": "state generation overlaps the previous slab's Gram (stategen_s and gram_s overlap in time)" if (args.overlap and not args.no_overlap) else "serial",
+           "host_wall": {k: round(v, 3) for k, v in host.items()},
            "feed": "device-resident global series" if args.global_series else "per-region host series",
            "global_series_upload_s": up_s}
     print(json.dumps(out))
