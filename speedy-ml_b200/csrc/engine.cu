@@ -12,6 +12,7 @@
 // No CPU fallback anywhere: every entry point that computes launches the kernels in kernels.cuh.
 #include "../../include/speedyml_engine.h"
 #include "kernels.cuh"
+#include <chrono>
 #include "resdomain.hpp"
 #include "train.cuh"
 #include "chol.cuh"

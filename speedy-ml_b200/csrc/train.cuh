@@ -535,6 +535,16 @@ struct TrainPool {
         free_blocks.erase(it);
         return p;
     }
+    // the smallest kept block that holds `bytes` (a wave's arena fits any wave that is not larger)
+    void *take_at_least(size_t bytes, size_t *got)
+    {
+        auto it = free_blocks.lower_bound(bytes);
+        if (it == free_blocks.end()) return nullptr;
+        void *p = it->second;
+        *got = it->first;
+        free_blocks.erase(it);
+        return p;
+    }
     void drop_all()
     {
         for (auto &b : free_blocks) cudaFree(b.second);
@@ -560,6 +570,8 @@ struct TrainState {
     int solved_by_cholesky = 0;
     // overlap mode: the Gram of slab buffer b runs on its own stream while the state generation fills buffer b^1
     bool overlap = false;
+    void *arena = nullptr;                    // ONE device allocation per wave, carved up by sml_train_begin
+    size_t arena_bytes = 0;
     int stategen_route = 0;                   // SML_TRAIN_STATEGEN: 0 auto (by wave size), 1 'steps' (k_train_update per time step), 2 'kernel' (k_train_stategen)
     unsigned slab_seq = 0;                    // slabs produced so far in this wave; buffer = slab_seq & 1
     cudaEvent_t ev_gram[2] = {nullptr, nullptr};   // end of the last Gram that read buffer b (owned by spans)
@@ -732,6 +744,12 @@ inline void train_release(TrainState &t, TrainPool *pool = nullptr)
             else cudaFree(a.first);
         }
     t.regs.clear();
+    if (t.arena) {
+        if (pool) pool->free_blocks.emplace(t.arena_bytes, t.arena);
+        else cudaFree(t.arena);
+        t.arena = nullptr;
+        t.arena_bytes = 0;
+    }
     for (auto &sp : t.spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     t.spans.clear();
     t.ev_gram[0] = t.ev_gram[1] = nullptr;

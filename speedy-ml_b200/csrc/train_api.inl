@@ -139,6 +139,44 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         }
     }
     std::vector<TrainRegionDev> devs;
+    const bool tb_timing = getenv("SML_TRAIN_TIMING") && atoi(getenv("SML_TRAIN_TIMING")) != 0;   // host clock split on stderr
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_alloc = 0.0, t_memset = 0.0, t_map = 0.0;
+    const double tb0 = now();
+    // ---- one device allocation for the whole wave: its regions' blocks are carved out of an arena.  (1536 separate
+    //      cudaMalloc calls for a wave of 192 cost 2.9-5.1 s in a process that already holds the model; one call of the
+    //      same 68 GB costs milliseconds -- tools/malloc_probe.py, gpurun_out/train_hostwall*.log.)
+    auto al256 = [](size_t b) { return (b + 255) / 256 * 256; };
+    size_t arena_need = 0;
+    for (int i = 0; i < nregions; ++i) {
+        int li;
+        if (local_of(h, kind, regions[i], &li)) { train_release(T); return -1; }
+        const RegionDev &R = K.regs[li].dev;
+        const size_t N = (size_t)R.n + R.S, ld = (N + R.P + 15) / 16 * 16;
+        arena_need += al256(ld * ld * 8) + al256(ld * T.ks * 8 * (T.overlap ? 2 : 1)) + 2 * al256((size_t)R.n * 8) +
+                      al256(((N + CH_NB - 1) / CH_NB) * CH_LINV * 8) + al256(ld * 8) + al256(sizeof(int)) + al256(sizeof(int) * R.P);
+    }
+    {
+        size_t got = 0;
+        void *a = h->train_pool.take_at_least(arena_need, &got);
+        if (!a) {
+            cudaError_t e = cudaMalloc(&a, arena_need);
+            if (e != cudaSuccess) {   // smaller arenas of earlier waves may be hoarding the memory: give them back and retry
+                cudaGetLastError();
+                h->train_pool.drop_all();
+                e = cudaMalloc(&a, arena_need);
+            }
+            if (e != cudaSuccess) {
+                h->err = std::string("training wave does not fit in HBM (cudaMalloc: ") + cudaGetErrorString(e) + "); use fewer regions per wave";
+                train_release(T);
+                return -1;
+            }
+            got = arena_need;
+        }
+        T.arena = a;
+        T.arena_bytes = got;
+    }
+    size_t arena_off = 0;
     for (int i = 0; i < nregions; ++i) {
         int li;
         if (local_of(h, kind, regions[i], &li)) { train_release(T); return -1; }
@@ -161,27 +199,21 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         T.D_max = std::max(T.D_max, d.R.D);
         T.hybrid = d.R.S > 0;
         auto alloc = [&](size_t bytes, void **p) -> int {
-            if ((*p = h->train_pool.take(bytes)) != nullptr) {  // a block of a finished wave
-                tr.allocs.emplace_back(*p, bytes);
-                return 0;
-            }
-            cudaError_t e = cudaMalloc(p, bytes);
-            if (e != cudaSuccess) {  // blocks of other sizes may be hoarding the memory: give them back and retry
-                cudaGetLastError();
-                h->train_pool.drop_all();
-                e = cudaMalloc(p, bytes);
-            }
-            if (e != cudaSuccess) {
-                h->err = std::string("training wave does not fit in HBM (cudaMalloc: ") + cudaGetErrorString(e) + "); use fewer regions per wave";
+            if (arena_off + al256(bytes) > T.arena_bytes) {
+                h->err = "internal: training arena overflow";
                 return -1;
             }
-            tr.allocs.emplace_back(*p, bytes);
+            *p = static_cast<char *>(T.arena) + arena_off;
+            arena_off += al256(bytes);
             return 0;
         };
         void *p = nullptr;
         bool bad = false;
+        double tq = now();
         bad = bad || alloc((size_t)d.ld * d.ld * 8, &p); d.gram = (double *)p;
+        t_alloc += now() - tq; tq = now();
         if (!bad) cudaMemsetAsync(d.gram, 0, (size_t)d.ld * d.ld * 8, h->stream);
+        t_memset += now() - tq; tq = now();
         bad = bad || alloc((size_t)d.ld * T.ks * 8 * (T.overlap ? 2 : 1), &p); d.slab = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xa = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xb = (double *)p;
@@ -192,10 +224,12 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         const std::vector<int32_t> &tmap = K.regs[li].target_map;
         if ((int)tmap.size() != d.R.P) { h->err = "internal: target map size"; train_release(T); return -1; }
         bad = bad || alloc(sizeof(int) * d.R.P, &p);
+        t_alloc += now() - tq; tq = now();
         if (!bad) {
             cudaMemcpyAsync(p, tmap.data(), sizeof(int) * d.R.P, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
         }
+        t_map += now() - tq;
         d.target_map = (const int *)p;
         T.regs.push_back(tr);
         if (bad) { train_release(T); h->train_pool.drop_all(); return -1; }
@@ -216,6 +250,9 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     CK(h, cudaFuncSetAttribute(k_chol_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
     CK(h, cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_DIAG_SMEM));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (tb_timing)
+        fprintf(stderr, "[sml train_begin] %d regions: %.3f s (allocation %.3f, memset enqueue %.3f, target map + sync %.3f)\n", nregions,
+                now() - tb0, t_alloc, t_memset, t_map);
     T.active = true;
     return 0;
 }
