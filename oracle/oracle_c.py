@@ -79,6 +79,8 @@ def lib():
         L.orc_coo_mv.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
         L.orc_dgesv.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _ip, _dp, C.c_int]
         L.orc_mldivide.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int]
+        L.orc_rolling_average_2d.argtypes = [_dp] + [C.c_int] * 5
+        L.orc_rolling_average_2d.restype = None
         L.orc_train_init.argtypes = [C.c_void_p, C.c_int]
         L.orc_train_phase_hybrid.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int]
         L.orc_train_phase_ml.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int]
@@ -393,6 +395,13 @@ def coo_mv(n, rows, cols, vals, x):
     y = np.zeros(n)
     lib().orc_coo_mv(n, rows.size, _i(rows), _i(cols), _d(vals), _d(x), _d(y))
     return y
+
+
+def rolling_average_over_a_period_2d(grid, period, keep_small=True):
+    """src/mod_utilities.f90:1773-1815 on a (rows, T) array; returns a copy"""
+    g = np.array(grid, dtype=np.float64, order="F", copy=True)
+    lib().orc_rolling_average_2d(_d(g), g.shape[0], g.shape[0], g.shape[1], int(period), int(bool(keep_small)))
+    return g
 
 
 def mldivide(A, B):

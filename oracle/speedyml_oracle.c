@@ -1104,6 +1104,33 @@ void orc_host_stub(const double *grid4d, const double *grid2d, const double *cli
     }
 }
 
+/* rolling_average_over_a_period_2d (src/mod_utilities.f90:1773-1815), in place on grid(i,t) = grid[ld*t + i], i < nrows:
+ *   t - period < 1 (1-based):  sum(copy(i,1:t)) / t
+ *   else:                      sum(copy(i,t-period:t)) / period   (period+1 values over period, as written), kept only
+ *                              when |sum| > 1e-7 (keep_small; the 3-D variant :1731-1771 has no such test)
+ * windows summed first to last, like the Fortran intrinsic without reassociation. */
+void orc_rolling_average_2d(double *grid, int ld, int nrows, int t_len, int period, int keep_small)
+{
+    double *copy = (double *)malloc(sizeof(double) * (size_t)nrows * (size_t)t_len);
+    if (!copy) return;
+    for (int t = 0; t < t_len; ++t)
+        for (int i = 0; i < nrows; ++i) copy[(size_t)nrows * t + i] = grid[(size_t)ld * t + i];
+    for (int i = 0; i < nrows; ++i) {
+        for (int t1 = 1; t1 <= t_len; ++t1) {   /* 1-based time index, as in the reference */
+            const int head = (t1 - period < 1);
+            const int lo = head ? 1 : t1 - period;
+            double s = 0.0;
+            for (int k = lo; k <= t1; ++k) s = s + copy[(size_t)nrows * (k - 1) + i];
+            double out;
+            if (head) out = s / (double)t1;
+            else if (keep_small && !(fabs(s) > 0.0000001)) out = copy[(size_t)nrows * (t1 - 1) + i];
+            else out = s / (double)period;
+            grid[(size_t)ld * (t1 - 1) + i] = out;
+        }
+    }
+    free(copy);
+}
+
 /* feedback / local_model construction: :581-604 (root), :606-739 (exchange, same tilers), :749-775.
  * tisr_grid is the global 96x48 TISR field (physical units) for this date; the reference keeps the
  * region's slice of the year table pre-standardised with (x-mean)/std (src/mod_reservoir.f90:905-907)

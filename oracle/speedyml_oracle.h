@@ -157,6 +157,9 @@ void orc_run_model_clamp(double *grid4d); /* q floor before/after the host model
 void orc_host_stub(const double *grid4d, const double *grid2d, const double *clim4d,
                    const double *clim2d, double *forecast_4d, double *forecast_2d);
 
+/* rolling_average_over_a_period_2d (src/mod_utilities.f90:1773-1815); keep_small = 0: the 3-D variant :1731-1771 */
+void orc_rolling_average_2d(double *grid, int ld, int nrows, int t_len, int period, int keep_small);
+
 /* ---- training (src/mod_reservoir.f90:1067-1334,1561-1701) ---- */
 int  orc_train_init(orc_region *r, int batch_size);
 void orc_train_phase_hybrid(orc_region *r, const double *trainingdata, int ld_t,

@@ -7,7 +7,7 @@ import importlib
 import numpy as np
 import pytest
 
-from helpers import on
+from helpers import oc, on
 
 
 def test_oracle_matches_the_code_as_written():
@@ -28,6 +28,17 @@ def test_oracle_matches_the_code_as_written():
     for t in range(28):
         assert np.allclose(o[:, t], r[:, :t + 1].mean(axis=1), rtol=1e-14, atol=0)
     assert np.allclose(o[:, 33], r[:, 5:34].sum(axis=1) / 28, rtol=1e-14, atol=0)
+
+
+def test_c_and_numpy_restatements_agree_bitwise():
+    rng = np.random.default_rng(3)
+    for rows, T, period in ((7, 50, 6), (80, 300, 28), (3, 10, 168), (5, 40, 1)):
+        g = np.asfortranarray(rng.standard_normal((rows, T)))
+        g[0, 5:5 + 2 * period + 2] = 0.0
+        g[1 % rows, 3:9] = 1e-9
+        for keep_small in (True, False):
+            assert np.array_equal(oc.rolling_average_over_a_period_2d(g, period, keep_small),
+                                  on.rolling_average_over_a_period_2d(g, period, keep_small))
 
 
 @pytest.mark.gpu
