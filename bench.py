@@ -5,14 +5,20 @@ Workload (BASELINE.json configs[1]): the full 1152-region hybrid atmosphere fore
 levels, reservoir size m=6000 (n = 5760..6160 per region class), degree 6, overlap 1, precip + SST +
 TISR inputs, regions sharded over N GPUs exactly as processor_decomposition does.
 A "step" is one hybrid 6-hour step: predict (state update + readout) for every region, the exchange of
-the outvec slabs (NCCL all-gather when N > 1), scatter into the global grids with the clamps, and the
+the outvec slabs (peer stores over NVLink when N > 1), scatter into the global grids with the clamps, and the
 rebuild of every region's feedback / local_model.  1 step = 0.25 sim-day.
 
   value  : sim-days per wall-second with everything resident in HBM (the host model's forecast grid F
            stays the one the last e2e step left on the device)
   e2e    : the same step through the reference-facing API with HOST buffers: sendrecievegrid's
-           wholegrid copy-out (D2H), the host model stub, forecast + TISR copy-in (H2D), every step
-  --impl reference : the CPU oracle (port of the reference's algorithmic form) on the host cores.
+           wholegrid copy-out (D2H), the host model stub, forecast + TISR copy-in (H2D), every step.  At N > 1
+           every exchange -- outvec all-gather, forecast distribution -- runs inside the engine
+           (sml_comm_bootstrap); this file issues no collective inside a step
+  grid_checksum : FP64 sum and XOR of the bit patterns of the global grids after 6 sequential hybrid steps from a
+           fixed start, on every rank: sharding does not change any region's arithmetic, so the value is the same
+           for N = 1, 2, 4, 8 (and all ranks of a run must agree)
+  train  : BASELINE's second metric at every N (regions sharded, no collective): aggregate Gram FP64 TFLOP/s
+  --impl reference : the CPU oracle (port of the reference's algorithmic form) on the host cores, ALL 1152 regions.
 
 One JSON line on stdout (rank 0).
 """
@@ -32,7 +38,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 R_TOTAL = 1152
 M_RES = 6000
@@ -40,18 +45,23 @@ SIM_DAYS_PER_STEP = 0.25
 METRIC = "hybrid forecast sim-days/wall-sec (1152 regions)"
 UNIT = "sim-days/s"
 WORKLOAD = "full 1152-region hybrid atmosphere prediction, T30 8-sigma, reservoir 6000"
+CHECK_STEPS = 6
 
 
 def sst_input_mask(region: int) -> bool:
     return region % 10 < 7  # 70 % of the regions carry an SST input slot
 
 
-def gen_region(region: int, dense_win: bool = False):
-    """seeded synthetic weights of one region (seed = 20251018 + region), reference construction recipe"""
-    syn = importlib.import_module("speedy-ml_b200.synthetic")
-    E = importlib.import_module("speedy-ml_b200.engine")
+def _synthetic():
+    return importlib.import_module("speedy-ml_b200.synthetic")   # NumPy only; loads no native library
+
+
+def gen_region(region: int, dims):
+    """seeded synthetic weights of one region (seed = 20251018 + region), reference construction recipe.
+    dims(region, sst_bool_input) -> dict(n, k, D, P, S, L): the engine's sizes in the GPU arm, the oracle's in the CPU arm"""
+    syn = _synthetic()
     sst_in = sst_input_mask(region)
-    d = E.region_dims(R_TOTAL, region, 1, M_RES, 6.0, True, True, sst_in, False)
+    d = dims(region, sst_in)
     rng = np.random.default_rng(20251018 + region)
     rows, cols, vals = syn.make_adjacency(d["n"], d["k"], rng, radius=0.7, power_iters=30)
     winc, wcol = syn.make_win_compact(d["n"], d["D"], rng, sigma=0.5)
@@ -60,34 +70,35 @@ def gen_region(region: int, dense_win: bool = False):
     flat = wout.reshape(-1, order="F")
     flat[:] = (rng.random(flat.size) - 0.5) * (np.sqrt(12.0) / np.sqrt(N))  # unit-variance/sqrt(N)
     mean, std = syn.make_mean_std(d["L"], rng)
-    w = dict(region=region, sst_bool_input=sst_in, rows=rows, cols=cols, vals=vals, winc=winc, wcol=wcol,
-             wout=wout, mean=mean, std=std, **d)
-    if dense_win:
-        w["win"] = syn.win_dense_from_compact(winc, wcol, d["D"])
-    return w
+    return dict(region=region, sst_bool_input=sst_in, rows=rows, cols=cols, vals=vals, winc=winc, wcol=wcol,
+                wout=wout, mean=mean, std=std, **d)
 
 
 def initial_fields(seed=7):
-    syn = importlib.import_module("speedy-ml_b200.synthetic")
     rng = np.random.default_rng(seed)
-    clim4d, clim2d, tisr, base_sst, sea_mask = syn.climatology(rng)
+    clim4d, clim2d, tisr, base_sst, sea_mask = _synthetic().climatology(rng)
     return dict(clim4d=clim4d, clim2d=clim2d, tisr=tisr, base_sst=base_sst, sea_mask=sea_mask)
 
 
-def host_stub(w4d, w2d, clim4d, clim2d, out=None):
+class HostStub:
     """deterministic stand-in for run_model/agcm_main (SPEEDY stays on the host and is out of scope):
-    forecast = 0.98*grid + 0.02*climatology, with run_model's q floor.  out=(f4, f2) reuses two F-order arrays."""
-    if out is None:
-        f4 = 0.98 * w4d + 0.02 * clim4d
-        f2 = 0.98 * w2d + 0.02 * clim2d
-    else:
-        f4, f2 = out
-        np.multiply(w4d, 0.98, out=f4)
-        f4 += 0.02 * clim4d
-        np.multiply(w2d, 0.98, out=f2)
-        f2 += 0.02 * clim2d
-    np.maximum(f4[3], 0.000001, out=f4[3])
-    return np.asfortranarray(f4), np.asfortranarray(f2)
+    forecast = 0.98*grid + 0.02*climatology with run_model's q floor (src/mpires.f90:1648-1650).  Two roundings and an
+    add per element, the arithmetic of the CPU arm's stub; writes into preallocated (pinned) arrays, no temporaries."""
+
+    def __init__(self, clim4d, clim2d, out4=None, out2=None):
+        self.c4 = np.asfortranarray(0.02 * clim4d)
+        self.c2 = np.asfortranarray(0.02 * clim2d)
+        self.f4 = out4 if out4 is not None else np.empty((4, 96, 48, 8), order="F")
+        self.f2 = out2 if out2 is not None else np.empty((96, 48), order="F")
+        self.q = self.f4.reshape(-1, order="F")[3::4]        # view: var 4 (q) of every cell
+
+    def __call__(self, w4d, w2d, wsst=None):
+        np.multiply(w4d, 0.98, out=self.f4)
+        self.f4 += self.c4
+        np.multiply(w2d, 0.98, out=self.f2)
+        self.f2 += self.c2
+        np.maximum(self.q, 0.000001, out=self.q)
+        return self.f4, self.f2
 
 
 class ClockSampler:
@@ -151,74 +162,138 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """dram bytes per launch of the step kernel from the committed ncu --set full summary, if any"""
-    path = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get("traffic_bytes_per_launch")
-        except Exception:
-            return None
+    """dram bytes per launch of the step kernel from the COMMITTED ncu --set full summary (static evidence, not
+    something this run measured) -> (bytes or None, source label)"""
+    for name in ("step_kernel_traffic_r02.json", "step_kernel_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            try:
+                d = json.load(open(path))
+                return d.get("traffic_bytes_per_launch"), f"profiles/{name} (static: committed ncu capture of kernel {d.get('kernel', '?')})"
+            except Exception:
+                continue
+    return None, "none"
+
+
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
     return None
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_run(seconds_target: float, nthreads: int, steps_fixed: int | None = None, nsample: int = 64):
-    """times the oracle (reference algorithmic form: COO SpMV, DENSE n x D W_in GEMV, dense W_out GEMV,
-    un-standardise, tile/standardise) on a bounded sample of regions.  Returns (sim_days_per_s, info)."""
-    from oracle import oracle_c as oc
+class CpuModel:
+    """the oracle (reference algorithmic form: COO SpMV, DENSE n x D W_in GEMV as the reference stores it, dense W_out
+    GEMV, un-standardise, gather with clamps, host stub, scatter + standardise) over a set of regions.  Only oracle/
+    and NumPy are touched: the engine library is never loaded by this class."""
 
-    # proportional class mix: every 18th region (64 regions) keeps interior/periodic/polar shares close
+    def __init__(self, regions, nthreads):
+        from oracle import oracle_c as oc
+        self.oc, self.nthreads, self.regions = oc, nthreads, list(regions)
+        self.full = len(self.regions) == R_TOTAL
+        self.F = initial_fields()
+
+        def dims(region, sst_in):
+            rc = oc.Region(R_TOTAL, region, m=M_RES, precip_bool=True, sst_bool=True, sst_bool_input=sst_in)
+            return dict(n=rc.n, k=rc.k, D=rc.D, P=rc.P, S=rc.S, L=rc.L)
+
+        def build(r):
+            w = gen_region(r, dims)
+            rc = oc.Region(R_TOTAL, r, m=M_RES, precip_bool=True, sst_bool=True, sst_bool_input=w["sst_bool_input"])
+            rc.set_weights(w["rows"], w["cols"], w["vals"], None, w["wout"], w["mean"], w["std"])
+            rc.set_win_compact(w["winc"], w["wcol"])
+            rc.densify_win()            # the dense win(n, D) of the reference, built inside the oracle
+            return rc, w["mean"][-1], w["std"][-1]
+
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=max(1, min(32, nthreads))) as ex:
+            built = list(ex.map(build, self.regions))
+        self.regs = [b[0] for b in built]
+        self.sst_mean = np.array([b[1] for b in built])
+        self.sst_std = np.array([b[2] for b in built])
+        self.setup_s = time.perf_counter() - t0
+        F = self.F
+        self.w4d, self.w2d = F["clim4d"].copy(order="F"), F["clim2d"].copy(order="F")
+        self.wp = np.zeros((96, 48), order="F")
+        self.wsst = np.maximum(F["base_sst"], 272.0)
+        self.has = np.ones(len(self.regs), dtype=np.int32)
+        self.oo = np.zeros((len(self.regs), 4))
+        for i, r in enumerate(self.regions):
+            xs, xe, ys, ye, *_ = oc.getxyresextent(R_TOTAL, r)
+            self.oo[i] = F["base_sst"][xs - 1:xe, ys - 1:ye].ravel(order="F")
+        # bytes the reference's form streams per region-step: dense W_in + W_out + COO adjacency
+        self.bytes_per_step = sum(8 * rc.n * rc.D + 8 * rc.P * (rc.n + rc.S) + 16 * rc.k for rc in self.regs)
+
+    def step(self):
+        oc, F = self.oc, self.F
+        oc.predict_all(self.regs, nthreads=self.nthreads)
+        if self.full:   # closed loop: the gather covers the whole grid only when every region is there
+            self.w4d, self.w2d, self.wp, self.wsst = oc.step_gather(self.regs, True, True, F["base_sst"], F["sea_mask"],
+                                                                    ocean_out=self.oo, has_ocean=self.has)
+        f4, f2 = oc.host_stub(self.w4d, self.w2d, F["clim4d"], F["clim2d"])
+        oc.step_scatter(self.regs, True, True, False, self.w4d, self.w2d, self.wp, self.wsst, f4, f2, F["tisr"],
+                        self.sst_mean, self.sst_std, nthreads=self.nthreads)
+
+    def time_steps(self, warmup, steps):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        return time.perf_counter() - t0
+
+
+def cpu_sample_baseline(seconds_target: float, nthreads: int, nsample: int = 128):
+    """cpu_baseline of the GPU arm: a bounded sample (every 9th region id keeps the class mix), scaled to the model"""
     regions = list(range(0, R_TOTAL, R_TOTAL // nsample))[:nsample]
-    F = initial_fields()
-    regs = []
-    for r in regions:
-        w = gen_region(r, dense_win=True)
-        rc = oc.Region(R_TOTAL, r, m=M_RES, precip_bool=True, sst_bool=True, sst_bool_input=w["sst_bool_input"])
-        rc.set_weights(w["rows"], w["cols"], w["vals"], w["win"], w["wout"], w["mean"], w["std"])
-        regs.append(rc)
-        del w
-    sst_mean = np.array([rc.view("mean", (rc.L,))[-1] for rc in regs])
-    sst_std = np.array([rc.view("std", (rc.L,))[-1] for rc in regs])
-    w4d, w2d = F["clim4d"].copy(order="F"), F["clim2d"].copy(order="F")
-    wp = np.zeros((96, 48), order="F")
-    wsst = np.maximum(F["base_sst"], 272.0)
-
-    def one_step():
-        oc.predict_all(regs, nthreads=nthreads)
-        f4, f2 = host_stub(w4d, w2d, F["clim4d"], F["clim2d"])
-        oc.step_scatter(regs, True, True, False, w4d, w2d, wp, wsst, f4, f2, F["tisr"], sst_mean, sst_std,
-                        nthreads=nthreads)
-
-    one_step()  # warm-up (page in the weights)
-    t0 = time.perf_counter()
-    one_step()
-    dt1 = time.perf_counter() - t0
-    steps = steps_fixed if steps_fixed is not None else max(2, int(seconds_target / max(dt1, 1e-6)))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one_step()
-    dt = time.perf_counter() - t0
-    region_steps_per_s = steps * len(regs) / dt
-    value = region_steps_per_s / R_TOTAL * SIM_DAYS_PER_STEP
-    info = {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": f"{len(regs)} of 1152 regions (every {R_TOTAL // nsample}th id, m=6000, dense W_in as the "
-                      f"reference stores it) x {steps} hybrid steps in {dt:.1f} s; scaled by 1152/{len(regs)}; "
-                      f"predict + feedback/local_model rebuild, host model stub included, NetCDF excluded"}
-    return value, info, dt / steps * 1e3
+    m = CpuModel(regions, nthreads)
+    dt1 = m.time_steps(1, 1)
+    steps = max(2, int(seconds_target / max(dt1, 1e-6)))
+    dt = m.time_steps(0, steps)
+    value = steps * len(regions) / dt / R_TOTAL * SIM_DAYS_PER_STEP
+    return {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "blas": "none: plain C loops (axpy-order dense GEMV, COO SpMV), gcc -O2",
+            "achieved_GBps": m.bytes_per_step * steps / dt / 1e9,
+            "sample": f"{len(regions)} of 1152 regions (every {R_TOTAL // nsample}th id, m=6000, dense W_in as the "
+                      f"reference stores it) x {steps} hybrid steps in {dt:.1f} s; scaled by 1152/{len(regions)}; predict + "
+                      f"host stub + feedback/local_model rebuild (the gather needs every region: only in --impl reference), "
+                      f"NetCDF excluded; the full-model figure is the --impl reference arm"}
 
 
 def run_reference(args):
+    """the reference's algorithmic form on the host cores, ALL 1152 regions, closed loop, honouring --steps/--warmup"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     nthreads = os.cpu_count() or 1
-    per_step_budget = 20.0 / max(1, args.steps + args.warmup)
-    value, info, ms = cpu_oracle_run(per_step_budget * args.steps, nthreads, steps_fixed=None)
+    avail = mem_available_gb()
+    regions = list(range(R_TOTAL))
+    note = ""
+    if avail is not None and avail < 48.0:   # 38 GB of dense W_in + W_out do not fit: say so instead of swapping
+        regions = list(range(0, R_TOTAL, 9))
+        note = f"; host has only {avail:.0f} GB available: {len(regions)} regions timed and scaled"
+    m = CpuModel(regions, nthreads)
+    dt = m.time_steps(args.warmup, args.steps)
+    value = args.steps * len(regions) / dt / R_TOTAL * SIM_DAYS_PER_STEP
+    info = {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "blas": "none: plain C loops (axpy-order dense GEMV, COO SpMV), gcc -O2; the path is memory-bound on the "
+                    "26.5 MB dense W_in per region, so a vendor BLAS would not change the order of magnitude",
+            "achieved_GBps": m.bytes_per_step * args.steps / dt / 1e9,
+            "setup_s": round(m.setup_s, 1),
+            "sample": f"{len(regions)} of 1152 regions x {args.steps} timed hybrid steps ({args.warmup} warm-up) in {dt:.1f} s: "
+                      f"predict (COO SpMV + dense W_in GEMV + tanh + dense W_out GEMV) + gather with clamps + host stub + "
+                      f"scatter/standardise, closed loop, NetCDF excluded{note}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * SIM_DAYS_PER_STEP / value, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps * (R_TOTAL / len(regions)), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference's algorithmic form; the "
-                       "Fortran/MPI/MKL reference cannot be built in this image"},
+            "config": {"workload": WORKLOAD, "regions": len(regions), "reservoir_m": M_RES, "degree": 6, "overlap": 1,
+                       "sim_days_per_step": SIM_DAYS_PER_STEP,
+                       "note": "CPU oracle port of the reference's algorithmic form on the host cores; the "
+                               "Fortran/MPI/MKL reference cannot be built in this image (no f951, MPI, MKL, ARPACK, NetCDF)"},
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -242,40 +317,59 @@ def update_leg(eng, E, regions, peak, peak_src, steps=40):
     ms /= max(1, n)
     nbytes = eng.update_algorithmic_bytes()
     achieved = nbytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "k_update_sx<2> (state update alone: synchronize)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(nbytes),
-            "kernel_ms_per_launch": ms, "launches_timed": int(n)}
+    return {"bound": "hbm", "kernel": "update-only path of sml_synchronize (state update alone)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": int(nbytes), "kernel_ms_per_launch": ms, "launches_timed": int(n)}
 
 
 # ------------------------------------------------------------------------------------------ training leg
-def train_leg(E, torch, nreg=16, cols=2000, discard=40, batch=98):
-    """BASELINE's second metric: training Gram FP64 TFLOP/s on USEFUL flops N(N+1)K + 2PNK (configs[2]), one
-    wave of full-size regions x one phase, next to the solve time and the box's cuBLAS DGEMM rate."""
-    syn = importlib.import_module("speedy-ml_b200.synthetic")
-    eng = E.Engine(number_of_regions=R_TOTAL, irank=1, numprocs=R_TOTAL // nreg)
-    regions = eng.region_indices
-    ws = {}
-    for r in regions:
-        w = gen_region(r)
-        ws[r] = w
-        eng.region_upload(r, w["rows"], w["cols"], w["vals"], None, w["mean"], w["std"], win_compact=w["winc"],
-                          win_col=w["wcol"], D=w["D"], sst_bool_input=w["sst_bool_input"], S=w["S"], P=w["P"])
-    eng.finalize()
+def train_leg(eng, E, torch, dist, world, regions, ws_dims, cols=2000, discard=40, batch=98, long_k=True):
+    """BASELINE's second metric: training Gram FP64 TFLOP/s on USEFUL flops N(N+1)K + 2PNK (configs[2]).
+    Every rank trains ONE wave of its own regions (all of them up to 144: the per-GPU shard at N = 8) for one phase;
+    no collective (the path shards by region).  The aggregate is the sum of the ranks' useful flops over the slowest
+    rank's Gram time.  Rank 0 also runs one long-K phase (K = 37 920, the 26-year setting of SURVEY 8(d) config 3) on a
+    small wave to show the rate holds when the accumulation is long.  Runs on the engine that held the forecast model:
+    the solve overwrites its W_out, so this leg is last."""
+    syn = _synthetic()
+    wave = regions[:144]
     rng = np.random.default_rng(1)
-    tds = [syn.ar1_series(ws[r]["D"], cols, rng) for r in regions]
-    ims = [np.asfortranarray(rng.standard_normal((ws[r]["S"], cols))) for r in regions]
+    cache = {}
+
+    def series(r, ncols):
+        d = ws_dims[r]
+        key = (d["D"], d["S"], ncols)
+        if key not in cache:   # regions of one shape class share the synthetic series (the arithmetic does not care)
+            cache[key] = (syn.ar1_series(d["D"], ncols, rng), np.asfortranarray(rng.standard_normal((d["S"], ncols))))
+        return cache[key]
+
+    tds = [series(r, cols)[0] for r in wave]
+    ims = [series(r, cols)[1] for r in wave]
     eng.train_set_overlap(False)               # serial schedule: the Gram kernel is timed alone
-    eng.train_begin(regions, batch)
-    eng.train_feed(tds, ims, discard)          # warm-up phase (also the second of two accumulated phases)
+    dmma_peak = eng.dmma_probe()
+    eng.train_begin(wave, batch)
+    eng.train_feed(tds, ims, discard)          # warm-up phase (also the first of two accumulated phases)
     st0 = eng.train_stats()
     eng.train_feed(tds, ims, discard)
     st = eng.train_stats()
     gram_ms = st["gram_ms"] - st0["gram_ms"]
+    stategen_ms = st["stategen_ms"] - st0["stategen_ms"]
     flops = st["gram_flops_useful"] - st0["gram_flops_useful"]
     info = eng.train_solve(1e-3, 1.0, True, 0.0)
     st = eng.train_stats()
+    solve_ms = st["solve_ms"]
+    by_chol = eng.train_solver_stats()
     eng.train_end()
-    eng.close()
+    out_long = None
+    if long_k and int(os.environ.get("RANK", "0")) == 0:
+        K_LONG, small = 37920, wave[:8]
+        tl = [series(r, K_LONG)[0] for r in small]
+        il = [series(r, K_LONG)[1] for r in small]
+        eng.train_begin(small, batch)
+        eng.train_feed(tl, il, discard)
+        s1 = eng.train_stats()
+        eng.train_end()
+        out_long = {"regions": len(small), "columns": K_LONG, "gram_tflops": s1["gram_flops_useful"] / (s1["gram_ms"] * 1e-3) / 1e12,
+                    "gram_ms": s1["gram_ms"], "stategen_ms": s1["stategen_ms"]}
     a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     torch.matmul(a, b)
@@ -288,21 +382,52 @@ def train_leg(E, torch, nreg=16, cols=2000, discard=40, batch=98):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     dgemm = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
-    tf = flops / (gram_ms * 1e-3) / 1e12
-    dmma_peak = 37.1   # tools/dmma_probe.cu on this pool's B200 (profiles/dmma_probe_r01.txt)
-    return {"metric": "training Gram FP64 TFLOP/s", "value": tf, "unit": "TFLOP/s",
-            "workload": f"ridge training, {nreg} regions x 1 phase x {cols} columns, m=6000 (N=5892..6292)",
+    # aggregate over the ranks: total useful flops / the slowest rank's Gram time
+    if world > 1:
+        t = torch.tensor([flops, gram_ms, stategen_ms, solve_ms, dmma_peak, float(len(wave)), float(max(info)), float(by_chol)],
+                         dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        allv = torch.stack(allv).cpu().numpy()
+        flops_total, gram_ms_max = float(allv[:, 0].sum()), float(allv[:, 1].max())
+        stategen_ms, solve_ms = float(allv[:, 2].max()), float(allv[:, 3].max())
+        per_rank = [float(f / (m * 1e-3) / 1e12) for f, m in zip(allv[:, 0], allv[:, 1])]
+        peak_total = float(allv[:, 4].sum())
+        nreg_total, info_max, chol_total = int(allv[:, 5].sum()), int(allv[:, 6].max()), int(allv[:, 7].sum())
+    else:
+        flops_total, gram_ms_max, per_rank, peak_total = flops, gram_ms, [flops / (gram_ms * 1e-3) / 1e12], dmma_peak
+        nreg_total, info_max, chol_total = len(wave), int(max(info)), int(by_chol)
+    tf = flops_total / (gram_ms_max * 1e-3) / 1e12
+    return {"metric": "training Gram FP64 TFLOP/s", "value": tf, "unit": "TFLOP/s", "n_gpus": world,
+            "workload": f"ridge training, {nreg_total} regions ({len(wave)} per GPU, one wave) x 1 phase x {cols} columns, m=6000 "
+                        f"(N=5892..6292); regions sharded as processor_decomposition, no collective",
             "flops_counted": "useful: N(N+1)K + 2PNK (symmetric half + Y*R^T)",
-            "schedule": "serial (sml_train_set_overlap(0)): the Gram kernel timed alone",
-            "gram_ms": gram_ms, "stategen_ms": st["stategen_ms"] / 2, "solve_ms_per_region": st["solve_ms"] / nreg,
-            "solve_info_max": int(max(info)),
-            "roofline": {"bound": "tensor", "kernel": "k_syrk_dmma (FP64 DMMA)", "achieved": tf, "peak": dmma_peak,
-                         "unit": "TFLOP/s", "frac": tf / dmma_peak,
-                         "peak_source": "measured DMMA issue peak (tools/dmma_probe.cu); FP64 is not in MEASURED_PEAKS.json",
-                         "cublas_dgemm_8192_tflops": dgemm, "frac_of_cublas_dgemm": tf / dgemm}}
+            "schedule": "serial (sml_train_set_overlap(0)): the Gram kernel timed alone; aggregate = total useful flops / slowest rank",
+            "gram_ms": gram_ms_max, "stategen_ms": stategen_ms, "solve_ms_per_region": solve_ms / max(1, len(wave)),
+            "solve_ms_wave": solve_ms, "solve_info_max": info_max, "solved_by_cholesky": chol_total,
+            "per_gpu_tflops": per_rank, "long_k": out_long,
+            "roofline": {"bound": "tensor", "kernel": "k_syrk_dmma (FP64 DMMA)", "achieved": tf, "peak": peak_total,
+                         "unit": "TFLOP/s", "frac": tf / peak_total,
+                         "peak_source": "DMMA m8n8k4 issue peak measured in this run on every GPU (sml_dmma_probe), summed; "
+                                        "FP64 is not in MEASURED_PEAKS.json",
+                         "cublas_dgemm_8192_tflops_rank0": dgemm, "frac_of_cublas_dgemm_rank0": per_rank[0] / dgemm}}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def grid_checksum(eng, torch, dist, world):
+    """FP64 sum + XOR of the bit patterns of the grids THIS rank assembled; all ranks must agree"""
+    g = np.concatenate([a.ravel(order="F") for a in eng.grids_get()])
+    s, x = float(np.sum(g)), int(np.bitwise_xor.reduce(g.view(np.uint64)))
+    agree = True
+    if world > 1:
+        t = torch.tensor([x & 0xFFFFFFFF, x >> 32], dtype=torch.int64, device="cuda")
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        agree = all(bool(torch.equal(v, allv[0])) for v in allv)
+    return {"sum": repr(s), "xor": f"{x:016x}", "steps": CHECK_STEPS, "ranks_agree": agree,
+            "what": "wholegrid4d|wholegrid2d|precip|sst after 6 sequential hybrid steps (host stub in the loop) from the fixed start"}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -328,17 +453,24 @@ def run_gpu(args):
     eng = E.Engine(number_of_regions=R_TOTAL, irank=rank, numprocs=eng_world, device=local_rank, sst_prescribed=True,
                    stream=stream)
     my_regions = eng.region_indices
-    t_gen = time.perf_counter()
+
+    def dims(region, sst_in):
+        return E.region_dims(R_TOTAL, region, 1, M_RES, 6.0, True, True, sst_in, False)
+
+    t_setup = time.perf_counter()
+    ws_dims = {}
     workers = max(1, min(16, (os.cpu_count() or 2) // max(1, world)))
     with ThreadPoolExecutor(max_workers=workers) as ex:
         batch = 4 * workers
         for i0 in range(0, len(my_regions), batch):
-            for w in ex.map(gen_region, my_regions[i0:i0 + batch]):
+            for w in ex.map(lambda r: gen_region(r, dims), my_regions[i0:i0 + batch]):
                 eng.region_upload(w["region"], w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"],
                                   win_compact=w["winc"], win_col=w["wcol"], D=w["D"],
                                   sst_bool_input=w["sst_bool_input"])
+                ws_dims[w["region"]] = {k: w[k] for k in ("n", "k", "D", "P", "S", "L")}
     eng.finalize()
-    t_gen = time.perf_counter() - t_gen
+    t_setup = time.perf_counter() - t_setup
+    setup = eng.setup_stats()
     F = initial_fields()
     eng.set_sst_static(F["base_sst"], F["sea_mask"])
     eng.set_sst_prescribed(F["base_sst"])
@@ -346,7 +478,7 @@ def run_gpu(args):
     H.check_contiguous_sharding(R_TOTAL, eng_world)
     shard = H.EngineShard(eng, torch)
     if world > 1 and args.peer:
-        shard.attach_peers(dist)   # fused all-gather: peer stores from the readout kernel over NVLink
+        shard.bootstrap(dist)      # sml_comm_bootstrap: every exchange of the step now runs inside the engine
     stepper = H.HybridStepper(shard, rank=rank, world=world, dist=dist if world > 1 else None)
     stepper_ovl = H.HybridStepper(shard, rank=rank, world=world, dist=dist if world > 1 else None)
     lay = E.global_layout()
@@ -354,8 +486,8 @@ def run_gpu(args):
     g0 = np.concatenate([F["clim4d"].ravel(order="F"), F["clim2d"].ravel(order="F"), np.zeros(96 * 48),
                          np.maximum(F["base_sst"], 272.0).ravel(order="F"), F["tisr"].ravel(order="F")])
     shard.G.copy_(torch.from_numpy(g0))
-    f4, f2 = host_stub(F["clim4d"], F["clim2d"], F["clim4d"], F["clim2d"])
-    shard.F.copy_(torch.from_numpy(np.concatenate([f4.ravel(order="F"), f2.ravel(order="F")])))
+    f4, f2 = HostStub(F["clim4d"], F["clim2d"])(F["clim4d"], F["clim2d"])
+    shard.F[:lay["f_total"]].copy_(torch.from_numpy(np.concatenate([f4.ravel(order="F"), f2.ravel(order="F")])))
     eng.step_unpack_device(1)
     torch.cuda.synchronize()
 
@@ -363,20 +495,23 @@ def run_gpu(args):
     # forecast straight into the pinned upload staging; the D2H / H2D transfers themselves are unchanged
     shard.zero_copy = True
     stub_out = shard.forecast_buffers(world)
-
-    def host_model(w4d, w2d, wsst):
-        # stand-in for run_model (SPEEDY stays on the host); same arithmetic as the CPU arm's stub
-        return host_stub(w4d, w2d, F["clim4d"], F["clim2d"], out=stub_out)
-
-    device_step = stepper.device_step
-
-    def e2e_step(t):
-        (stepper_ovl if args.overlap else stepper).step(t, host_model, F["tisr"])
+    host_model = HostStub(F["clim4d"], F["clim2d"], stub_out[0], stub_out[1])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- correctness inside the scaling run: 6 sequential hybrid steps from the fixed start, checksum of the grids
+    for t in range(1, CHECK_STEPS + 1):
+        stepper.step(t, host_model, F["tisr"])
+    barrier()
+    checksum = grid_checksum(eng, torch, dist, world)
+
+    device_step = stepper.device_step
+
+    def e2e_step(t):
+        (stepper_ovl if args.overlap else stepper).step(t, host_model, F["tisr"])
 
     def timed(fn, steps, t0_index):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -400,8 +535,8 @@ def run_gpu(args):
         stepper_ovl.overlap = True
         eng.set_overlap(True)
     for i in range(args.warmup):
-        e2e_step(i + 1)
-    e2e_ms, e2e_wall = timed(e2e_step, args.steps, args.warmup + 1)
+        e2e_step(CHECK_STEPS + i + 1)
+    e2e_ms, e2e_wall = timed(e2e_step, args.steps, CHECK_STEPS + args.warmup + 1)
     if args.overlap:
         eng.set_overlap(False)
         stepper_ovl.overlap = False
@@ -423,6 +558,7 @@ def run_gpu(args):
     x = eng.state_get(my_regions[0])
     ov = eng.outvec_get(my_regions[0])
     finite = bool(np.isfinite(x).all() and np.isfinite(ov).all())
+    status = eng.grid_status()
 
     eng_peer = eng.peer_attached()
     if eng_peer:
@@ -434,9 +570,11 @@ def run_gpu(args):
     peak, peak_src = measured_peak()
     step_kernel_ms = k_step_ms / max(1, k_cnt)
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
+    plan = eng.step_plan()
     # the committed ncu capture is of the N=1 launch (all 1152 regions); per-rank launches are proportionally smaller
-    traffic = ncu_traffic() if world == 1 else None
+    traffic, traffic_src = ncu_traffic() if world == 1 else (None, "none (the committed capture is of the N=1 launch)")
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -446,8 +584,10 @@ def run_gpu(args):
                        "reservoir_m": M_RES, "degree": 6, "overlap": 1, "sim_days_per_step": SIM_DAYS_PER_STEP,
                        "sharding": f"processor_decomposition over {world} rank(s)",
                        "exchange": ("none (single rank)" if world == 1 else
-                                    "fused all-gather: peer stores from the readout kernel over NVLink (CUDA IPC)"
-                                    if eng_peer else "NCCL all_gather_into_tensor of the outvec slabs"),
+                                    "inside the engine (sml_comm_bootstrap): outvecs pushed by the readout-finish kernel, "
+                                    "forecast block pushed by the root's k_peer_push, device-side flags; no host collective"
+                                    if shard.comm_ready else "NCCL all_gather_into_tensor of the outvec slabs + NCCL broadcast"),
+                       "step_kernel": plan,
                        "l2": "per-GPU weights streamed every step (8.1 GB / n_gpus) exceed the 126 MB L2; no flush",
                        "value_path": "device-resident: predict + all-gather + scatter/clamp + feedback rebuild; "
                                      "host model excluded (F resident)",
@@ -455,33 +595,39 @@ def run_gpu(args):
                                    "sml_step_exchange_end (H2D), wall clock; "
                                    + ("overlapped mode: the next predict's state update and x~ readout run while the "
                                       "host model works (SURVEY.md Appendix D)" if args.overlap else "sequential mode"),
-                       "state_finite": finite, "setup_s": round(t_gen, 1),
+                       "state_finite": finite, "grid_status_bits": status,
+                       "setup_s": round(t_setup, 1), "setup_upload_s": round(setup["upload_s"], 2),
+                       "setup_weight_arena": {"bytes": setup["arena_bytes"], "device_allocations": setup["arena_chunks"]},
                        **({"emulate_world": eng_world, "note": "DIAGNOSTIC: one rank's shard of an emulated "
                            f"{eng_world}-rank run, not a whole-model number"} if eng_world != world else {})},
+            "grid_checksum": checksum,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((lay["f_total"] + 96 * 48) * 8),
                     "d2h_bytes_per_step": int(lay["tisr"] * 8), "ms_per_step": e2e_wall / args.steps,
                     "ms_per_step_device_events": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_step (fused state update + readout)",
+            "roofline": {"bound": "hbm", "kernel": f"{plan['kernel']} (fused state update + readout)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms_per_launch": step_kernel_ms,
                          "finish_kernel_ms_per_launch": k_fin_ms / max(1, k_cnt), "launches_timed": k_cnt,
                          "pack_kernel_ms_per_launch": pack_ms / max(1, ph_cnt),
                          "unpack_kernel_ms_per_launch": unpack_ms / max(1, ph_cnt),
-                         "chunk_rows": eng.step_chunk_rows()},
+                         "other_ms_per_step": ms_per_step - (step_kernel_ms + (k_fin_ms + pack_ms + unpack_ms) / max(1, k_cnt))},
             "clocks": clocks,
             "wall_ms_per_step": dev_wall / args.steps,
         }
         if world == 1 and eng_world == 1:
             line["update_roofline"] = update_leg(eng, E, my_regions, peak, peak_src)
-        if world == 1 and not args.no_cpu_baseline:
-            _, info, _ = cpu_oracle_run(args.cpu_seconds, os.cpu_count() or 1)
-            line["cpu_baseline"] = info
+    if not args.no_train and eng_world == world:
+        tr = train_leg(eng, E, torch, dist, world, my_regions, ws_dims, long_k=(world == 1))
+        if rank == 0:
+            line["train"] = tr
+    if world > 1:
+        dist.barrier()      # nobody frees its exchange block while a peer may still push into it
     eng.close()
     if rank == 0:
-        if world == 1 and not args.no_train:
-            line["train"] = train_leg(E, torch)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_sample_baseline(args.cpu_seconds, os.cpu_count() or 1)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -498,7 +644,7 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--emulate-world", type=int, default=0)
     ap.add_argument("--no-peer", dest="peer", action="store_false",
-                    help="multi-GPU: NCCL all-gather of the outvec slabs instead of the fused peer-store exchange")
+                    help="multi-GPU: NCCL host collectives instead of the exchange inside the engine")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="e2e in the sequential (reference-order) mode instead of the overlapped one")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -155,6 +155,8 @@ int sml_outvec_get(sml_engine *h, int kind, int region, double *outvec);
 /* start_prediction_slab seeds reservoir%outvec with the last observed SST/OHTC tile
  * (src/mod_slab_ocean_reservoir.f90:853-859); the exchange uses it until the first ocean step */
 int sml_outvec_set(sml_engine *h, int kind, int region, const double *outvec);
+/* all local outvecs of a kind in one copy: slab[i*chunk_size_prediction + p], i = local region order */
+int sml_outvec_get_all(sml_engine *h, int kind, double *slab);
 int sml_wout_get(sml_engine *h, int kind, int region, double *wout);
 int sml_wout_set(sml_engine *h, int kind, int region, const double *wout);
 
@@ -216,6 +218,26 @@ int sml_step_predict_ahead(sml_engine *h, int timestep);
 int sml_step_exchange_begin_view(sml_engine *h, int timestep, const double **wholegrid4d, const double **wholegrid2d,
                                  const double **wholegrid_precip, const double **wholegrid_sst);
 int sml_forecast_staging(sml_engine *h, double **forecast_4d, double **forecast_2d, double **tisr_grid);
+/* the grids of the last assembly, read back from the device on ANY rank (every rank rebuilds the whole grid; the
+ * reference holds them on the root only).  NULL arrays are skipped.  Synchronises the engine's stream. */
+int sml_grids_get(sml_engine *h, double *wholegrid4d, double *wholegrid2d, double *wholegrid_precip,
+                  double *wholegrid_sst);
+/* ---- failure detection.  sml_step_exchange_begin / _begin_view return 1 (grids still delivered) when the assembled
+ * grid holds a non-finite value.  The status word also carries the bounds SPEEDY's own input check applies before it
+ * agrees to run (src/ppo_iogrid.f90:562-577), evaluated on the grid handed to run_model; bits are sticky until
+ * sml_grid_status_reset.  sml_grid_status synchronises the engine's stream. */
+#define SML_GRID_NONFINITE 1
+#define SML_GRID_U_RANGE 2   /* u outside [-150, 150] */
+#define SML_GRID_V_RANGE 4   /* v outside [-120, 120] */
+#define SML_GRID_T_RANGE 8   /* T outside [160, 330] */
+#define SML_GRID_Q_RANGE 16  /* q outside [-6, 30] */
+int sml_grid_status(sml_engine *h, int *bits);
+int sml_grid_status_reset(sml_engine *h);
+/* model_parameters%run_speedy: the root sets it after run_model (src/mpires.f90:1655-1659) BEFORE
+ * sml_step_exchange_end; it travels to every rank with the forecast (MPI_Bcast, :744) and the step loop leaves when
+ * it is false (src/parallelmain.f90:269-271).  sml_run_speedy on a non-root rank synchronises that rank's stream. */
+int sml_set_run_speedy(sml_engine *h, int run_speedy);
+int sml_run_speedy(sml_engine *h, int *run_speedy);
 /* static fields of the exchange: base_sst_grid and sea_mask (src/mod_reservoir.f90:847-887) */
 int sml_set_sst_static(sml_engine *h, const double *base_sst_grid, const double *sea_mask);
 /* sst_prescribed == 1: the SST field (96x48) the next exchanges start from instead of ocean-reservoir
@@ -237,6 +259,22 @@ int sml_exchange_buffers(sml_engine *h, void **outvec_slab, int64_t *slab_count,
  * number_of_regions divisible by numprocs (contiguous shards) and numprocs <= 8.  sml_peer_check reports a rank
  * that never published (the wait gives up after ~10 s instead of hanging). ---- */
 int sml_peer_export(sml_engine *h, void *handle64);
+/* the same set-up behind one call (replaces the MPI communicator the reference's sendrecievegrid uses,
+ * src/mpires.f90:218-804): the host supplies ONE primitive, an all-gather of `bytes_per_rank` bytes from every rank
+ * into recv in rank order (MPI_Allgather(send, n, MPI_BYTE, recv, n, MPI_BYTE, mpi_world) on the reference's
+ * communicator; torch.distributed; a shared-memory rendezvous) returning 0 on success.  The library exchanges and
+ * attaches the IPC handles itself and checks that every rank was built for the same model.  Afterwards the WHOLE
+ * multi-rank step lives behind sml_predict / sml_step_exchange_begin / sml_step_exchange_end:
+ *   - atmosphere outvecs: pushed into every rank's gathered copy by the readout-finish kernel (gather, :346-454);
+ *   - ocean outvecs: pushed after every ocean step, and once for the seeded values (also after sml_ocean_ring_reset);
+ *   - forecast: sml_step_exchange_end on rank 0 uploads [forecast_4d | forecast_2d | tisr | run_speedy] once and one
+ *     kernel pushes the block into every rank's landing buffer (scatter :606-739, bcast :744); on the other ranks
+ *     sml_step_exchange_end takes no forecast (arguments may be NULL; a non-NULL tisr_grid is that rank's own
+ *     get_tisr_by_date field), waits for the block ON THE DEVICE and never blocks the host;
+ *   - sml_step_exchange_begin with NULL arrays (ranks other than the root) only enqueues the grid assembly.
+ * There is no host collective on the data path.  Ranks of ONE node, numprocs <= 8. */
+typedef int (*sml_allgather_fn)(void *ctx, const void *send, void *recv, int bytes_per_rank);
+int sml_comm_bootstrap(sml_engine *h, sml_allgather_fn allgather, void *ctx);
 int sml_peer_attach(sml_engine *h, const void *handles /* numprocs x 64 bytes, rank order */, int count);
 int sml_peer_attached(const sml_engine *h);
 int sml_peer_check(sml_engine *h);
@@ -315,6 +353,9 @@ int sml_train_trim(sml_engine *h);
  * the Gram kernels, the state generation and the solves of the current wave */
 int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms,
                     double *solve_ms);
+/* the roof the Gram figure is reported against: FP64 tensor-core (DMMA m8n8k4) issue peak of this GPU in TFLOP/s,
+ * measured on the spot by back-to-back register-resident MMAs (about 10 ms) */
+int sml_dmma_probe(sml_engine *h, double *tflops);
 
 /* rolling_average_over_a_period_2d(grid, period) (src/mod_utilities.f90:1773-1815), the time smoothing
  * get_training_data_from_atmo / get_prediction_data_from_atmo apply to the atmosphere rows of a slab-ocean reservoir's
@@ -335,6 +376,11 @@ int sml_kernel_times(sml_engine *h, double *step_ms_sum, double *finish_ms_sum, 
 int sml_phase_times(sml_engine *h, double *pack_ms_sum, double *unpack_ms_sum, int *count);
 int sml_sync_times(sml_engine *h, double *update_ms_sum, int64_t *steps); /* update-only launches of sml_synchronize */
 int sml_step_chunk_rows(const sml_engine *h, int kind); /* rows per CTA the step plan chose */
+/* the step plan in use: kernel 0 = k_step (one CTA per item), 1 = k_step_persist; slots = persistent CTAs,
+ * part_rows = rows per fixed row block, parts = partial outvecs per launch */
+int sml_step_plan(const sml_engine *h, int kind, int *kernel, int *slots, int *part_rows, int *parts);
+/* set-up cost: host seconds spent inside sml_region_upload so far, bytes of the weight arena, device allocations made for it */
+int sml_setup_stats(const sml_engine *h, double *upload_seconds, int64_t *arena_bytes, int *arena_chunks);
 int64_t sml_kernel_launch_count(const sml_engine *h);
 /* algorithmic bytes one sml_predict(kind) moves */
 int64_t sml_predict_algorithmic_bytes(const sml_engine *h, int kind);

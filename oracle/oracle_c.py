@@ -66,6 +66,7 @@ def lib():
         L.orc_region_set_weights.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int]
         L.orc_region_set_leakage.argtypes = [C.c_void_p, C.c_double]
         L.orc_region_set_win_compact.argtypes = [C.c_void_p, _dp, _ip]
+        L.orc_region_densify_win.argtypes = [C.c_void_p]
         L.orc_synchronize.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int]
         L.orc_predict.argtypes = [C.c_void_p, _dp]
         L.orc_predict_ml.argtypes = [C.c_void_p, _dp]
@@ -235,6 +236,11 @@ class Region:
         assert winc.size == self.n and wcol.size == self.n
         if lib().orc_region_set_win_compact(self.h, _d(winc), _i(wcol)):
             raise ValueError("win_col out of range")
+
+    def densify_win(self):
+        """compact one-per-row W_in -> the dense (n, D) matrix the reference stores; predict uses the dense GEMV again"""
+        if lib().orc_region_densify_win(self.h):
+            raise MemoryError("orc_region_densify_win")
 
     def set_leakage(self, leak):
         lib().orc_region_set_leakage(self.h, float(leak))

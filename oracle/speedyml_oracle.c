@@ -859,6 +859,27 @@ void orc_region_set_leakage(orc_region *r, double leakage) { r->d.leakage = leak
 
 /* compact W_in: value and 0-based column of the single non-zero of each row (src/mod_reservoir.f90:270-280).
  * Frees the dense copy. */
+/* expand the one-per-row form back into the dense win(n, D) the reference stores (src/mod_reservoir.f90:262-283) and
+ * drop the compact copy: predict then runs the reference's dense matmul(win, feedback) again.  Used by bench.py's CPU
+ * arm, which must time the reference's algorithmic form for all 1152 regions without pushing 30 GB of zeros through
+ * Python first. */
+int orc_region_densify_win(orc_region *r)
+{
+    if (!r->winc) return r->win ? 0 : 1;
+    const int n = r->d.n, D = r->d.reservoir_numinputs;
+    /* malloc + memset, not calloc: the reference stores real zeros (reservoir%win = 0.0_dp, then the non-zeros), so
+     * its GEMV streams 8*n*D bytes from memory; untouched calloc pages would all alias the kernel's zero page */
+    double *w = (double *)malloc((size_t)n * D * sizeof(double));
+    if (!w) return 2;
+    memset(w, 0, (size_t)n * D * sizeof(double));
+    for (int j = 0; j < n; ++j) w[(size_t)r->wcol[j] * n + j] = r->winc[j];
+    free(r->win);
+    r->win = w;
+    free(r->winc); free(r->wcol);
+    r->winc = NULL; r->wcol = NULL;
+    return 0;
+}
+
 int orc_region_set_win_compact(orc_region *r, const double *winc, const int *wcol)
 {
     const int n = r->d.n, D = r->d.reservoir_numinputs;

@@ -124,6 +124,8 @@ int  orc_region_set_weights(orc_region *r, const int *rows, const int *cols, con
                             const double *std, int mean_std_length);
 void orc_region_set_leakage(orc_region *r, double leakage);
 int  orc_region_set_win_compact(orc_region *r, const double *winc, const int *wcol);
+/* compact W_in -> the dense win(n, D) the reference stores; predict runs the dense GEMV again (bench.py CPU arm) */
+int  orc_region_densify_win(orc_region *r);
 double *orc_region_ptr(orc_region *r, const char *field); /* x feedback local_model outvec wout ... */
 const orc_grid *orc_region_grid(const orc_region *r);
 const orc_dims *orc_region_dims(const orc_region *r);

@@ -37,6 +37,8 @@ namespace {
 std::string g_create_err;
 
 constexpr int STAGES = 4;
+// the forecast block the root hands to every rank: [forecast_4d | forecast_2d | tisr grid | run_speedy + padding]
+constexpr long long FCST_TISR = F_TOTAL, FCST_FLAG = F_TOTAL + XG * YG, FCST_DOUBLES = FCST_FLAG + 8;
 constexpr int STAGE_BYTES_TARGET = 20 * 1088;  // 20 columns of a 136-row W_out
 constexpr int PROFILE_RING = 4096;
 
@@ -69,6 +71,13 @@ struct KindState {
     long long x_total = 0, fb_total = 0, lm_total = 0;
     int stage_cols = 0, stage_bytes = 0, xs_cap = 0, n_max = 0, chunk_rows = 0, D_max = 0;
     int *d_order = nullptr;  // launch order of the items: largest first
+    // persistent step kernel (k_step_persist): fixed row blocks ("parts") per region, items = runs of whole blocks,
+    // slots = statically balanced contiguous runs of items, one CTA each
+    bool persist = false;
+    StepSeg *d_segs = nullptr, *d_segs_split = nullptr;
+    int2 *d_slots = nullptr;
+    int nslots = 0, nparts = 0, part_rows = 0, p_stage_cols = 0, p_ldp = 0, p_xs_cap = 0, p_cpi = 0;
+    size_t p_smem_bytes = 0;
     int *d_one_region = nullptr;  // region index for one region's synchronize
     int one_region = -1;
     size_t smem_bytes = 0;
@@ -82,9 +91,50 @@ struct KindState {
 
 }  // namespace
 
+// device memory of the uploaded weights: bump-allocated from a few large chunks instead of ~14 cudaMalloc calls per
+// region (16 k allocations for the whole model made set-up allocation-bound; the training path learnt the same lesson)
+struct DevArena {
+    static constexpr size_t CHUNK = 512ull << 20;
+    std::vector<void *> chunks;
+    char *cur = nullptr;
+    size_t left = 0;
+    size_t total = 0;
+    cudaError_t alloc(size_t bytes, void **out)
+    {
+        bytes = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+        if (bytes > left) {
+            const size_t want = std::max(bytes, CHUNK);
+            void *c = nullptr;
+            cudaError_t e = cudaMalloc(&c, want);
+            if (e != cudaSuccess) return e;
+            chunks.push_back(c);
+            total += want;
+            if (bytes >= CHUNK) {   // an oversized array gets a chunk of its own; the open chunk stays open
+                *out = c;
+                return cudaSuccess;
+            }
+            cur = static_cast<char *>(c);
+            left = want;
+        }
+        *out = cur;
+        cur += bytes;
+        left -= bytes;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        for (void *c : chunks) cudaFree(c);
+        chunks.clear();
+        cur = nullptr;
+        left = 0;
+        total = 0;
+    }
+};
+
 struct sml_engine {
     sml_params p{};
     std::string err;
+    DevArena arena;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Tiling tiling;
     std::vector<int32_t> local_ids;
@@ -134,14 +184,25 @@ struct sml_engine {
     // outvec_component_contribs (src/mod_reservoir.f90:1458-1461): v_p and v_ml of every local atmosphere region
     bool contribs = false;
     double *d_vp = nullptr, *d_vml = nullptr;
-    // peer exchange (fused all-gather over NVLink; kernels.cuh PeerTable)
-    void *d_xchg = nullptr;            // this rank's exchange block: [2][R*P] doubles + MAX_PEERS flags
-    size_t xchg_flags_off = 0;         // byte offset of the flags inside the block
+    // peer exchange over NVLink (kernels.cuh PeerTable): this rank's exchange block
+    //   [2][R*P] atmosphere outvecs | [2][R*P_ocean] ocean outvecs | forecast landing [F | tisr | run_speedy] | flags
+    void *d_xchg = nullptr;
+    size_t xchg_bytes = 0;
+    long long xo_atmo = 0, xo_ocean = 0, xo_fcst = 0, xo_flags = 0;   // byte offsets of the sections
     PeerTable peers{};                 // world == 0/1: not attached
     std::vector<void *> peer_mapped;   // cudaIpcOpenMemHandle results to close
-    unsigned long long peer_seq = 0;   // number of atmosphere predicts published so far
-    unsigned int *d_done = nullptr;
+    unsigned long long peer_seq = 0;   // atmosphere predicts published so far
+    unsigned long long ocean_seq = 0;  // ocean slabs published so far
+    unsigned long long fcst_seq = 0;   // forecasts pushed (root) / expected (others) so far
+    bool ocean_publish_pending = true; // the seeded ocean outvecs have not been pushed yet (start_prediction_slab)
+    unsigned int *d_done = nullptr;    // [4] completion counters of the pushing kernels
     int *d_peer_err = nullptr;
+    // failure detection: sticky status bits of the assembled grid (k_pack_grids) and the root's run_speedy flag
+    int *d_status = nullptr;
+    int *h_status = nullptr;           // pinned
+    int run_speedy = 1;                // what the root passed to sml_set_run_speedy (travels with the forecast)
+    double *h_pin_flag = nullptr;      // pinned read-back of the run_speedy slot on the other ranks
+    double setup_upload_s = 0.0;       // host wall clock spent inside sml_region_upload (bench: setup split)
 };
 
 #define FAIL(h, ...)                                      \
@@ -160,15 +221,16 @@ struct sml_engine {
 
 namespace {
 
+// one array of a region's weights: space from the rank's arena, copy enqueued on the engine stream.  The caller
+// synchronises ONCE per region (sml_region_upload) before the host staging vectors go out of scope.
 template <typename T>
 int dev_upload(sml_engine *h, HostRegion *hr, const T *src, size_t count, const T **out)
 {
-    T *d = nullptr;
-    CK(h, cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
-    if (hr) hr->allocs.push_back(d);
+    (void)hr;
+    void *d = nullptr;
+    CK(h, h->arena.alloc(std::max<size_t>(count, 1) * sizeof(T), &d));
     if (count) CK(h, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    *out = d;
+    *out = static_cast<const T *>(d);
     return 0;
 }
 
@@ -249,6 +311,9 @@ int sml_create(sml_engine **out, const sml_params *p)
 
 // which update-only kernel sml_synchronize launches when SML_UPDATE_KERNEL is not set (profiles/round1_summary.md section 3)
 constexpr bool SML_UPDATE_SX_DEFAULT = true;
+// which fused step kernel sml_predict launches when SML_STEP_KERNEL is not set: k_step_persist (persistent, statically
+// balanced slots) or the classic one-CTA-per-item k_step
+constexpr bool SML_STEP_PERSIST_DEFAULT = true;
 
 static void free_kind(KindState &K)
 {
@@ -257,6 +322,7 @@ static void free_kind(KindState &K)
     cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_items_split); cudaFree(K.d_order); cudaFree(K.d_one_region); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
     cudaFree(K.d_lm); cudaFree(K.d_out); cudaFree(K.d_partials); cudaFree(K.d_temp); cudaFree(K.d_fb_offs);
     cudaFree(K.d_in); cudaFree(K.d_in_offs);
+    cudaFree(K.d_segs); cudaFree(K.d_segs_split); cudaFree(K.d_slots);
 }
 
 int sml_destroy(sml_engine *h)
@@ -268,6 +334,9 @@ int sml_destroy(sml_engine *h)
     h->train_pool.drop_all();
     cudaFree(h->train_global.d_G); cudaFree(h->train_global.d_F);
     for (int k = 0; k < 2; ++k) free_kind(h->kinds[k]);
+    h->arena.release();
+    if (h->d_xchg) h->d_F = nullptr;   // the forecast landing buffer lives inside the exchange block
+    cudaFree(h->d_status); cudaFreeHost(h->h_status); cudaFreeHost(h->h_pin_flag);
     cudaFree(h->d_G); cudaFree(h->d_F); cudaFree(h->d_gathered); cudaFree(h->d_base_sst); cudaFree(h->d_mask);
     cudaFree(h->d_prescribed); cudaFree(h->d_out_dst); cudaFree(h->d_cell_region); cudaFree(h->d_cell_slot);
     cudaFree(h->d_ocean_gathered); cudaFree(h->d_ocean_fb); cudaFree(h->d_ocean_ring);
@@ -410,6 +479,7 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
     if (h->finalized) FAIL(h, "upload after sml_finalize");
     if (w->kind != SML_ATMO && w->kind != SML_OCEAN) FAIL(h, "bad kind %d", w->kind);
     CK(h, cudaSetDevice(h->p.device));
+    const auto t_up0 = std::chrono::steady_clock::now();
     auto it = h->local_index.find(w->region);
     if (it == h->local_index.end()) FAIL(h, "region %d is not owned by rank %d", w->region, h->p.irank);
     KindState &K = h->kinds[w->kind];
@@ -516,10 +586,11 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
 
     // --- W_out, padded to an even leading dimension
     const size_t N = (size_t)n + S;
+    std::vector<double> wp;   // lives until the synchronisation at the end of this function
     if (ldw == P && w->wout) {
         if (dev_upload(h, &hr, w->wout, (size_t)P * N, &d.wout)) return -1;
     } else {
-        std::vector<double> wp((size_t)ldw * N, 0.0);
+        wp.assign((size_t)ldw * N, 0.0);
         if (w->wout)
             for (size_t j = 0; j < N; ++j) std::memcpy(&wp[j * ldw], w->wout + j * P, sizeof(double) * P);
         if (dev_upload(h, &hr, wp.data(), wp.size(), &d.wout)) return -1;
@@ -538,10 +609,12 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
     if (dev_upload(h, &hr, maps.model_map.data(), maps.model_map.size(), &d.lm_src)) return -1;
     if (dev_upload(h, &hr, maps.model_ms.data(), maps.model_ms.size(), &d.lm_ms)) return -1;
     if (dev_upload(h, &hr, maps.output_ms.data(), maps.output_ms.size(), &d.out_ms)) return -1;
+    CK(h, cudaStreamSynchronize(h->stream));   // one synchronisation per region: the engine owns copies from here on
 
     hr.region = w->region;
     hr.uploaded = true;
     K.any = true;
+    h->setup_upload_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_up0).count();
     return 0;
 }
 
@@ -608,6 +681,7 @@ extern "C" int sml_region_upload_file(sml_engine *h, const char *path, int regio
     w.n = t.n; w.k = t.k; w.D = t.D; w.P = t.P; w.S = t.N - t.n; w.L = t.L;
     w.sst_bool_input = sst_bool_input;
     w.leakage = leakage;
+    if (t.L <= 0 || t.mean.empty() || t.std.empty()) FAIL(h, "%s: mean / std are empty", path);
     w.sst_mean = t.mean.back();
     w.sst_std = t.std.back();
     w.rows = t.rows.data(); w.cols = t.cols.data(); w.vals = t.vals.data();
@@ -615,6 +689,111 @@ extern "C" int sml_region_upload_file(sml_engine *h, const char *path, int regio
     w.wout = t.wout.data();
     w.mean = t.mean.data(); w.std = t.std.data();
     return sml_region_upload(h, &w);
+}
+
+// ---- plan of the persistent step kernel (kernels.cuh k_step_persist) -----------------------------------------
+// Every region is cut into fixed row blocks of part_rows rows -- independent of the rank count, so the summation
+// structure of a region's readout (one partial per block, summed in block order by k_readout_finish) is the same for
+// any sharding.  The blocks of all local regions, in region order, are dealt to nslots = 2 x SMs slots in contiguous
+// runs of equal cost (cost = W_out columns streamed); inside a slot, consecutive blocks of one region form an item
+// of at most max_item_rows rows (the x~ tile in shared memory).
+static int build_persistent_plan(sml_engine *h, KindState &K, int S_max)
+{
+    const char *sk = getenv("SML_STEP_KERNEL");
+    K.persist = sk ? std::string(sk) == "persist" : SML_STEP_PERSIST_DEFAULT;
+    const int HP = K.ldw / 2;
+    // column groups per warp: the largest power of two <= 32 whose row pairs still fit the 17 consumer warps
+    int cpi = 32;
+    while (cpi > 1 && (HP + (32 / cpi) - 1) / (32 / cpi) > NCONS_WARPS) cpi >>= 1;
+    if ((HP + (32 / cpi) - 1) / (32 / cpi) > NCONS_WARPS) {
+        K.persist = false;   // chunk_size_prediction too large for the shuffle layout: classic kernel
+        return 0;
+    }
+    K.p_cpi = cpi;
+    // padded column stride: the 8 lanes of one 128-bit shared-memory load phase must hit 32 distinct banks.
+    // Lane -> (cs = lane % cpi, row pair lane / cpi); word address = cs * 2*ldp + 4 * rowpair.
+    int ldp = K.ldw;
+    for (;; ldp += 2) {
+        bool ok = true;
+        unsigned seen = 0;
+        for (int l = 0; l < 8 && ok; ++l) {
+            const int c = l % cpi, r = l / cpi;
+            const int bank4 = ((c * 2 * ldp + 4 * r) % 32) / 4;   // which group of 4 banks the 16-byte access starts in
+            if (seen & (1u << bank4)) ok = false;
+            seen |= 1u << bank4;
+        }
+        if (ok || ldp > K.ldw + 64) break;
+    }
+    K.p_ldp = ldp;
+    const int unit = std::max(16, 2 * cpi);   // tile and block sizes are multiples of this (fixed column -> group map)
+    int stage_cols = std::max(unit, (STAGE_BYTES_TARGET / (ldp * 8)) / unit * unit);
+    if (const char *e = getenv("SML_PERSIST_STAGE_COLS")) stage_cols = std::max(unit, atoi(e) / unit * unit);
+    K.p_stage_cols = stage_cols;
+    int part_rows = std::max(stage_cols, 192 / stage_cols * stage_cols);
+    if (const char *e = getenv("SML_PART_ROWS")) part_rows = std::max(stage_cols, atoi(e) / stage_cols * stage_cols);
+    K.part_rows = part_rows;
+    const int max_item_rows = std::max(part_rows, 1152 / part_rows * part_rows);
+
+    struct Part { int reg, row0, nrows, part; long long cost; };
+    std::vector<Part> parts;
+    const int nloc = (int)K.regs.size();
+    long long total_cost = 0;
+    for (int i = 0; i < nloc; ++i) {
+        HostRegion &hr = K.regs[i];
+        if (!hr.uploaded) continue;
+        RegionDev &d = hr.dev;
+        d.part0 = (int)parts.size();
+        for (int r0 = 0; r0 < d.n; r0 += part_rows) {
+            Part pt{i, r0, std::min(part_rows, d.n - r0), (int)parts.size(), 0};
+            pt.cost = pt.nrows + (r0 == 0 ? d.S : 0);
+            total_cost += pt.cost;
+            parts.push_back(pt);
+        }
+        d.nparts = (int)parts.size() - d.part0;
+    }
+    K.nparts = (int)parts.size();
+    int nslots = 2 * h->num_sms;
+    if (const char *e = getenv("SML_STEP_SLOTS")) nslots = std::max(1, atoi(e));
+    nslots = std::max(1, std::min(nslots, K.nparts));
+    K.nslots = nslots;
+    std::vector<StepSeg> segs;
+    std::vector<int2> slots(nslots, make_int2(0, 0));
+    long long cum = 0;
+    int cur_slot = -1;
+    for (const Part &pt : parts) {
+        // the slot is chosen by the block's midpoint on the cost axis: contiguous runs, balanced to within one block
+        int sl = (int)(((cum + pt.cost / 2) * (long long)nslots) / std::max<long long>(1, total_cost));
+        sl = std::min(std::max(sl, std::max(cur_slot, 0)), nslots - 1);
+        cum += pt.cost;
+        const bool new_slot = sl != cur_slot;
+        if (new_slot) {
+            cur_slot = sl;
+            slots[sl].x = (int)segs.size();
+        }
+        if (!new_slot && !segs.empty() && segs.back().reg == pt.reg && segs.back().row0 + segs.back().nrows == pt.row0 &&
+            segs.back().nrows + pt.nrows <= max_item_rows) {
+            segs.back().nrows += pt.nrows;
+        } else {
+            StepSeg sg{pt.reg, pt.row0, pt.nrows, pt.part, pt.row0 == 0 ? 1 : 0};
+            segs.push_back(sg);
+            slots[sl].y++;
+        }
+    }
+    K.p_xs_cap = (S_max + max_item_rows + 1) & ~1;
+    K.p_smem_bytes = (size_t)STAGES * stage_cols * ldp * 8 + (size_t)K.p_xs_cap * 8 + 2 * STAGES * 8;
+    if (K.p_smem_bytes > 113 * 1024) {   // two CTAs per SM or nothing
+        K.persist = false;
+        return 0;
+    }
+    std::vector<StepSeg> split = segs;
+    for (StepSeg &sg : split) sg.with_model = 0;
+    CK(h, cudaMalloc(&K.d_segs, sizeof(StepSeg) * std::max<size_t>(1, segs.size())));
+    CK(h, cudaMemcpy(K.d_segs, segs.data(), sizeof(StepSeg) * segs.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&K.d_segs_split, sizeof(StepSeg) * std::max<size_t>(1, split.size())));
+    CK(h, cudaMemcpy(K.d_segs_split, split.data(), sizeof(StepSeg) * split.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&K.d_slots, sizeof(int2) * nslots));
+    CK(h, cudaMemcpy(K.d_slots, slots.data(), sizeof(int2) * nslots, cudaMemcpyHostToDevice));
+    return 0;
 }
 
 static int finalize_kind(sml_engine *h, int kind)
@@ -689,6 +868,7 @@ static int finalize_kind(sml_engine *h, int kind)
     K.smem_bytes = (size_t)STAGES * K.stage_bytes + ((size_t)K.xs_cap + 2 * NCONS) * 8 + 2 * STAGES * 8;
     if (K.smem_bytes > 227 * 1024) FAIL(h, "step kernel needs %zu B of shared memory", K.smem_bytes);
 
+    if (build_persistent_plan(h, K, S_max)) return -1;   // fills part0 / nparts of every RegionDev
     std::vector<RegionDev> regs(nloc);
     for (int i = 0; i < nloc; ++i) regs[i] = K.regs[i].dev;
     CK(h, cudaMalloc(&K.d_regs, sizeof(RegionDev) * nloc));
@@ -729,7 +909,7 @@ static int finalize_kind(sml_engine *h, int kind)
         CK(h, cudaMalloc(&K.d_out, sizeof(double) * init.size()));
         CK(h, cudaMemcpy(K.d_out, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice));
     }
-    CK(h, cudaMalloc(&K.d_partials, sizeof(double) * (size_t)std::max(1, K.nitems) * K.ldw));
+    CK(h, cudaMalloc(&K.d_partials, sizeof(double) * (size_t)std::max(std::max(1, K.nitems), K.nparts) * K.ldw));
     if (K.any_dense) {
         CK(h, cudaMalloc(&K.d_temp, sizeof(double) * std::max<long long>(1, xo)));
         CK(h, cudaMemset(K.d_temp, 0, sizeof(double) * std::max<long long>(1, xo)));
@@ -749,6 +929,8 @@ int sml_finalize(sml_engine *h)
         // the dynamic shared-memory limit is a property of the kernel, not of a launch: take the larger kind
         const size_t smem = std::max(h->kinds[SML_ATMO].smem_bytes, h->kinds[SML_OCEAN].smem_bytes);
         CK(h, cudaFuncSetAttribute(k_step<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t psmem = std::max(h->kinds[SML_ATMO].p_smem_bytes, h->kinds[SML_OCEAN].p_smem_bytes);
+        CK(h, cudaFuncSetAttribute(k_step_persist<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
     }
     const int R = h->p.number_of_regions, P = h->kinds[SML_ATMO].P;
     h->P_atmo = P;
@@ -810,8 +992,25 @@ int sml_finalize(sml_engine *h)
     CK(h, cudaMemcpy(h->d_cell_slot, cell_slot.data(), sizeof(int) * XG * YG, cudaMemcpyHostToDevice));
     CK(h, cudaMalloc(&h->d_G, sizeof(double) * G_TOTAL));
     CK(h, cudaMemset(h->d_G, 0, sizeof(double) * G_TOTAL));
-    CK(h, cudaMalloc(&h->d_F, sizeof(double) * F_TOTAL));
-    CK(h, cudaMemset(h->d_F, 0, sizeof(double) * F_TOTAL));
+    if (h->p.numprocs > 1) {
+        // the exchange block every peer maps (kernels.cuh PeerTable); the forecast buffer F is its landing section
+        auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+        h->xo_atmo = 0;
+        h->xo_ocean = (long long)al(sizeof(double) * 2 * (size_t)R * P);
+        h->xo_fcst = h->xo_ocean + (long long)al(sizeof(double) * 2 * (size_t)R * h->P_ocean);
+        h->xo_flags = h->xo_fcst + (long long)al(sizeof(double) * FCST_DOUBLES);
+        h->xchg_bytes = (size_t)h->xo_flags + al(sizeof(unsigned long long) * XF_KINDS * MAX_PEERS);
+        CK(h, cudaMalloc(&h->d_xchg, h->xchg_bytes));
+        CK(h, cudaMemset(h->d_xchg, 0, h->xchg_bytes));
+        {
+            std::vector<double> init(2 * (size_t)R * h->P_ocean, 272.0);   // src/mpires.f90:323-326
+            CK(h, cudaMemcpy((char *)h->d_xchg + h->xo_ocean, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice));
+        }
+        h->d_F = (double *)((char *)h->d_xchg + h->xo_fcst);
+    } else {
+        CK(h, cudaMalloc(&h->d_F, sizeof(double) * FCST_DOUBLES));
+        CK(h, cudaMemset(h->d_F, 0, sizeof(double) * FCST_DOUBLES));
+    }
     CK(h, cudaMalloc(&h->d_gathered, sizeof(double) * (size_t)R * P));
     CK(h, cudaMemset(h->d_gathered, 0, sizeof(double) * (size_t)R * P));
     CK(h, cudaMalloc(&h->d_base_sst, sizeof(double) * XG * YG));
@@ -826,18 +1025,20 @@ int sml_finalize(sml_engine *h)
         CK(h, cudaMemcpy(h->d_ocean_gathered, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice));
     }
     CK(h, cudaMallocHost(&h->h_pin_G, sizeof(double) * G_TOTAL));
-    CK(h, cudaMallocHost(&h->h_pin_F, sizeof(double) * (F_TOTAL + XG * YG)));
+    CK(h, cudaMallocHost(&h->h_pin_F, sizeof(double) * FCST_DOUBLES));
+    std::memset(h->h_pin_F, 0, sizeof(double) * FCST_DOUBLES);
+    h->h_pin_F[FCST_FLAG] = 1.0;
     CK(h, cudaMallocHost(&h->h_pin_tisr, sizeof(double) * XG * YG));
-    CK(h, cudaMalloc(&h->d_done, sizeof(unsigned int)));
-    CK(h, cudaMemset(h->d_done, 0, sizeof(unsigned int)));
+    CK(h, cudaMalloc(&h->d_done, 4 * sizeof(unsigned int)));
+    CK(h, cudaMemset(h->d_done, 0, 4 * sizeof(unsigned int)));
     CK(h, cudaMalloc(&h->d_peer_err, sizeof(int)));
     CK(h, cudaMemset(h->d_peer_err, 0, sizeof(int)));
-    if (h->p.numprocs > 1) {
-        h->xchg_flags_off = (sizeof(double) * 2 * (size_t)R * P + 255) / 256 * 256;
-        const size_t bytes = h->xchg_flags_off + sizeof(unsigned long long) * MAX_PEERS;
-        CK(h, cudaMalloc(&h->d_xchg, bytes));
-        CK(h, cudaMemset(h->d_xchg, 0, bytes));
-    }
+    CK(h, cudaMalloc(&h->d_status, sizeof(int)));
+    CK(h, cudaMemset(h->d_status, 0, sizeof(int)));
+    CK(h, cudaMallocHost(&h->h_status, sizeof(int)));
+    *h->h_status = 0;
+    CK(h, cudaMallocHost(&h->h_pin_flag, sizeof(double)));
+    *h->h_pin_flag = 1.0;
     CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CK(h, cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
     CK(h, cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
@@ -878,6 +1079,19 @@ int sml_local_model_get(sml_engine *h, int kind, int region, double *v) { return
 int sml_outvec_get(sml_engine *h, int kind, int region, double *v) { return copy_vec(h, kind, region, v, nullptr, 3); }
 int sml_outvec_set(sml_engine *h, int kind, int region, const double *v) { return copy_vec(h, kind, region, nullptr, v, 3); }
 
+// every local region's outvec in ONE copy: slab[i*P + p] for local region i (rows of regions without a reservoir of
+// the kind hold what the exchange uses for them); the batched form of the per-region reads of reservoir%outvec
+int sml_outvec_get_all(sml_engine *h, int kind, double *slab)
+{
+    if (check_ready(h, kind)) return -1;
+    if (!slab) return -1;
+    KindState &K = h->kinds[kind];
+    CK(h, cudaSetDevice(h->p.device));
+    CK(h, cudaMemcpyAsync(slab, K.d_out, sizeof(double) * K.regs.size() * K.P, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int sml_wout_get(sml_engine *h, int kind, int region, double *wout)
 {
     if (check_ready(h, kind)) return -1;
@@ -903,12 +1117,34 @@ int sml_wout_set(sml_engine *h, int kind, int region, const double *wout)
 
 /* ------------------------------------------------------------------ step launches */
 static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int nitems, const double *u_pool,
-                       const long long *u_offs, int u_t, int do_readout)
+                       const long long *u_offs, int u_t, int do_readout, int cur_override = -1)
 {
     if (nitems == 0) return 0;
+    // which buffer of the state ping-pong pair is read (the other one is written)
+    struct CurGuard {
+        KindState &K; int saved;
+        ~CurGuard() { K.cur = saved; }
+    } cur_guard{K, K.cur};
+    if (cur_override >= 0) K.cur = cur_override;
+    const bool all = (d_items == K.d_items || d_items == K.d_items_split) && nitems == K.nitems;
+    int nreg = (int)K.regs.size();
+    const int *list = nullptr;
+    if (!all) {
+        // one region's synchronize: every kernel of the step is restricted to it (the other regions' input slots in
+        // K.d_in are not theirs, so the dense-W_in kernel must not touch them either)
+        if (!K.d_one_region) CK(h, cudaMalloc(&K.d_one_region, sizeof(int)));
+        const int reg = K.items[(int)(d_items - K.d_items)].reg;
+        if (reg != K.one_region) {
+            CK(h, cudaMemcpyAsync(K.d_one_region, &reg, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            CK(h, cudaStreamSynchronize(h->stream));
+            K.one_region = reg;
+        }
+        list = K.d_one_region;
+        nreg = 1;
+    }
     if (K.any_dense) {
-        dim3 grid((K.n_max + 255) / 256, (unsigned)K.regs.size());
-        k_win_dense<<<grid, 256, 0, h->stream>>>(K.d_regs, u_pool, u_offs, u_t, K.d_temp);
+        dim3 grid((K.n_max + 255) / 256, (unsigned)nreg);
+        k_win_dense<<<grid, 256, 0, h->stream>>>(K.d_regs, list, u_pool, u_offs, u_t, K.d_temp);
         h->launches++;
     }
     if (!do_readout) {
@@ -916,20 +1152,6 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
         // rows per thread: measured 0.200 / 0.206 / 0.151 ms for 1 / 2 / 4 at the bench config (profiles/round1_summary.md)
         const int rpt = getenv("SML_UPDATE_RPT") ? atoi(getenv("SML_UPDATE_RPT")) : 4;  // A/B switch
         const int RPT = (rpt == 1 || rpt == 2 || rpt == 8) ? rpt : 4;
-        const bool all = d_items == K.d_items && nitems == K.nitems;
-        int nreg = (int)K.regs.size();
-        const int *list = nullptr;
-        if (!all) {
-            if (!K.d_one_region) CK(h, cudaMalloc(&K.d_one_region, sizeof(int)));
-            const int reg = K.items[(int)(d_items - K.d_items)].reg;
-            if (reg != K.one_region) {
-                CK(h, cudaMemcpyAsync(K.d_one_region, &reg, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-                CK(h, cudaStreamSynchronize(h->stream));
-                K.one_region = reg;
-            }
-            list = K.d_one_region;
-            nreg = 1;
-        }
         // SML_UPDATE_KERNEL=sx: state vector staged in shared memory (k_update_sx); =global: gathers from L2 (k_update)
         const char *uk = getenv("SML_UPDATE_KERNEL");
         const int xs_cap = (K.n_max + 1) & ~1;
@@ -970,6 +1192,16 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
             k_update<8><<<grid, 256, 0, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp);
         else
             k_update<4><<<grid, 256, 0, h->stream>>>(K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        return 0;
+    }
+    if (K.persist && all) {
+        // persistent kernel: one CTA per slot, each with its statically balanced run of items
+        const StepSeg *segs = (d_items == K.d_items_split) ? K.d_segs_split : K.d_segs;
+        k_step_persist<STAGES><<<K.nslots, NTHREADS, K.p_smem_bytes, h->stream>>>(
+            K.d_regs, segs, K.d_slots, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm, K.d_temp, K.d_partials,
+            K.ldw, K.p_stage_cols, K.p_ldp, K.p_xs_cap, K.part_rows, K.p_cpi);
         h->launches++;
         CK(h, cudaGetLastError());
         return 0;
@@ -1021,18 +1253,42 @@ static int launch_finish(sml_engine *h, KindState &K, int model_part)
     }
     // sequential mode: one group of threads sums the partials; overlapped mode: 4 groups share the model columns
     const int threads = model_part ? FIN_GROUPS * FIN_PMAX : FIN_PMAX;
-    const size_t fsmem = model_part ? sizeof(double) * FIN_GROUPS * ((K.P + 1) & ~1) : 0;
+    const size_t fsmem = sizeof(double) * ((K.P + 1) & ~1) * (model_part ? FIN_GROUPS + 1 : 1);
     k_readout_finish<<<(unsigned)K.regs.size(), threads, fsmem, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1,
                                                                          model_part, K.d_lm, pt, seq, peer_off, h->d_done,
                                                                          (atmo && h->contribs && model_part) ? h->d_vp : nullptr,
-                                                                         (atmo && h->contribs && model_part) ? h->d_vml : nullptr);
+                                                                         (atmo && h->contribs && model_part) ? h->d_vml : nullptr,
+                                                                         K.persist ? 1 : 0);
     h->launches++;
     CK(h, cudaGetLastError());
+    if (!atmo && h->peers.world > 1) h->ocean_publish_pending = true;   // pushed by the next grid assembly
+    return 0;
+}
+
+// the ocean reservoirs' outvec slab [nloc][P_ocean] into every rank's gathered copy (the all-gather after
+// predict_slab_ml, src/mpires.f90:375-454): one push kernel over NVLink, double-buffered by ocean-step parity
+static int push_ocean_slab(sml_engine *h)
+{
+    KindState &KO = h->kinds[SML_OCEAN];
+    const long long Po = h->P_ocean, nloc = (long long)KO.regs.size();
+    const unsigned long long seq = ++h->ocean_seq;
+    const long long dst_off = (long long)(seq & 1) * h->p.number_of_regions * Po + (long long)h->local_ids[0] * Po;
+    k_peer_push<<<dim3(1, h->peers.world), 256, 0, h->stream>>>(KO.d_out, nloc * Po, h->peers, XF_OCEAN, dst_off, 0, seq,
+                                                                h->p.irank, h->d_done + 1);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    h->ocean_publish_pending = false;
     return 0;
 }
 
 int sml_predict(sml_engine *h, int kind)
 {
+    if (h && h->finalized && kind == SML_OCEAN && h->p.slab_ocean_model_bool && !h->kinds[SML_OCEAN].any) {
+        // a rank whose regions are all land: nothing to step, but the ocean slabs are still re-published with the
+        // other ranks' (every rank pushes after every ocean step)
+        if (h->peers.world > 1) h->ocean_publish_pending = true;
+        return 0;
+    }
     if (check_ready(h, kind)) return -1;
     CK(h, cudaSetDevice(h->p.device));
     KindState &K = h->kinds[kind];
@@ -1123,16 +1379,18 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
     }
     for (int t = 0; t < length; ++t) {
         if (region != SML_ALL_REGIONS) {
-            // the untouched regions keep their state: copy theirs forward is avoided by updating only
-            // this region's slice of the ping-pong pair
-            if (launch_step(h, K, items, nitems, K.d_in, K.d_in_offs, t, 0)) return -1;
-            const RegionDev &d = K.regs[first].dev;
-            CK(h, cudaMemcpyAsync(K.d_x[K.cur] + d.x_off, K.d_x[K.cur ^ 1] + d.x_off, (size_t)d.n * 8,
-                                  cudaMemcpyDeviceToDevice, h->stream));
+            // the untouched regions keep their state: only this region's slice of the ping-pong pair alternates, and
+            // ONE copy at the end brings it back to the current buffer when the step count is odd
+            if (launch_step(h, K, items, nitems, K.d_in, K.d_in_offs, t, 0, K.cur ^ (t & 1))) return -1;
         } else {
             if (launch_step(h, K, items, nitems, K.d_in, K.d_in_offs, t, 0)) return -1;
             K.cur ^= 1;
         }
+    }
+    if (region != SML_ALL_REGIONS && (length & 1)) {
+        const RegionDev &d = K.regs[first].dev;
+        CK(h, cudaMemcpyAsync(K.d_x[K.cur] + d.x_off, K.d_x[K.cur ^ 1] + d.x_off, (size_t)d.n * 8,
+                              cudaMemcpyDeviceToDevice, h->stream));
     }
     if (se0) CK(h, cudaEventRecord(se1, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -1150,16 +1408,21 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
 /* ------------------------------------------------------------------ exchange */
 int sml_set_sst_static(sml_engine *h, const double *base, const double *mask)
 {
-    if (!h || !h->finalized) return -1;
-    CK(h, cudaMemcpy(h->d_base_sst, base, sizeof(double) * XG * YG, cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->d_mask, mask, sizeof(double) * XG * YG, cudaMemcpyHostToDevice));
+    if (!h || !h->finalized || !base || !mask) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    // ordered on the engine's stream: a grid assembly still in flight reads the old fields
+    CK(h, cudaMemcpyAsync(h->d_base_sst, base, sizeof(double) * XG * YG, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_mask, mask, sizeof(double) * XG * YG, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));   // caller-owned arrays: the engine holds copies when this returns
     h->sst_static_set = true;
     return 0;
 }
 int sml_set_sst_prescribed(sml_engine *h, const double *sst)
 {
-    if (!h || !h->finalized) return -1;
-    CK(h, cudaMemcpy(h->d_prescribed, sst, sizeof(double) * XG * YG, cudaMemcpyHostToDevice));
+    if (!h || !h->finalized || !sst) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    CK(h, cudaMemcpyAsync(h->d_prescribed, sst, sizeof(double) * XG * YG, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     h->sst_prescribed_set = true;
     return 0;
 }
@@ -1214,14 +1477,20 @@ int sml_step_pack_device(sml_engine *h, int timestep)
     a.precip_lo = G_PRECIP; a.precip_hi = G_SST; a.w4d_hi = G_W2D; a.sst_off = G_SST;
     a.nsc = (a.total + 255) / 256;
     a.err = h->d_peer_err;
+    a.status = h->d_status;
+    const bool peers = h->peers.world > 1;
+    const bool ocean_live = h->p.slab_ocean_model_bool && !h->p.sst_prescribed;
+    if (peers && ocean_live && h->ocean_publish_pending)
+        if (push_ocean_slab(h)) return -1;
     if (h->p.numprocs == 1) {
         a.gathered = K.d_out;
-    } else if (h->peers.world > 1) {
+    } else if (peers) {
         // fused all-gather: wait for every rank's flag of this step, read this step's half of the exchange block
-        a.gathered = (const double *)h->d_xchg + (size_t)(h->peer_seq & 1) * a.total;
-        a.my_flags = (const unsigned long long *)((const char *)h->d_xchg + h->xchg_flags_off);
+        a.gathered = h->peers.atmo(h->p.irank) + (size_t)(h->peer_seq & 1) * a.total;
+        a.my_flags = h->peers.flag(h->p.irank, 0, 0);
         a.world = h->peers.world;
         a.seq = h->peer_seq;
+        a.ocean_seq = ocean_live ? h->ocean_seq : 0;
     } else {
         a.gathered = h->d_gathered;  // filled by the host's collective (NCCL all-gather)
     }
@@ -1232,8 +1501,11 @@ int sml_step_pack_device(sml_engine *h, int timestep)
         if (a.sst_mode == 1 && !h->sst_prescribed_set) FAIL(h, "sst_prescribed is on but sml_set_sst_prescribed was never called");
         a.base = h->d_base_sst; a.mask = h->d_mask; a.prescribed = h->d_prescribed;
         a.cell_region = h->d_cell_region; a.cell_slot = h->d_cell_slot;
-        // single rank: the ocean outvec slab already holds every region; otherwise the host all-gathers it
-        a.ocean_out = (h->p.numprocs == 1) ? h->kinds[SML_OCEAN].d_out : h->d_ocean_gathered;
+        // single rank: the ocean outvec slab already holds every region; with peers: the pushed copy of the latest
+        // ocean step; otherwise the host all-gathers it
+        a.ocean_out = (h->p.numprocs == 1) ? h->kinds[SML_OCEAN].d_out
+                      : peers ? h->peers.ocean(h->p.irank) + (size_t)(h->ocean_seq & 1) * h->p.number_of_regions * h->P_ocean
+                              : h->d_ocean_gathered;
         a.ocean_P = h->P_ocean;
     }
     const int nsst = (a.sst_mode >= 0) ? (XG * YG + 255) / 256 : 0;
@@ -1271,6 +1543,7 @@ int sml_peer_attach(sml_engine *h, const void *handles, int count)
     PeerTable pt{};
     pt.world = count;
     pt.rank = h->p.irank;
+    pt.off_atmo = h->xo_atmo; pt.off_ocean = h->xo_ocean; pt.off_fcst = h->xo_fcst; pt.off_flags = h->xo_flags;
     for (int k = 0; k < count; ++k) {
         void *base = nullptr;
         if (k == h->p.irank) {
@@ -1287,12 +1560,59 @@ int sml_peer_attach(sml_engine *h, const void *handles, int count)
             }
             h->peer_mapped.push_back(base);
         }
-        pt.gathered[k] = (double *)base;
-        pt.flags[k] = (unsigned long long *)((char *)base + h->xchg_flags_off);
+        pt.base[k] = (char *)base;
     }
     CK(h, cudaStreamSynchronize(h->stream));
     h->peers = pt;
     h->peer_seq = 0;
+    h->ocean_seq = 0;
+    h->fcst_seq = 0;
+    h->ocean_publish_pending = h->p.slab_ocean_model_bool && !h->p.sst_prescribed;
+    return 0;
+}
+
+// ---- sml_comm_bootstrap: the whole multi-rank set-up behind one call.  The host supplies ONE primitive -- an
+// all-gather of a fixed-size byte block per rank (MPI_Allgather on the reference's mpi_world, torch.distributed, a
+// shared-memory rendezvous) -- and the library does the rest: checks that every rank was built for the same model,
+// exchanges the IPC handles of the exchange blocks and attaches them.  From then on sml_predict /
+// sml_step_exchange_begin / sml_step_exchange_end are complete at numprocs > 1 with no host collective on the data
+// path: outvec all-gather, ocean-slab gather and the distribution of the root's forecast (src/mpires.f90:346-454,
+// :606-739, :744) are peer stores over NVLink from the engine's own kernels.
+int sml_comm_bootstrap(sml_engine *h, sml_allgather_fn allgather, void *ctx)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (h->p.numprocs == 1) return 0;   // nothing to connect
+    if (!allgather) FAIL(h, "sml_comm_bootstrap: the all-gather callback is required");
+    const int W = h->p.numprocs;
+    struct Hello {
+        int32_t rank, world, regions, P, P_ocean, slab, prescribed, pad;
+        long long xchg_bytes;
+        unsigned char handle[64];
+    } mine{};
+    mine.rank = h->p.irank; mine.world = W; mine.regions = h->p.number_of_regions; mine.P = h->P_atmo;
+    mine.P_ocean = h->P_ocean; mine.slab = h->p.slab_ocean_model_bool; mine.prescribed = h->p.sst_prescribed;
+    mine.xchg_bytes = (long long)h->xchg_bytes;
+    if (sml_peer_export(h, mine.handle)) return -1;
+    std::vector<Hello> all(W);
+    if (allgather(ctx, &mine, all.data(), (int)sizeof(Hello)) != 0) FAIL(h, "sml_comm_bootstrap: the host all-gather failed");
+    std::vector<unsigned char> handles(64 * (size_t)W);
+    for (int k = 0; k < W; ++k) {
+        const Hello &o = all[k];
+        if (o.rank != k || o.world != W) FAIL(h, "sml_comm_bootstrap: slot %d holds rank %d of %d (the all-gather must be in rank order)", k, o.rank, o.world);
+        if (o.regions != mine.regions || o.P != mine.P || o.P_ocean != mine.P_ocean || o.slab != mine.slab ||
+            o.prescribed != mine.prescribed || o.xchg_bytes != mine.xchg_bytes)
+            FAIL(h, "sml_comm_bootstrap: rank %d was built for a different model configuration", k);
+        std::memcpy(&handles[64 * (size_t)k], o.handle, 64);
+    }
+    // second round: nobody may push into a block before its owner has zeroed and mapped everything; a rank whose
+    // attach failed still takes part so that the others do not hang in the all-gather
+    int32_t ok = sml_peer_attach(h, handles.data(), W) == 0 ? 1 : 0;
+    const std::string attach_err = h->err;
+    std::vector<int32_t> oks(W, 0);
+    if (allgather(ctx, &ok, oks.data(), (int)sizeof(int32_t)) != 0) FAIL(h, "sml_comm_bootstrap: the host all-gather failed");
+    if (!ok) { h->err = attach_err; return -1; }
+    for (int k = 0; k < W; ++k)
+        if (oks[k] != 1) FAIL(h, "sml_comm_bootstrap: rank %d did not attach", k);
     return 0;
 }
 
@@ -1305,7 +1625,8 @@ int sml_peer_check(sml_engine *h)
     int err = 0;
     CK(h, cudaMemcpyAsync(&err, h->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    if (err) FAIL(h, "peer exchange timed out: a rank did not publish its outvecs");
+    if (err == 1) FAIL(h, "peer exchange timed out: a rank did not publish its outvecs");
+    if (err) FAIL(h, "peer exchange timed out: the root never published its forecast");
     return 0;
 }
 
@@ -1347,10 +1668,12 @@ int sml_step_predict_ahead(sml_engine *h, int timestep)
     return 0;
 }
 
-int sml_step_exchange_begin(sml_engine *h, int timestep, double *w4d, double *w2d, double *wprecip, double *wsst)
+// pack (+ the look-ahead predict in the overlapped mode) and, when the caller wants the grids, their copy-out through
+// the pinned staging together with the grid-status word.  Returns 1 when the assembled grid holds a non-finite value
+// (the grids are delivered all the same), 0 otherwise; without a copy-out nothing is waited for.
+static int begin_common(sml_engine *h, int timestep, bool copy_out)
 {
     if (sml_step_pack_device(h, timestep)) return -1;
-    const bool copy_out = w4d || w2d || wprecip || wsst;
     if (h->overlap) {
         // D2H of the grids on the copy stream, the look-ahead predict on the main stream; the host only
         // waits for the copy
@@ -1358,21 +1681,31 @@ int sml_step_exchange_begin(sml_engine *h, int timestep, double *w4d, double *w2
             CK(h, cudaEventRecord(h->ev_pack, h->stream));
             CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pack, 0));
             CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->copy_stream));
+            CK(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
             CK(h, cudaEventRecord(h->ev_d2h, h->copy_stream));
         }
         if (sml_step_predict_ahead(h, timestep)) return -1;
         if (copy_out) CK(h, cudaEventSynchronize(h->ev_d2h));
     } else if (copy_out) {
         CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
     }
+    return (copy_out && (*h->h_status & SML_GRID_NONFINITE)) ? 1 : 0;
+}
+
+int sml_step_exchange_begin(sml_engine *h, int timestep, double *w4d, double *w2d, double *wprecip, double *wsst)
+{
+    const bool copy_out = w4d || w2d || wprecip || wsst;
+    const int rc = begin_common(h, timestep, copy_out);
+    if (rc < 0) return rc;
     if (copy_out) {
         if (w4d) std::memcpy(w4d, h->h_pin_G + G_W4D, sizeof(double) * G_W2D);
         if (w2d) std::memcpy(w2d, h->h_pin_G + G_W2D, sizeof(double) * XG * YG);
         if (wprecip) std::memcpy(wprecip, h->h_pin_G + G_PRECIP, sizeof(double) * XG * YG);
         if (wsst) std::memcpy(wsst, h->h_pin_G + G_SST, sizeof(double) * XG * YG);
     }
-    return 0;
+    return rc;
 }
 
 // zero-copy variant for hosts that can consume the grids in place: the same as sml_step_exchange_begin, but instead of
@@ -1381,22 +1714,69 @@ int sml_step_exchange_begin_view(sml_engine *h, int timestep, const double **w4d
                                  const double **wprecip, const double **wsst)
 {
     if (!w4d || !w2d || !wprecip || !wsst) return -1;
-    if (sml_step_pack_device(h, timestep)) return -1;
-    if (h->overlap) {
-        CK(h, cudaEventRecord(h->ev_pack, h->stream));
-        CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pack, 0));
-        CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(h, cudaEventRecord(h->ev_d2h, h->copy_stream));
-        if (sml_step_predict_ahead(h, timestep)) return -1;
-        CK(h, cudaEventSynchronize(h->ev_d2h));
-    } else {
-        CK(h, cudaMemcpyAsync(h->h_pin_G, h->d_G, sizeof(double) * G_TISR, cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-    }
+    const int rc = begin_common(h, timestep, true);
+    if (rc < 0) return rc;
     *w4d = h->h_pin_G + G_W4D;
     *w2d = h->h_pin_G + G_W2D;
     *wprecip = h->h_pin_G + G_PRECIP;
     *wsst = h->h_pin_G + G_SST;
+    return rc;
+}
+
+// the grids of the last assembly as they stand on the device -- on ANY rank, since every rank rebuilds the whole grid
+// (the reference only has them on the root)
+int sml_grids_get(sml_engine *h, double *w4d, double *w2d, double *wprecip, double *wsst)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    if (w4d) CK(h, cudaMemcpyAsync(w4d, h->d_G + G_W4D, sizeof(double) * G_W2D, cudaMemcpyDeviceToHost, h->stream));
+    if (w2d) CK(h, cudaMemcpyAsync(w2d, h->d_G + G_W2D, sizeof(double) * XG * YG, cudaMemcpyDeviceToHost, h->stream));
+    if (wprecip) CK(h, cudaMemcpyAsync(wprecip, h->d_G + G_PRECIP, sizeof(double) * XG * YG, cudaMemcpyDeviceToHost, h->stream));
+    if (wsst) CK(h, cudaMemcpyAsync(wsst, h->d_G + G_SST, sizeof(double) * XG * YG, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- failure detection: the grid-status word of k_pack_grids and the run_speedy flag
+// sticky bits since the last reset; synchronises the engine stream (after a begin with copy-out it is current anyway)
+int sml_grid_status(sml_engine *h, int *bits)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    CK(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (bits) *bits = *h->h_status;
+    return 0;
+}
+int sml_grid_status_reset(sml_engine *h)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    CK(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream));
+    *h->h_status = 0;
+    return 0;
+}
+// model_parameters%run_speedy: set on the root after run_model (src/mpires.f90:1655-1659), broadcast to every rank
+// with the forecast (MPI_Bcast, :744); the step loop leaves when it is false (src/parallelmain.f90:269-271)
+int sml_set_run_speedy(sml_engine *h, int run_speedy)
+{
+    if (!h) return -1;
+    h->run_speedy = run_speedy ? 1 : 0;
+    return 0;
+}
+int sml_run_speedy(sml_engine *h, int *run_speedy)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    if (!run_speedy) return -1;
+    if (h->peers.world > 1 && h->p.irank != 0) {
+        // what the root sent with the last forecast this rank has consumed
+        CK(h, cudaSetDevice(h->p.device));
+        CK(h, cudaMemcpyAsync(h->h_pin_flag, h->d_F + FCST_FLAG, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        *run_speedy = (h->fcst_seq == 0 || *h->h_pin_flag != 0.0) ? 1 : 0;
+    } else {
+        *run_speedy = h->run_speedy;
+    }
     return 0;
 }
 
@@ -1407,7 +1787,7 @@ int sml_forecast_staging(sml_engine *h, double **forecast_4d, double **forecast_
     if (check_ready(h, SML_ATMO)) return -1;
     if (forecast_4d) *forecast_4d = h->h_pin_F + F_F4D;
     if (forecast_2d) *forecast_2d = h->h_pin_F + F_F2D;
-    if (tisr_grid) *tisr_grid = h->h_pin_F + F_TOTAL;
+    if (tisr_grid) *tisr_grid = h->h_pin_F + FCST_TISR;
     return 0;
 }
 
@@ -1449,6 +1829,27 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const 
     if (check_ready(h, SML_ATMO)) return -1;
     CK(h, cudaSetDevice(h->p.device));
     const bool ahead = h->overlap && h->ahead_pending;
+    const bool peers = h->peers.world > 1;
+    const bool root = h->p.irank == 0;
+    if (h->p.numprocs > 1 && !peers && !root)
+        FAIL(h, "sml_step_exchange_end on rank %d needs sml_comm_bootstrap (or the device-only pieces with a host collective)", h->p.irank);
+    if (peers && !root) {
+        // ---- consumer rank: the forecast block comes from the root over NVLink (scatter + bcast of
+        // src/mpires.f90:606-744); wait for it on the device -- the host never blocks here -- and rebuild the inputs
+        const unsigned long long seq = ++h->fcst_seq;
+        const bool own_tisr = tisr != nullptr && !ahead;
+        if (own_tisr) {   // every rank holds the TISR table (get_tisr_by_date, :751-753): its own copy goes up
+            CK(h, cudaStreamSynchronize(h->stream));   // the pinned staging may still feed the previous upload
+            std::memcpy(h->h_pin_F + FCST_TISR, tisr, sizeof(double) * XG * YG);
+            CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_F + FCST_TISR, sizeof(double) * XG * YG, cudaMemcpyHostToDevice, h->stream));
+        }
+        const bool take_tisr = !own_tisr && !ahead;   // else: the root's field, which travels with the forecast
+        k_wait_flag<<<1, 256, 0, h->stream>>>(h->peers.flag(h->p.irank, XF_FCST, 0), seq, h->d_peer_err,
+                                              take_tisr ? h->d_F + FCST_TISR : nullptr, h->d_G + G_TISR, take_tisr ? XG * YG : 0);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        return sml_step_unpack_device(h, timestep);
+    }
     if (!tisr && !ahead) FAIL(h, "tisr_grid is required");
     // the forecast goes up on the copy stream in the overlapped mode (the main stream is busy with the look-ahead
     // predict); its pinned staging is free again: the last copy from it finished before this step's pack ran
@@ -1457,16 +1858,30 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const 
         if (!f4d || !f2d) FAIL(h, "hybrid mode needs forecast_4d and forecast_2d");
         if (f4d != h->h_pin_F + F_F4D) std::memcpy(h->h_pin_F + F_F4D, f4d, sizeof(double) * G_W2D);
         if (f2d != h->h_pin_F + F_F2D) std::memcpy(h->h_pin_F + F_F2D, f2d, sizeof(double) * XG * YG);
-        CK(h, cudaMemcpyAsync(h->d_F, h->h_pin_F, sizeof(double) * F_TOTAL, cudaMemcpyHostToDevice, up));
+    }
+    if (tisr && tisr != h->h_pin_F + FCST_TISR) std::memcpy(h->h_pin_F + FCST_TISR, tisr, sizeof(double) * XG * YG);
+    if (peers) {
+        // ---- root of a multi-rank run: ONE upload of [forecast | tisr | run_speedy] into the landing section of its
+        // own exchange block, then one kernel pushes the block into every other rank's landing section and publishes
+        // the forecast sequence number (no NCCL broadcast on the critical path)
+        h->h_pin_F[FCST_FLAG] = (double)h->run_speedy;
+        CK(h, cudaMemcpyAsync(h->d_F, h->h_pin_F, sizeof(double) * FCST_DOUBLES, cudaMemcpyHostToDevice, up));
+        if (tisr && !ahead)
+            CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->d_F + FCST_TISR, sizeof(double) * XG * YG, cudaMemcpyDeviceToDevice, up));
+        const unsigned long long seq = ++h->fcst_seq;
+        k_peer_push<<<dim3(16, h->peers.world), 256, 0, up>>>(h->d_F, FCST_DOUBLES, h->peers, XF_FCST, 0, 1, seq, 0, h->d_done + 2);
+        h->launches++;
+        CK(h, cudaGetLastError());
+    } else {
+        if (!h->p.ml_only) CK(h, cudaMemcpyAsync(h->d_F, h->h_pin_F, sizeof(double) * F_TOTAL, cudaMemcpyHostToDevice, up));
+        if (!ahead)
+            CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_F + FCST_TISR, sizeof(double) * XG * YG, cudaMemcpyHostToDevice, up));
     }
     if (ahead) {
         CK(h, cudaEventRecord(h->ev_h2d, h->copy_stream));
         CK(h, cudaStreamWaitEvent(h->stream, h->ev_h2d, 0));
         return sml_step_unpack_device(h, timestep);
     }
-    if (tisr != h->h_pin_F + F_TOTAL) std::memcpy(h->h_pin_F + F_TOTAL, tisr, sizeof(double) * XG * YG);
-    CK(h, cudaMemcpyAsync(h->d_G + G_TISR, h->h_pin_F + F_TOTAL, sizeof(double) * XG * YG, cudaMemcpyHostToDevice,
-                          h->stream));
     if (sml_step_unpack_device(h, timestep)) return -1;
     CK(h, cudaStreamSynchronize(h->stream));  // pinned staging is reused by the next call
     return 0;
@@ -1652,6 +2067,24 @@ int sml_sync_times(sml_engine *h, double *ms_sum, int64_t *steps)
     return 0;
 }
 int64_t sml_kernel_launch_count(const sml_engine *h) { return h ? h->launches : 0; }
+int sml_step_plan(const sml_engine *h, int kind, int *kernel, int *slots, int *part_rows, int *parts)
+{
+    if (!h || kind < 0 || kind > 1) return -1;
+    const KindState &K = h->kinds[kind];
+    if (kernel) *kernel = K.persist ? 1 : 0;
+    if (slots) *slots = K.persist ? K.nslots : K.nitems;
+    if (part_rows) *part_rows = K.persist ? K.part_rows : K.chunk_rows;
+    if (parts) *parts = K.persist ? K.nparts : K.nitems;
+    return 0;
+}
+int sml_setup_stats(const sml_engine *h, double *upload_seconds, int64_t *arena_bytes, int *arena_chunks)
+{
+    if (!h) return -1;
+    if (upload_seconds) *upload_seconds = h->setup_upload_s;
+    if (arena_bytes) *arena_bytes = (int64_t)h->arena.total;
+    if (arena_chunks) *arena_chunks = (int)h->arena.chunks.size();
+    return 0;
+}
 int sml_step_chunk_rows(const sml_engine *h, int kind) { return (h && kind >= 0 && kind < 2) ? h->kinds[kind].chunk_rows : 0; }
 int64_t sml_predict_algorithmic_bytes(const sml_engine *h, int kind)
 {

@@ -23,6 +23,7 @@ struct RegionDev {
     int ell_w;      // ELL width (max entries per row; every row padded with (col 0, val 0.0))
     int win_mode;   // 0: compact one-per-row W_in, 1: dense fallback (temp pool)
     int item0, nitems;
+    int part0, nparts;  // fixed row blocks of the persistent step kernel: the region's partial outvecs
     int L;          // mean/std length; slot L holds the SST feedback mean/std
     double leak;
     const int *ell_col;      // [ell_w][n] slot-major, 0-based
@@ -99,17 +100,30 @@ __device__ __forceinline__ void consumer_bar()
 }
 
 // ---------------------------------------------------------------------------------------------
-// peer exchange over NVLink (one process per GPU, buffers mapped with CUDA IPC): every rank owns an exchange
-// block  [2][R*P] doubles (the all-gathered outvecs, double-buffered by step parity) + MAX_PEERS step flags.
-// The readout-finish kernel stores each region's outvec straight into EVERY rank's block and, once all local
-// regions are out, publishes the step number in every rank's flag slot; the pack kernel of each rank waits for
-// all slots to reach the step.  This replaces the per-step NCCL all-gather (1152 x 136 doubles in total).
+// peer exchange over NVLink (one process per GPU, blocks mapped with CUDA IPC).  Every rank owns ONE exchange block:
+//     atmo   [2][R*P]        the all-gathered atmosphere outvecs, double-buffered by step parity
+//     ocean  [2][R*P_ocean]  the all-gathered ocean outvecs, double-buffered by ocean-step parity
+//     fcst   [F_TOTAL + 96*48 + 8]  landing buffer of the root's host-model forecast, TISR field and run_speedy flag
+//     flags  [XF_KINDS][MAX_PEERS] u64: slot [kind][r] is written by rank r (kind 2: only the root, slot 0)
+// The readout-finish kernel stores each region's outvec straight into EVERY rank's block and, once all local regions
+// are out, publishes the step number in every rank's flag slot; the pack kernel of each rank waits for all slots to
+// reach the step (src/mpires.f90:346-454 gather without the root).  The forecast goes the other way: the root's
+// push kernel writes it into every rank's landing buffer (src/mpires.f90:606-739 scatter, :744 bcast) and the
+// consumers' wait kernel spins on the forecast flag.  No host collective on the data path.
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_PEERS = 8;
+constexpr int XF_ATMO = 0, XF_OCEAN = 1, XF_FCST = 2, XF_KINDS = 3;
 struct PeerTable {
     int world, rank;
-    double *gathered[MAX_PEERS];             // rank k's [2][R*P] buffer as mapped into this process
-    unsigned long long *flags[MAX_PEERS];    // rank k's flags[MAX_PEERS]; slot r is written by rank r
+    char *base[MAX_PEERS];                   // rank k's exchange block as mapped into this process
+    long long off_atmo, off_ocean, off_fcst, off_flags;   // byte offsets of the sections (same on every rank)
+    __host__ __device__ double *atmo(int k) const { return reinterpret_cast<double *>(base[k] + off_atmo); }
+    __host__ __device__ double *ocean(int k) const { return reinterpret_cast<double *>(base[k] + off_ocean); }
+    __host__ __device__ double *fcst(int k) const { return reinterpret_cast<double *>(base[k] + off_fcst); }
+    __host__ __device__ unsigned long long *flag(int k, int kind, int slot) const
+    {
+        return reinterpret_cast<unsigned long long *>(base[k] + off_flags) + kind * MAX_PEERS + slot;
+    }
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -290,6 +304,166 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_step_persist: the same fused step as k_step, as a PERSISTENT kernel: one CTA per slot (2 per SM), each slot owning
+// a contiguous, statically balanced run of work -- no tail wave, no per-item CTA start-up, and the TMA producer warp
+// keeps streaming the next item's W_out columns while the consumers reduce / update.
+//   * every region is cut into fixed row blocks of part_rows rows (independent of the rank count); a slot's items are
+//     runs of whole blocks of one region.  Each block yields its own partial outvec, so the summation structure of a
+//     region's readout does not depend on how the model is sharded: results are bit-identical for any numprocs.
+//   * consumer thread (rp, cs): lanes of a warp hold the cpi column groups of 32/cpi row pairs; column c of a block
+//     goes to group c mod cpi (two alternating accumulators), and a block's partial is reduced over the groups with
+//     warp shuffles -- no shared-memory reduction, no block barrier per partial.
+//   * W_out columns arrive one TMA bulk copy per column into slots of ldp doubles (ldp = ldw padded so that the 8
+//     lanes of a 128-bit shared-memory load phase hit 32 distinct banks).
+// Item layout in xs: [local_model (S, only with_model) | x~ of the item's rows].
+// ---------------------------------------------------------------------------------------------
+struct StepSeg {
+    int reg;          // local region index
+    int row0, nrows;  // state rows of the item; row0 is a multiple of part_rows
+    int part0;        // index of the partial of the item's first row block
+    int with_model;   // the item also carries the S local_model columns (first item of a region, fused order)
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ segs, const int2 *__restrict__ slots,
+               const double *__restrict__ x_old, double *__restrict__ x_new, const double *__restrict__ u_pool,
+               const long long *__restrict__ u_offs, int u_t, const double *__restrict__ lm_pool,
+               const double *__restrict__ temp_pool, double *__restrict__ partials, int ldw_max, int stage_cols, int ldp,
+               int xs_cap, int part_rows, int cpi)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int stage_bytes = stage_cols * ldp * 8;
+    double *xs = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(xs + xs_cap);
+    uint64_t *empty = full + STAGES;
+
+    const int2 slot = slots[blockIdx.x];   // (first item, item count)
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCONS_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NCONS_WARPS) {
+        // ---------------- TMA producer warp: the tile sequence of every item of the slot, back to back ----------------
+        int kk = 0;
+        for (int i = 0; i < slot.y; ++i) {
+            const StepSeg sg = segs[slot.x + i];
+            const int ldw = regs[sg.reg].ldw, S = regs[sg.reg].S;
+            const double *wout = regs[sg.reg].wout;
+            const int tilesA = sg.with_model ? (S + stage_cols - 1) / stage_cols : 0;
+            const int ntile = tilesA + (sg.nrows + stage_cols - 1) / stage_cols;
+            const uint32_t colbytes = (uint32_t)ldw * 8u;
+            for (int t = 0; t < ntile; ++t, ++kk) {
+                const int s = kk % STAGES;
+                int c0, nc, wc;
+                if (t < tilesA) {
+                    c0 = t * stage_cols; nc = min(stage_cols, S - c0); wc = c0;
+                } else {
+                    c0 = (t - tilesA) * stage_cols; nc = min(stage_cols, sg.nrows - c0); wc = S + sg.row0 + c0;
+                }
+                mbar_wait(&empty[s], ((kk / STAGES) & 1) ^ 1);   // passes at once on the first lap
+                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nc * colbytes);
+                __syncwarp();
+                unsigned char *dst = smem_raw + (size_t)s * stage_bytes;
+                for (int c = lane; c < nc; c += 32)
+                    tma_load_1d(dst + (size_t)c * ldp * 8, wout + (size_t)(wc + c) * ldw, colbytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int rpw = 32 / cpi;                     // row pairs per warp
+    const int cs = lane & (cpi - 1);
+    int kk = 0;
+    for (int i = 0; i < slot.y; ++i) {
+        const StepSeg sg = segs[slot.x + i];
+        const RegionDev R = regs[sg.reg];
+        const int xs_off = sg.with_model ? R.S : 0;
+        // state update of the item's rows -> x_new (global) and x~ (shared)
+        {
+            const double *xo = x_old + R.x_off;
+            double *xn = x_new + R.x_off;
+            const double *u = u_pool + u_offs[sg.reg] + (long long)u_t * R.D;
+            if (sg.with_model) {
+                const double *lm = lm_pool + R.lm_off;
+                for (int j = tid; j < R.S; j += NCONS) xs[j] = lm[j];
+            }
+            for (int j = tid; j < sg.nrows; j += NCONS) {
+                const int row = sg.row0 + j;
+                const double xv = update_row(R, row, xo, u, temp_pool);
+                xn[row] = xv;
+                xs[xs_off + j] = (row & 1) ? __dmul_rn(xv, xv) : xv;  // even 1-based index squared
+            }
+        }
+        consumer_bar();
+
+        const int HP = R.ldw >> 1;
+        const int rp = warp * rpw + lane / cpi;
+        const bool active = rp < HP;
+        const int tilesA = sg.with_model ? (R.S + stage_cols - 1) / stage_cols : 0;
+        const int ntile = tilesA + (sg.nrows + stage_cols - 1) / stage_cols;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        for (int t = 0; t < ntile; ++t, ++kk) {
+            const int s = kk % STAGES;
+            int c0, nc;
+            const double *xk;
+            bool flush = false;
+            if (t < tilesA) {
+                c0 = t * stage_cols; nc = min(stage_cols, R.S - c0); xk = xs + c0;
+            } else {
+                c0 = (t - tilesA) * stage_cols; nc = min(stage_cols, sg.nrows - c0); xk = xs + xs_off + c0;
+                flush = ((c0 + nc) % part_rows == 0) || (c0 + nc == sg.nrows);
+            }
+            mbar_wait(&full[s], (kk / STAGES) & 1);
+            if (active) {
+                const double *sb = reinterpret_cast<const double *>(smem_raw + (size_t)s * stage_bytes) + 2 * rp;
+                int c = cs;
+                for (; c + cpi < nc; c += 2 * cpi) {
+                    const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldp);
+                    const double2 w1 = *reinterpret_cast<const double2 *>(sb + (size_t)(c + cpi) * ldp);
+                    const double x0 = xk[c], x1 = xk[c + cpi];
+                    a0 = fma(w0.x, x0, a0);
+                    a1 = fma(w0.y, x0, a1);
+                    b0 = fma(w1.x, x1, b0);
+                    b1 = fma(w1.y, x1, b1);
+                }
+                if (c < nc) {
+                    const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldp);
+                    const double x0 = xk[c];
+                    a0 = fma(w0.x, x0, a0);
+                    a1 = fma(w0.y, x0, a1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (flush) {
+                // the row block is complete: reduce over the column groups (lanes cs = 0..cpi-1) in butterfly order
+                double r0 = a0 + b0, r1 = a1 + b1;
+                for (int m = 1; m < cpi; m <<= 1) {
+                    r0 += __shfl_xor_sync(0xffffffffu, r0, m);
+                    r1 += __shfl_xor_sync(0xffffffffu, r1, m);
+                }
+                if (active && cs == 0) {
+                    const int part = sg.part0 + (c0 / part_rows);
+                    *reinterpret_cast<double2 *>(partials + (size_t)part * ldw_max + 2 * rp) = make_double2(r0, r1);
+                }
+                a0 = a1 = b0 = b1 = 0.0;
+            }
+        }
+        consumer_bar();   // xs is rewritten by the next item's update
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_update: the state update alone (synchronize, src/mod_reservoir.f90:1354-1381; slab :1237-1266).
 // The fused kernel hides this phase behind the W_out stream; on its own it is a latency problem (four dependent
 // global loads per row), so this variant keeps more loads in flight: 256-thread CTAs at high occupancy, RPT rows
@@ -463,14 +637,16 @@ k_update_sx(const RegionDev *__restrict__ regs, const int *__restrict__ region_l
 
 // dense W_in fallback: temp = matmul(win, u) for regions with win_mode == 1 (src/mod_reservoir.f90:1445).
 // grid: (ceil(n_max/256), nregions)
-__global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__restrict__ u_pool,
-                            const long long *__restrict__ u_offs, int u_t, double *__restrict__ temp_pool)
+__global__ void k_win_dense(const RegionDev *__restrict__ regs, const int *__restrict__ region_list,
+                            const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
+                            double *__restrict__ temp_pool)
 {
-    const RegionDev R = regs[blockIdx.y];
+    const int reg = region_list ? region_list[blockIdx.y] : (int)blockIdx.y;
+    const RegionDev R = regs[reg];
     if (R.win_mode != 1) return;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= R.n) return;
-    const double *u = u_pool + u_offs[blockIdx.y] + (long long)u_t * R.D;
+    const double *u = u_pool + u_offs[reg] + (long long)u_t * R.D;
     double acc = 0.0;
     for (int i = 0; i < R.D; ++i) acc = fma(R.win_dense[(size_t)i * R.n + row], u[i], acc);
     temp_pool[R.x_off + row] = acc;
@@ -481,6 +657,11 @@ __global__ void k_win_dense(const RegionDev *__restrict__ regs, const double *__
 // model_part != 0 (split-order readout of the overlapped step): the partials hold only W_out[:, S:]*x~ (the
 // reference's v_ml, src/mod_reservoir.f90:1460) and this kernel adds v_p = W_out[:, 0:S]*local_model (:1459)
 // once the host model's forecast has arrived.
+// use_parts != 0: the partials are those of the persistent step kernel (one per fixed row block of the region,
+// RegionDev::part0 / nparts) instead of one per classic step item.
+// Fused all-gather (pt.world > 1): the outvec is staged in shared memory and each warp pushes it to one rank's
+// gathered buffer with coalesced 16-byte stores over NVLink; ONE system fence per CTA, and the last CTA publishes
+// the step in every rank's flag slot, one lane per rank (the release stores overlap instead of queueing).
 constexpr int FIN_GROUPS = 4;     // column groups of the model-part GEMV
 constexpr int FIN_PMAX = 160;     // threads per group (outputs are strided over them: any chunk_size_prediction)
 
@@ -489,12 +670,15 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
                  double *__restrict__ out_pool, int unstandardize, int model_part,
                  const double *__restrict__ lm_pool, PeerTable pt, unsigned long long seq,
                  long long peer_off, unsigned int *__restrict__ done_counter, double *__restrict__ vp_pool,
-                 double *__restrict__ vml_pool)
+                 double *__restrict__ vml_pool, int use_parts)
 {
-    extern __shared__ double s_vp[];   // [FIN_GROUPS][pstride], overlapped mode only
+    extern __shared__ __align__(16) double s_fin[];   // [pstride] outvec staging, then [FIN_GROUPS][pstride] (overlapped mode)
+    __shared__ int s_last;
     const RegionDev R = regs[blockIdx.x];
     const int pstride = (R.P + 1) & ~1;
+    double *s_out = s_fin, *s_vp = s_fin + pstride;
     const int grp = threadIdx.x / FIN_PMAX, p0 = threadIdx.x % FIN_PMAX;
+    const int first = use_parts ? R.part0 : R.item0, cnt = use_parts ? R.nparts : R.nitems;
     if (model_part) {
         // v_p = W_out[:, 0:S] * local_model: group g takes columns g, g+4, ...; 4 independent FMA chains per thread
         // keep the loads in flight; the groups are combined in fixed order below (deterministic)
@@ -522,35 +706,112 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
                 // reservoir%v_p / reservoir%v_ml (outvec_component_contribs, src/mod_reservoir.f90:1458-1461): the two
                 // halves of the readout, in standardised units as the reference keeps them
                 double vml = 0.0;
-                for (int c = 0; c < R.nitems; ++c) vml += partials[(size_t)(R.item0 + c) * ldw_max + p];
+                for (int c = 0; c < cnt; ++c) vml += partials[(size_t)(first + c) * ldw_max + p];
                 vp_pool[R.out_off + p] = v;
                 vml_pool[R.out_off + p] = vml;
             }
-            for (int c = 0; c < R.nitems; ++c) v += partials[(size_t)(R.item0 + c) * ldw_max + p];
+            for (int c = 0; c < cnt; ++c) v += partials[(size_t)(first + c) * ldw_max + p];
             if (unstandardize) {
                 const int ms = R.out_ms[p];
                 if (ms >= 0) v = __dadd_rn(__dmul_rn(v, R.std[ms]), R.mean[ms]);
             }
             out_pool[R.out_off + p] = v;
-            // fused all-gather: the outvec goes straight into every rank's gathered buffer (peer stores over NVLink)
-            if (pt.world > 1) {
-                const long long dst = peer_off + R.out_off + p;
-                for (int k = 0; k < pt.world; ++k) pt.gathered[k][dst] = v;
-            }
+            s_out[p] = v;
         }
     }
     if (pt.world > 1) {
-        __threadfence_system();
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        const long long dst0 = peer_off + R.out_off;
+        const bool vec = ((R.P & 1) == 0) && ((dst0 & 1) == 0);
+        for (int k = warp; k < pt.world; k += nwarps) {
+            double *dst = pt.atmo(k) + dst0;
+            if (vec) {
+                for (int i = lane; i < (R.P >> 1); i += 32)
+                    reinterpret_cast<double2 *>(dst)[i] = reinterpret_cast<const double2 *>(s_out)[i];
+            } else {
+                for (int i = lane; i < R.P; i += 32) dst[i] = s_out[i];
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();   // cumulative: covers the block's peer stores ordered before the barrier
             const unsigned int old = atomicAdd(done_counter, 1u);
-            if (old == gridDim.x - 1) {  // every local region's outvec is on its way: publish the step
+            s_last = (old == gridDim.x - 1) ? 1 : 0;
+            if (s_last) {
                 *done_counter = 0;
-                __threadfence_system();
-                for (int k = 0; k < pt.world; ++k) st_release_sys(pt.flags[k] + pt.rank, seq);
+                __threadfence();
+            }
+        }
+        __syncthreads();
+        if (s_last && (int)threadIdx.x < pt.world) {   // every local region's outvec is on its way: publish the step
+            __threadfence_system();
+            st_release_sys(pt.flag(threadIdx.x, XF_ATMO, pt.rank), seq);
+        }
+    }
+}
+
+// k_peer_push: `count` doubles from src into the `section` of every rank's exchange block at dst_off, then the
+// sequence number into flag [section][flag_slot] of every rank.  Used for the ocean reservoirs' outvec slab (the
+// all-gather after predict_slab_ml, src/mpires.f90:375-454) and for the root's forecast block (scatter + bcast,
+// :606-744).  grid (nchunk, world); block (c, k) copies chunk c to rank k with 16-byte stores.
+__global__ void __launch_bounds__(256)
+k_peer_push(const double *__restrict__ src, long long count, PeerTable pt, int section, long long dst_off, int skip_self,
+            unsigned long long seq, int flag_slot, unsigned int *__restrict__ done_counter)
+{
+    __shared__ int s_last;
+    const int k = blockIdx.y;
+    if (!(skip_self && k == pt.rank)) {
+        double *dst = (section == XF_OCEAN ? pt.ocean(k) : pt.fcst(k)) + dst_off;
+        long long per = (count + gridDim.x - 1) / gridDim.x;
+        per = (per + 1) & ~1LL;
+        const long long i0 = (long long)blockIdx.x * per, i1 = min(count, i0 + per);
+        const bool vec = ((reinterpret_cast<unsigned long long>(src) | reinterpret_cast<unsigned long long>(dst)) & 15ULL) == 0;
+        if (vec) {
+            const long long n2 = (i1 - i0) >> 1;
+            const double2 *s2 = reinterpret_cast<const double2 *>(src + i0);
+            double2 *d2 = reinterpret_cast<double2 *>(dst + i0);
+            for (long long i = threadIdx.x; i < n2; i += blockDim.x) d2[i] = s2[i];
+            if (((i1 - i0) & 1) && threadIdx.x == 0) dst[i1 - 1] = src[i1 - 1];
+        } else {
+            for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = src[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int old = atomicAdd(done_counter, 1u);
+        s_last = (old == gridDim.x * gridDim.y - 1) ? 1 : 0;
+        if (s_last) {
+            *done_counter = 0;
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < pt.world) {
+        __threadfence_system();
+        st_release_sys(pt.flag(threadIdx.x, section, flag_slot), seq);
+    }
+}
+
+// k_wait_flag: the consumer side of the forecast push: wait until the root has published sequence number seq, then
+// (optionally) move the TISR field that came with the forecast into G.  One block; it gives up after ~10 s and
+// raises *err instead of hanging (sml_peer_check reports it).
+__global__ void __launch_bounds__(256)
+k_wait_flag(const unsigned long long *__restrict__ flag, unsigned long long seq, int *__restrict__ err,
+            const double *__restrict__ copy_src, double *__restrict__ copy_dst, int copy_n)
+{
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) < seq) {
+            if (clock64() - t0 > 20000000000LL) {
+                *err = 2;
+                break;
             }
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < copy_n; i += blockDim.x) copy_dst[i] = ld_cg_f64(copy_src + i);
 }
 
 // k_pack_grids: the root's grid assembly of sendrecievegrid in one launch.
@@ -560,6 +821,9 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
 //  blocks [nsc, ..): wholegrid_sst (src/mpires.f90:288-290, 315-328, 470-484).  mode 0: every cell takes the first
 //     fx*fy outputs of its region's ocean reservoir (tile_full_2d_grid_with_local_res, src/res_domain.f90:828-850);
 //     regions without one hold 272.0 in their slab row (:323-326, 383); mode 1: prescribed field; mode -1: no SST.
+//  Failure detection: the assembled atmosphere grid is checked on the way -- non-finite values and the bounds SPEEDY's
+//     own input check applies before it agrees to run (src/ppo_iogrid.f90:562-577: u in [-150,150], v in [-120,120],
+//     T in [160,330], q in [-6,30]) set bits in *status (sticky; SML_GRID_* in the header).
 struct PackArgs {
     const double *gathered;
     const int *out_dst;
@@ -568,10 +832,11 @@ struct PackArgs {
     long long precip_lo, precip_hi, w4d_hi, sst_off;
     int nsc;
     // peers
-    const unsigned long long *my_flags;
+    const unsigned long long *my_flags;   // this rank's flags [XF_KINDS][MAX_PEERS]
     int world;
-    unsigned long long seq;
+    unsigned long long seq, ocean_seq;
     int *err;
+    int *status;
     // sst
     const double *base, *mask, *prescribed, *ocean_out;
     const int *cell_region, *cell_slot;
@@ -580,28 +845,39 @@ struct PackArgs {
 
 __global__ void k_pack_grids(PackArgs a)
 {
-    if ((int)blockIdx.x < a.nsc) {
-        if (a.world > 1) {
-            if ((int)threadIdx.x < a.world) {
-                const long long t0 = clock64();
-                while (ld_acquire_sys(a.my_flags + threadIdx.x) < a.seq) {
-                    if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; report instead of hanging
-                        *a.err = 1;
-                        break;
-                    }
+    if (a.world > 1) {
+        if ((int)threadIdx.x < 2 * a.world) {
+            const int kind = threadIdx.x / a.world, r = threadIdx.x % a.world;
+            const unsigned long long want = kind ? a.ocean_seq : a.seq;
+            const unsigned long long *f = a.my_flags + kind * MAX_PEERS + r;
+            const long long t0 = clock64();
+            while (want > 0 && ld_acquire_sys(f) < want) {
+                if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; report instead of hanging
+                    *a.err = 1;
+                    break;
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
+    }
+    if ((int)blockIdx.x < a.nsc) {
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= a.total) return;
         const int dst = a.out_dst[i];
         double v = ld_cg_f64(a.gathered + i);
+        int bad = 0;
         if (dst < a.w4d_hi) {
-            if ((dst & 3) == 3 && v < 0.000001) v = 0.000001;
+            const int var = dst & 3;   // wholegrid4d(var, x, y, z): 0 T, 1 u, 2 v, 3 q
+            if (var == 3 && v < 0.000001) v = 0.000001;
+            if (var == 0) bad = (v < 160.0 || v > 330.0) ? 8 : 0;
+            else if (var == 1) bad = (v < -150.0 || v > 150.0) ? 2 : 0;
+            else if (var == 2) bad = (v < -120.0 || v > 120.0) ? 4 : 0;
+            else bad = (v < -6.0 || v > 30.0) ? 16 : 0;
         } else if (dst >= a.precip_lo && dst < a.precip_hi) {
             if (v < 0.00001) v = 0.0;
         }
+        if (!(fabs(v) <= 1.7976931348623157e308)) bad = 1;   // NaN or Inf
+        if (bad) atomicOr(a.status, bad);
         a.G[dst] = v;
         return;
     }
@@ -609,7 +885,7 @@ __global__ void k_pack_grids(PackArgs a)
     if (e >= 96 * 48 || a.sst_mode < 0) return;
     double v;
     if (a.sst_mode == 1) v = a.prescribed[e];
-    else v = a.ocean_out[(size_t)a.cell_region[e] * a.ocean_P + a.cell_slot[e]];
+    else v = ld_cg_f64(a.ocean_out + (size_t)a.cell_region[e] * a.ocean_P + a.cell_slot[e]);
     if (a.mask[e] > 0.0) v = a.base[e];
     if (v < 272.0) v = 272.0;
     a.G[a.sst_off + e] = v;

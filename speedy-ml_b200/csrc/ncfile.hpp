@@ -36,6 +36,9 @@ public:
     {
         if (!f_) throw std::runtime_error("cannot open " + path);
         try {
+            if (fseeko(f_, 0, SEEK_END)) throw std::runtime_error("NetCDF seek failed");
+            file_size_ = (int64_t)ftello(f_);
+            seek(0);
             parse_header();
         } catch (...) {
             std::fclose(f_);
@@ -152,7 +155,9 @@ private:
         for (int32_t a = 0; a < n; ++a) {
             name();
             const int32_t t = i32(), ne = i32();
+            if (ne < 0) throw std::runtime_error("bad NetCDF attribute length");
             const int64_t bytes = (int64_t)type_size(t) * ne;
+            if (bytes > file_size_) throw std::runtime_error("NetCDF attribute runs past the end of the file");
             if (fseeko(f_, (off_t)bytes, SEEK_CUR)) throw std::runtime_error("NetCDF seek failed");
             skip_pad(bytes);
         }
@@ -168,9 +173,13 @@ private:
         std::vector<int64_t> dimlen;
         int32_t tag = i32(), n = i32();
         if (tag == 0x0A) {
+            if (n < 0 || n > 1024) throw std::runtime_error("bad NetCDF dimension count");
             for (int32_t d = 0; d < n; ++d) {
                 name();
-                dimlen.push_back(i32());
+                const int32_t len = i32();
+                // length 0 marks the record dimension, which write_trained_res never uses (src/mod_io.f90:1298-1340)
+                if (len <= 0) throw std::runtime_error("NetCDF record / non-positive dimensions are not supported");
+                dimlen.push_back(len);
             }
         } else if (!(tag == 0 && n == 0)) {
             throw std::runtime_error("bad NetCDF dimension list");
@@ -180,10 +189,12 @@ private:
         n = i32();
         if (tag == 0 && n == 0) return;
         if (tag != 0x0B) throw std::runtime_error("bad NetCDF variable list");
+        if (n < 0 || n > 65536) throw std::runtime_error("bad NetCDF variable count");
         for (int32_t v = 0; v < n; ++v) {
             const std::string nm = name();
             Var var;
             const int32_t nd = i32();
+            if (nd < 0 || nd > 1024) throw std::runtime_error("bad NetCDF variable rank");
             for (int32_t d = 0; d < nd; ++d) {
                 const int32_t id = i32();
                 if (id < 0 || id >= (int32_t)dimlen.size()) throw std::runtime_error("bad NetCDF dimension id");
@@ -193,11 +204,21 @@ private:
             var.type = i32();
             i32();  // vsize
             var.begin = off64 ? i64() : (int64_t)i32();
+            // the data block must lie inside the file: count() * element size from begin
+            int64_t cnt = 1;
+            for (int64_t sdim : var.shape) {   // no overflow: stop as soon as the product leaves the file
+                cnt *= sdim;
+                if (cnt > file_size_) throw std::runtime_error("NetCDF variable '" + nm + "' is larger than the file");
+            }
+            if (var.begin < 0 || var.begin > file_size_ ||
+                cnt * type_size(var.type) > file_size_ - var.begin)
+                throw std::runtime_error("NetCDF variable '" + nm + "' runs past the end of the file");
             vars_[nm] = var;
         }
     }
 
     std::FILE *f_;
+    int64_t file_size_ = 0;
     std::map<std::string, Var> vars_;
 };
 

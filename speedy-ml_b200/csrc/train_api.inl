@@ -109,7 +109,62 @@ int device_dgesv(sml_engine *h, double *dA, int lda, double *dB, int ldb, int n,
 
 }  // namespace
 
+namespace {
+// issue-rate probe of the FP64 tensor pipe: back-to-back DMMA m8n8k4 from registers, 16 independent accumulators per
+// warp, 8 warps per CTA, 2 CTAs per SM -- the roof the Gram kernel is reported against, measured in the same run
+__global__ void __launch_bounds__(256)
+k_dmma_probe(double *out, int iters)
+{
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = threadIdx.x * 1e-3, b = threadIdx.x * 2e-3 + 1.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
 extern "C" {
+
+// FP64 tensor-core (DMMA) issue peak of this GPU in TFLOP/s, measured now (about 10 ms): best of 3 timed launches
+int sml_dmma_probe(sml_engine *h, double *tflops)
+{
+    if (!h || !tflops) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    const int ctas = 2 * h->num_sms, iters = 4000;
+    double *out = nullptr;
+    CK(h, cudaMalloc(&out, sizeof(double) * ctas * 256));
+    cudaEvent_t e0, e1;
+    CK(h, cudaEventCreate(&e0));
+    CK(h, cudaEventCreate(&e1));
+    k_dmma_probe<<<ctas, 256, 0, h->stream>>>(out, 50);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(h, cudaEventRecord(e0, h->stream));
+        k_dmma_probe<<<ctas, 256, 0, h->stream>>>(out, iters);
+        CK(h, cudaEventRecord(e1, h->stream));
+        CK(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)ctas * 8 * iters * 16 * (2.0 * 8 * 8 * 4);
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    h->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    CK(h, cudaGetLastError());
+    *tflops = best;
+    return 0;
+}
 
 int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregions, int batch_size)
 {
@@ -119,9 +174,22 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     if (T.active) FAIL(h, "sml_train_begin while a training wave is active (call sml_train_end)");
     if (nregions <= 0 || batch_size < 2) FAIL(h, "bad training wave (nregions %d, batch_size %d)", nregions, batch_size);
     KindState &K = h->kinds[kind];
+    {
+        // two entries for one region would make two Gram accumulations write the same W_out
+        std::vector<int32_t> sorted(regions, regions + nregions);
+        std::sort(sorted.begin(), sorted.end());
+        for (int i = 1; i < nregions; ++i)
+            if (sorted[i] == sorted[i - 1]) FAIL(h, "sml_train_begin: region %d is listed twice in the wave", sorted[i]);
+    }
     T = TrainState{};
     T.kind = kind;
     T.batch_size = batch_size;
+    // every early return below gives the arena back to the pool instead of leaking it (the next begin resets T)
+    struct BeginGuard {
+        sml_engine *h;
+        bool armed = true;
+        ~BeginGuard() { if (armed) train_release(h->train, &h->train_pool); }
+    } guard{h};
     if (const char *s = getenv("SML_TRAIN_SLAB")) T.ks = std::max(16, atoi(s) / 16 * 16);
     {
         int ov = h->train_overlap;
@@ -150,7 +218,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
     size_t arena_need = 0;
     for (int i = 0; i < nregions; ++i) {
         int li;
-        if (local_of(h, kind, regions[i], &li)) { train_release(T); return -1; }
+        if (local_of(h, kind, regions[i], &li)) return -1;
         const RegionDev &R = K.regs[li].dev;
         const size_t N = (size_t)R.n + R.S, ld = (N + R.P + 15) / 16 * 16;
         arena_need += al256(ld * ld * 8) + al256(ld * T.ks * 8 * (T.overlap ? 2 : 1)) + 2 * al256((size_t)R.n * 8) +
@@ -168,7 +236,6 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
             }
             if (e != cudaSuccess) {
                 h->err = std::string("training wave does not fit in HBM (cudaMalloc: ") + cudaGetErrorString(e) + "); use fewer regions per wave";
-                train_release(T);
                 return -1;
             }
             got = arena_need;
@@ -177,9 +244,10 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         T.arena_bytes = got;
     }
     size_t arena_off = 0;
+    std::vector<std::pair<void *, const std::vector<int32_t> *>> tmap_copies;
     for (int i = 0; i < nregions; ++i) {
         int li;
-        if (local_of(h, kind, regions[i], &li)) { train_release(T); return -1; }
+        if (local_of(h, kind, regions[i], &li)) return -1;
         TrainRegionHost tr;
         tr.local = li;
         tr.region = regions[i];
@@ -212,7 +280,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         double tq = now();
         bad = bad || alloc((size_t)d.ld * d.ld * 8, &p); d.gram = (double *)p;
         t_alloc += now() - tq; tq = now();
-        if (!bad) cudaMemsetAsync(d.gram, 0, (size_t)d.ld * d.ld * 8, h->stream);
+        if (!bad) CK(h, cudaMemsetAsync(d.gram, 0, (size_t)d.ld * d.ld * 8, h->stream));
         t_memset += now() - tq; tq = now();
         bad = bad || alloc((size_t)d.ld * T.ks * 8 * (T.overlap ? 2 : 1), &p); d.slab = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xa = (double *)p;
@@ -222,18 +290,23 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         bad = bad || alloc(sizeof(int), &p); d.chol_info = (int *)p;
         // target rows (tile_full_input_to_target_data2d / _ocean_model), flattened at upload
         const std::vector<int32_t> &tmap = K.regs[li].target_map;
-        if ((int)tmap.size() != d.R.P) { h->err = "internal: target map size"; train_release(T); return -1; }
+        if ((int)tmap.size() != d.R.P) FAIL(h, "internal: target map size");
         bad = bad || alloc(sizeof(int) * d.R.P, &p);
         t_alloc += now() - tq; tq = now();
-        if (!bad) {
-            cudaMemcpyAsync(p, tmap.data(), sizeof(int) * d.R.P, cudaMemcpyHostToDevice, h->stream);
-            cudaStreamSynchronize(h->stream);
-        }
+        if (!bad) tmap_copies.push_back({p, &tmap});
         t_map += now() - tq;
         d.target_map = (const int *)p;
         T.regs.push_back(tr);
-        if (bad) { train_release(T); h->train_pool.drop_all(); return -1; }
+        if (bad) return -1;
         devs.push_back(d);
+    }
+    {
+        // the wave's target maps go up with one pass of asynchronous copies and a single synchronisation
+        const double tq = now();
+        for (auto &c : tmap_copies)
+            CK(h, cudaMemcpyAsync(c.first, c.second->data(), sizeof(int) * c.second->size(), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        t_map += now() - tq;
     }
     CK(h, cudaMalloc(&T.d_regs, sizeof(TrainRegionDev) * devs.size()));
     // lower-triangle tile list, row-major so that neighbouring CTAs share slab row blocks in L2
@@ -254,6 +327,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         fprintf(stderr, "[sml train_begin] %d regions: %.3f s (allocation %.3f, memset enqueue %.3f, target map + sync %.3f)\n", nregions,
                 now() - tb0, t_alloc, t_memset, t_map);
     T.active = true;
+    guard.armed = false;
     return 0;
 }
 

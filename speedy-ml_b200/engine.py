@@ -42,6 +42,11 @@ class EngineError(RuntimeError):
 
 _LIB = None
 
+# the one primitive sml_comm_bootstrap asks of the host: int allgather(ctx, send, recv, bytes_per_rank)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int)
+
+GRID_NONFINITE, GRID_U_RANGE, GRID_V_RANGE, GRID_T_RANGE, GRID_Q_RANGE = 1, 2, 4, 8, 16
+
 _SIGNATURES = {
     "sml_create": ([C.POINTER(C.c_void_p), C.POINTER(SmlParams)], C.c_int),
     "sml_destroy": ([C.c_void_p], C.c_int),
@@ -75,6 +80,7 @@ _SIGNATURES = {
     "sml_local_model_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_outvec_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_outvec_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
+    "sml_outvec_get_all": ([C.c_void_p, C.c_int, _dp], C.c_int),
     "sml_wout_get": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_wout_set": ([C.c_void_p, C.c_int, C.c_int, _dp], C.c_int),
     "sml_synchronize": ([C.c_void_p, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _lp], C.c_int),
@@ -84,6 +90,7 @@ _SIGNATURES = {
     "sml_step_exchange_begin": ([C.c_void_p, C.c_int, _dp, _dp, _dp, _dp], C.c_int),
     "sml_step_exchange_begin_view": ([C.c_void_p, C.c_int] + [C.POINTER(_dp)] * 4, C.c_int),
     "sml_forecast_staging": ([C.c_void_p] + [C.POINTER(_dp)] * 3, C.c_int),
+    "sml_grids_get": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
     "sml_step_exchange_end": ([C.c_void_p, C.c_int, _dp, _dp, _dp], C.c_int),
     "sml_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
     "sml_set_tisr": ([C.c_void_p, _dp], C.c_int),
@@ -96,6 +103,13 @@ _SIGNATURES = {
     "sml_peer_export": ([C.c_void_p, C.c_void_p], C.c_int),
     "sml_peer_attach": ([C.c_void_p, C.c_void_p, C.c_int], C.c_int),
     "sml_peer_attached": ([C.c_void_p], C.c_int),
+    "sml_comm_bootstrap": ([C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "sml_grid_status": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
+    "sml_grid_status_reset": ([C.c_void_p], C.c_int),
+    "sml_set_run_speedy": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_run_speedy": ([C.c_void_p, C.POINTER(C.c_int)], C.c_int),
+    "sml_step_plan": ([C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4, C.c_int),
+    "sml_setup_stats": ([C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int)], C.c_int),
     "sml_peer_check": ([C.c_void_p], C.c_int),
     "sml_step_pack_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_step_unpack_device": ([C.c_void_p, C.c_int], C.c_int),
@@ -115,6 +129,7 @@ _SIGNATURES = {
     "sml_train_trim": ([C.c_void_p], C.c_int),
     "sml_train_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_stats": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
+    "sml_dmma_probe": ([C.c_void_p, _dp], C.c_int),
     "sml_rolling_average_2d": ([C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_profile": ([C.c_void_p, C.c_int], C.c_int),
@@ -425,6 +440,12 @@ class Engine:
     def outvec_get(self, region, kind=ATMO):
         return self._get(self.lib.sml_outvec_get, kind, region, self.dims[(kind, region)]["P"])
 
+    def outvec_get_all(self, P, kind=ATMO):
+        """-> (nloc, P) array: every local region's outvec in one copy (local region order)"""
+        out = np.zeros((self.num_of_regions_on_proc, P))
+        self._ck(self.lib.sml_outvec_get_all(self.h, kind, _d(out)))
+        return out
+
     def outvec_set(self, region, v, kind=ATMO):
         v = np.ascontiguousarray(v, dtype=np.float64)
         assert v.size == self.dims[(kind, region)]["P"]
@@ -488,6 +509,7 @@ class Engine:
         if not copy_out:
             self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, None, None, None, None))
             return None
+        self.grid_nonfinite = False
         if reuse and getattr(self, "_grids", None) is not None:
             w4d, w2d, wp, wsst = self._grids
         else:
@@ -497,13 +519,17 @@ class Engine:
             wsst = np.empty((XGRID, YGRID), order="F")
             if reuse:
                 self._grids = (w4d, w2d, wp, wsst)
-        self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, _d(w4d), _d(w2d), _d(wp), _d(wsst)))
+        rc = self._ck(self.lib.sml_step_exchange_begin(self.h, timestep, _d(w4d), _d(w2d), _d(wp), _d(wsst)),
+                      allow_positive=True)
+        self.grid_nonfinite = rc > 0        # the assembled grid holds a NaN / Inf (the grids are returned all the same)
         return w4d, w2d, wp, wsst
 
     def step_exchange_begin_view(self, timestep):
         """zero-copy: the four grids as read-only views of the engine's pinned staging (valid until the next begin)"""
         p = [_dp() for _ in range(4)]
-        self._ck(self.lib.sml_step_exchange_begin_view(self.h, timestep, *[C.byref(a) for a in p]))
+        rc = self._ck(self.lib.sml_step_exchange_begin_view(self.h, timestep, *[C.byref(a) for a in p]),
+                      allow_positive=True)
+        self.grid_nonfinite = rc > 0
         shapes = ((4, XGRID, YGRID, ZGRID), (XGRID, YGRID), (XGRID, YGRID), (XGRID, YGRID))
         out = []
         for ptr, shp in zip(p, shapes):
@@ -511,6 +537,13 @@ class Engine:
             a.flags.writeable = False
             out.append(a)
         return tuple(out)
+
+    def grids_get(self):
+        """(wholegrid4d, wholegrid2d, wholegrid_precip, wholegrid_sst) of the last assembly, from the device, on any rank"""
+        w4d = np.empty((4, XGRID, YGRID, ZGRID), order="F")
+        w2d, wp, wsst = (np.empty((XGRID, YGRID), order="F") for _ in range(3))
+        self._ck(self.lib.sml_grids_get(self.h, _d(w4d), _d(w2d), _d(wp), _d(wsst)))
+        return w4d, w2d, wp, wsst
 
     def forecast_staging(self):
         """(forecast_4d, forecast_2d, tisr) views of the pinned staging step_exchange_end uploads from: write the host
@@ -565,6 +598,55 @@ class Engine:
         """handles: list of the 64-byte exports of every rank, in rank order"""
         blob = b"".join(handles)
         self._ck(self.lib.sml_peer_attach(self.h, blob, len(handles)))
+
+    def comm_bootstrap(self, allgather_bytes):
+        """the whole multi-rank set-up behind one call.  allgather_bytes(blob: bytes) -> list of every rank's blob in
+        rank order is the only thing the host supplies (torch.distributed.all_gather_object, mpi4py allgather, ...)."""
+        world = self.p.numprocs
+
+        def cb(_ctx, send, recv, nbytes):
+            try:
+                blobs = allgather_bytes(C.string_at(send, nbytes))
+                if len(blobs) != world or any(len(b) != nbytes for b in blobs):
+                    return 1
+                C.memmove(recv, b"".join(blobs), nbytes * world)
+                return 0
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        fn = ALLGATHER_FN(cb)
+        self._ck(self.lib.sml_comm_bootstrap(self.h, C.cast(fn, C.c_void_p), None))
+
+    def grid_status(self) -> int:
+        """sticky GRID_* bits of the assembled grids since the last reset (synchronises the engine's stream)"""
+        bits = C.c_int()
+        self._ck(self.lib.sml_grid_status(self.h, C.byref(bits)))
+        return bits.value
+
+    def grid_status_reset(self):
+        self._ck(self.lib.sml_grid_status_reset(self.h))
+
+    def set_run_speedy(self, flag: bool):
+        """model_parameters%run_speedy, set by the root after run_model; travels with the next forecast"""
+        self._ck(self.lib.sml_set_run_speedy(self.h, int(bool(flag))))
+
+    def run_speedy(self) -> bool:
+        v = C.c_int()
+        self._ck(self.lib.sml_run_speedy(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def step_plan(self, kind=ATMO):
+        v = [C.c_int() for _ in range(4)]
+        self._ck(self.lib.sml_step_plan(self.h, kind, *[C.byref(a) for a in v]))
+        return dict(kernel="k_step_persist" if v[0].value else "k_step", slots=v[1].value, part_rows=v[2].value,
+                    parts=v[3].value)
+
+    def setup_stats(self):
+        a, b, c = C.c_double(), C.c_int64(), C.c_int()
+        self._ck(self.lib.sml_setup_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(upload_s=a.value, arena_bytes=b.value, arena_chunks=c.value)
 
     def peer_attached(self) -> bool:
         return bool(self.lib.sml_peer_attached(self.h))
@@ -679,6 +761,12 @@ class Engine:
         v = [C.c_double() for _ in range(4)]
         self._ck(self.lib.sml_train_stats(self.h, *[C.byref(a) for a in v]))
         return dict(zip(("gram_flops_useful", "gram_ms", "stategen_ms", "solve_ms"), (a.value for a in v)))
+
+    def dmma_probe(self) -> float:
+        """FP64 tensor-core issue peak of this GPU, TFLOP/s, measured now"""
+        v = C.c_double()
+        self._ck(self.lib.sml_dmma_probe(self.h, C.byref(v)))
+        return v.value
 
     def train_end(self):
         self._ck(self.lib.sml_train_end(self.h))

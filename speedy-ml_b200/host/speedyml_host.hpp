@@ -15,12 +15,20 @@
 #pragma once
 #include "../../include/speedyml_engine.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace speedyml {
 
@@ -56,6 +64,86 @@ struct reservoir_type {
     std::vector<dp> feedback, local_model, outvec, current_state, saved_state, v_p, v_ml;
 };
 
+// The one primitive sml_comm_bootstrap asks of the host, for ranks that are processes of ONE node and have no MPI at
+// hand (the reference would pass MPI_Allgather on mpi_res%mpi_world): an all-gather through a POSIX shared-memory
+// segment.  Rank 0 creates the segment, every rank writes its block and waits until all `world` blocks of the round
+// are in.  Rounds alternate between two halves of the segment so that a fast rank cannot overwrite a slow one's read.
+class ShmAllgather {
+public:
+    static constexpr int MAX_BYTES = 512;
+    ShmAllgather(const std::string &name, int rank, int world) : name_("/" + name), rank_(rank), world_(world)
+    {
+        const size_t bytes = sizeof(Header) + 2 * (size_t)world * MAX_BYTES;
+        int fd = -1;
+        if (rank == 0) {
+            shm_unlink(name_.c_str());
+            fd = shm_open(name_.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+            if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) throw std::runtime_error("ShmAllgather: cannot create " + name_);
+        } else {
+            for (int tries = 0; tries < 60000; ++tries) {   // up to ~60 s for rank 0 to get there
+                fd = shm_open(name_.c_str(), O_RDWR, 0600);
+                struct stat st;
+                if (fd >= 0 && fstat(fd, &st) == 0 && (size_t)st.st_size >= bytes) break;
+                if (fd >= 0) { close(fd); fd = -1; }
+                usleep(1000);
+            }
+            if (fd < 0) throw std::runtime_error("ShmAllgather: rank 0 never created " + name_);
+        }
+        void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) throw std::runtime_error("ShmAllgather: mmap failed");
+        base_ = static_cast<unsigned char *>(m);
+        bytes_ = bytes;
+    }
+    ~ShmAllgather()
+    {
+        if (base_) munmap(base_, bytes_);
+        if (rank_ == 0) shm_unlink(name_.c_str());
+    }
+    ShmAllgather(const ShmAllgather &) = delete;
+    ShmAllgather &operator=(const ShmAllgather &) = delete;
+
+    int allgather(const void *send, void *recv, int nbytes)
+    {
+        if (nbytes > MAX_BYTES) return 1;
+        Header *hd = reinterpret_cast<Header *>(base_);
+        unsigned char *half = base_ + sizeof(Header) + (size_t)(round_ & 1) * world_ * MAX_BYTES;
+        std::memcpy(half + (size_t)rank_ * MAX_BYTES, send, (size_t)nbytes);
+        hd->arrived.fetch_add(1, std::memory_order_acq_rel);
+        const unsigned want = (unsigned)world_ * (unsigned)(round_ + 1);
+        for (long spins = 0; hd->arrived.load(std::memory_order_acquire) < want; ++spins) {
+            if (spins > 120000) return 1;   // ~2 min: a rank died
+            usleep(1000);
+        }
+        for (int k = 0; k < world_; ++k)
+            std::memcpy(static_cast<unsigned char *>(recv) + (size_t)k * nbytes, half + (size_t)k * MAX_BYTES, (size_t)nbytes);
+        ++round_;
+        return 0;
+    }
+    // signature of sml_allgather_fn; ctx is the ShmAllgather
+    static int callback(void *ctx, const void *send, void *recv, int nbytes)
+    {
+        return static_cast<ShmAllgather *>(ctx)->allgather(send, recv, nbytes);
+    }
+    void barrier()
+    {
+        int32_t one = 1;
+        std::vector<int32_t> all((size_t)world_);
+        if (allgather(&one, all.data(), (int)sizeof(one))) throw std::runtime_error("ShmAllgather: barrier timed out");
+    }
+
+private:
+    struct Header {
+        std::atomic<unsigned> arrived;
+        unsigned pad[15];
+    };
+    std::string name_;
+    int rank_, world_;
+    unsigned char *base_ = nullptr;
+    size_t bytes_ = 0;
+    int round_ = 0;
+};
+
 class Engine {
 public:
     static constexpr int ATMO = SML_ATMO, OCEAN = SML_OCEAN;
@@ -77,7 +165,10 @@ public:
         if (sml_create(&h_, &p)) throw std::runtime_error(std::string("sml_create: ") + sml_last_error(nullptr));
         mp.region_indices.resize(sml_num_local_regions(h_));
         sml_local_region_ids(h_, mp.region_indices.data());
+        for (size_t i = 0; i < mp.region_indices.size(); ++i) local_of_[mp.region_indices[i]] = (int)i;
         contribs_ = mp.outvec_component_contribs;
+        irank_ = mp.irank;
+        numprocs_ = mp.numprocs;
     }
     ~Engine() { sml_destroy(h_); }
     Engine(const Engine &) = delete;
@@ -121,6 +212,11 @@ public:
         if (contribs_) ck(sml_set_contribs(h_, 1), "sml_set_contribs");
     }
 
+    // multi-rank runs (numprocs > 1), once after finalize on every rank: the host hands over its all-gather (the
+    // reference's MPI communicator, or ShmAllgather above) and the engine connects the ranks' exchange blocks; from
+    // then on sendrecievegrid is complete on every rank without another host collective
+    void comm_bootstrap(sml_allgather_fn allgather, void *ctx) { ck(sml_comm_bootstrap(h_, allgather, ctx), "sml_comm_bootstrap"); }
+
     // gen_res: spectral radius (sparse_eigen) and vals = vals/eig*radius on the device copy and on reservoir%vals
     void gen_res(std::vector<reservoir_type *> &local, int kind = ATMO, int maxit = 500, double tol = 1e-13)
     {
@@ -143,6 +239,24 @@ public:
         ck(sml_state_get(h_, kind, r.assigned_region, x.data()), "sml_state_get");
     }
 
+    // the same for EVERY local region in one call (the loop over regions of initialize_prediction / start_prediction,
+    // src/mod_reservoir.f90:818-824, :951): one batched launch per time step instead of one per region and step.
+    // local[i] is the reservoir of mp.region_indices[i]; inputs[i] its (reservoir_numinputs, length) series; the
+    // states start from and return to local[i]->saved_state.
+    void synchronize_all(std::vector<reservoir_type *> &local, const std::vector<const dp *> &inputs, int length, int kind = ATMO)
+    {
+        std::vector<dp> flat;
+        std::vector<int64_t> offs(local.size(), 0);
+        for (size_t i = 0; i < local.size(); ++i) {
+            offs[i] = (int64_t)flat.size();
+            flat.insert(flat.end(), inputs[i], inputs[i] + (size_t)local[i]->reservoir_numinputs * length);
+            ck(sml_state_set(h_, kind, local[i]->assigned_region, local[i]->saved_state.data()), "sml_state_set");
+        }
+        ck(sml_synchronize(h_, kind, SML_ALL_REGIONS, flat.data(), 0, length, offs.data()), "synchronize");
+        for (size_t i = 0; i < local.size(); ++i)
+            ck(sml_state_get(h_, kind, local[i]->assigned_region, local[i]->saved_state.data()), "sml_state_get");
+    }
+
     // start_prediction: reservoir%current_state = reservoir%saved_state; feedback / local_model as the host set them
     void start_prediction(reservoir_type &r, int kind = ATMO)
     {
@@ -160,9 +274,15 @@ public:
         if (step_predicted_ != current_step_) {
             ck(sml_predict(h_, ATMO), "predict");
             step_predicted_ = current_step_;
+            // ... and ONE read-back of every local outvec (a blocking 1 KB copy per region would cost more than the step)
+            outvec_cache_.resize(local_of_.size() * (size_t)r.chunk_size_prediction);
+            if (fetch_outvecs_) ck(sml_outvec_get_all(h_, ATMO, outvec_cache_.data()), "sml_outvec_get_all");
         }
         r.outvec.resize(r.chunk_size_prediction);
-        ck(sml_outvec_get(h_, ATMO, r.assigned_region, r.outvec.data()), "sml_outvec_get");
+        if (fetch_outvecs_) {
+            const dp *src = outvec_cache_.data() + (size_t)local_of_.at(r.assigned_region) * r.chunk_size_prediction;
+            r.outvec.assign(src, src + r.chunk_size_prediction);
+        }
         if (contribs_) {
             r.v_p.resize(r.chunk_size_prediction);
             r.v_ml.resize(r.chunk_size_prediction);
@@ -171,6 +291,9 @@ public:
     }
     void predict_ml(reservoir_type &r) { predict(r); }
     void predict_all() { ck(sml_predict(h_, ATMO), "predict"); step_predicted_ = current_step_; }
+    // reservoir%outvec is only read by the exchange, which lives on the device: a host that does not look at it can
+    // switch the per-step read-back off and the predict calls never block
+    void set_fetch_outvecs(bool on) { fetch_outvecs_ = on; }
 
     // predict_slab_ml: the caller keeps the schedule test mod(t*timestep, timestep_slab) == 0 (parallelmain.f90:238)
     void predict_slab_ml(reservoir_type &r)
@@ -193,13 +316,36 @@ public:
                         wholegrid_precip = std::vector<dp>(SML_XGRID * SML_YGRID), wholegrid_sst = std::vector<dp>(SML_XGRID * SML_YGRID),
                         forecast_4d = std::vector<dp>(4 * SML_XGRID * SML_YGRID * SML_ZGRID), forecast_2d = std::vector<dp>(SML_XGRID * SML_YGRID);
     };
-    void sendrecievegrid(model_parameters_type &mp, int timestep, const run_model_fn &run_model, const dp *tisr_grid, grids &G)
+    // Multi-rank (after comm_bootstrap): the root (irank 0) does exactly the above; every other rank only enqueues the
+    // grid assembly and the wait for the root's forecast block -- it never blocks on the host model -- and
+    // mp.run_speedy follows the root's flag (MPI_Bcast of run_speedy, src/mpires.f90:744) when check_run_speedy is set.
+    void sendrecievegrid(model_parameters_type &mp, int timestep, const run_model_fn &run_model, const dp *tisr_grid, grids &G,
+                         bool check_run_speedy = false)
     {
-        ck(sml_step_exchange_begin(h_, timestep, G.wholegrid4d.data(), G.wholegrid2d.data(), G.wholegrid_precip.data(),
-                                   G.wholegrid_sst.data()), "sendrecievegrid/begin");
-        if (!mp.ml_only) run_model(timestep, G.wholegrid4d, G.wholegrid2d, G.wholegrid_sst, G.forecast_4d, G.forecast_2d);
-        ck(sml_step_exchange_end(h_, timestep, G.forecast_4d.data(), G.forecast_2d.data(), tisr_grid), "sendrecievegrid/end");
+        if (numprocs_ > 1 && irank_ != 0) {
+            ck(sml_step_exchange_begin(h_, timestep, nullptr, nullptr, nullptr, nullptr), "sendrecievegrid/begin");
+            ck(sml_step_exchange_end(h_, timestep, nullptr, nullptr, nullptr), "sendrecievegrid/end");
+        } else {
+            const int rc = ck(sml_step_exchange_begin(h_, timestep, G.wholegrid4d.data(), G.wholegrid2d.data(),
+                                                      G.wholegrid_precip.data(), G.wholegrid_sst.data()), "sendrecievegrid/begin");
+            if (rc > 0) mp.run_speedy = false;   // a non-finite grid: SPEEDY must not be run on it
+            if (!mp.ml_only && mp.run_speedy)
+                run_model(timestep, G.wholegrid4d, G.wholegrid2d, G.wholegrid_sst, G.forecast_4d, G.forecast_2d);
+            ck(sml_set_run_speedy(h_, mp.run_speedy ? 1 : 0), "sml_set_run_speedy");
+            ck(sml_step_exchange_end(h_, timestep, G.forecast_4d.data(), G.forecast_2d.data(), tisr_grid), "sendrecievegrid/end");
+        }
+        if (check_run_speedy) {
+            int flag = 1;
+            ck(sml_run_speedy(h_, &flag), "sml_run_speedy");
+            mp.run_speedy = flag != 0;
+        }
         current_step_ = timestep + 1;
+    }
+    // the assembled grids on ANY rank (every rank rebuilds the whole grid): device -> host copy of the current step
+    void grids_get(int timestep_just_exchanged, grids &G)
+    {
+        (void)timestep_just_exchanged;
+        ck(sml_grids_get(h_, G.wholegrid4d.data(), G.wholegrid2d.data(), G.wholegrid_precip.data(), G.wholegrid_sst.data()), "sml_grids_get");
     }
     void set_sst_prescribed(const dp *sst) { ck(sml_set_sst_prescribed(h_, sst), "sml_set_sst_prescribed"); }
     void set_overlap(bool on) { ck(sml_set_overlap(h_, on), "sml_set_overlap"); }
@@ -275,7 +421,10 @@ private:
     }
     sml_engine *h_ = nullptr;
     int step_predicted_ = -1, ocean_step_predicted_ = -1, current_step_ = 0;
-    bool contribs_ = false;
+    bool contribs_ = false, fetch_outvecs_ = true;
+    int irank_ = 0, numprocs_ = 1;
+    std::unordered_map<int, int> local_of_;
+    std::vector<dp> outvec_cache_;
 };
 
 }  // namespace speedyml

@@ -5,11 +5,19 @@ predict, :226-251) and mpires.f90:sendrecievegrid (:218-804): predict on every l
 outvec slabs, assembly of the global grids with the clamps, the host model (SPEEDY's run_model, a callable
 here) on rank 0, and the rebuild of every region's feedback / local_model.
 
-Ranks are one process per GPU.  The data path has ONE collective per step -- the all-gather of the outvec
-slabs (1152 x 136 doubles in total) -- plus the broadcast of rank 0's host-model forecast and the date's TISR
+Ranks are one process per GPU.  The data path has ONE exchange per step -- the all-gather of the outvec
+slabs (1152 x 136 doubles in total) -- plus the distribution of rank 0's host-model forecast and the date's TISR
 field; every rank then rebuilds the whole grid and gathers its own halo'd inputs locally.  Regions are sharded
 as processor_decomposition (src/res_domain.f90:31-62) does; with number_of_regions divisible by the rank count
 the shards are contiguous ascending blocks, so rank-major all-gather order IS region order (`slab_rows`).
+
+Two transports, same arithmetic (bit-identical grids):
+  * library (default on a GPU box, `EngineShard.bootstrap`): after sml_comm_bootstrap the engine does the whole
+    exchange itself over NVLink peer stores -- outvecs from the readout-finish kernel, ocean slabs and the root's
+    forecast block from push kernels -- and this file issues NO collective: every rank just calls
+    predict / exchange_begin / exchange_end, exactly like the Fortran shim's sendrecievegrid.
+  * host collectives (`dist` given, not bootstrapped): NCCL / gloo all-gather and broadcast on the engine's buffers
+    (the CPU tests with the oracle-backed shard, and the A/B of the fused path).
 
 The stepper only needs the small `shard` protocol below, so the multi-rank sequencing is testable on CPU with
 the gloo backend (tests/test_multirank_gloo.py drives it with an oracle-backed shard); on a GPU box the shard
@@ -54,6 +62,11 @@ class EngineShard:
     def __init__(self, eng: "E.Engine", torch_module, ocean: bool = False):
         self.eng = eng
         torch = torch_module
+        # the host collectives below are ordered against torch's CURRENT stream only, so the engine must launch on it:
+        # otherwise an all-gather would read outvecs the readout has not written yet, silently
+        eng.set_stream(torch.cuda.current_stream())
+        self._stream = torch.cuda.current_stream()
+        self.comm_ready = False
         bufs = eng.exchange_buffers()
         self.slab = torch.as_tensor(bufs["outvec_slab"], device="cuda")
         self.gathered = torch.as_tensor(bufs["gathered"], device="cuda")
@@ -79,6 +92,15 @@ class EngineShard:
     def peer_attached(self):
         return self.eng.peer_attached()
 
+    def bootstrap(self, dist):
+        """sml_comm_bootstrap over torch.distributed: afterwards the engine runs the whole multi-rank exchange itself"""
+        def allgather_bytes(blob):
+            out = [None] * dist.get_world_size()
+            dist.all_gather_object(out, blob)
+            return out
+        self.eng.comm_bootstrap(allgather_bytes)
+        self.comm_ready = True
+
     def attach_peers(self, dist):
         """exchange the CUDA IPC handles of the ranks' exchange blocks and switch the atmosphere all-gather to
         peer stores from the readout kernel (ranks of one node)"""
@@ -100,7 +122,9 @@ class EngineShard:
     def unpack(self, t):
         self.eng.step_unpack_device(t)
 
-    def exchange_begin(self, t):
+    def exchange_begin(self, t, copy_out=True):
+        if not copy_out:
+            return self.eng.step_exchange_begin(t, copy_out=False)   # only enqueues the grid assembly
         if self.zero_copy:
             return self.eng.step_exchange_begin_view(t)      # views of the engine's pinned staging
         return self.eng.step_exchange_begin(t, reuse=self.reuse_grids)
@@ -108,7 +132,7 @@ class EngineShard:
     def forecast_buffers(self, world):
         """(forecast_4d, forecast_2d) arrays the host model may write in place: the engine's pinned upload staging on a
         single rank, this shard's pinned broadcast staging otherwise"""
-        if world == 1:
+        if world == 1 or self.comm_ready:
             return self.eng.forecast_staging()[:2]
         lay = self.lay
         return (self._pin_f_np[:lay["w2d"]].reshape((4, E.XGRID, E.YGRID, E.ZGRID), order="F"),
@@ -171,16 +195,11 @@ class HybridStepper:
             self.s.ocean_predict()
         return stepped or (t == 1 and self.s.ocean_slab is not None)  # first step publishes the seeded ocean outvecs
 
-    def device_step(self, t: int):
-        """everything resident on the device; the forecast buffer F keeps what the last host step left"""
-        stepped = self._predict(t)
-        self._gather_outvecs(stepped)
-        self.s.pack(t)
-        self.s.unpack(t)
-
     def step(self, t: int, host_model, tisr_grid):
         """the reference-facing step: host buffers, the host model (run_model) between begin and end.
         host_model(w4d, w2d, wsst) -> (forecast_4d, forecast_2d); tisr_grid is the date's global TISR field."""
+        if self.world > 1 and getattr(self.s, "comm_ready", False):
+            return self._step_library(t, host_model, tisr_grid)
         stepped = self._predict(t)
         self._gather_outvecs(stepped)
         if self.overlap:
@@ -202,3 +221,26 @@ class HybridStepper:
             self.dist.broadcast(self.s.tisr_dev, 0)
         self.s.unpack(t)
         return (w4d, w2d, wp, wsst) if self.rank == 0 else None
+
+    def _step_library(self, t, host_model, tisr_grid):
+        """multi-rank step with the exchange inside the engine (after EngineShard.bootstrap): the call sequence of
+        parallelmain.f90:226-262 on every rank, no collective here.  Ranks other than the root never wait on the host."""
+        self._predict(t)
+        if self.overlap:
+            self.s.set_tisr(tisr_grid)
+        if self.rank == 0:
+            grids = self.s.exchange_begin(t)
+            f4d, f2d = host_model(grids[0], grids[1], grids[3])
+            self.s.exchange_end(t, f4d, f2d, None if self.overlap else tisr_grid)
+            return grids
+        self.s.exchange_begin(t, copy_out=False)
+        self.s.exchange_end(t, None, None, None)
+        return None
+
+    def device_step(self, t: int):
+        """everything resident on the device; the forecast buffer F keeps what the last host step left"""
+        stepped = self._predict(t)
+        if not getattr(self.s, "comm_ready", False):
+            self._gather_outvecs(stepped)
+        self.s.pack(t)
+        self.s.unpack(t)

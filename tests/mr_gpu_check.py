@@ -1,11 +1,14 @@
-"""Multi-GPU parity check, launched by torchrun (one rank per GPU):
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU; 2, 4 or 8 ranks):
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mr_gpu_check.py
 Runs the same closed hybrid loop (small reservoirs on the full 1152-region tiling) with
-  (a) the host collective (NCCL all-gather of the outvec slabs),
-  (b) the fused all-gather (peer stores from the readout kernel over NVLink, CUDA IPC),
+  (a) host collectives (NCCL all-gather of the outvec slabs, NCCL broadcast of the forecast),
+  (b) the exchange INSIDE the engine after sml_comm_bootstrap: outvecs pushed by the readout-finish kernel, the root's
+      forecast block pushed by k_peer_push, consumers waiting on device flags -- no collective issued by the host,
   (c) (b) in the overlapped mode,
-and requires on rank 0: (a) == (b) bit for bit, (c) within 1e-11 of (a), and (a) within 1e-10 of the
-single-process CPU oracle.  Prints MULTIGPU_OK on success (tests/test_multigpu.py looks for it)."""
+and requires: (a) == (b) bit for bit on rank 0, (c) within 1e-11 of (a), (a) within 1e-10 of the single-process CPU
+oracle, the grids assembled on EVERY rank bit-identical to rank 0's, and run_speedy = .false. reaching every rank.
+Then the coupled model (ocean reservoirs; their slabs pushed by the engine as well) against the oracle.
+Prints MULTIGPU_OK on success (tests/test_multigpu.py looks for it)."""
 import importlib
 import os
 import sys
@@ -70,21 +73,42 @@ def main():
                 out.append([a.copy() for a in g])
         torch.cuda.synchronize()
         fbs = {r: eng.feedback_get(r) for r in list(ws)[:3]}
+        mine = eng.grids_get()          # what THIS rank assembled in the last step (every rank rebuilds the whole grid)
         if overlap:
             eng.set_overlap(False)
         dist.barrier()
-        return out, fbs
+        return out, fbs, mine
 
-    nccl, fb_nccl = run(False)
-    assert not eng.peer_attached()
-    shard.attach_peers(dist)
-    assert eng.peer_attached()
-    peer, fb_peer = run(False)
-    ovl, fb_ovl = run(True)
+    def same_on_every_rank(grids):
+        """the last step's grids of every rank against rank 0's, bit for bit"""
+        flat = torch.from_numpy(np.concatenate([a.ravel(order="F") for a in grids])).cuda()
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        return bool(torch.equal(flat.view(torch.int64), ref.view(torch.int64)))
+
+    nccl, fb_nccl, g_nccl = run(False)
+    assert not eng.peer_attached() and not shard.comm_ready
+    shard.bootstrap(dist)               # sml_comm_bootstrap: from here on the host issues no collective in a step
+    assert eng.peer_attached() and shard.comm_ready
+    peer, fb_peer, g_peer = run(False)
+    ovl, fb_ovl, g_ovl = run(True)
     eng.peer_check()
     ok = True
+    ok &= same_on_every_rank(g_nccl) and same_on_every_rank(g_peer) and same_on_every_rank(g_ovl)
     for r in fb_nccl:
         ok &= np.array_equal(fb_nccl[r], fb_peer[r]) and rel_inf(fb_ovl[r], fb_nccl[r]) < 1e-11
+    # run_speedy: the root refuses the next SPEEDY step; the flag travels with the forecast to every rank
+    st = H.HybridStepper(shard, rank=rank, world=world, dist=dist)
+    ok &= eng.run_speedy() is True
+    if rank == 0:
+        eng.set_run_speedy(False)
+    st.step(NSTEPS + 1, host_model, G["tisr"])
+    ok &= eng.run_speedy() is False
+    if rank == 0:
+        eng.set_run_speedy(True)
+    st.step(NSTEPS + 2, host_model, G["tisr"])
+    ok &= eng.run_speedy() is True
+    dist.barrier()
     if rank == 0:
         for t in range(NSTEPS):
             for a, b, c in zip(nccl[t], peer[t], ovl[t]):
@@ -113,11 +137,14 @@ def main():
             f4, f2 = oc.host_stub(gc[0], gc[1], G["clim4d"], G["clim2d"])
             oc.step_scatter(rcs, True, True, False, *gc, f4, f2, G["tisr"], sst_mean, sst_std, nthreads=8)
         ok &= worst < 1e-10
-        print(f"rank0: nccl==peer bitwise, overlap within 1e-11, oracle worst rel err {worst:.2e}, ok={ok}")
+        print(f"rank0 of {world}: host collectives == engine exchange bitwise, overlap within 1e-11, every rank's grid "
+              f"identical, run_speedy broadcast, oracle worst rel err {worst:.2e}, ok={ok}")
+    dist.barrier()
     eng.close()
 
-    # ---- coupled model: ocean reservoirs on the 'ocean' regions; their slabs are all-gathered by NCCL after each
-    # ocean step, the atmosphere slabs by peer stores.  Rank 0 compares the grids with a single-process oracle.
+    # ---- coupled model: ocean reservoirs on the 'ocean' regions; their slabs are pushed to every rank by the engine
+    # after each ocean step (and once for the seeded outvecs), the atmosphere slabs by the readout kernel, the forecast
+    # by the root's push kernel.  Rank 0 compares the grids with a single-process oracle.
     from helpers import c_ocean, ocean_weights, sst_input_mask
     eng = E.Engine(number_of_regions=R, irank=rank, numprocs=world, device=local, sst_prescribed=False, stream=stream)
     for r, w in ws.items():
@@ -131,7 +158,7 @@ def main():
     eng.finalize()
     eng.set_sst_static(G["base_sst"], G["sea_mask"])
     shard2 = H.EngineShard(eng, torch, ocean=True)
-    shard2.attach_peers(dist)
+    shard2.bootstrap(dist)
     rng = np.random.default_rng(9)
     odraw = {r: (rng.standard_normal(128), 285.0 + 5.0 * rng.random(8)) for r in range(R)}   # same stream on every rank
     draws = reset_engine(eng, ws)
@@ -182,9 +209,10 @@ def main():
             for r, co in cos.items():
                 co.build_feedback(rcs[r], t, gc[3])
         ok &= worst2 < 1e-10
-        print(f"rank0: coupled 2-rank loop (ocean slabs over NCCL, atmosphere over peer stores) vs oracle: {worst2:.2e}, ok={ok}")
+        print(f"rank0: coupled {world}-rank loop (every exchange inside the engine) vs oracle: {worst2:.2e}, ok={ok}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()      # nobody frees its exchange block while a peer may still push into it
     eng.close()
     dist.destroy_process_group()
     if int(flag.item()) != 1:
