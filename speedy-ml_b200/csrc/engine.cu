@@ -76,7 +76,7 @@ struct KindState {
     bool persist = false;
     StepSeg *d_segs = nullptr, *d_segs_split = nullptr;
     int2 *d_slots = nullptr;
-    int nslots = 0, nparts = 0, part_rows = 0, p_stage_cols = 0, p_ldp = 0, p_xs_cap = 0, p_cpi = 0;
+    int nslots = 0, nparts = 0, part_rows = 0, p_stage_cols = 0, p_ldp = 0, p_xs_cap = 0, p_cpi = 0, p_stages = 0;
     size_t p_smem_bytes = 0;
     int *d_one_region = nullptr;  // region index for one region's synchronize
     int one_region = -1;
@@ -729,11 +729,19 @@ static int build_persistent_plan(sml_engine *h, KindState &K, int S_max)
     int stage_cols = std::max(unit, (STAGE_BYTES_TARGET / (ldp * 8)) / unit * unit);
     if (const char *e = getenv("SML_PERSIST_STAGE_COLS")) stage_cols = std::max(unit, atoi(e) / unit * unit);
     K.p_stage_cols = stage_cols;
-    int part_rows = std::max(stage_cols, 192 / stage_cols * stage_cols);
+    // fixed row blocks: the granularity of the slot balance and of the partial sums.  Items are runs of whole blocks of
+    // at most item_rows rows -- ONE sweep of the 544 consumer threads, so an item's update phase is a single latency
+    // chain (~3 us), about what the ring's prefetch covers; longer items stall the CTA's W_out stream for the excess
+    // (measured: 1152-row items, three sweeps, ran at 0.82 of the roof where the classic kernel reaches 1.00)
+    int part_rows = std::max(stage_cols, 272 / stage_cols * stage_cols);
     if (const char *e = getenv("SML_PART_ROWS")) part_rows = std::max(stage_cols, atoi(e) / stage_cols * stage_cols);
     K.part_rows = part_rows;
-    const int max_item_rows = std::max(part_rows, 1152 / part_rows * part_rows);
-
+    int item_rows = NCONS;
+    if (const char *e = getenv("SML_ITEM_ROWS")) item_rows = atoi(e);
+    const int max_item_rows = std::max(part_rows, item_rows / part_rows * part_rows);
+    K.p_stages = 5;
+    if (const char *e = getenv("SML_PERSIST_STAGES")) K.p_stages = std::max(2, std::min(8, atoi(e)));
+    const bool stagger = !(getenv("SML_PERSIST_STAGGER") && atoi(getenv("SML_PERSIST_STAGGER")) == 0);
     struct Part { int reg, row0, nrows, part; long long cost; };
     std::vector<Part> parts;
     const int nloc = (int)K.regs.size();
@@ -770,8 +778,10 @@ static int build_persistent_plan(sml_engine *h, KindState &K, int S_max)
             cur_slot = sl;
             slots[sl].x = (int)segs.size();
         }
-        if (!new_slot && !segs.empty() && segs.back().reg == pt.reg && segs.back().row0 + segs.back().nrows == pt.row0 &&
-            segs.back().nrows + pt.nrows <= max_item_rows) {
+        // the two CTAs of an SM start half an item apart: every other slot opens with a one-block item
+        const bool first_of_slot_short = stagger && (sl & 1) && slots[sl].y == 1 && segs.size() == (size_t)slots[sl].x + 1;
+        if (!new_slot && !first_of_slot_short && !segs.empty() && segs.back().reg == pt.reg &&
+            segs.back().row0 + segs.back().nrows == pt.row0 && segs.back().nrows + pt.nrows <= max_item_rows) {
             segs.back().nrows += pt.nrows;
         } else {
             StepSeg sg{pt.reg, pt.row0, pt.nrows, pt.part, pt.row0 == 0 ? 1 : 0};
@@ -780,8 +790,8 @@ static int build_persistent_plan(sml_engine *h, KindState &K, int S_max)
         }
     }
     K.p_xs_cap = (S_max + max_item_rows + 1) & ~1;
-    K.p_smem_bytes = (size_t)STAGES * stage_cols * ldp * 8 + (size_t)K.p_xs_cap * 8 + 2 * STAGES * 8;
-    if (K.p_smem_bytes > 113 * 1024) {   // two CTAs per SM or nothing
+    K.p_smem_bytes = (size_t)K.p_stages * stage_cols * ldp * 8 + (size_t)K.p_xs_cap * 8 + 2 * (size_t)K.p_stages * 8;
+    if (K.p_smem_bytes > 112 * 1024) {   // two CTAs per SM or nothing
         K.persist = false;
         return 0;
     }
@@ -930,7 +940,7 @@ int sml_finalize(sml_engine *h)
         const size_t smem = std::max(h->kinds[SML_ATMO].smem_bytes, h->kinds[SML_OCEAN].smem_bytes);
         CK(h, cudaFuncSetAttribute(k_step<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const size_t psmem = std::max(h->kinds[SML_ATMO].p_smem_bytes, h->kinds[SML_OCEAN].p_smem_bytes);
-        CK(h, cudaFuncSetAttribute(k_step_persist<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
+        CK(h, cudaFuncSetAttribute(k_step_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
     }
     const int R = h->p.number_of_regions, P = h->kinds[SML_ATMO].P;
     h->P_atmo = P;
@@ -1199,9 +1209,9 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
     if (K.persist && all) {
         // persistent kernel: one CTA per slot, each with its statically balanced run of items
         const StepSeg *segs = (d_items == K.d_items_split) ? K.d_segs_split : K.d_segs;
-        k_step_persist<STAGES><<<K.nslots, NTHREADS, K.p_smem_bytes, h->stream>>>(
+        k_step_persist<<<K.nslots, NTHREADS, K.p_smem_bytes, h->stream>>>(
             K.d_regs, segs, K.d_slots, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm, K.d_temp, K.d_partials,
-            K.ldw, K.p_stage_cols, K.p_ldp, K.p_xs_cap, K.part_rows, K.p_cpi);
+            K.ldw, K.p_stage_cols, K.p_ldp, K.p_xs_cap, K.part_rows, K.p_cpi, K.p_stages);
         h->launches++;
         CK(h, cudaGetLastError());
         return 0;

@@ -324,25 +324,24 @@ struct StepSeg {
     int with_model;   // the item also carries the S local_model columns (first item of a region, fused order)
 };
 
-template <int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 2)
 k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ segs, const int2 *__restrict__ slots,
                const double *__restrict__ x_old, double *__restrict__ x_new, const double *__restrict__ u_pool,
                const long long *__restrict__ u_offs, int u_t, const double *__restrict__ lm_pool,
                const double *__restrict__ temp_pool, double *__restrict__ partials, int ldw_max, int stage_cols, int ldp,
-               int xs_cap, int part_rows, int cpi)
+               int xs_cap, int part_rows, int cpi, int nstages)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int stage_bytes = stage_cols * ldp * 8;
-    double *xs = reinterpret_cast<double *>(smem_raw + (size_t)STAGES * stage_bytes);
+    double *xs = reinterpret_cast<double *>(smem_raw + (size_t)nstages * stage_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(xs + xs_cap);
-    uint64_t *empty = full + STAGES;
+    uint64_t *empty = full + nstages;
 
     const int2 slot = slots[blockIdx.x];   // (first item, item count)
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < nstages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], NCONS_WARPS);
         }
@@ -353,28 +352,27 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
 
     if (warp == NCONS_WARPS) {
         // ---------------- TMA producer warp: the tile sequence of every item of the slot, back to back ----------------
-        int kk = 0;
+        int s = 0;
+        uint32_t par = 1;   // parity to wait for on empty[s]: passes at once on the first lap
         for (int i = 0; i < slot.y; ++i) {
             const StepSeg sg = segs[slot.x + i];
             const int ldw = regs[sg.reg].ldw, S = regs[sg.reg].S;
             const double *wout = regs[sg.reg].wout;
-            const int tilesA = sg.with_model ? (S + stage_cols - 1) / stage_cols : 0;
-            const int ntile = tilesA + (sg.nrows + stage_cols - 1) / stage_cols;
             const uint32_t colbytes = (uint32_t)ldw * 8u;
-            for (int t = 0; t < ntile; ++t, ++kk) {
-                const int s = kk % STAGES;
-                int c0, nc, wc;
-                if (t < tilesA) {
-                    c0 = t * stage_cols; nc = min(stage_cols, S - c0); wc = c0;
-                } else {
-                    c0 = (t - tilesA) * stage_cols; nc = min(stage_cols, sg.nrows - c0); wc = S + sg.row0 + c0;
+            // segment A: the S local_model columns (fused order only); segment B: the item's state rows
+            for (int seg = sg.with_model ? 0 : 1; seg < 2; ++seg) {
+                const int ncol = seg == 0 ? S : sg.nrows;
+                const double *src = wout + (size_t)(seg == 0 ? 0 : S + sg.row0) * ldw;
+                for (int c0 = 0; c0 < ncol; c0 += stage_cols) {
+                    const int nc = min(stage_cols, ncol - c0);
+                    mbar_wait(&empty[s], par);
+                    if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nc * colbytes);
+                    __syncwarp();
+                    unsigned char *dst = smem_raw + (size_t)s * stage_bytes;
+                    for (int c = lane; c < nc; c += 32)
+                        tma_load_1d(dst + (size_t)c * ldp * 8, src + (size_t)(c0 + c) * ldw, colbytes, &full[s]);
+                    if (++s == nstages) { s = 0; par ^= 1; }
                 }
-                mbar_wait(&empty[s], ((kk / STAGES) & 1) ^ 1);   // passes at once on the first lap
-                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nc * colbytes);
-                __syncwarp();
-                unsigned char *dst = smem_raw + (size_t)s * stage_bytes;
-                for (int c = lane; c < nc; c += 32)
-                    tma_load_1d(dst + (size_t)c * ldp * 8, wout + (size_t)(wc + c) * ldw, colbytes, &full[s]);
             }
         }
         return;
@@ -383,12 +381,15 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
     // ---------------- consumers ----------------
     const int rpw = 32 / cpi;                     // row pairs per warp
     const int cs = lane & (cpi - 1);
-    int kk = 0;
+    const int rp = warp * rpw + lane / cpi;
+    int s = 0;
+    uint32_t par = 0;
     for (int i = 0; i < slot.y; ++i) {
         const StepSeg sg = segs[slot.x + i];
         const RegionDev R = regs[sg.reg];
         const int xs_off = sg.with_model ? R.S : 0;
-        // state update of the item's rows -> x_new (global) and x~ (shared)
+        // state update of the item's rows -> x_new (global) and x~ (shared).  An item is at most one sweep of the
+        // consumer threads, so this phase is ONE latency chain -- about what the ring's prefetch covers
         {
             const double *xo = x_old + R.x_off;
             double *xn = x_new + R.x_off;
@@ -406,57 +407,55 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
         }
         consumer_bar();
 
-        const int HP = R.ldw >> 1;
-        const int rp = warp * rpw + lane / cpi;
-        const bool active = rp < HP;
-        const int tilesA = sg.with_model ? (R.S + stage_cols - 1) / stage_cols : 0;
-        const int ntile = tilesA + (sg.nrows + stage_cols - 1) / stage_cols;
+        const bool active = rp < (R.ldw >> 1);
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-        for (int t = 0; t < ntile; ++t, ++kk) {
-            const int s = kk % STAGES;
-            int c0, nc;
-            const double *xk;
-            bool flush = false;
-            if (t < tilesA) {
-                c0 = t * stage_cols; nc = min(stage_cols, R.S - c0); xk = xs + c0;
-            } else {
-                c0 = (t - tilesA) * stage_cols; nc = min(stage_cols, sg.nrows - c0); xk = xs + xs_off + c0;
-                flush = ((c0 + nc) % part_rows == 0) || (c0 + nc == sg.nrows);
-            }
-            mbar_wait(&full[s], (kk / STAGES) & 1);
-            if (active) {
-                const double *sb = reinterpret_cast<const double *>(smem_raw + (size_t)s * stage_bytes) + 2 * rp;
-                int c = cs;
-                for (; c + cpi < nc; c += 2 * cpi) {
-                    const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldp);
-                    const double2 w1 = *reinterpret_cast<const double2 *>(sb + (size_t)(c + cpi) * ldp);
-                    const double x0 = xk[c], x1 = xk[c + cpi];
-                    a0 = fma(w0.x, x0, a0);
-                    a1 = fma(w0.y, x0, a1);
-                    b0 = fma(w1.x, x1, b0);
-                    b1 = fma(w1.y, x1, b1);
+        int part = sg.part0;
+        for (int seg = sg.with_model ? 0 : 1; seg < 2; ++seg) {
+            const int ncol = seg == 0 ? R.S : sg.nrows;
+            const double *xseg = seg == 0 ? xs : xs + xs_off;
+            int to_flush = part_rows;             // columns left in the current row block (segment B only)
+            for (int c0 = 0; c0 < ncol; c0 += stage_cols) {
+                const int nc = min(stage_cols, ncol - c0);
+                const double *xk = xseg + c0;
+                mbar_wait(&full[s], par);
+                if (active) {
+                    const double *sb = reinterpret_cast<const double *>(smem_raw + (size_t)s * stage_bytes) + 2 * rp;
+                    int c = cs;
+                    for (; c + cpi < nc; c += 2 * cpi) {
+                        const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldp);
+                        const double2 w1 = *reinterpret_cast<const double2 *>(sb + (size_t)(c + cpi) * ldp);
+                        const double x0 = xk[c], x1 = xk[c + cpi];
+                        a0 = fma(w0.x, x0, a0);
+                        a1 = fma(w0.y, x0, a1);
+                        b0 = fma(w1.x, x1, b0);
+                        b1 = fma(w1.y, x1, b1);
+                    }
+                    if (c < nc) {
+                        const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldp);
+                        const double x0 = xk[c];
+                        a0 = fma(w0.x, x0, a0);
+                        a1 = fma(w0.y, x0, a1);
+                    }
                 }
-                if (c < nc) {
-                    const double2 w0 = *reinterpret_cast<const double2 *>(sb + (size_t)c * ldp);
-                    const double x0 = xk[c];
-                    a0 = fma(w0.x, x0, a0);
-                    a1 = fma(w0.y, x0, a1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == nstages) { s = 0; par ^= 1; }
+                if (seg == 1) {
+                    to_flush -= nc;
+                    if (to_flush == 0 || c0 + nc == ncol) {
+                        // the row block is complete: reduce over the column groups (lanes cs = 0..cpi-1), butterfly order
+                        double r0 = a0 + b0, r1 = a1 + b1;
+                        for (int m = 1; m < cpi; m <<= 1) {
+                            r0 += __shfl_xor_sync(0xffffffffu, r0, m);
+                            r1 += __shfl_xor_sync(0xffffffffu, r1, m);
+                        }
+                        if (active && cs == 0)
+                            *reinterpret_cast<double2 *>(partials + (size_t)part * ldw_max + 2 * rp) = make_double2(r0, r1);
+                        a0 = a1 = b0 = b1 = 0.0;
+                        ++part;
+                        to_flush = part_rows;
+                    }
                 }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            if (flush) {
-                // the row block is complete: reduce over the column groups (lanes cs = 0..cpi-1) in butterfly order
-                double r0 = a0 + b0, r1 = a1 + b1;
-                for (int m = 1; m < cpi; m <<= 1) {
-                    r0 += __shfl_xor_sync(0xffffffffu, r0, m);
-                    r1 += __shfl_xor_sync(0xffffffffu, r1, m);
-                }
-                if (active && cs == 0) {
-                    const int part = sg.part0 + (c0 / part_rows);
-                    *reinterpret_cast<double2 *>(partials + (size_t)part * ldw_max + 2 * rp) = make_double2(r0, r1);
-                }
-                a0 = a1 = b0 = b1 = 0.0;
             }
         }
         consumer_bar();   // xs is rewritten by the next item's update

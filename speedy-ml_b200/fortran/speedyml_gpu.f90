@@ -13,9 +13,16 @@
 !>     mpif90 -c speedyml_gpu.f90 ; link imp.exe with -lspeedyml_b200
 !>
 !> Execution model: the device holds every local region's weights and state.  predict() enqueues nothing per
-!> region; the first predict call of a hybrid step launches ONE batched kernel for all local regions, later
-!> calls in the same step only copy that region's outvec back (reservoir%outvec stays valid for host code such
-!> as the diagnostics writers).  sendrecievegrid() closes the step.
+!> region; the first predict call of a hybrid step launches ONE batched kernel for all local regions and reads
+!> every local outvec back in ONE copy, later calls in the same step only hand out that region's row
+!> (reservoir%outvec stays valid for host code such as the diagnostics writers).  sendrecievegrid() closes the step.
+!>
+!> Multi-rank (numprocs > 1, one rank per GPU of one node): call gpu_comm_bootstrap(mpi_world) once after
+!> gpu_engine_finalize.  It hands the engine ONE host primitive -- MPI_Allgather of a few bytes on the reference's
+!> communicator -- and the engine connects the ranks' exchange blocks over NVLink.  From then on sendrecievegrid is
+!> complete on every rank: the gather of the outvecs (src/mpires.f90:346-454), the scatter of the forecast (:606-739)
+!> and the broadcast of run_speedy (:744) are done by the engine's kernels; ranks other than the root enqueue their
+!> part and never wait for the host model.
 module speedyml_gpu
   use, intrinsic :: iso_c_binding
   use mod_utilities, only : dp, main_type, reservoir_type, grid_type, model_parameters_type, xgrid, ygrid, zgrid
@@ -26,6 +33,7 @@ module speedyml_gpu
   public :: gpu_train_begin, gpu_train_phase, gpu_fit_chunk, gpu_train_end, mldivide
   public :: gen_res, read_trained_res, gpu_train_global_series, gpu_train_phase_global, gpu_set_overlap, gpu_set_tisr
   public :: rolling_average_over_a_period_2d
+  public :: gpu_comm_bootstrap, gpu_synchronize_all, gpu_grid_status
 
   integer(c_int), parameter :: SML_ATMO = 0, SML_OCEAN = 1, SML_ALL_REGIONS = -1
 
@@ -44,6 +52,10 @@ module speedyml_gpu
   type(c_ptr), save :: h = c_null_ptr          !< the engine of this MPI rank (one rank per GPU)
   integer, save     :: step_predicted = -1     !< hybrid step whose batched predict has been launched
   integer, save     :: current_step = 0
+  integer, save     :: my_rank = 0, my_numprocs = 1
+  integer, save     :: bootstrap_comm = -1     !< MPI communicator handed to gpu_comm_bootstrap
+  integer, allocatable, save :: local_of(:)    !< region id -> 1-based local index (0: not on this rank)
+  real(dp), allocatable, save :: outvec_cache(:,:), ocean_outvec_cache(:,:)   !< (chunk_size_prediction, local regions)
 
   interface
      integer(c_int) function sml_create(h, p) bind(C, name='sml_create')
@@ -135,16 +147,52 @@ module speedyml_gpu
        integer(c_int), value :: kind
      end function
      integer(c_int) function sml_step_exchange_begin(h, timestep, w4d, w2d, wprecip, wsst) bind(C, name='sml_step_exchange_begin')
-       import :: c_ptr, c_int, c_double
+       import :: c_ptr, c_int
        type(c_ptr), value :: h
        integer(c_int), value :: timestep
-       real(c_double), intent(out) :: w4d(*), w2d(*), wprecip(*), wsst(*)
+       type(c_ptr), value :: w4d, w2d, wprecip, wsst       ! c_loc(array), or c_null_ptr on ranks that take no grids
      end function
      integer(c_int) function sml_step_exchange_end(h, timestep, f4d, f2d, tisr) bind(C, name='sml_step_exchange_end')
-       import :: c_ptr, c_int, c_double
+       import :: c_ptr, c_int
        type(c_ptr), value :: h
        integer(c_int), value :: timestep
-       real(c_double), intent(in) :: f4d(*), f2d(*), tisr(*)
+       type(c_ptr), value :: f4d, f2d, tisr                 ! c_null_ptr on ranks other than the root
+     end function
+     integer(c_int) function sml_comm_bootstrap(h, allgather, ctx) bind(C, name='sml_comm_bootstrap')
+       import :: c_ptr, c_int, c_funptr
+       type(c_ptr), value :: h
+       type(c_funptr), value :: allgather
+       type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function sml_grid_status(h, bits) bind(C, name='sml_grid_status')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), intent(out) :: bits
+     end function
+     integer(c_int) function sml_set_run_speedy(h, run_speedy) bind(C, name='sml_set_run_speedy')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: run_speedy
+     end function
+     integer(c_int) function sml_run_speedy(h, run_speedy) bind(C, name='sml_run_speedy')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), intent(out) :: run_speedy
+     end function
+     integer(c_int) function sml_outvec_get_all(h, kind, slab) bind(C, name='sml_outvec_get_all')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: kind
+       real(c_double), intent(out) :: slab(*)
+     end function
+     integer(c_int) function sml_num_local_regions(h) bind(C, name='sml_num_local_regions')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+     end function
+     integer(c_int) function sml_local_region_ids(h, ids) bind(C, name='sml_local_region_ids')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), intent(out) :: ids(*)
      end function
      integer(c_int) function sml_set_sst_static(h, base_sst, sea_mask) bind(C, name='sml_set_sst_static')
        import :: c_ptr, c_int, c_double
@@ -268,7 +316,51 @@ contains
     p%sst_prescribed = 0
     p%reserved = 0
     call ck(sml_create(h, p), 'sml_create')
+    my_rank = model_parameters%irank
+    my_numprocs = model_parameters%numprocs
+    block
+      integer(c_int), allocatable :: ids(:)
+      integer :: i, nloc
+      nloc = sml_num_local_regions(h)
+      allocate(ids(nloc))
+      call ck(sml_local_region_ids(h, ids), 'sml_local_region_ids')
+      if (allocated(local_of)) deallocate(local_of)
+      allocate(local_of(0:model_parameters%number_of_regions-1))
+      local_of = 0
+      do i = 1, nloc
+         local_of(ids(i)) = i
+      end do
+    end block
   end subroutine
+
+  !> the one host primitive sml_comm_bootstrap needs, on the reference's communicator (mpi_res%mpi_world)
+  integer(c_int) function allgather_cb(ctx, send, recv, nbytes) bind(C)
+    use mpi
+    type(c_ptr), value :: ctx, send, recv
+    integer(c_int), value :: nbytes
+    character(kind=c_char), pointer :: s(:), r(:)
+    integer :: ierr
+    call c_f_pointer(send, s, [nbytes])
+    call c_f_pointer(recv, r, [nbytes * my_numprocs])
+    call MPI_Allgather(s, nbytes, MPI_BYTE, r, nbytes, MPI_BYTE, bootstrap_comm, ierr)
+    allgather_cb = ierr
+  end function
+
+  !> multi-rank runs: once, after gpu_engine_finalize, on every rank (replaces nothing; the reference's ranks meet in
+  !> every MPI call of sendrecievegrid, these meet here once).  Ranks of ONE node, numprocs <= 8.
+  subroutine gpu_comm_bootstrap(mpi_world)
+    integer, intent(in) :: mpi_world
+    if (my_numprocs == 1) return
+    bootstrap_comm = mpi_world
+    call ck(sml_comm_bootstrap(h, c_funloc(allgather_cb), c_null_ptr), 'sml_comm_bootstrap')
+  end subroutine
+
+  !> sticky status bits of the assembled grids (non-finite values, SPEEDY's input bounds of src/ppo_iogrid.f90:562-577)
+  integer function gpu_grid_status()
+    integer(c_int) :: bits
+    call ck(sml_grid_status(h, bits), 'sml_grid_status')
+    gpu_grid_status = bits
+  end function
 
   !> mklsparse(reservoir): the reference builds the MKL COO handle here; the engine takes the whole reservoir
   !> (adjacency, W_in, W_out) because that is the moment all of them exist (src/mod_reservoir.f90:1852).
@@ -348,6 +440,30 @@ contains
     call ck(sml_state_get(h, k, reservoir%assigned_region, x), 'sml_state_get')
   end subroutine
 
+  !> The same for EVERY local region in one call -- the region loops of initialize_prediction / start_prediction
+  !> (src/mod_reservoir.f90:818-824, :951) collapse into one batched launch per time step instead of `length` launches
+  !> and two state copies per region.  inputs holds the regions' (reservoir_numinputs, length) series back to back in
+  !> local region order, offsets(i) the 0-based position of region i's block; states start from and return to
+  !> reservoirs(i)%saved_state.
+  subroutine gpu_synchronize_all(reservoirs, inputs, offsets, length, kind)
+    type(reservoir_type), intent(inout) :: reservoirs(:)
+    real(kind=dp), intent(in) :: inputs(:)
+    integer(c_int64_t), intent(in), target :: offsets(:)
+    integer, intent(in) :: length
+    integer, intent(in), optional :: kind
+    integer(c_int) :: k
+    integer :: i
+    k = SML_ATMO
+    if (present(kind)) k = kind
+    do i = 1, size(reservoirs)
+       call ck(sml_state_set(h, k, reservoirs(i)%assigned_region, reservoirs(i)%saved_state), 'sml_state_set')
+    end do
+    call ck(sml_synchronize(h, k, SML_ALL_REGIONS, inputs, 0, length, c_loc(offsets)), 'sml_synchronize(all)')
+    do i = 1, size(reservoirs)
+       call ck(sml_state_get(h, k, reservoirs(i)%assigned_region, reservoirs(i)%saved_state), 'sml_state_get')
+    end do
+  end subroutine
+
   !> predict(reservoir,model_parameters,grid,x,local_model_in), src/mod_reservoir.f90:1418-1489.
   !> The first call of a hybrid step runs the batched kernel for every local region; x (current_state) lives
   !> on the device between steps and is only copied back on request (sml_state_get).
@@ -360,8 +476,11 @@ contains
     if (step_predicted /= current_step) then
        call ck(sml_predict(h, SML_ATMO), 'sml_predict')
        step_predicted = current_step
+       ! ONE read-back for all local regions (a blocking 1 KB copy per region would cost more than the step)
+       if (.not. allocated(outvec_cache)) allocate(outvec_cache(reservoir%chunk_size_prediction, sml_num_local_regions(h)))
+       call ck(sml_outvec_get_all(h, SML_ATMO, outvec_cache), 'sml_outvec_get_all')
     end if
-    call ck(sml_outvec_get(h, SML_ATMO, reservoir%assigned_region, reservoir%outvec), 'sml_outvec_get')
+    reservoir%outvec = outvec_cache(:, local_of(reservoir%assigned_region))
   end subroutine
 
   !> predict_ml, src/mod_reservoir.f90:1491-1535: same entry, the engine was created with ml_only
@@ -385,22 +504,28 @@ contains
     if (ocean_step_predicted /= current_step) then
        call ck(sml_predict(h, SML_OCEAN), 'sml_predict(ocean)')
        ocean_step_predicted = current_step
+       if (.not. allocated(ocean_outvec_cache)) &
+            allocate(ocean_outvec_cache(reservoir%chunk_size_prediction, sml_num_local_regions(h)))
+       call ck(sml_outvec_get_all(h, SML_OCEAN, ocean_outvec_cache), 'sml_outvec_get_all(ocean)')
     end if
-    call ck(sml_outvec_get(h, SML_OCEAN, reservoir%assigned_region, reservoir%outvec), 'sml_outvec_get(ocean)')
+    reservoir%outvec = ocean_outvec_cache(:, local_of(reservoir%assigned_region))
   end subroutine
 
   !> sendrecievegrid(res,timestep,ocean_model), src/mpires.f90:218-804.  The MPI star through the root, the
   !> clamps (:456-490) and the feedback / local_model rebuild (:581-604,749-791) happen on the devices; the
   !> root still owns NetCDF output and run_model (:565-569), passed in as procedure arguments so this module
   !> does not depend on mod_io / speedy_res_interface.  tisr_grid: get_tisr_by_date's field for timestep-1.
-  !> With more than one rank the outvec slabs are all-gathered by NCCL inside the library's host layer
-  !> (see INTEGRATION.md: the Python/torch.distributed driver does it today; an MPI_Allgather on the device
-  !> pointers of sml_exchange_buffers is the Fortran equivalent with a CUDA-aware MPI).
-  subroutine sendrecievegrid(res, timestep, ocean_model, run_model, write_prediction, tisr_grid)
+  !> Complete at numprocs > 1 (after gpu_comm_bootstrap): the root copies the assembled grids out, runs the host
+  !> model and hands [forecast | tisr | run_speedy] to the engine, which pushes the block into every rank's landing
+  !> buffer; the other ranks only enqueue the grid assembly and the device-side wait for that block.  run_speedy
+  !> (MPI_Bcast at :744) comes back on every rank when check_run_speedy is present and true -- that read is the only
+  !> point where a non-root rank waits for the root.
+  subroutine sendrecievegrid(res, timestep, ocean_model, run_model, write_prediction, tisr_grid, check_run_speedy)
     type(main_type), intent(inout) :: res
     integer, intent(in) :: timestep
     logical, intent(in) :: ocean_model
-    real(kind=dp), intent(in) :: tisr_grid(:,:)
+    real(kind=dp), intent(in), target :: tisr_grid(:,:)
+    logical, intent(in), optional :: check_run_speedy
     interface
        subroutine run_model(model_parameters, timestep, grid4d, grid2d, sst_grid, speedy_grid4d, speedy_grid2d)
          import :: model_parameters_type, dp
@@ -416,22 +541,42 @@ contains
          real(kind=dp), intent(in) :: grid4d(:,:,:,:), grid2d(:,:), precip_grid(:,:), sst_grid(:,:)
        end subroutine
     end interface
-    real(kind=dp), allocatable :: wholegrid4d(:,:,:,:), wholegrid2d(:,:), wholegrid_precip(:,:), wholegrid_sst(:,:)
-    real(kind=dp), allocatable :: forecast_4d(:,:,:,:), forecast_2d(:,:)
+    real(kind=dp), allocatable, target :: wholegrid4d(:,:,:,:), wholegrid2d(:,:), wholegrid_precip(:,:), wholegrid_sst(:,:)
+    real(kind=dp), allocatable, target :: forecast_4d(:,:,:,:), forecast_2d(:,:)
     integer :: nv
-    nv = res%model_parameters%full_predictvars
-    allocate(wholegrid4d(nv, xgrid, ygrid, zgrid), wholegrid2d(xgrid, ygrid))
-    allocate(wholegrid_precip(xgrid, ygrid), wholegrid_sst(xgrid, ygrid))
-    allocate(forecast_4d(nv, xgrid, ygrid, zgrid), forecast_2d(xgrid, ygrid))
-    call ck(sml_step_exchange_begin(h, timestep, wholegrid4d, wholegrid2d, wholegrid_precip, wholegrid_sst), &
-            'sml_step_exchange_begin')
-    if (res%model_parameters%irank == 0) then
+    integer(c_int) :: rc, flag
+    if (my_numprocs > 1 .and. my_rank /= 0) then
+       ! enqueue only: grid assembly (waits for every rank's outvecs on the device), then the wait for the root's forecast
+       call ck(sml_step_exchange_begin(h, timestep, c_null_ptr, c_null_ptr, c_null_ptr, c_null_ptr), 'sml_step_exchange_begin')
+       call ck(sml_step_exchange_end(h, timestep, c_null_ptr, c_null_ptr, c_null_ptr), 'sml_step_exchange_end')
+    else
+       nv = res%model_parameters%full_predictvars
+       allocate(wholegrid4d(nv, xgrid, ygrid, zgrid), wholegrid2d(xgrid, ygrid))
+       allocate(wholegrid_precip(xgrid, ygrid), wholegrid_sst(xgrid, ygrid))
+       allocate(forecast_4d(nv, xgrid, ygrid, zgrid), forecast_2d(xgrid, ygrid))
+       rc = sml_step_exchange_begin(h, timestep, c_loc(wholegrid4d), c_loc(wholegrid2d), c_loc(wholegrid_precip), &
+                                    c_loc(wholegrid_sst))
+       call ck(rc, 'sml_step_exchange_begin')
+       if (rc > 0) then   ! a non-finite value in the assembled grid: SPEEDY must not be run on it
+          print *, 'hybrid grid is not finite, stopping hybrid prediction'
+          res%model_parameters%run_speedy = .False.
+       end if
        call write_prediction(res, timestep, wholegrid4d, wholegrid2d, wholegrid_precip, wholegrid_sst)
-       if (.not. res%model_parameters%ml_only) then
+       forecast_4d = 0.0_dp
+       forecast_2d = 0.0_dp
+       if (.not. res%model_parameters%ml_only .and. res%model_parameters%run_speedy) then
           call run_model(res%model_parameters, timestep, wholegrid4d, wholegrid2d, wholegrid_sst, forecast_4d, forecast_2d)
        end if
+       call ck(sml_set_run_speedy(h, merge(1_c_int, 0_c_int, res%model_parameters%run_speedy)), 'sml_set_run_speedy')
+       call ck(sml_step_exchange_end(h, timestep, c_loc(forecast_4d), c_loc(forecast_2d), c_loc(tisr_grid)), &
+               'sml_step_exchange_end')
     end if
-    call ck(sml_step_exchange_end(h, timestep, forecast_4d, forecast_2d, tisr_grid), 'sml_step_exchange_end')
+    if (present(check_run_speedy)) then
+       if (check_run_speedy) then
+          call ck(sml_run_speedy(h, flag), 'sml_run_speedy')
+          res%model_parameters%run_speedy = flag /= 0
+       end if
+    end if
     current_step = timestep + 1
   end subroutine
 

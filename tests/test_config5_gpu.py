@@ -59,7 +59,7 @@ def make_engine(E, w, kernel):
 def test_corner_update_step_and_open_loop(E, m, deg):
     region = 555
     w = region_weights(1152, region, m=m, deg=deg, with_dense_win=False)
-    assert abs(w["k"] - int(deg * w["n"])) <= w["n"]          # k = int(density * n * n), density = deg / n
+    assert abs(w["k"] - (deg / m) * w["n"] * w["n"]) < 2.0    # k = int(density * n * n), density = deg / m (:172)
     rng = np.random.default_rng(int(m + deg))
     T_SYNC, T_LOOP = 7, 20
     series = syn.ar1_series(w["D"], T_SYNC + T_LOOP, rng)
