@@ -56,12 +56,18 @@ def _synthetic():
     return importlib.import_module("speedy-ml_b200.synthetic")   # NumPy only; loads no native library
 
 
-def gen_region(region: int, dims):
+def engine_dims(region, sst_in):
+    E = importlib.import_module("speedy-ml_b200.engine")
+    return E.region_dims(R_TOTAL, region, 1, M_RES, 6.0, True, True, sst_in, False)
+
+
+def gen_region(region: int, dims=None):
     """seeded synthetic weights of one region (seed = 20251018 + region), reference construction recipe.
-    dims(region, sst_bool_input) -> dict(n, k, D, P, S, L): the engine's sizes in the GPU arm, the oracle's in the CPU arm"""
+    dims(region, sst_bool_input) -> dict(n, k, D, P, S, L): the engine's sizes by default (GPU arm, tests, tools); the CPU
+    arm passes the oracle's so that it never loads the engine library"""
     syn = _synthetic()
     sst_in = sst_input_mask(region)
-    d = dims(region, sst_in)
+    d = (dims or engine_dims)(region, sst_in)
     rng = np.random.default_rng(20251018 + region)
     rows, cols, vals = syn.make_adjacency(d["n"], d["k"], rng, radius=0.7, power_iters=30)
     winc, wcol = syn.make_win_compact(d["n"], d["D"], rng, sigma=0.5)
@@ -101,6 +107,11 @@ class HostStub:
         return self.f4, self.f2
 
 
+def host_stub(w4d, w2d, clim4d, clim2d, out=None):
+    """one-shot form of HostStub (tests and tools)"""
+    return HostStub(clim4d, clim2d, *(out or (None, None)))(w4d, w2d)
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -114,7 +125,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.idx), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(self.idx), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -454,16 +465,13 @@ def run_gpu(args):
                    stream=stream)
     my_regions = eng.region_indices
 
-    def dims(region, sst_in):
-        return E.region_dims(R_TOTAL, region, 1, M_RES, 6.0, True, True, sst_in, False)
-
     t_setup = time.perf_counter()
     ws_dims = {}
     workers = max(1, min(16, (os.cpu_count() or 2) // max(1, world)))
     with ThreadPoolExecutor(max_workers=workers) as ex:
         batch = 4 * workers
         for i0 in range(0, len(my_regions), batch):
-            for w in ex.map(lambda r: gen_region(r, dims), my_regions[i0:i0 + batch]):
+            for w in ex.map(gen_region, my_regions[i0:i0 + batch]):
                 eng.region_upload(w["region"], w["rows"], w["cols"], w["vals"], w["wout"], w["mean"], w["std"],
                                   win_compact=w["winc"], win_col=w["wcol"], D=w["D"],
                                   sst_bool_input=w["sst_bool_input"])
@@ -536,15 +544,18 @@ def run_gpu(args):
         eng.set_overlap(True)
     for i in range(args.warmup):
         e2e_step(CHECK_STEPS + i + 1)
+    # clocks and throttle reasons are sampled across BOTH timed regions (e2e, then device-resident) and the warm-up
+    # between them: a 20-step timed region lasts ~30 ms, too short on its own for nvidia-smi's sampling period
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.05)
     e2e_ms, e2e_wall = timed(e2e_step, args.steps, CHECK_STEPS + args.warmup + 1)
     if args.overlap:
         eng.set_overlap(False)
         stepper_ovl.overlap = False
     for i in range(args.warmup):
         device_step(i + 1)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     launches0 = eng.kernel_launch_count()
     eng.profile(True)
     dev_ms, dev_wall = timed(device_step, args.steps, 1)
@@ -616,7 +627,7 @@ def run_gpu(args):
             "clocks": clocks,
             "wall_ms_per_step": dev_wall / args.steps,
         }
-        if world == 1 and eng_world == 1:
+        if world == 1:   # also in the emulated-shard diagnostic: the update-only kernel at 144 regions per GPU
             line["update_roofline"] = update_leg(eng, E, my_regions, peak, peak_src)
     if not args.no_train and eng_world == world:
         tr = train_leg(eng, E, torch, dist, world, my_regions, ws_dims, long_k=(world == 1))

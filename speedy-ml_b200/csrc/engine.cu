@@ -311,6 +311,8 @@ int sml_create(sml_engine **out, const sml_params *p)
 
 // which update-only kernel sml_synchronize launches when SML_UPDATE_KERNEL is not set (profiles/round1_summary.md section 3)
 constexpr bool SML_UPDATE_SX_DEFAULT = true;
+// round 2: the TMA-fed ELL ring kernel (k_update_ring) when the region's state vector and a ring fit in shared memory
+constexpr const char *SML_UPDATE_DEFAULT = "ring";
 // which fused step kernel sml_predict launches when SML_STEP_KERNEL is not set: k_step_persist (persistent, statically
 // balanced slots) or the classic one-CTA-per-item k_step
 constexpr bool SML_STEP_PERSIST_DEFAULT = true;
@@ -710,14 +712,17 @@ static int build_persistent_plan(sml_engine *h, KindState &K, int S_max)
         return 0;
     }
     K.p_cpi = cpi;
-    // padded column stride: the 8 lanes of one 128-bit shared-memory load phase must hit 32 distinct banks.
-    // Lane -> (cs = lane % cpi, row pair lane / cpi); word address = cs * 2*ldp + 4 * rowpair.
+    // column stride in shared memory: the 8 lanes of one 128-bit load phase must hit 32 distinct banks.
+    // Lane -> (row pair r = lane % rpw, column group c = lane / rpw); word address = c * 2*ldp + 4 * r.  ldp = ldw (no
+    // padding, ONE bulk copy per stage) whenever that is already conflict-free -- e.g. ldw = 136 with 4 row pairs per warp.
+    const int rpw = 32 / cpi;
     int ldp = K.ldw;
+    if (getenv("SML_PERSIST_PAD")) ldp += 2 * atoi(getenv("SML_PERSIST_PAD"));   // A/B: force per-column copies
     for (;; ldp += 2) {
         bool ok = true;
         unsigned seen = 0;
         for (int l = 0; l < 8 && ok; ++l) {
-            const int c = l % cpi, r = l / cpi;
+            const int r = l % rpw, c = l / rpw;
             const int bank4 = ((c * 2 * ldp + 4 * r) % 32) / 4;   // which group of 4 banks the 16-byte access starts in
             if (seen & (1u << bank4)) ok = false;
             seen |= 1u << bank4;
@@ -793,6 +798,7 @@ static int build_persistent_plan(sml_engine *h, KindState &K, int S_max)
     K.p_smem_bytes = (size_t)K.p_stages * stage_cols * ldp * 8 + (size_t)K.p_xs_cap * 8 + 2 * (size_t)K.p_stages * 8;
     if (K.p_smem_bytes > 112 * 1024) {   // two CTAs per SM or nothing
         K.persist = false;
+        K.p_smem_bytes = 0;
         return 0;
     }
     std::vector<StepSeg> split = segs;
@@ -1162,11 +1168,40 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
         // rows per thread: measured 0.200 / 0.206 / 0.151 ms for 1 / 2 / 4 at the bench config (profiles/round1_summary.md)
         const int rpt = getenv("SML_UPDATE_RPT") ? atoi(getenv("SML_UPDATE_RPT")) : 4;  // A/B switch
         const int RPT = (rpt == 1 || rpt == 2 || rpt == 8) ? rpt : 4;
-        // SML_UPDATE_KERNEL=sx: state vector staged in shared memory (k_update_sx); =global: gathers from L2 (k_update)
+        // SML_UPDATE_KERNEL=ring: TMA-fed ELL ring with a producer warp (k_update_ring, the default when it fits);
+        //                   =sx: state vector staged in shared memory (k_update_sx); =global: gathers from L2 (k_update)
         const char *uk = getenv("SML_UPDATE_KERNEL");
+        {
+            const std::string want = uk ? uk : SML_UPDATE_DEFAULT;
+            const int xs_cap_r = (K.n_max + 1) & ~1, us_cap_r = (K.D_max + 1) & ~1;
+            int w_max = 1;
+            bool aligned = true;
+            for (const HostRegion &hr : K.regs)
+                if (hr.uploaded) {
+                    w_max = std::max(w_max, hr.dev.ell_w);
+                    if (hr.dev.n % 4 != 0) aligned = false;   // the tile copies need 16-byte multiples
+                }
+            const size_t tile_stride = (size_t)UR_TR * (12 * w_max + 12);
+            const size_t fixed = sizeof(double) * ((size_t)xs_cap_r + us_cap_r) + 64;
+            int nst = getenv("SML_UPDATE_STAGES") ? atoi(getenv("SML_UPDATE_STAGES")) : 8;
+            nst = std::max(2, std::min(nst, 16));
+            while (nst > 2 && fixed + (size_t)nst * (tile_stride + 16) > 227 * 1024) --nst;
+            const size_t ring_smem = fixed + (size_t)nst * (tile_stride + 16) + 16;
+            if (want == "ring" && aligned && ring_smem <= 227 * 1024) {
+                // one CTA per SM: split a region's rows only when there are fewer regions than SMs
+                int nsplit = getenv("SML_UPDATE_SPLIT") ? atoi(getenv("SML_UPDATE_SPLIT")) : h->num_sms / std::max(1, nreg);
+                nsplit = std::max(1, std::min(nsplit, 16));
+                CK(h, cudaFuncSetAttribute(k_update_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+                k_update_ring<<<dim3((unsigned)nsplit, (unsigned)nreg), UR_THREADS, ring_smem, h->stream>>>(
+                    K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp, nsplit, xs_cap_r, us_cap_r, w_max, nst);
+                h->launches++;
+                CK(h, cudaGetLastError());
+                return 0;
+            }
+        }
         const int xs_cap = (K.n_max + 1) & ~1;
         const size_t sx_smem = sizeof(double) * ((size_t)xs_cap + ((K.D_max + 1) & ~1)) + 16;
-        const bool use_sx = (uk ? std::string(uk) == "sx" : SML_UPDATE_SX_DEFAULT) && sx_smem <= 110 * 1024;
+        const bool use_sx = (uk ? std::string(uk) != "global" : SML_UPDATE_SX_DEFAULT) && sx_smem <= 110 * 1024;
         if (use_sx) {
             // about one wave of 2 CTAs per SM when there are few regions (each split stages the whole x: L2 hits after
             // the first); measured best: 1 split at 1152 regions, 2 at 144 (tools/ab_update.py)

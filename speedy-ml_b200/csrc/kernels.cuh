@@ -313,8 +313,8 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
 //   * consumer thread (rp, cs): lanes of a warp hold the cpi column groups of 32/cpi row pairs; column c of a block
 //     goes to group c mod cpi (two alternating accumulators), and a block's partial is reduced over the groups with
 //     warp shuffles -- no shared-memory reduction, no block barrier per partial.
-//   * W_out columns arrive one TMA bulk copy per column into slots of ldp doubles (ldp = ldw padded so that the 8
-//     lanes of a 128-bit shared-memory load phase hit 32 distinct banks).
+//   * a stage is one TMA bulk copy of stage_cols whole W_out columns when the unpadded column stride is already
+//     bank-conflict-free for the lane layout (ldw = 136: yes); otherwise one copy per column into slots of ldp doubles.
 // Item layout in xs: [local_model (S, only with_model) | x~ of the item's rows].
 // ---------------------------------------------------------------------------------------------
 struct StepSeg {
@@ -369,8 +369,12 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
                     if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nc * colbytes);
                     __syncwarp();
                     unsigned char *dst = smem_raw + (size_t)s * stage_bytes;
-                    for (int c = lane; c < nc; c += 32)
-                        tma_load_1d(dst + (size_t)c * ldp * 8, src + (size_t)(c0 + c) * ldw, colbytes, &full[s]);
+                    if (ldp == ldw) {   // unpadded tile: the nc columns are one contiguous block -- ONE bulk copy
+                        if (lane == 0) tma_load_1d(dst, src + (size_t)c0 * ldw, (uint32_t)nc * colbytes, &full[s]);
+                    } else {
+                        for (int c = lane; c < nc; c += 32)
+                            tma_load_1d(dst + (size_t)c * ldp * 8, src + (size_t)(c0 + c) * ldw, colbytes, &full[s]);
+                    }
                     if (++s == nstages) { s = 0; par ^= 1; }
                 }
             }
@@ -379,9 +383,12 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
     }
 
     // ---------------- consumers ----------------
+    // lane -> (row pair within the warp, column group): the 8 lanes of one 128-bit load phase are rpw consecutive row
+    // pairs (contiguous 16-byte pieces of a column) x 8/rpw column groups, which hit 32 distinct banks when the column
+    // stride is 2*ldp = 16 (mod 32) words -- true for the UNPADDED W_out of the standard tiling (ldw = 136)
     const int rpw = 32 / cpi;                     // row pairs per warp
-    const int cs = lane & (cpi - 1);
-    const int rp = warp * rpw + lane / cpi;
+    const int cs = lane / rpw;
+    const int rp = warp * rpw + (lane % rpw);
     int s = 0;
     uint32_t par = 0;
     for (int i = 0; i < slot.y; ++i) {
@@ -445,7 +452,7 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
                     if (to_flush == 0 || c0 + nc == ncol) {
                         // the row block is complete: reduce over the column groups (lanes cs = 0..cpi-1), butterfly order
                         double r0 = a0 + b0, r1 = a1 + b1;
-                        for (int m = 1; m < cpi; m <<= 1) {
+                        for (int m = rpw; m < 32; m <<= 1) {
                             r0 += __shfl_xor_sync(0xffffffffu, r0, m);
                             r1 += __shfl_xor_sync(0xffffffffu, r1, m);
                         }
@@ -631,6 +638,124 @@ k_update_sx(const RegionDev *__restrict__ regs, const int *__restrict__ region_l
             const double xv2 = __dadd_rn(__dmul_rn(1.0 - leak, xs[row[i]]), __dmul_rn(leak, xt));
             if (ok[i]) xn[row[i]] = xv2;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_update_ring: the state update alone with the adjacency STREAMED by a producer warp (round 2).
+// k_update_sx still stalls on its own ELL loads: a thread issues a group of loads, waits a full HBM round trip, gathers,
+// issues the next group -- ncu showed 12 of 18 stall cycles per issue on that long scoreboard, and nothing is in flight
+// while the warps compute.  Here the loads are decoupled from the arithmetic:
+//   * ONE CTA per (region, row split) and per SM: 1024 consumer threads + 1 TMA producer warp, the region's whole state
+//     vector staged once in shared memory (one TMA bulk copy), the input vector beside it;
+//   * the producer warp streams row tiles of UR_TR rows through an nstages-deep ring: per tile 2W+2 bulk copies (the W
+//     column-index slots, the W value slots, W_in value and column of the tile's rows -- all contiguous in the
+//     slot-major ELL), completion counted in bytes on the stage's mbarrier; up to ~170 KB in flight per SM regardless of
+//     what the consumers are doing;
+//   * consumer group g (8 warps) takes tiles g, g+4, ...: one row per thread, everything from shared memory except the
+//     coalesced x_new store.  Accumulation order per row is the entry order, as in update_row: bit-identical states.
+// grid (nsplit, regions); dynamic shared memory xs_cap*8 + us_cap*8 + nstages*tile_stride + barriers.
+// ---------------------------------------------------------------------------------------------
+constexpr int UR_CONS = 1024, UR_THREADS = UR_CONS + 32, UR_TR = 256, UR_GROUPS = UR_CONS / UR_TR;
+__global__ void __launch_bounds__(UR_THREADS, 1)
+k_update_ring(const RegionDev *__restrict__ regs, const int *__restrict__ region_list, const double *__restrict__ x_old,
+              double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
+              const double *__restrict__ temp_pool, int nsplit, int xs_cap, int us_cap, int w_max, int nstages)
+{
+    extern __shared__ __align__(128) unsigned char ur_smem[];
+    const int reg = region_list ? region_list[blockIdx.y] : (int)blockIdx.y;
+    const RegionDev &R = regs[reg];
+    const int n = R.n, D = R.D, W = R.ell_w;
+    const int per = (((n + nsplit - 1) / nsplit) + UR_TR - 1) / UR_TR * UR_TR;
+    const int r0 = blockIdx.x * per, r1 = min(n, r0 + per);
+    if (r0 >= n) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double *xs = reinterpret_cast<double *>(ur_smem), *us = xs + xs_cap;
+    unsigned char *ring = reinterpret_cast<unsigned char *>(us + us_cap);
+    const int tile_stride = UR_TR * (12 * w_max + 12);
+    const int off_val = w_max * UR_TR * 4, off_winc = off_val + w_max * UR_TR * 8, off_wcol = off_winc + UR_TR * 8;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)nstages * tile_stride);
+    uint64_t *empty = full + nstages, *xbar = empty + nstages;
+    const int ntiles = (r1 - r0 + UR_TR - 1) / UR_TR;
+    const bool compact = R.win_mode == 0;
+    const double *__restrict__ xo = x_old + R.x_off;
+    if (tid == 0) {
+        for (int s = 0; s < nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], UR_TR / 32);
+        }
+        mbar_init(xbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const uint32_t bytes = (uint32_t)((n + 1) & ~1) * 8u;   // inside the region's padded slot of the x pool
+        mbar_expect_tx(xbar, bytes);
+        tma_load_1d(xs, xo, bytes, xbar);
+    }
+    if (compact) {
+        const double *__restrict__ u = u_pool + u_offs[reg] + (long long)u_t * D;
+        for (int i = tid; i < D; i += UR_THREADS) us[i] = u[i];
+    }
+    __syncthreads();
+
+    if (warp == UR_CONS / 32) {
+        // ---------------- producer: the tiles of this CTA's rows, in order ----------------
+        const int ncopy = 2 * W + (compact ? 2 : 0);
+        int s = 0;
+        uint32_t par = 1;
+        for (int k = 0; k < ntiles; ++k) {
+            const int t0 = r0 + k * UR_TR, rows = min(UR_TR, r1 - t0);
+            mbar_wait(&empty[s], par);
+            if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)rows * (uint32_t)(12 * W + (compact ? 12 : 0)));
+            __syncwarp();
+            unsigned char *dst = ring + (size_t)s * tile_stride;
+            for (int c = lane; c < ncopy; c += 32) {
+                if (c < W) tma_load_1d(dst + (size_t)c * UR_TR * 4, R.ell_col + (size_t)c * n + t0, (uint32_t)rows * 4u, &full[s]);
+                else if (c < 2 * W) tma_load_1d(dst + off_val + (size_t)(c - W) * UR_TR * 8, R.ell_val + (size_t)(c - W) * n + t0, (uint32_t)rows * 8u, &full[s]);
+                else if (c == 2 * W) tma_load_1d(dst + off_winc, R.winc + t0, (uint32_t)rows * 8u, &full[s]);
+                else tma_load_1d(dst + off_wcol, R.wcol + t0, (uint32_t)rows * 4u, &full[s]);
+            }
+            if (++s == nstages) { s = 0; par ^= 1; }
+        }
+        return;
+    }
+
+    // ---------------- consumers: group g takes tiles g, g + UR_GROUPS, ... ----------------
+    const int g = warp / (UR_TR / 32), t = tid % UR_TR;
+    double *__restrict__ xn = x_new + R.x_off;
+    const double leak = R.leak;
+    mbar_wait(xbar, 0);
+    for (int k = g; k < ntiles; k += UR_GROUPS) {
+        const int s = k % nstages;
+        mbar_wait(&full[s], (uint32_t)(k / nstages) & 1u);
+        const unsigned char *tile = ring + (size_t)s * tile_stride;
+        const int row = r0 + k * UR_TR + t;
+        if (row < r1) {
+            const int *tc = reinterpret_cast<const int *>(tile) + t;
+            const double *tv = reinterpret_cast<const double *>(tile + off_val) + t;
+            double acc = 0.0;
+            int sl = 0;
+            for (; sl + 3 <= W; sl += 3) {
+                const int c0 = tc[(size_t)sl * UR_TR], c1 = tc[(size_t)(sl + 1) * UR_TR], c2 = tc[(size_t)(sl + 2) * UR_TR];
+                const double v0 = tv[(size_t)sl * UR_TR], v1 = tv[(size_t)(sl + 1) * UR_TR], v2 = tv[(size_t)(sl + 2) * UR_TR];
+                const double x0 = xs[c0], x1 = xs[c1], x2 = xs[c2];
+                acc = fma(v0, x0, acc);
+                acc = fma(v1, x1, acc);
+                acc = fma(v2, x2, acc);
+            }
+            for (; sl < W; ++sl) acc = fma(tv[(size_t)sl * UR_TR], xs[tc[(size_t)sl * UR_TR]], acc);
+            double tin;
+            if (compact) {
+                const double wv = reinterpret_cast<const double *>(tile + off_winc)[t];
+                const int wc = reinterpret_cast<const int *>(tile + off_wcol)[t];
+                tin = __dmul_rn(wv, us[wc]);
+            } else {
+                tin = temp_pool[R.x_off + row];
+            }
+            const double xt = tanh(__dadd_rn(acc, tin));
+            xn[row] = __dadd_rn(__dmul_rn(1.0 - leak, xs[row]), __dmul_rn(leak, xt));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
 }
 

@@ -140,7 +140,7 @@ def test_corner_m12000_gram_and_solve(E):
     rc = c_region(w)
     rc.train_init(batch)
     rc.train_phase(td, im, discard)
-    sxs_ref, sxt_ref = rc.sxs().copy(), rc.sxt().copy()
+    sxs_ref, sxt_ref = rc.sxs.copy(), rc.sxt.copy()
 
     eng = E.Engine(number_of_regions=1152, irank=region, numprocs=1152)
     eng.region_upload(region, w["rows"], w["cols"], w["vals"], None, w["mean"], w["std"], win_compact=w["winc"],

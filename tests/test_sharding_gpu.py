@@ -120,10 +120,15 @@ def test_nonfinite_and_range_detection(E):
     assert not np.isfinite(grids[0]).all()
     assert eng.grid_status() & E.GRID_NONFINITE
     eng.step_exchange_end(2, G["clim4d"], G["clim2d"], G["tisr"])
-    # sticky until reset; after repairing the weights and resetting it stays clear
+    # sticky until reset; after repairing the weights, clearing what the NaN has reached through the exchange (the
+    # neighbours' feedback and states) and resetting the status it stays clear
     eng.wout_set(700, ws[700]["wout"])
+    for r, w in ws.items():
+        eng.state_set(r, np.zeros(w["n"]))
+        eng.feedback_set(r, np.zeros(w["D"]))
+        eng.local_model_set(r, np.zeros(w["S"]))
+    assert eng.grid_status() & E.GRID_NONFINITE       # still raised: sticky
     eng.grid_status_reset()
-    eng.state_set(700, np.zeros(ws[700]["n"]))
     eng.predict()
     eng.step_exchange_begin(3)
     assert not eng.grid_nonfinite and eng.grid_status() & E.GRID_NONFINITE == 0
