@@ -142,6 +142,19 @@ int sml_finalize(sml_engine *h); /* after the last upload: builds the batched st
  *   sml_adjacency_scale applies vals *= factor[i] (factor = radius / eig, :193-195) to the device copy; the host
  *                      applies the same factor to reservoir%vals ---- */
 int sml_sparse_eigen(sml_engine *h, int kind, int maxit, double tol, double *eigs, int *iterations);
+/* the rest of gen_res on the device: makesparse (src/mod_linalg.f90:180-218: vals = random_number, rows / cols = rounds of
+ * the k-shuffle, src/mod_utilities.f90:1569-1596) and the W_in build of train_reservoir (src/mod_reservoir.f90:262-283:
+ * rows (i-1)q+1..iq of column i = sigma*(-1 + 2*rand), q = n / reservoir_numinputs).  Call INSTEAD of sml_region_upload
+ * with the sizes of allocate_res_new in w (rows, cols, vals and the win_* pointers are ignored; wout may be NULL);
+ * sml_finalize then constructs every such region in two launches, after which sml_sparse_eigen / sml_adjacency_scale
+ * complete gen_res.  The draws come from the engine's counter-based generator keyed by (seed, region, stream, index) --
+ * reproducible, restated in oracle/ from the same streams, but not the Fortran random_number stream.
+ * sml_region_coo_get returns reservoir%rows / cols / vals (1-based, makesparse's entry order; vals rescaled once
+ * sml_adjacency_scale has run), sml_region_win_get the W_in value and 0-based column of every row -- what
+ * write_trained_res needs on the host. */
+int sml_region_generate(sml_engine *h, const sml_region_weights *w, unsigned long long seed, double sigma);
+int sml_region_coo_get(sml_engine *h, int kind, int region, int32_t *rows, int32_t *cols, double *vals);
+int sml_region_win_get(sml_engine *h, int kind, int region, double *win_compact, int32_t *win_col);
 int sml_adjacency_scale(sml_engine *h, int kind, const double *factor);
 
 /* ---- per-region state (reservoir%current_state / saved_state / feedback / local_model / outvec) ---- */

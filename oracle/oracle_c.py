@@ -67,6 +67,14 @@ def lib():
         L.orc_region_set_leakage.argtypes = [C.c_void_p, C.c_double]
         L.orc_region_set_win_compact.argtypes = [C.c_void_p, _dp, _ip]
         L.orc_region_densify_win.argtypes = [C.c_void_p]
+        L.orc_counter_bits.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_longlong]
+        L.orc_counter_bits.restype = C.c_uint64
+        L.orc_shuffle.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _ip]
+        L.orc_shuffle.restype = None
+        L.orc_makesparse.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, _ip, _ip, _dp]
+        L.orc_makesparse.restype = None
+        L.orc_gen_win.argtypes = [C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, _dp, _ip]
+        L.orc_gen_win.restype = None
         L.orc_synchronize.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int]
         L.orc_predict.argtypes = [C.c_void_p, _dp]
         L.orc_predict_ml.argtypes = [C.c_void_p, _dp]
@@ -391,6 +399,30 @@ def host_stub(w4d, w2d, clim4d, clim2d):
 def run_model_clamp(grid4d):
     assert grid4d.flags.f_contiguous
     lib().orc_run_model_clamp(_d(grid4d))
+
+
+def makesparse(n, k, seed, region):
+    """src/mod_linalg.f90:180-218 with the counter-based generator -> (rows, cols 1-based int32, vals U[0,1))"""
+    rows, cols, vals = np.zeros(k, dtype=np.int32), np.zeros(k, dtype=np.int32), np.zeros(k)
+    lib().orc_makesparse(n, k, seed, region, _i(rows), _i(cols), _d(vals))
+    return rows, cols, vals
+
+
+def shuffle(n, returnsize, seed, region, stream):
+    out = np.zeros(returnsize, dtype=np.int32)
+    lib().orc_shuffle(n, returnsize, seed, region, stream, _i(out))
+    return out
+
+
+def gen_win(n, D, sigma, seed, region):
+    """src/mod_reservoir.f90:262-283 -> (winc[n], wcol[n] 0-based)"""
+    winc, wcol = np.zeros(n), np.zeros(n, dtype=np.int32)
+    lib().orc_gen_win(n, D, float(sigma), seed, region, _d(winc), _i(wcol))
+    return winc, wcol
+
+
+def counter_bits(seed, region, stream, index):
+    return int(lib().orc_counter_bits(seed, region, stream, index))
 
 
 def coo_mv(n, rows, cols, vals, x):

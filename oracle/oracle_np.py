@@ -692,3 +692,69 @@ def pinv_svd(A, thres=1e-2):
     U, s, VT = np.linalg.svd(A, full_matrices=False)
     sinv = np.where(s > thres, 1.0 / np.where(s > thres, s, 1.0), 0.0)
     return (VT.T * sinv) @ U.T
+
+
+# ---- reservoir construction with the counter-based generator (second, independent restatement) --------------------
+_M64 = (1 << 64) - 1
+STREAM_WIN = 4096
+
+
+def _mix64(z):
+    z = (z + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def counter_bits(seed, region, stream, index):
+    """the draw for (seed, region, stream, index): a pure function of the four numbers (splitmix64 finaliser)"""
+    h1 = _mix64((seed ^ ((region & 0xFFFFFFFF) << 32) ^ (stream & 0xFFFFFFFF)) & _M64)
+    return _mix64((h1 + index) & _M64)
+
+
+def shuffle(n, returnsize, seed, region, stream):
+    """src/mod_utilities.f90:1569-1596: the k-shuffle; `a` is a default real, so this = a*(n - n_chosen) + 1 is
+    evaluated in single precision and truncated; the pick is clamped to the live range (guard, see the C oracle)"""
+    choices = list(range(1, n + 1))
+    out = np.zeros(returnsize, dtype=np.int32)
+    for i in range(returnsize):
+        a = np.float32(counter_bits(seed, region, stream, i) >> 40) * np.float32(1.0 / 16777216.0)
+        live = n - i
+        this = int(np.float32(np.float32(a * np.float32(live)) + np.float32(1.0)))
+        this = min(this, live)
+        tmp = choices[this - 1]
+        out[i] = tmp
+        choices[this - 1] = choices[live - 1]
+        choices[live - 1] = tmp
+    return out
+
+
+def makesparse(n, k, seed, region):
+    """src/mod_linalg.f90:180-218 -> rows, cols (1-based int32), vals"""
+    vals = np.array([(counter_bits(seed, region, 0, e) >> 11) * (1.0 / 9007199254740992.0) for e in range(k)])
+    rows, cols = np.zeros(k, dtype=np.int32), np.zeros(k, dtype=np.int32)
+    if k > n:
+        counter, leftover = k // n, k % n
+        for i in range(counter):
+            rows[i * n:(i + 1) * n] = shuffle(n, n, seed, region, 1 + 2 * i)
+            cols[i * n:(i + 1) * n] = shuffle(n, n, seed, region, 2 + 2 * i)
+        if leftover:
+            rows[counter * n:] = shuffle(n, leftover, seed, region, 1 + 2 * counter)
+            cols[counter * n:] = shuffle(n, leftover, seed, region, 2 + 2 * counter)
+    else:
+        rows[:] = shuffle(n, k, seed, region, 1)
+        cols[:] = shuffle(n, k, seed, region, 2)
+    return rows, cols, vals
+
+
+def gen_win(n, D, sigma, seed, region):
+    """src/mod_reservoir.f90:262-283 in the one-per-row form -> (winc[n], wcol[n] 0-based)"""
+    q = n // D
+    winc, wcol = np.zeros(n), np.zeros(n, dtype=np.int32)
+    for i in range(D):
+        for t in range(q):
+            j = i * q + t
+            rnd = (counter_bits(seed, region, STREAM_WIN, j) >> 11) * (1.0 / 9007199254740992.0)
+            winc[j] = sigma * (-1.0 + 2.0 * rnd)
+            wcol[j] = i
+    return winc, wcol

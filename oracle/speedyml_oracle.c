@@ -669,6 +669,97 @@ void orc_unstandardize_state_vec_res(const orc_grid *g, const orc_dims *d, const
 /* mod_linalg.f90                                                      */
 /* ------------------------------------------------------------------ */
 
+/* ------------------------------------------------------------------ */
+/* reservoir construction: makesparse + shuffle + the W_in build        */
+/* ------------------------------------------------------------------ */
+
+/* The reference draws from the Fortran random_number stream, which cannot be reproduced.  The
+ * engine and this restatement use a COUNTER-BASED generator instead: the draw for (seed, region, stream, index) is a
+ * pure function of those four numbers (splitmix64 finaliser, the one behind the training noise), so the two sides can
+ * be compared bit for bit whatever order the draws are made in.  Streams: 0 = vals, 1 + 2*round = row shuffle of a
+ * round, 2 + 2*round = column shuffle, ORC_STREAM_WIN = the W_in values. */
+static unsigned long long orc_mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+unsigned long long orc_counter_bits(unsigned long long seed, int region, int stream, long long index)
+{
+    const unsigned long long h1 = orc_mix64(seed ^ ((unsigned long long)(unsigned)region << 32) ^ (unsigned long long)(unsigned)stream);
+    return orc_mix64(h1 + (unsigned long long)index);
+}
+/* random_number into a default real (shuffle's `real :: a`): 24 random bits, [0, 1) */
+static float orc_u24(unsigned long long bits) { return (float)(bits >> 40) * (1.0f / 16777216.0f); }
+/* random_number into real(dp): 53 random bits, [0, 1) */
+static double orc_u53(unsigned long long bits) { return (double)(bits >> 11) * (1.0 / 9007199254740992.0); }
+
+/* src/mod_utilities.f90:1569-1596 shuffle(n, returnsize, shufflereturn): the "k-shuffle".  choices = 1..n; step i
+ * picks this = a*(n - n_chosen) + 1 in DEFAULT-REAL arithmetic (a is `real`, the product and the sum are single
+ * precision, the assignment to the integer truncates), swaps it to the end of the live range.  Only the first
+ * returnsize picks are returned, so the loop may stop there.  Guard (not in the reference): `this` is clamped to the
+ * live range -- for n - n_chosen = 8192 and the largest a the single-precision product rounds up to 8192 and the
+ * reference would read one element past the live range. */
+void orc_shuffle(int n, int returnsize, unsigned long long seed, int region, int stream, int *shufflereturn)
+{
+    int *choices = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; ++i) choices[i] = i + 1;
+    int n_chosen = 0;
+    for (int i = 0; i < returnsize; ++i) {
+        const float a = orc_u24(orc_counter_bits(seed, region, stream, i));
+        const int live = n - n_chosen;
+        const float prod = a * (float)live;
+        const float sum = prod + 1.0f;
+        int pick = (int)sum;
+        if (pick > live) pick = live;
+        const int tmp = choices[pick - 1];
+        shufflereturn[i] = tmp;
+        choices[pick - 1] = choices[live - 1];
+        choices[live - 1] = tmp;
+        n_chosen++;
+    }
+    free(choices);
+}
+
+/* src/mod_linalg.f90:180-218 makesparse: vals = random_number; rows / cols = `counter` full k-shuffles each plus a
+ * partial one of `leftover` picks (k > n), or one partial shuffle each (k <= n).  1-based indices. */
+void orc_makesparse(int n, int k, unsigned long long seed, int region, int *rows, int *cols, double *vals)
+{
+    for (int e = 0; e < k; ++e) vals[e] = orc_u53(orc_counter_bits(seed, region, 0, e));
+    if (k > n) {
+        const int counter = k / n, leftover = k % n;
+        int i;
+        for (i = 0; i < counter; ++i) {
+            orc_shuffle(n, n, seed, region, 1 + 2 * i, rows + (size_t)i * n);
+            orc_shuffle(n, n, seed, region, 2 + 2 * i, cols + (size_t)i * n);
+        }
+        if (leftover != 0) {
+            orc_shuffle(n, leftover, seed, region, 1 + 2 * i, rows + (size_t)i * n);
+            orc_shuffle(n, leftover, seed, region, 2 + 2 * i, cols + (size_t)i * n);
+        }
+    } else {
+        orc_shuffle(n, k, seed, region, 1, rows);
+        orc_shuffle(n, k, seed, region, 2, cols);
+    }
+}
+
+/* src/mod_reservoir.f90:262-283: q = n / reservoir_numinputs; win = 0; for every input i the rows (i-1)q+1 .. iq get
+ * sigma * (-1 + 2*rand).  Returned in the one-per-row form: winc[j] and the 0-based column wcol[j] = j / q. */
+void orc_gen_win(int n, int D, double sigma, unsigned long long seed, int region, double *winc, int *wcol)
+{
+    const int q = n / D;
+    for (int j = 0; j < n; ++j) { winc[j] = 0.0; wcol[j] = 0; }
+    for (int i = 0; i < D; ++i)
+        for (int t = 0; t < q; ++t) {
+            const int j = i * q + t;
+            const double rnd = orc_u53(orc_counter_bits(seed, region, ORC_STREAM_WIN, j));
+            const double ip = -1.0 + 2.0 * rnd;
+            winc[j] = sigma * ip;
+            wcol[j] = i;
+        }
+}
+
 /* MKL_SPARSE_D_MV on the COO handle of mklsparse (src/mod_linalg.f90:10-25): y = A*x, 1-based
  * indices, general matrix, duplicate (row,col) entries sum.  alpha=1, beta=0. */
 void orc_coo_mv(int n, int k, const int *rows, const int *cols, const double *vals, const double *x, double *y)

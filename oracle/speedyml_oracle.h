@@ -124,6 +124,13 @@ int  orc_region_set_weights(orc_region *r, const int *rows, const int *cols, con
                             const double *std, int mean_std_length);
 void orc_region_set_leakage(orc_region *r, double leakage);
 int  orc_region_set_win_compact(orc_region *r, const double *winc, const int *wcol);
+/* reservoir construction with the counter-based generator shared with the engine (makesparse src/mod_linalg.f90:180-218,
+ * shuffle src/mod_utilities.f90:1569-1596, W_in src/mod_reservoir.f90:262-283) */
+#define ORC_STREAM_WIN 4096
+unsigned long long orc_counter_bits(unsigned long long seed, int region, int stream, long long index);
+void orc_shuffle(int n, int returnsize, unsigned long long seed, int region, int stream, int *shufflereturn);
+void orc_makesparse(int n, int k, unsigned long long seed, int region, int *rows, int *cols, double *vals);
+void orc_gen_win(int n, int D, double sigma, unsigned long long seed, int region, double *winc, int *wcol);
 /* compact W_in -> the dense win(n, D) the reference stores; predict runs the dense GEMV again (bench.py CPU arm) */
 int  orc_region_densify_win(orc_region *r);
 double *orc_region_ptr(orc_region *r, const char *field); /* x feedback local_model outvec wout ... */

@@ -53,6 +53,8 @@ struct HostRegion {
     std::vector<int32_t> target_map;   // rows of the input vector that form the training target
     const int *d_sst_src = nullptr;    // ocean: offsets of the halo'd SST tile in G
     double sst_mean = 0.0, sst_std = 1.0;
+    int gen_index = -1;                // >= 0: the adjacency and W_in are generated on the device (K.gen[gen_index])
+    int k = 0;
 };
 
 struct KindState {
@@ -83,6 +85,10 @@ struct KindState {
     size_t smem_bytes = 0;
     bool any_dense = false;
     int64_t alg_bytes = 0, alg_bytes_update = 0;
+    // reservoirs constructed on the device (sml_region_generate): descriptors, run by sml_finalize
+    std::vector<GenDesc> gen;
+    GenDesc *d_gen = nullptr;
+    int *d_gen_of_local = nullptr;
     // synchronize input staging
     double *d_in = nullptr;
     size_t d_in_cap = 0;
@@ -325,6 +331,7 @@ static void free_kind(KindState &K)
     cudaFree(K.d_lm); cudaFree(K.d_out); cudaFree(K.d_partials); cudaFree(K.d_temp); cudaFree(K.d_fb_offs);
     cudaFree(K.d_in); cudaFree(K.d_in_offs);
     cudaFree(K.d_segs); cudaFree(K.d_segs_split); cudaFree(K.d_slots);
+    cudaFree(K.d_gen); cudaFree(K.d_gen_of_local);
 }
 
 int sml_destroy(sml_engine *h)
@@ -475,7 +482,19 @@ int sml_global_layout(int64_t off[5], int64_t *g_total, int64_t *f_total)
 }
 
 /* ------------------------------------------------------------------ upload */
-int sml_region_upload(sml_engine *h, const sml_region_weights *w)
+static int region_install(sml_engine *h, const sml_region_weights *w, bool generate, unsigned long long seed, double sigma);
+
+int sml_region_upload(sml_engine *h, const sml_region_weights *w) { return region_install(h, w, false, 0, 0.0); }
+
+// gen_res's makesparse and train_reservoir's W_in build on the device (src/mod_linalg.f90:180-218,
+// src/mod_reservoir.f90:262-283): the region is installed like an uploaded one, but its adjacency structure, its
+// (unscaled) values and its W_in are drawn by the engine's counter-based generator when sml_finalize runs.
+int sml_region_generate(sml_engine *h, const sml_region_weights *w, unsigned long long seed, double sigma)
+{
+    return region_install(h, w, true, seed, sigma);
+}
+
+static int region_install(sml_engine *h, const sml_region_weights *w, bool generate, unsigned long long seed, double sigma)
 {
     if (!h || !w) return -1;
     if (h->finalized) FAIL(h, "upload after sml_finalize");
@@ -489,10 +508,16 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
     if (hr.uploaded) FAIL(h, "region %d kind %d uploaded twice", w->region, w->kind);
     const int n = w->n, k = w->k, D = w->D, P = w->P, S = w->S, L = w->L;
     if (n <= 0 || k < 0 || D <= 0 || P <= 0 || S < 0 || L <= 0) FAIL(h, "bad dimensions for region %d", w->region);
-    if (!w->rows || !w->cols || !w->vals || !w->mean || !w->std) FAIL(h, "null weight array for region %d", w->region);
-    if ((w->win_dense != nullptr) == (w->win_compact != nullptr))
-        FAIL(h, "exactly one of win_dense / win_compact must be given (region %d)", w->region);
-    if (w->win_compact && !w->win_col) FAIL(h, "win_compact needs win_col (region %d)", w->region);
+    if (!w->mean || !w->std) FAIL(h, "null mean / std for region %d", w->region);
+    if (!generate) {
+        if (!w->rows || !w->cols || !w->vals) FAIL(h, "null weight array for region %d", w->region);
+        if ((w->win_dense != nullptr) == (w->win_compact != nullptr))
+            FAIL(h, "exactly one of win_dense / win_compact must be given (region %d)", w->region);
+        if (w->win_compact && !w->win_col) FAIL(h, "win_compact needs win_col (region %d)", w->region);
+    } else {
+        if (k <= 0) FAIL(h, "region %d: k must be positive to generate an adjacency", w->region);
+        if (n % D != 0) FAIL(h, "region %d: n = %d is not a multiple of reservoir_numinputs %d (allocate_res_new gives n = nodes_per_input * D)", w->region, n, D);
+    }
 
     RegionGeom g = make_geom(h->tiling, w->region, h->p.overlap);
     RegionMaps maps;
@@ -530,6 +555,31 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
     K.P = P;
     K.ldw = ldw;
 
+    RegionDev &d = hr.dev;
+    d = RegionDev{};
+    std::vector<double> wp;   // lives until the synchronisation at the end of this function
+    hr.k = k;
+    if (generate) {
+        // ---- device construction: reserve the arrays, describe the job; sml_finalize launches it for all regions at once
+        const int W = k > n ? k / n + (k % n != 0 ? 1 : 0) : 1;   // one ELL slot per shuffle round (each row at most once per round)
+        d.n = n; d.D = D; d.P = P; d.S = S; d.ldw = ldw; d.ell_w = W; d.L = L; d.leak = w->leakage;
+        d.win_mode = 0;
+        GenDesc g{};
+        g.local = it->second; g.region = w->region; g.n = n; g.k = k; g.D = D; g.W = W; g.seed = seed; g.sigma = sigma;
+        void *p = nullptr;
+        CK(h, h->arena.alloc(sizeof(int) * (size_t)W * n, &p)); g.ell_col = (int *)p;
+        CK(h, cudaMemsetAsync(p, 0, sizeof(int) * (size_t)W * n, h->stream));
+        CK(h, h->arena.alloc(sizeof(double) * (size_t)W * n, &p)); g.ell_val = (double *)p;
+        CK(h, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)W * n, h->stream));
+        CK(h, h->arena.alloc(sizeof(double) * (size_t)n, &p)); g.winc = (double *)p;
+        CK(h, h->arena.alloc(sizeof(int) * (size_t)n, &p)); g.wcol = (int *)p;
+        CK(h, h->arena.alloc(sizeof(int) * (size_t)k, &p)); g.coo_rows = (int *)p;
+        CK(h, h->arena.alloc(sizeof(int) * (size_t)k, &p)); g.coo_cols = (int *)p;
+        CK(h, h->arena.alloc(sizeof(double) * (size_t)k, &p)); g.coo_vals = (double *)p;
+        d.ell_col = g.ell_col; d.ell_val = g.ell_val; d.winc = g.winc; d.wcol = g.wcol;
+        hr.gen_index = (int)K.gen.size();
+        K.gen.push_back(g);
+    } else {
     // --- adjacency: COO (1-based, duplicates kept, entry order preserved per row) -> ELL, slot-major
     std::vector<int> cnt(n, 0);
     for (int e = 0; e < k; ++e) {
@@ -549,8 +599,6 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
         ecol[(size_t)s * n + r] = w->cols[e] - 1;
         eval[(size_t)s * n + r] = w->vals[e];
     }
-    RegionDev &d = hr.dev;
-    d = RegionDev{};
     d.n = n; d.D = D; d.P = P; d.S = S; d.ldw = ldw; d.ell_w = W; d.L = L; d.leak = w->leakage;
     if (dev_upload(h, &hr, ecol.data(), ecol.size(), &d.ell_col)) return -1;
     if (dev_upload(h, &hr, eval.data(), eval.size(), &d.ell_val)) return -1;
@@ -585,10 +633,10 @@ int sml_region_upload(sml_engine *h, const sml_region_weights *w)
     }
     if (dev_upload(h, &hr, winc.data(), winc.size(), &d.winc)) return -1;
     if (dev_upload(h, &hr, wcol.data(), wcol.size(), &d.wcol)) return -1;
+    }   // uploaded (not generated) adjacency and W_in
 
     // --- W_out, padded to an even leading dimension
     const size_t N = (size_t)n + S;
-    std::vector<double> wp;   // lives until the synchronisation at the end of this function
     if (ldw == P && w->wout) {
         if (dev_upload(h, &hr, w->wout, (size_t)P * N, &d.wout)) return -1;
     } else {
@@ -826,6 +874,29 @@ static int finalize_kind(sml_engine *h, int kind)
             CK(h, cudaMemcpy(K.d_out, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice));
         }
         return 0;
+    }
+    if (!K.gen.empty()) {
+        // ---- makesparse + W_in for every generated region of the kind, two launches for all of them
+        int n_cap = 0, w_gen = 1, ek = 0;
+        std::vector<int> gen_of_local(nloc, -1);
+        for (size_t i = 0; i < K.gen.size(); ++i) {
+            n_cap = std::max(n_cap, K.gen[i].n);
+            w_gen = std::max(w_gen, K.gen[i].W);
+            ek = std::max(ek, std::max(K.gen[i].k, K.gen[i].n));
+            gen_of_local[K.gen[i].local] = (int)i;
+        }
+        CK(h, cudaMalloc(&K.d_gen, sizeof(GenDesc) * K.gen.size()));
+        CK(h, cudaMemcpy(K.d_gen, K.gen.data(), sizeof(GenDesc) * K.gen.size(), cudaMemcpyHostToDevice));
+        CK(h, cudaMalloc(&K.d_gen_of_local, sizeof(int) * nloc));
+        CK(h, cudaMemcpy(K.d_gen_of_local, gen_of_local.data(), sizeof(int) * nloc, cudaMemcpyHostToDevice));
+        const size_t ms_smem = sizeof(int) * 3 * (size_t)n_cap;
+        if (ms_smem > 227 * 1024) FAIL(h, "reservoir of %d nodes is too large for the device k-shuffle", n_cap);
+        CK(h, cudaFuncSetAttribute(k_makesparse_shuffle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms_smem));
+        k_makesparse_shuffle<<<dim3(2 * w_gen, (unsigned)K.gen.size()), 256, ms_smem, h->stream>>>(K.d_gen, n_cap);
+        k_makesparse_fill<<<dim3((ek + 255) / 256, (unsigned)K.gen.size()), 256, 0, h->stream>>>(K.d_gen);
+        h->launches += 2;
+        CK(h, cudaGetLastError());
+        CK(h, cudaStreamSynchronize(h->stream));
     }
     // rows per CTA of the step kernel: 8-9 chunks per region.  Measured on B200 (profiles/round1_summary.md): 360..1027
     // rows differ by < 3 % at every shard size (1152..144 regions per GPU), 720 is best or within noise of the best
@@ -1183,7 +1254,7 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
                 }
             const size_t tile_stride = (size_t)UR_TR * (12 * w_max + 12);
             const size_t fixed = sizeof(double) * ((size_t)xs_cap_r + us_cap_r) + 64;
-            int nst = getenv("SML_UPDATE_STAGES") ? atoi(getenv("SML_UPDATE_STAGES")) : 8;
+            int nst = getenv("SML_UPDATE_STAGES") ? atoi(getenv("SML_UPDATE_STAGES")) : 10;
             nst = std::max(2, std::min(nst, 16));
             while (nst > 2 && fixed + (size_t)nst * (tile_stride + 16) > 227 * 1024) --nst;
             const size_t ring_smem = fixed + (size_t)nst * (tile_stride + 16) + 16;
@@ -2045,9 +2116,47 @@ int sml_adjacency_scale(sml_engine *h, int kind, const double *factor)
     CK(h, cudaMemcpyAsync(df, factor, sizeof(double) * nloc, cudaMemcpyHostToDevice, h->stream));
     k_adj_scale<<<dim3(32, nloc), 256, 0, h->stream>>>(K.d_regs, df);
     h->launches++;
+    if (K.d_gen) {   // generated regions keep their COO on the device: reservoir%vals is rescaled there as well
+        k_coo_scale<<<dim3(32, nloc), 256, 0, h->stream>>>(K.d_gen, K.d_gen_of_local, df);
+        h->launches++;
+    }
     CK(h, cudaStreamSynchronize(h->stream));
     cudaFree(df);
     CK(h, cudaGetLastError());
+    return 0;
+}
+
+// what makesparse left in reservoir%rows / cols / vals (and, after sml_adjacency_scale, gen_res's rescaled vals) for a
+// region constructed by sml_region_generate: k entries each, 1-based, in makesparse's entry order
+int sml_region_coo_get(sml_engine *h, int kind, int region, int32_t *rows, int32_t *cols, double *vals)
+{
+    if (check_ready(h, kind)) return -1;
+    int li;
+    if (local_of(h, kind, region, &li)) return -1;
+    KindState &K = h->kinds[kind];
+    const HostRegion &hr = K.regs[li];
+    if (hr.gen_index < 0) FAIL(h, "region %d was uploaded, not generated: the host already holds its COO arrays", region);
+    const GenDesc &g = K.gen[hr.gen_index];
+    CK(h, cudaSetDevice(h->p.device));
+    if (rows) CK(h, cudaMemcpyAsync(rows, g.coo_rows, sizeof(int) * (size_t)g.k, cudaMemcpyDeviceToHost, h->stream));
+    if (cols) CK(h, cudaMemcpyAsync(cols, g.coo_cols, sizeof(int) * (size_t)g.k, cudaMemcpyDeviceToHost, h->stream));
+    if (vals) CK(h, cudaMemcpyAsync(vals, g.coo_vals, sizeof(double) * (size_t)g.k, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// reservoir%win in the one-non-zero-per-row form: value and 0-based column of every row
+int sml_region_win_get(sml_engine *h, int kind, int region, double *win_compact, int32_t *win_col)
+{
+    if (check_ready(h, kind)) return -1;
+    int li;
+    if (local_of(h, kind, region, &li)) return -1;
+    const RegionDev &d = h->kinds[kind].regs[li].dev;
+    if (d.win_mode != 0) FAIL(h, "region %d keeps a dense W_in", region);
+    CK(h, cudaSetDevice(h->p.device));
+    if (win_compact) CK(h, cudaMemcpyAsync(win_compact, d.winc, sizeof(double) * (size_t)d.n, cudaMemcpyDeviceToHost, h->stream));
+    if (win_col) CK(h, cudaMemcpyAsync(win_col, d.wcol, sizeof(int) * (size_t)d.n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -646,17 +646,18 @@ k_update_sx(const RegionDev *__restrict__ regs, const int *__restrict__ region_l
 // k_update_sx still stalls on its own ELL loads: a thread issues a group of loads, waits a full HBM round trip, gathers,
 // issues the next group -- ncu showed 12 of 18 stall cycles per issue on that long scoreboard, and nothing is in flight
 // while the warps compute.  Here the loads are decoupled from the arithmetic:
-//   * ONE CTA per (region, row split) and per SM: 1024 consumer threads + 1 TMA producer warp, the region's whole state
+//   * ONE CTA per (region, row split) and per SM: 960 consumer threads + 1 TMA producer warp, the region's whole state
 //     vector staged once in shared memory (one TMA bulk copy), the input vector beside it;
 //   * the producer warp streams row tiles of UR_TR rows through an nstages-deep ring: per tile 2W+2 bulk copies (the W
 //     column-index slots, the W value slots, W_in value and column of the tile's rows -- all contiguous in the
 //     slot-major ELL), completion counted in bytes on the stage's mbarrier; up to ~170 KB in flight per SM regardless of
 //     what the consumers are doing;
-//   * consumer group g (8 warps) takes tiles g, g+4, ...: one row per thread, everything from shared memory except the
+//   * consumer group g (6 warps) takes tiles g, g+5, ...: one row per thread, everything from shared memory except the
 //     coalesced x_new store.  Accumulation order per row is the entry order, as in update_row: bit-identical states.
 // grid (nsplit, regions); dynamic shared memory xs_cap*8 + us_cap*8 + nstages*tile_stride + barriers.
 // ---------------------------------------------------------------------------------------------
-constexpr int UR_CONS = 1024, UR_THREADS = UR_CONS + 32, UR_TR = 256, UR_GROUPS = UR_CONS / UR_TR;
+constexpr int UR_TR = 192, UR_GROUPS = 5, UR_CONS = UR_TR * UR_GROUPS, UR_THREADS = UR_CONS + 32;   // 992 threads
+static_assert(UR_THREADS <= 1024 && UR_TR % 32 == 0, "one CTA: at most 1024 threads");
 __global__ void __launch_bounds__(UR_THREADS, 1)
 k_update_ring(const RegionDev *__restrict__ regs, const int *__restrict__ region_list, const double *__restrict__ x_old,
               double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,

@@ -67,6 +67,9 @@ _SIGNATURES = {
     "sml_ocean_region_maps": ([C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int)], C.c_int),
     "sml_global_layout": ([_lp, _lp, _lp], C.c_int),
     "sml_region_upload": ([C.c_void_p, C.POINTER(SmlRegionWeights)], C.c_int),
+    "sml_region_generate": ([C.c_void_p, C.POINTER(SmlRegionWeights), C.c_uint64, C.c_double], C.c_int),
+    "sml_region_coo_get": ([C.c_void_p, C.c_int, C.c_int, _ip, _ip, _dp], C.c_int),
+    "sml_region_win_get": ([C.c_void_p, C.c_int, C.c_int, _dp, _ip], C.c_int),
     "sml_trained_res_dims": ([C.c_char_p] + [C.POINTER(C.c_int)] * 6, C.c_int),
     "sml_region_upload_file": ([C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double], C.c_int),
     "sml_finalize": ([C.c_void_p], C.c_int),
@@ -374,6 +377,41 @@ class Engine:
         w.rows, w.cols, w.vals, w.mean, w.std = _i(rows), _i(cols), _d(vals), _d(mean), _d(std)
         self._ck(self.lib.sml_region_upload(self.h, C.byref(w)))
         self.dims[(kind, region)] = dict(n=n, D=Dw, P=Pw, S=Sw, L=mean.size)
+
+    def region_generate(self, region, n, k, D, P, S, mean, std, seed, sigma, wout=None, kind=ATMO, leakage=1.0,
+                        sst_bool_input=True, sst_mean=None, sst_std=None):
+        """gen_res's makesparse + the W_in build ON THE DEVICE (src/mod_linalg.f90:180-218, src/mod_reservoir.f90:262-283):
+        the region is installed with the sizes of allocate_res_new; its structure is drawn at finalize()"""
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        std = np.ascontiguousarray(std, dtype=np.float64)
+        w = SmlRegionWeights()
+        keep = [mean, std]
+        if wout is not None:
+            wout = _farr(wout, (P, n + S))
+            w.wout = _d(wout)
+            keep.append(wout)
+        w.region, w.kind, w.n, w.k, w.D, w.P, w.S, w.L = region, kind, n, k, D, P, S, mean.size
+        w.sst_bool_input = int(sst_bool_input)
+        w.leakage = float(leakage)
+        w.sst_mean = float(mean[-1] if sst_mean is None else sst_mean)
+        w.sst_std = float(std[-1] if sst_std is None else sst_std)
+        w.mean, w.std = _d(mean), _d(std)
+        self._ck(self.lib.sml_region_generate(self.h, C.byref(w), int(seed), float(sigma)))
+        self.dims[(kind, region)] = dict(n=n, D=D, P=P, S=S, L=mean.size, k=k)
+
+    def region_coo_get(self, region, kind=ATMO):
+        """reservoir%rows / cols / vals of a generated region (1-based, makesparse's entry order)"""
+        k = self.dims[(kind, region)]["k"]
+        rows, cols, vals = np.zeros(k, dtype=np.int32), np.zeros(k, dtype=np.int32), np.zeros(k)
+        self._ck(self.lib.sml_region_coo_get(self.h, kind, region, _i(rows), _i(cols), _d(vals)))
+        return rows, cols, vals
+
+    def region_win_get(self, region, kind=ATMO):
+        """(value, 0-based column) of the single non-zero of every W_in row"""
+        n = self.dims[(kind, region)]["n"]
+        winc, wcol = np.zeros(n), np.zeros(n, dtype=np.int32)
+        self._ck(self.lib.sml_region_win_get(self.h, kind, region, _d(winc), _i(wcol)))
+        return winc, wcol
 
     def region_upload_file(self, path, region, kind=ATMO, sst_bool_input=True, leakage=1.0):
         """read_trained_res + mklsparse from the region's NetCDF-classic weight file (float32 -> FP64 on the way)"""
