@@ -1252,19 +1252,25 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
                     w_max = std::max(w_max, hr.dev.ell_w);
                     if (hr.dev.n % 4 != 0) aligned = false;   // the tile copies need 16-byte multiples
                 }
-            const size_t tile_stride = (size_t)UR_TR * (12 * w_max + 12);
+            // tile rows: as many as fit twice beside the state vector, at most one per consumer thread.  Large tiles keep
+            // the bulk copies long (>= several KB each): the producer's issue cost per copy does not depend on its size
             const size_t fixed = sizeof(double) * ((size_t)xs_cap_r + us_cap_r) + 64;
-            int nst = getenv("SML_UPDATE_STAGES") ? atoi(getenv("SML_UPDATE_STAGES")) : 10;
-            nst = std::max(2, std::min(nst, 16));
-            while (nst > 2 && fixed + (size_t)nst * (tile_stride + 16) > 227 * 1024) --nst;
+            int nst = getenv("SML_UPDATE_STAGES") ? atoi(getenv("SML_UPDATE_STAGES")) : 2;
+            nst = std::max(2, std::min(nst, 8));
+            const size_t row_bytes = 12 * (size_t)w_max + 12;
+            const size_t budget = 227 * 1024 - 64;
+            int tr = fixed + 64 < budget ? (int)((budget - fixed - 16 * (size_t)nst) / ((size_t)nst * row_bytes)) : 0;
+            tr = std::min(tr, UR_CONS) / 32 * 32;
+            if (getenv("SML_UPDATE_TILE_ROWS")) tr = std::min(tr, std::max(32, atoi(getenv("SML_UPDATE_TILE_ROWS")) / 32 * 32));
+            const size_t tile_stride = (size_t)tr * row_bytes;
             const size_t ring_smem = fixed + (size_t)nst * (tile_stride + 16) + 16;
-            if (want == "ring" && aligned && ring_smem <= 227 * 1024) {
+            if (want == "ring" && aligned && tr >= 256 && ring_smem <= 227 * 1024) {
                 // one CTA per SM: split a region's rows only when there are fewer regions than SMs
                 int nsplit = getenv("SML_UPDATE_SPLIT") ? atoi(getenv("SML_UPDATE_SPLIT")) : h->num_sms / std::max(1, nreg);
                 nsplit = std::max(1, std::min(nsplit, 16));
                 CK(h, cudaFuncSetAttribute(k_update_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
                 k_update_ring<<<dim3((unsigned)nsplit, (unsigned)nreg), UR_THREADS, ring_smem, h->stream>>>(
-                    K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp, nsplit, xs_cap_r, us_cap_r, w_max, nst);
+                    K.d_regs, list, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_temp, nsplit, xs_cap_r, us_cap_r, w_max, nst, tr);
                 h->launches++;
                 CK(h, cudaGetLastError());
                 return 0;

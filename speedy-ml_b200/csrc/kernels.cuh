@@ -648,42 +648,44 @@ k_update_sx(const RegionDev *__restrict__ regs, const int *__restrict__ region_l
 // while the warps compute.  Here the loads are decoupled from the arithmetic:
 //   * ONE CTA per (region, row split) and per SM: 960 consumer threads + 1 TMA producer warp, the region's whole state
 //     vector staged once in shared memory (one TMA bulk copy), the input vector beside it;
-//   * the producer warp streams row tiles of UR_TR rows through an nstages-deep ring: per tile 2W+2 bulk copies (the W
-//     column-index slots, the W value slots, W_in value and column of the tile's rows -- all contiguous in the
-//     slot-major ELL), completion counted in bytes on the stage's mbarrier; up to ~170 KB in flight per SM regardless of
-//     what the consumers are doing;
-//   * consumer group g (6 warps) takes tiles g, g+5, ...: one row per thread, everything from shared memory except the
-//     coalesced x_new store.  Accumulation order per row is the entry order, as in update_row: bit-identical states.
+//   * the producer warp streams row tiles of `tr` rows (up to 960: one row per consumer thread) through an
+//     nstages-deep ring: per tile 2W+2 bulk copies (the W column-index slots, the W value slots, W_in value and column
+//     of the tile's rows -- each contiguous in the slot-major ELL), completion counted in bytes on the stage's
+//     mbarrier.  Tiles are LARGE on purpose: issuing one bulk copy costs the producer warp ~140 cycles whatever its
+//     size (measured: 1 KB copies capped both this kernel and the persistent step kernel near 3 TB/s), so each copy
+//     must carry several KB; with tr = 960 and W = 6 a tile is 80 KB in 14 copies;
+//   * the consumers take the tiles in order, one row per thread, everything from shared memory except the coalesced
+//     x_new store.  Accumulation order per row is the entry order, as in update_row: bit-identical states.
 // grid (nsplit, regions); dynamic shared memory xs_cap*8 + us_cap*8 + nstages*tile_stride + barriers.
 // ---------------------------------------------------------------------------------------------
-constexpr int UR_TR = 192, UR_GROUPS = 5, UR_CONS = UR_TR * UR_GROUPS, UR_THREADS = UR_CONS + 32;   // 992 threads
-static_assert(UR_THREADS <= 1024 && UR_TR % 32 == 0, "one CTA: at most 1024 threads");
+constexpr int UR_CONS = 960, UR_THREADS = UR_CONS + 32;   // 992 threads
+static_assert(UR_THREADS <= 1024 && UR_CONS % 32 == 0, "one CTA: at most 1024 threads");
 __global__ void __launch_bounds__(UR_THREADS, 1)
 k_update_ring(const RegionDev *__restrict__ regs, const int *__restrict__ region_list, const double *__restrict__ x_old,
               double *__restrict__ x_new, const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int u_t,
-              const double *__restrict__ temp_pool, int nsplit, int xs_cap, int us_cap, int w_max, int nstages)
+              const double *__restrict__ temp_pool, int nsplit, int xs_cap, int us_cap, int w_max, int nstages, int tr)
 {
     extern __shared__ __align__(128) unsigned char ur_smem[];
     const int reg = region_list ? region_list[blockIdx.y] : (int)blockIdx.y;
     const RegionDev &R = regs[reg];
     const int n = R.n, D = R.D, W = R.ell_w;
-    const int per = (((n + nsplit - 1) / nsplit) + UR_TR - 1) / UR_TR * UR_TR;
+    const int per = (((n + nsplit - 1) / nsplit) + 31) / 32 * 32;
     const int r0 = blockIdx.x * per, r1 = min(n, r0 + per);
     if (r0 >= n) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double *xs = reinterpret_cast<double *>(ur_smem), *us = xs + xs_cap;
     unsigned char *ring = reinterpret_cast<unsigned char *>(us + us_cap);
-    const int tile_stride = UR_TR * (12 * w_max + 12);
-    const int off_val = w_max * UR_TR * 4, off_winc = off_val + w_max * UR_TR * 8, off_wcol = off_winc + UR_TR * 8;
+    const int tile_stride = tr * (12 * w_max + 12);
+    const int off_val = w_max * tr * 4, off_winc = off_val + w_max * tr * 8, off_wcol = off_winc + tr * 8;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)nstages * tile_stride);
     uint64_t *empty = full + nstages, *xbar = empty + nstages;
-    const int ntiles = (r1 - r0 + UR_TR - 1) / UR_TR;
+    const int ntiles = (r1 - r0 + tr - 1) / tr;
     const bool compact = R.win_mode == 0;
     const double *__restrict__ xo = x_old + R.x_off;
     if (tid == 0) {
         for (int s = 0; s < nstages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], UR_TR / 32);
+            mbar_init(&empty[s], UR_CONS / 32);
         }
         mbar_init(xbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -704,14 +706,14 @@ k_update_ring(const RegionDev *__restrict__ regs, const int *__restrict__ region
         int s = 0;
         uint32_t par = 1;
         for (int k = 0; k < ntiles; ++k) {
-            const int t0 = r0 + k * UR_TR, rows = min(UR_TR, r1 - t0);
+            const int t0 = r0 + k * tr, rows = min(tr, r1 - t0);
             mbar_wait(&empty[s], par);
             if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)rows * (uint32_t)(12 * W + (compact ? 12 : 0)));
             __syncwarp();
             unsigned char *dst = ring + (size_t)s * tile_stride;
             for (int c = lane; c < ncopy; c += 32) {
-                if (c < W) tma_load_1d(dst + (size_t)c * UR_TR * 4, R.ell_col + (size_t)c * n + t0, (uint32_t)rows * 4u, &full[s]);
-                else if (c < 2 * W) tma_load_1d(dst + off_val + (size_t)(c - W) * UR_TR * 8, R.ell_val + (size_t)(c - W) * n + t0, (uint32_t)rows * 8u, &full[s]);
+                if (c < W) tma_load_1d(dst + (size_t)c * tr * 4, R.ell_col + (size_t)c * n + t0, (uint32_t)rows * 4u, &full[s]);
+                else if (c < 2 * W) tma_load_1d(dst + off_val + (size_t)(c - W) * tr * 8, R.ell_val + (size_t)(c - W) * n + t0, (uint32_t)rows * 8u, &full[s]);
                 else if (c == 2 * W) tma_load_1d(dst + off_winc, R.winc + t0, (uint32_t)rows * 8u, &full[s]);
                 else tma_load_1d(dst + off_wcol, R.wcol + t0, (uint32_t)rows * 4u, &full[s]);
             }
@@ -720,34 +722,34 @@ k_update_ring(const RegionDev *__restrict__ regs, const int *__restrict__ region
         return;
     }
 
-    // ---------------- consumers: group g takes tiles g, g + UR_GROUPS, ... ----------------
-    const int g = warp / (UR_TR / 32), t = tid % UR_TR;
+    // ---------------- consumers: every tile in order, one row per thread ----------------
     double *__restrict__ xn = x_new + R.x_off;
     const double leak = R.leak;
     mbar_wait(xbar, 0);
-    for (int k = g; k < ntiles; k += UR_GROUPS) {
-        const int s = k % nstages;
-        mbar_wait(&full[s], (uint32_t)(k / nstages) & 1u);
+    int s = 0;
+    uint32_t par = 0;
+    for (int k = 0; k < ntiles; ++k) {
+        mbar_wait(&full[s], par);
         const unsigned char *tile = ring + (size_t)s * tile_stride;
-        const int row = r0 + k * UR_TR + t;
-        if (row < r1) {
-            const int *tc = reinterpret_cast<const int *>(tile) + t;
-            const double *tv = reinterpret_cast<const double *>(tile + off_val) + t;
+        const int row = r0 + k * tr + tid;
+        if (tid < tr && row < r1) {
+            const int *tc = reinterpret_cast<const int *>(tile) + tid;
+            const double *tv = reinterpret_cast<const double *>(tile + off_val) + tid;
             double acc = 0.0;
             int sl = 0;
             for (; sl + 3 <= W; sl += 3) {
-                const int c0 = tc[(size_t)sl * UR_TR], c1 = tc[(size_t)(sl + 1) * UR_TR], c2 = tc[(size_t)(sl + 2) * UR_TR];
-                const double v0 = tv[(size_t)sl * UR_TR], v1 = tv[(size_t)(sl + 1) * UR_TR], v2 = tv[(size_t)(sl + 2) * UR_TR];
+                const int c0 = tc[(size_t)sl * tr], c1 = tc[(size_t)(sl + 1) * tr], c2 = tc[(size_t)(sl + 2) * tr];
+                const double v0 = tv[(size_t)sl * tr], v1 = tv[(size_t)(sl + 1) * tr], v2 = tv[(size_t)(sl + 2) * tr];
                 const double x0 = xs[c0], x1 = xs[c1], x2 = xs[c2];
                 acc = fma(v0, x0, acc);
                 acc = fma(v1, x1, acc);
                 acc = fma(v2, x2, acc);
             }
-            for (; sl < W; ++sl) acc = fma(tv[(size_t)sl * UR_TR], xs[tc[(size_t)sl * UR_TR]], acc);
+            for (; sl < W; ++sl) acc = fma(tv[(size_t)sl * tr], xs[tc[(size_t)sl * tr]], acc);
             double tin;
             if (compact) {
-                const double wv = reinterpret_cast<const double *>(tile + off_winc)[t];
-                const int wc = reinterpret_cast<const int *>(tile + off_wcol)[t];
+                const double wv = reinterpret_cast<const double *>(tile + off_winc)[tid];
+                const int wc = reinterpret_cast<const int *>(tile + off_wcol)[tid];
                 tin = __dmul_rn(wv, us[wc]);
             } else {
                 tin = temp_pool[R.x_off + row];
@@ -757,6 +759,7 @@ k_update_ring(const RegionDev *__restrict__ regs, const int *__restrict__ region
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == nstages) { s = 0; par ^= 1; }
     }
 }
 
