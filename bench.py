@@ -551,6 +551,15 @@ def run_gpu(args):
         sampler.start()
         time.sleep(0.05)
     e2e_ms, e2e_wall = timed(e2e_step, args.steps, CHECK_STEPS + args.warmup + 1)
+    # where the host side of an e2e step spends its time (a few extra steps after the timed region, clocked per section)
+    e2e_sections = {}
+    if world == 1 or shard.comm_ready:
+        nb = max(10, args.steps // 2)
+        st_b = stepper_ovl if args.overlap else stepper
+        base = CHECK_STEPS + args.warmup + args.steps + 1
+        for i in range(nb):
+            st_b.timed_step(base + i, host_model, F["tisr"], e2e_sections)
+        e2e_sections = {k: round(v / nb * 1e3, 4) for k, v in e2e_sections.items()}   # ms per step
     if args.overlap:
         eng.set_overlap(False)
         stepper_ovl.overlap = False
@@ -614,7 +623,8 @@ def run_gpu(args):
             "grid_checksum": checksum,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((lay["f_total"] + 96 * 48) * 8),
                     "d2h_bytes_per_step": int(lay["tisr"] * 8), "ms_per_step": e2e_wall / args.steps,
-                    "ms_per_step_device_events": e2e_ms / args.steps},
+                    "ms_per_step_device_events": e2e_ms / args.steps,
+                    "host_sections_ms_rank0": e2e_sections},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": f"{plan['kernel']} (fused state update + readout)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -319,6 +319,8 @@ int sml_create(sml_engine **out, const sml_params *p)
 constexpr bool SML_UPDATE_SX_DEFAULT = true;
 // round 2: the TMA-fed ELL ring kernel (k_update_ring) when the region's state vector and a ring fit in shared memory
 constexpr const char *SML_UPDATE_DEFAULT = "ring";
+// evict-first loads for the ELL / W_in streams of the fused step kernels (keeps the gathered state vector in L1)
+constexpr int SML_ELL_STREAM_DEFAULT = 0;
 // which fused step kernel sml_predict launches when SML_STEP_KERNEL is not set: k_step_persist (persistent, statically
 // balanced slots) or the classic one-CTA-per-item k_step
 constexpr bool SML_STEP_PERSIST_DEFAULT = true;
@@ -917,6 +919,7 @@ static int finalize_kind(sml_engine *h, int kind)
             continue;
         }
         RegionDev &d = hr.dev;
+        d.ell_stream = getenv("SML_ELL_STREAM") ? atoi(getenv("SML_ELL_STREAM")) : SML_ELL_STREAM_DEFAULT;
         d.x_off = xo; d.fb_off = fo; d.lm_off = lo; d.out_off = (long long)i * K.P;
         fb_offs[i] = fo;
         xo += (d.n + 31) / 32 * 32;
@@ -1014,10 +1017,13 @@ int sml_finalize(sml_engine *h)
     if (!h->kinds[SML_ATMO].any) FAIL(h, "no atmosphere reservoirs uploaded");
     {
         // the dynamic shared-memory limit is a property of the kernel, not of a launch: take the larger kind
-        const size_t smem = std::max(h->kinds[SML_ATMO].smem_bytes, h->kinds[SML_OCEAN].smem_bytes);
-        CK(h, cudaFuncSetAttribute(k_step<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const size_t psmem = std::max(h->kinds[SML_ATMO].p_smem_bytes, h->kinds[SML_OCEAN].p_smem_bytes);
-        CK(h, cudaFuncSetAttribute(k_step_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
+        // ... and of the process, not of an engine: several engines may live side by side (tests, one process driving
+        // two GPUs), so the limits only ever grow
+        static size_t smem_max = 0, psmem_max = 0;
+        smem_max = std::max(smem_max, std::max(h->kinds[SML_ATMO].smem_bytes, h->kinds[SML_OCEAN].smem_bytes));
+        psmem_max = std::max(psmem_max, std::max<size_t>(1024, std::max(h->kinds[SML_ATMO].p_smem_bytes, h->kinds[SML_OCEAN].p_smem_bytes)));
+        CK(h, cudaFuncSetAttribute(k_step<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CK(h, cudaFuncSetAttribute(k_step_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem_max));
     }
     const int R = h->p.number_of_regions, P = h->kinds[SML_ATMO].P;
     h->P_atmo = P;
@@ -1255,7 +1261,9 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
             // tile rows: as many as fit twice beside the state vector, at most one per consumer thread.  Large tiles keep
             // the bulk copies long (>= several KB each): the producer's issue cost per copy does not depend on its size
             const size_t fixed = sizeof(double) * ((size_t)xs_cap_r + us_cap_r) + 64;
-            int nst = getenv("SML_UPDATE_STAGES") ? atoi(getenv("SML_UPDATE_STAGES")) : 2;
+            // 3 stages of ~640 rows measured better than 2 of 960 (0.794 / 0.719 of the roof at 1152 / 144 regions against
+            // 0.758 / 0.651): a deeper ring matters more than the longest possible copies
+            int nst = getenv("SML_UPDATE_STAGES") ? atoi(getenv("SML_UPDATE_STAGES")) : 3;
             nst = std::max(2, std::min(nst, 8));
             const size_t row_bytes = 12 * (size_t)w_max + 12;
             const size_t budget = 227 * 1024 - 64;

@@ -25,6 +25,8 @@ struct RegionDev {
     int item0, nitems;
     int part0, nparts;  // fixed row blocks of the persistent step kernel: the region's partial outvecs
     int L;          // mean/std length; slot L holds the SST feedback mean/std
+    int ell_stream; // 1: the ELL / W_in streams of the fused step are loaded evict-first (ld.global.cs) so that they do
+                    //    not push the region's state vector -- the target of the random gathers -- out of L1
     double leak;
     const int *ell_col;      // [ell_w][n] slot-major, 0-based
     const double *ell_val;   // [ell_w][n]
@@ -148,8 +150,15 @@ __device__ __forceinline__ double ld_cg_f64(const double *p)
 // temp = W_in u (one product), x <- (1-leak) x + leak tanh(y + temp)
 // src/mod_reservoir.f90:1444-1448 (predict), :1373-1377 (synchronize)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double update_row(const RegionDev &R, int row, const double *__restrict__ xo,
-                                             const double *__restrict__ u, const double *__restrict__ temp_pool)
+template <bool EF, typename T>
+__device__ __forceinline__ T ld_stream(const T *p)
+{
+    return EF ? __ldcs(p) : __ldg(p);
+}
+
+template <bool EF>
+__device__ __forceinline__ double update_row_t(const RegionDev &R, int row, const double *__restrict__ xo,
+                                               const double *__restrict__ u, const double *__restrict__ temp_pool)
 {
     const int n = R.n;
     const int *__restrict__ ec = R.ell_col + row;
@@ -162,8 +171,8 @@ __device__ __forceinline__ double update_row(const RegionDev &R, int row, const 
         double v[6], xv[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            c[i] = __ldg(ec + (size_t)(s + i) * n);
-            v[i] = __ldg(ev + (size_t)(s + i) * n);
+            c[i] = ld_stream<EF>(ec + (size_t)(s + i) * n);
+            v[i] = ld_stream<EF>(ev + (size_t)(s + i) * n);
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) xv[i] = xo[c[i]];
@@ -171,15 +180,21 @@ __device__ __forceinline__ double update_row(const RegionDev &R, int row, const 
         for (int i = 0; i < 6; ++i) acc = fma(v[i], xv[i], acc);
     }
     for (; s < W; ++s) {
-        const int c = __ldg(ec + (size_t)s * n);
-        const double v = __ldg(ev + (size_t)s * n);
+        const int c = ld_stream<EF>(ec + (size_t)s * n);
+        const double v = ld_stream<EF>(ev + (size_t)s * n);
         acc = fma(v, xo[c], acc);
     }
     double t;
-    if (R.win_mode == 0) t = __dmul_rn(__ldg(R.winc + row), u[__ldg(R.wcol + row)]);
+    if (R.win_mode == 0) t = __dmul_rn(ld_stream<EF>(R.winc + row), u[ld_stream<EF>(R.wcol + row)]);
     else t = temp_pool[R.x_off + row];
     const double xt = tanh(__dadd_rn(acc, t));
     return __dadd_rn(__dmul_rn(1.0 - R.leak, xo[row]), __dmul_rn(R.leak, xt));
+}
+
+__device__ __forceinline__ double update_row(const RegionDev &R, int row, const double *__restrict__ xo,
+                                             const double *__restrict__ u, const double *__restrict__ temp_pool)
+{
+    return R.ell_stream ? update_row_t<true>(R, row, xo, u, temp_pool) : update_row_t<false>(R, row, xo, u, temp_pool);
 }
 
 // ---------------------------------------------------------------------------------------------

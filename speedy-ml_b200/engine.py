@@ -310,6 +310,9 @@ class Engine:
         self.region_indices = ids.tolist()        # model_parameters%region_indices
         self.num_of_regions_on_proc = n
         self.dims = {}                             # (kind, region) -> dict(n, D, P, S, L)
+        self._view_ptrs = [_dp() for _ in range(4)]
+        self._view_refs = [C.byref(a) for a in self._view_ptrs]
+        self._views, self._view_addr = None, None
 
     # -- plumbing
     def _ck(self, rc, allow_positive=False):
@@ -564,17 +567,19 @@ class Engine:
 
     def step_exchange_begin_view(self, timestep):
         """zero-copy: the four grids as read-only views of the engine's pinned staging (valid until the next begin)"""
-        p = [_dp() for _ in range(4)]
-        rc = self._ck(self.lib.sml_step_exchange_begin_view(self.h, timestep, *[C.byref(a) for a in p]),
-                      allow_positive=True)
+        p = self._view_ptrs
+        rc = self._ck(self.lib.sml_step_exchange_begin_view(self.h, timestep, *self._view_refs), allow_positive=True)
         self.grid_nonfinite = rc > 0
-        shapes = ((4, XGRID, YGRID, ZGRID), (XGRID, YGRID), (XGRID, YGRID), (XGRID, YGRID))
-        out = []
-        for ptr, shp in zip(p, shapes):
-            a = np.ctypeslib.as_array(ptr, shape=(int(np.prod(shp)),)).reshape(shp, order="F")
-            a.flags.writeable = False
-            out.append(a)
-        return tuple(out)
+        addr = tuple(C.cast(a, C.c_void_p).value for a in p)
+        if addr != self._view_addr:      # the staging is fixed for the engine's life: the NumPy views are built once
+            shapes = ((4, XGRID, YGRID, ZGRID), (XGRID, YGRID), (XGRID, YGRID), (XGRID, YGRID))
+            out = []
+            for ptr, shp in zip(p, shapes):
+                a = np.ctypeslib.as_array(ptr, shape=(int(np.prod(shp)),)).reshape(shp, order="F")
+                a.flags.writeable = False
+                out.append(a)
+            self._views, self._view_addr = tuple(out), addr
+        return self._views
 
     def grids_get(self):
         """(wholegrid4d, wholegrid2d, wholegrid_precip, wholegrid_sst) of the last assembly, from the device, on any rank"""

@@ -222,6 +222,34 @@ class HybridStepper:
         self.s.unpack(t)
         return (w4d, w2d, wp, wsst) if self.rank == 0 else None
 
+    def timed_step(self, t, host_model, tisr_grid, acc):
+        """step() with the host-side sections clocked into acc (a dict of seconds): where the root's chain spends its
+        time -- predict call, TISR upload, exchange_begin (grid assembly + copy-out wait), the host model, exchange_end"""
+        import time
+        c = time.perf_counter
+        t0 = c()
+        self._predict(t)
+        t1 = c()
+        if self.overlap:
+            self.s.set_tisr(tisr_grid)
+        t2 = c()
+        root = self.rank == 0
+        grids = self.s.exchange_begin(t) if root else self.s.exchange_begin(t, copy_out=False)
+        t3 = c()
+        f4d = f2d = None
+        if root:
+            f4d, f2d = host_model(grids[0], grids[1], grids[3])
+        t4 = c()
+        if root:
+            self.s.exchange_end(t, f4d, f2d, None if self.overlap else tisr_grid)
+        else:
+            self.s.exchange_end(t, None, None, None)
+        t5 = c()
+        for k, v in (("predict", t1 - t0), ("set_tisr", t2 - t1), ("exchange_begin", t3 - t2), ("host_model", t4 - t3),
+                     ("exchange_end", t5 - t4)):
+            acc[k] = acc.get(k, 0.0) + v
+        return grids
+
     def _step_library(self, t, host_model, tisr_grid):
         """multi-rank step with the exchange inside the engine (after EngineShard.bootstrap): the call sequence of
         parallelmain.f90:226-262 on every rank, no collective here.  Ranks other than the root never wait on the host."""
