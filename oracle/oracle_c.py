@@ -99,6 +99,7 @@ def lib():
         L.orc_setup_region.argtypes = [C.c_int] * 7 + [C.c_double] + [C.c_int] * 4 + [C.POINTER(Grid), C.POINTER(Dims)]
         L.orc_setup_ocean_region.argtypes = [C.c_int] * 4 + [C.c_double, C.c_int, C.POINTER(Grid), C.POINTER(Dims)]
         L.orc_predict_slab_ml.argtypes = [C.c_void_p, _dp]
+        L.orc_predict_slab.argtypes = [C.c_void_p, _dp]
         L.orc_ocean_feedback.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int, _dp]
         L.orc_tile_full_input_to_target_data2d.argtypes = [C.POINTER(Grid), C.POINTER(Dims), _dp, C.c_int, C.c_int, _dp]
         L.orc_tileoverlapgrid4d.argtypes = [_dp] + [C.c_int] * 7 + [_dp]
@@ -323,15 +324,18 @@ class Region:
 class OceanRegion(Region):
     """res%reservoir_special / res%grid_special of one region (src/mod_slab_ocean_reservoir.f90)"""
 
-    def __init__(self, num_regions, region, overlap=1, m=4000, deg=6.0, precip_bool=True, nslots=27):
+    def __init__(self, num_regions, region, overlap=1, m=4000, deg=6.0, precip_bool=True, nslots=27, hybrid=False):
         self.g, self.d = Grid(), Dims()
         rc = lib().orc_setup_ocean_region(num_regions, region, overlap, m, float(deg), int(precip_bool),
                                           C.byref(self.g), C.byref(self.d))
         if rc:
             raise ValueError("orc_setup_ocean_region failed")
+        self.hybrid = bool(hybrid)
+        if self.hybrid:   # ml_only_ocean = .False.: the feature vector carries chunk_size_prediction model entries
+            self.d.chunk_size_speedy = self.d.chunk_size_prediction
         self.h = C.c_void_p(lib().orc_region_new(C.byref(self.g), C.byref(self.d)))
         self.n, self.D = self.d.n, self.d.reservoir_numinputs
-        self.P, self.S, self.k = self.d.chunk_size_prediction, 0, self.d.k
+        self.P, self.S, self.k = self.d.chunk_size_prediction, self.d.chunk_size_speedy, self.d.k
         self.L = self.g.mean_std_length
         self.region, self.num_regions = region, num_regions
         self.A = self.g.logp_end
@@ -339,7 +343,10 @@ class OceanRegion(Region):
         self.ring = np.zeros((self.A, nslots), order="F")  # averaged_atmo_input_vec, zeroed (:810-811)
 
     def predict(self):
-        lib().orc_predict_slab_ml(self.h, _d(self.x))
+        if self.hybrid:
+            lib().orc_predict_slab(self.h, _d(self.x))      # predict_slab: local_model <- standardised outvec
+        else:
+            lib().orc_predict_slab_ml(self.h, _d(self.x))
 
     def build_feedback(self, atmo: Region, timestep: int, wholegrid_sst):
         sst = np.asfortranarray(wholegrid_sst, dtype=np.float64)

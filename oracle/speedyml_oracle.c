@@ -1118,6 +1118,31 @@ void orc_predict_slab_ml(orc_region *r, double *x)
     free(temp);
 }
 
+/* src/mod_slab_ocean_reservoir.f90:1268-1316 predict_slab (the HYBRID ocean reservoir, ml_only_ocean = .False.):
+ * x = tanh(A x + W_in u) with no leak term (:1294), features [local_model ; x~] with local_model of length
+ * chunk_size_prediction (:1299-1300), outvec = wout * features, then the quirk local_model = outvec BEFORE the
+ * un-standardisation (:1303) -- the reservoir's own standardised prediction is its "imperfect model" of the next
+ * step -- and outvec*std(sst)+mean(sst).  The region must have been created with chunk_size_speedy =
+ * chunk_size_prediction. */
+void orc_predict_slab(orc_region *r, double *x)
+{
+    const int n = r->d.n, P = r->d.chunk_size_prediction;
+    double *y = (double *)malloc(sizeof(double) * (size_t)n), *temp = (double *)malloc(sizeof(double) * (size_t)n);
+    const double leak = r->d.leakage;
+    r->d.leakage = 1.0;                       /* x = tanh(y + temp): (1-1)*x + 1*tanh(.) is exactly tanh(.) */
+    state_update(r, r->feedback, x, y, temp);
+    r->d.leakage = leak;
+    readout(r, x, P);
+    const int si = r->g.sst_mean_std_idx - 1;
+    for (int p = 0; p < P; ++p) {
+        r->local_model[p] = r->outvec[p];
+        double v = r->outvec[p] * r->std[si];
+        r->outvec[p] = v + r->mean[si];
+    }
+    free(y);
+    free(temp);
+}
+
 /* ocean feedback, intended semantics: src/mpires.f90:594-600 (SST tile, standardised
  * with grid_special's SST mean/std), :776-781 (ring of the atmosphere reservoir's standardised lowest-level
  * + logp feedback, slot mod(timestep-1,nslots)+1, mean = sum/nslots even while slots are still zero). */

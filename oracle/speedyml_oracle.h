@@ -143,6 +143,7 @@ void orc_predict_ml(orc_region *r, double *x);
 void orc_predict_all(orc_region **regs, int nreg, int ml_only, int nthreads);
 /* predict_slab_ml (src/mod_slab_ocean_reservoir.f90:1318-1363): all outputs * std(sst) + mean(sst) */
 void orc_predict_slab_ml(orc_region *r, double *x);
+void orc_predict_slab(orc_region *r, double *x);   /* hybrid ocean reservoir, src/mod_slab_ocean_reservoir.f90:1268-1316 */
 /* ocean feedback of one hybrid step, intended semantics of SURVEY.md Appendix C (src/mpires.f90:594-600,
  * 776-781): ring(:, mod(timestep-1,nslots)+1) = atmosphere feedback(atmo3d_end-4*ixy+1 : logp_end) (already
  * standardised); feedback(1:logp_end) = sum(ring,dim=2)/nslots; feedback(sst_start:sst_end) = standardised

@@ -538,8 +538,10 @@ static int region_install(sml_engine *h, const sml_region_weights *w, bool gener
         // res%reservoir_special: sizes of initialize_slab_ocean_model, always ML-only
         if (!h->p.slab_ocean_model_bool) FAIL(h, "ocean reservoir uploaded but slab_ocean_model_bool is off");
         OceanSizes s = make_ocean_sizes(h->tiling, g, 4000, 6.0);
-        if (s.D != D || s.P != P || S != 0)
-            FAIL(h, "ocean region %d: D/P/S = %d/%d/%d but the tiling gives %d/%d/0", w->region, D, P, S, s.D, s.P);
+        // S = 0: predict_slab_ml (ml_only_ocean, the reference's setting); S = P: the hybrid predict_slab, whose feature
+        // vector carries chunk_size_prediction "model" entries = its own previous standardised prediction
+        if (s.D != D || s.P != P || (S != 0 && S != P))
+            FAIL(h, "ocean region %d: D/P/S = %d/%d/%d but the tiling gives %d/%d/(0 or %d)", w->region, D, P, S, s.D, s.P, s.P);
         if (n % D != 0) FAIL(h, "ocean region %d: n = %d is not a multiple of reservoir_numinputs %d", w->region, n, D);
         if (w->sst_std == 0.0) FAIL(h, "ocean region %d: sst_std must be the SST slot of grid_special%%std", w->region);
         hr.osizes = s;
@@ -663,6 +665,10 @@ static int region_install(sml_engine *h, const sml_region_weights *w, bool gener
     if (dev_upload(h, &hr, maps.output_ms.data(), maps.output_ms.size(), &d.out_ms)) return -1;
     CK(h, cudaStreamSynchronize(h->stream));   // one synchronisation per region: the engine owns copies from here on
 
+    if (w->kind == SML_OCEAN && S > 0) {
+        d.lm_self = 1;
+        d.leak = 1.0;   // predict_slab has no leak term: x = tanh(A x + W_in u) (src/mod_slab_ocean_reservoir.f90:1294)
+    }
     hr.region = w->region;
     hr.uploaded = true;
     K.any = true;
@@ -791,10 +797,12 @@ static int build_persistent_plan(sml_engine *h, KindState &K, int S_max)
     int part_rows = std::max(stage_cols, 272 / stage_cols * stage_cols);
     if (const char *e = getenv("SML_PART_ROWS")) part_rows = std::max(stage_cols, atoi(e) / stage_cols * stage_cols);
     K.part_rows = part_rows;
-    int item_rows = NCONS;
+    // two sweeps per item (1088 rows) at 4 ring stages measured best at both ends: 0.985 of the roof at 1152 regions per
+    // GPU (one-sweep items: 0.959; the classic kernel: 0.98-0.99) and 0.90 at 144 (classic: 0.85)
+    int item_rows = 2 * NCONS;
     if (const char *e = getenv("SML_ITEM_ROWS")) item_rows = atoi(e);
     const int max_item_rows = std::max(part_rows, item_rows / part_rows * part_rows);
-    K.p_stages = 5;
+    K.p_stages = 4;   // 3 / 4 / 5 stages at 144 regions: 0.889 / 0.903 / 0.866 (a deeper ring takes L1 from the x gathers)
     if (const char *e = getenv("SML_PERSIST_STAGES")) K.p_stages = std::max(2, std::min(8, atoi(e)));
     const bool stagger = !(getenv("SML_PERSIST_STAGGER") && atoi(getenv("SML_PERSIST_STAGGER")) == 0);
     struct Part { int reg, row0, nrows, part; long long cost; };
@@ -1388,7 +1396,7 @@ static int launch_finish(sml_engine *h, KindState &K, int model_part)
                                                                          model_part, K.d_lm, pt, seq, peer_off, h->d_done,
                                                                          (atmo && h->contribs && model_part) ? h->d_vp : nullptr,
                                                                          (atmo && h->contribs && model_part) ? h->d_vml : nullptr,
-                                                                         K.persist ? 1 : 0);
+                                                                         K.persist ? 1 : 0, (!atmo && !model_part) ? K.d_lm : nullptr);
     h->launches++;
     CK(h, cudaGetLastError());
     if (!atmo && h->peers.world > 1) h->ocean_publish_pending = true;   // pushed by the next grid assembly

@@ -25,6 +25,8 @@ struct RegionDev {
     int item0, nitems;
     int part0, nparts;  // fixed row blocks of the persistent step kernel: the region's partial outvecs
     int L;          // mean/std length; slot L holds the SST feedback mean/std
+    int lm_self;    // hybrid slab-ocean reservoir (predict_slab, src/mod_slab_ocean_reservoir.f90:1303): after every readout
+                    // local_model <- the STANDARDISED outvec (the reservoir's own prediction is its next "imperfect model")
     int ell_stream; // 1: the ELL / W_in streams of the fused step are loaded evict-first (ld.global.cs) so that they do
                     //    not push the region's state vector -- the target of the random gathers -- out of L1
     double leak;
@@ -813,7 +815,7 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
                  double *__restrict__ out_pool, int unstandardize, int model_part,
                  const double *__restrict__ lm_pool, PeerTable pt, unsigned long long seq,
                  long long peer_off, unsigned int *__restrict__ done_counter, double *__restrict__ vp_pool,
-                 double *__restrict__ vml_pool, int use_parts)
+                 double *__restrict__ vml_pool, int use_parts, double *__restrict__ lm_out)
 {
     extern __shared__ __align__(16) double s_fin[];   // [pstride] outvec staging, then [FIN_GROUPS][pstride] (overlapped mode)
     __shared__ int s_last;
@@ -854,6 +856,7 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
                 vml_pool[R.out_off + p] = vml;
             }
             for (int c = 0; c < cnt; ++c) v += partials[(size_t)(first + c) * ldw_max + p];
+            if (R.lm_self && lm_out) lm_out[R.lm_off + p] = v;   // before the un-standardisation, as the reference does
             if (unstandardize) {
                 const int ms = R.out_ms[p];
                 if (ms >= 0) v = __dadd_rn(__dmul_rn(v, R.std[ms]), R.mean[ms]);

@@ -84,19 +84,20 @@ def rel_inf(a, b):
 
 # ---- slab-ocean reservoirs (res%reservoir_special) --------------------------------------------
 def ocean_weights(num_regions, region, m=4000, precip_bool=True, radius=0.9, sigma=0.6, wout_scale=None, deg=6.0,
-                  with_dense_win=True, mean=None, std=None):
+                  with_dense_win=True, mean=None, std=None, hybrid=False):
     """weights of one ocean reservoir; mean/std default to a fresh atmosphere-style vector (grid_special is a
-    copy of the atmosphere grid, so the SST slot is the atmosphere's sst_mean_std_idx)"""
-    rc = oc.OceanRegion(num_regions, region, m=m, deg=deg, precip_bool=precip_bool)
+    copy of the atmosphere grid, so the SST slot is the atmosphere's sst_mean_std_idx).  hybrid: the predict_slab
+    variant (ml_only_ocean = .False.) whose W_out has chunk_size_prediction extra "model" columns"""
+    rc = oc.OceanRegion(num_regions, region, m=m, deg=deg, precip_bool=precip_bool, hybrid=hybrid)
     rng = np.random.default_rng(SEED0 + 100000 + region)
     rows, cols, vals = syn.make_adjacency(rc.n, rc.k, rng, radius=radius)
     winc, wcol = syn.make_win_compact(rc.n, rc.D, rng, sigma=sigma)
     scale = (1.0 / np.sqrt(rc.n)) if wout_scale is None else wout_scale
-    wout = np.asfortranarray(rng.standard_normal((rc.P, rc.n)) * scale)
+    wout = np.asfortranarray(rng.standard_normal((rc.P, rc.n + rc.S)) * scale)
     if mean is None:
         mean, std = syn.make_mean_std(rc.L, rng)
     w = dict(num_regions=num_regions, region=region, m=m, deg=deg, precip_bool=precip_bool, n=rc.n, D=rc.D, P=rc.P,
-             S=0, k=rc.k, L=rc.L, A=rc.A, rows=rows, cols=cols, vals=vals, winc=winc, wcol=wcol, wout=wout,
+             S=rc.S, hybrid=hybrid, k=rc.k, L=rc.L, A=rc.A, rows=rows, cols=cols, vals=vals, winc=winc, wcol=wcol, wout=wout,
              mean=np.array(mean), std=np.array(std), sst_idx=rc.g.sst_mean_std_idx)
     if with_dense_win:
         w["win"] = syn.win_dense_from_compact(winc, wcol, rc.D)
@@ -104,7 +105,8 @@ def ocean_weights(num_regions, region, m=4000, precip_bool=True, radius=0.9, sig
 
 
 def c_ocean(w) -> "oc.OceanRegion":
-    r = oc.OceanRegion(w["num_regions"], w["region"], m=w["m"], deg=w["deg"], precip_bool=w["precip_bool"])
+    r = oc.OceanRegion(w["num_regions"], w["region"], m=w["m"], deg=w["deg"], precip_bool=w["precip_bool"],
+                       hybrid=w.get("hybrid", False))
     r.set_weights(w["rows"], w["cols"], w["vals"], w.get("win"), w["wout"], w["mean"], w["std"])
     if w.get("win") is None:
         r.set_win_compact(w["winc"], w["wcol"])

@@ -77,6 +77,41 @@ def test_predict_slab_ml_single_region(E, region, m):
     eng.close()
 
 
+@pytest.mark.parametrize("region,m", [(555, 500), (23, 900)])
+def test_predict_slab_hybrid_single_region(E, region, m):
+    """predict_slab (src/mod_slab_ocean_reservoir.f90:1268-1316), the ocean reservoir with ml_only_ocean = .False.:
+    no leak term, chunk_size_prediction model columns, and local_model <- the standardised outvec after every step"""
+    wa = region_weights(1152, region, m=300, sst_bool_input=True, with_dense_win=False)
+    wo = ocean_weights(1152, region, m=m, mean=wa["mean"], std=wa["std"], with_dense_win=False, hybrid=True)
+    assert wo["S"] == wo["P"] == 8
+    eng = E.Engine(number_of_regions=1152, irank=region, numprocs=1152)
+    upload_atmo(eng, wa)
+    eng.region_upload(region, wo["rows"], wo["cols"], wo["vals"], wo["wout"], wo["mean"], wo["std"],
+                      win_compact=wo["winc"], win_col=wo["wcol"], D=wo["D"], kind=E.OCEAN, leakage=0.4,   # ignored: no leak term
+                      sst_mean=wo["mean"][wo["sst_idx"] - 1], sst_std=wo["std"][wo["sst_idx"] - 1])
+    eng.finalize()
+    co = c_ocean(wo)
+    rng = np.random.default_rng(region + m)
+    x0 = 0.3 * rng.standard_normal(wo["n"])
+    lm0 = rng.standard_normal(wo["S"])           # start_prediction_slab: the last observed SST / OHTC tile (:861-864)
+    co.x[:] = x0
+    co.local_model[:] = lm0
+    eng.state_set(region, x0, kind=E.OCEAN)
+    eng.local_model_set(region, lm0, kind=E.OCEAN)
+    worst = 0.0
+    for step in range(5):
+        fb = rng.standard_normal(wo["D"])
+        co.feedback[:] = fb
+        eng.feedback_set(region, fb, kind=E.OCEAN)
+        co.predict()
+        eng.predict(kind=E.OCEAN)
+        worst = max(worst, rel_inf(eng.outvec_get(region, kind=E.OCEAN), co.outvec),
+                    rel_inf(eng.state_get(region, kind=E.OCEAN), co.x),
+                    rel_inf(eng.local_model_get(region, kind=E.OCEAN), co.local_model))
+    assert worst < TOL_STEP * 100           # five closed steps: the prediction feeds back through local_model
+    eng.close()
+
+
 def test_ocean_synchronize(E):
     region = 700
     wa = region_weights(1152, region, m=300, sst_bool_input=True, with_dense_win=False)
