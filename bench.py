@@ -478,6 +478,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    # torchrun pins OMP_NUM_THREADS to 1; the root's host-model stand-in is the only host compute of a step and may use
+    # the cores the other ranks leave idle (they only enqueue)
+    if rank == 0:
+        torch.set_num_threads(max(1, min(8, (os.cpu_count() or 8) // max(1, world) * 2)))
 
     # --emulate-world W (single process): this GPU carries rank 0's shard of a W-rank run, no exchange -- isolates
     # the per-rank step cost at that scale (diagnostic; not a bench line)

@@ -119,6 +119,21 @@ int sml_ocean_region_maps(int num_regions, int region, int overlap, int32_t *sst
 int sml_region_maps(int num_regions, int region, int overlap, int precip_bool, int sst_bool_input,
                     int32_t *input_map, int32_t *input_ms, int32_t *output_map, int32_t *output_ms,
                     int32_t *model_map, int32_t *model_ms, int32_t *target_map);
+/* vertical localisation, num_vert_levels in {1, 2, 4, 8}: get_z_res_extent (src/res_domain.f90:143-153),
+ * getoverlapindices_vert (:206-256), get_trainingdataindices_vert (:576-600) and the sizes / flattened maps of ONE
+ * vertical slab (only the bottom slab carries logp, precip and SST, src/mod_reservoir.f90:1793-1818).  Host integer
+ * arithmetic, bit-exact against the oracle.  The engine's kernels step num_vert_levels == 1, the reference's
+ * configuration (src/mod_reservoir.f90:57); these entries are what a multi-level host would build its tables from. */
+int sml_get_z_res_extent(int num_vert_levels, int vert_level, int *zs, int *ze, int *zchunk);
+int sml_getoverlapindices_vert(int num_vert_levels, int vert_level, int vert_overlap, int *izs, int *ize, int *izc,
+                               int *top, int *bottom);
+int sml_get_trainingdataindices_vert(int num_vert_levels, int vert_level, int vert_overlap, int *zs, int *ze);
+int sml_region_dims_vert(int num_regions, int region, int overlap, int num_vert_levels, int vert_level, int vert_overlap,
+                         int m, double deg, int precip_bool, int sst_bool, int sst_bool_input, int ml_only, int *n, int *k,
+                         int *D, int *P, int *S, int *L);
+int sml_region_maps_vert(int num_regions, int region, int overlap, int num_vert_levels, int vert_level, int vert_overlap,
+                         int precip_bool, int sst_bool_input, int32_t *input_map, int32_t *input_ms, int32_t *output_map,
+                         int32_t *output_ms, int32_t *model_map, int32_t *model_ms, int32_t *target_map);
 /* offsets (in doubles) of wholegrid4d, wholegrid2d, wholegrid_precip, wholegrid_sst, tisr in G and the
  * total; F = [forecast_4d | forecast_2d] */
 int sml_global_layout(int64_t off[5], int64_t *g_total, int64_t *f_total);

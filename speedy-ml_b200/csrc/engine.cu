@@ -475,6 +475,59 @@ int sml_region_maps(int R, int region, int ov, int precip, int sst_in, int32_t *
     if (target_map) std::copy(m.target_map.begin(), m.target_map.end(), target_map);
     return 0;
 }
+/* vertical localisation: the res_domain.f90 functions for num_vert_levels in {1, 2, 4, 8} and the sizes / maps of one
+ * vertical slab (the engine itself steps num_vert_levels == 1, the reference's configuration) */
+int sml_get_z_res_extent(int nvl, int level, int *zs, int *ze, int *zchunk)
+{
+    VertGeom v = make_vert(nvl, level, 0);
+    if (!v.ok) return -1;
+    *zs = v.zs; *ze = v.ze; *zchunk = v.zc;
+    return 0;
+}
+int sml_getoverlapindices_vert(int nvl, int level, int vov, int *izs, int *ize, int *izc, int *top, int *bottom)
+{
+    VertGeom v = make_vert(nvl, level, vov);
+    if (!v.ok) return -1;
+    *izs = v.izs; *ize = v.ize; *izc = v.izc; *top = v.top; *bottom = v.bottom;
+    return 0;
+}
+int sml_get_trainingdataindices_vert(int nvl, int level, int vov, int *zs, int *ze)
+{
+    VertGeom v = make_vert(nvl, level, vov);
+    if (!v.ok) return -1;
+    *zs = v.tdzs; *ze = v.tdze;
+    return 0;
+}
+int sml_region_dims_vert(int R, int region, int ov, int nvl, int level, int vov, int m, double deg, int precip, int sst_bool,
+                         int sst_in, int ml_only, int *n, int *k, int *D, int *P, int *S, int *L)
+{
+    Tiling t = make_tiling(R);
+    VertGeom v = make_vert(nvl, level, vov);
+    if (!t.ok || !v.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    RegionSizes s = make_sizes_vert(t, g, v, m, deg, precip, sst_bool, sst_in, ml_only);
+    *n = s.n; *k = s.k; *D = s.D; *P = s.P; *S = s.S; *L = s.L;
+    return 0;
+}
+int sml_region_maps_vert(int R, int region, int ov, int nvl, int level, int vov, int precip, int sst_in,
+                         int32_t *input_map, int32_t *input_ms, int32_t *output_map, int32_t *output_ms,
+                         int32_t *model_map, int32_t *model_ms, int32_t *target_map)
+{
+    Tiling t = make_tiling(R);
+    VertGeom v = make_vert(nvl, level, vov);
+    if (!t.ok || !v.ok) return -1;
+    RegionGeom g = make_geom(t, region, ov);
+    RegionSizes s = make_sizes_vert(t, g, v, 6000, 6.0, precip, true, sst_in, false);
+    RegionMaps m = make_maps_vert(t, g, v, s, precip, sst_in);
+    if (input_map) std::copy(m.input_map.begin(), m.input_map.end(), input_map);
+    if (input_ms) std::copy(m.input_ms.begin(), m.input_ms.end(), input_ms);
+    if (output_map) std::copy(m.output_map.begin(), m.output_map.end(), output_map);
+    if (output_ms) std::copy(m.output_ms.begin(), m.output_ms.end(), output_ms);
+    if (model_map) std::copy(m.model_map.begin(), m.model_map.end(), model_map);
+    if (model_ms) std::copy(m.model_ms.begin(), m.model_ms.end(), model_ms);
+    if (target_map) std::copy(m.target_map.begin(), m.target_map.end(), target_map);
+    return 0;
+}
 int sml_global_layout(int64_t off[5], int64_t *g_total, int64_t *f_total)
 {
     off[0] = G_W4D; off[1] = G_W2D; off[2] = G_PRECIP; off[3] = G_SST; off[4] = G_TISR;

@@ -208,6 +208,157 @@ inline RegionMaps make_maps(const Tiling &t, const RegionGeom &g, const RegionSi
     return m;
 }
 
+// ---- vertical localisation (num_vert_levels in {1, 2, 4, 8}) ---------------------------------------------
+// get_z_res_extent (src/res_domain.f90:143-153), getoverlapindices_vert (:206-256), get_trainingdataindices_vert
+// (:576-600).  1-based inclusive like the reference; tdz0 is the 0-based position of the reservoir's own levels
+// inside its halo'd input column.
+struct VertGeom {
+    int zs = 1, ze = ZG, zc = ZG;        // levels the reservoir predicts
+    int izs = 1, ize = ZG, izc = ZG;     // levels it reads (vertical overlap, clipped at the top / bottom)
+    bool top = true, bottom = true;
+    int tdzs = 1, tdze = ZG;             // get_trainingdataindices_vert: position of zs..ze inside izs..ize (1-based)
+    bool ok = false;
+};
+
+inline VertGeom make_vert(int num_vert_levels, int vert_level, int vert_overlap)
+{
+    VertGeom v;
+    if (num_vert_levels < 1 || ZG % num_vert_levels != 0 || vert_level < 1 || vert_level > num_vert_levels || vert_overlap < 0)
+        return v;
+    v.zc = ZG / num_vert_levels;
+    v.zs = (vert_level - 1) * v.zc + 1;
+    v.ze = vert_level * v.zc;
+    v.top = v.zs == 1;
+    v.bottom = v.ze == ZG;
+    if (v.zs - vert_overlap >= 1 && v.ze + vert_overlap <= ZG) {
+        v.izs = v.zs - vert_overlap; v.ize = v.ze + vert_overlap; v.izc = v.zc + 2 * vert_overlap;
+    } else if (v.zs - vert_overlap < 1) {
+        v.izs = 1; v.ize = v.ze + vert_overlap; v.izc = v.zc + vert_overlap + (v.zs - 1);
+    } else {
+        v.izs = v.zs - vert_overlap; v.ize = ZG; v.izc = v.zc + vert_overlap + (ZG - v.ze);
+    }
+    // the reference's second branch does not clip input_zend when BOTH ends overflow (it prints no error either):
+    // such layouts (vert_overlap >= the slab height next to both boundaries) are rejected here
+    if (v.ize > ZG || v.izs < 1) return v;
+    if (v.zs - vert_overlap < 1) { v.tdzs = 1 + (v.zs - 1); v.tdze = v.izc - vert_overlap; }
+    else if (v.ze + vert_overlap > ZG) { v.tdzs = 1 + vert_overlap; v.tdze = v.izc - (ZG - v.ze); }
+    else { v.tdzs = 1 + vert_overlap; v.tdze = v.izc - vert_overlap; }
+    v.ok = true;
+    return v;
+}
+
+// allocate_res_new + trained_reservoir_prediction for ONE vertical slab (src/mod_reservoir.f90:80-180, 1793-1885):
+// only the bottom slab carries logp, precip and SST; every slab carries TISR.  Sizes and vector offsets as make_sizes.
+inline RegionSizes make_sizes_vert(const Tiling &t, const RegionGeom &g, const VertGeom &v, int m, double deg, bool precip,
+                                   bool sst_bool, bool sst_in, bool ml_only)
+{
+    RegionSizes s{};
+    const int ixy = g.ixc * g.iyc, rxy = t.fx * t.fy;
+    const bool logp = v.bottom;
+    precip = precip && v.bottom;
+    sst_bool = sst_bool && v.bottom;
+    sst_in = sst_in && sst_bool;
+    int L = NVAR * v.izc;
+    s.logp_ms = logp ? L++ : -1;
+    s.tisr_ms = L++;
+    s.precip_ms = precip ? L++ : -1;
+    s.sst_ms = sst_bool ? L++ : -1;
+    s.L = L;
+    s.P = rxy * NVAR * v.zc + (logp ? rxy : 0) + (precip ? rxy : 0);
+    s.S = ml_only ? 0 : rxy * NVAR * v.zc + (logp ? rxy : 0);
+    s.atmo_len = NVAR * ixy * v.izc;
+    int nxt = s.atmo_len;
+    s.logp_off = -1; s.precip_off = -1; s.sst_off = -1;
+    if (logp) { s.logp_off = nxt; nxt += ixy; }
+    if (precip) { s.precip_off = nxt; nxt += ixy; }
+    if (sst_in) { s.sst_off = nxt; nxt += ixy; }
+    s.tisr_off = nxt; nxt += ixy;
+    s.D = nxt;
+    s.q = (int)std::floor((double)m / (double)s.D + 0.5);
+    s.n = s.q * s.D;
+    s.k = (int)((deg / (double)m) * s.n * s.n);
+    return s;
+}
+
+// the flattened maps of one vertical slab: same walks as make_maps over the slab's own levels
+inline RegionMaps make_maps_vert(const Tiling &t, const RegionGeom &g, const VertGeom &v, const RegionSizes &s, bool precip,
+                                 bool sst_in)
+{
+    RegionMaps m;
+    precip = precip && v.bottom;
+    sst_in = sst_in && v.bottom;
+    m.input_map.assign(s.D, 0); m.input_ms.assign(s.D, -1);
+    for (int lz = 0; lz < v.izc; ++lz)
+        for (int ly = 0; ly < g.iyc; ++ly)
+            for (int lx = 0; lx < g.ixc; ++lx)
+                for (int var = 0; var < NVAR; ++var) {
+                    const int idx = var + NVAR * (lx + g.ixc * (ly + g.iyc * lz));
+                    m.input_map[idx] = (int32_t)(G_W4D + off4(var, g.gx[lx], g.iys - 1 + ly, v.izs - 1 + lz));
+                    m.input_ms[idx] = var * v.izc + lz;
+                }
+    auto fill2d = [&](int base, int64_t goff, int ms) {
+        for (int ly = 0; ly < g.iyc; ++ly)
+            for (int lx = 0; lx < g.ixc; ++lx) {
+                m.input_map[base + lx + g.ixc * ly] = (int32_t)(goff + off2(g.gx[lx], g.iys - 1 + ly));
+                m.input_ms[base + lx + g.ixc * ly] = ms;
+            }
+    };
+    if (s.logp_off >= 0) fill2d(s.logp_off, G_W2D, s.logp_ms);
+    if (precip) fill2d(s.precip_off, G_PRECIP, s.precip_ms);
+    if (sst_in) fill2d(s.sst_off, G_SST, s.L);
+    fill2d(s.tisr_off, G_TISR, s.tisr_ms);
+
+    m.output_map.assign(s.P, 0); m.output_ms.assign(s.P, -1);
+    m.target_map.assign(s.P, 0);
+    int e = 0;
+    for (int z = 0; z < v.zc; ++z)
+        for (int ry = 0; ry < t.fy; ++ry)
+            for (int rx = 0; rx < t.fx; ++rx)
+                for (int var = 0; var < NVAR; ++var) {
+                    m.output_map[e] = (int32_t)(G_W4D + off4(var, g.xs - 1 + rx, g.ys - 1 + ry, v.zs - 1 + z));
+                    // unstandardize_state_vec_res (:1447-1457): the slot of input level tdata_zstart + z
+                    m.output_ms[e] = var * v.izc + (v.tdzs - 1 + z);
+                    m.target_map[e] = var + NVAR * ((g.tdx0 + rx) + g.ixc * ((g.tdy0 + ry) + g.iyc * (v.tdzs - 1 + z)));
+                    ++e;
+                }
+    if (s.logp_off >= 0)
+        for (int ry = 0; ry < t.fy; ++ry)
+            for (int rx = 0; rx < t.fx; ++rx) {
+                m.output_map[e] = (int32_t)(G_W2D + off2(g.xs - 1 + rx, g.ys - 1 + ry));
+                m.output_ms[e] = s.logp_ms;
+                m.target_map[e] = s.logp_off + (g.tdx0 + rx) + g.ixc * (g.tdy0 + ry);
+                ++e;
+            }
+    if (precip)
+        for (int ry = 0; ry < t.fy; ++ry)
+            for (int rx = 0; rx < t.fx; ++rx) {
+                m.output_map[e] = (int32_t)(G_PRECIP + off2(g.xs - 1 + rx, g.ys - 1 + ry));
+                m.output_ms[e] = s.precip_ms;
+                m.target_map[e] = s.precip_off + (g.tdx0 + rx) + g.ixc * (g.tdy0 + ry);
+                ++e;
+            }
+    m.model_map.assign(s.S, 0); m.model_ms.assign(s.S, -1);
+    if (s.S > 0) {
+        e = 0;
+        for (int z = 0; z < v.zc; ++z)
+            for (int ry = 0; ry < t.fy; ++ry)
+                for (int rx = 0; rx < t.fx; ++rx)
+                    for (int var = 0; var < NVAR; ++var) {
+                        m.model_map[e] = (int32_t)(F_F4D + off4(var, g.xs - 1 + rx, g.ys - 1 + ry, v.zs - 1 + z));
+                        m.model_ms[e] = var * v.izc + (v.tdzs - 1 + z);
+                        ++e;
+                    }
+        if (s.logp_off >= 0)
+            for (int ry = 0; ry < t.fy; ++ry)
+                for (int rx = 0; rx < t.fx; ++rx) {
+                    m.model_map[e] = (int32_t)(F_F2D + off2(g.xs - 1 + rx, g.ys - 1 + ry));
+                    m.model_ms[e] = s.logp_ms;
+                    ++e;
+                }
+    }
+    return m;
+}
+
 // ---- slab-ocean reservoir (res%reservoir_special / res%grid_special) ------------------------------------
 // initialize_slab_ocean_model (src/mod_slab_ocean_reservoir.f90:9-133): input vector
 //   [ atmosphere lowest level (var,lx,ly) 4*ixy | logp ixy | sst ixy | tisr ixy | ohtc ixy ],  D = 8*ixy,

@@ -63,6 +63,11 @@ _SIGNATURES = {
     "sml_region_dims": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
                         + [C.POINTER(C.c_int)] * 6, C.c_int),
     "sml_region_maps": ([C.c_int] * 5 + [_ip] * 7, C.c_int),
+    "sml_get_z_res_extent": ([C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3, C.c_int),
+    "sml_getoverlapindices_vert": ([C.c_int] * 3 + [C.POINTER(C.c_int)] * 5, C.c_int),
+    "sml_get_trainingdataindices_vert": ([C.c_int] * 3 + [C.POINTER(C.c_int)] * 2, C.c_int),
+    "sml_region_dims_vert": ([C.c_int] * 7 + [C.c_double] + [C.c_int] * 4 + [C.POINTER(C.c_int)] * 6, C.c_int),
+    "sml_region_maps_vert": ([C.c_int] * 8 + [_ip] * 7, C.c_int),
     "sml_ocean_region_dims": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_double] + [C.POINTER(C.c_int)] * 5, C.c_int),
     "sml_ocean_region_maps": ([C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int)], C.c_int),
     "sml_global_layout": ([_lp, _lp, _lp], C.c_int),
@@ -250,6 +255,55 @@ def region_maps(num_regions, region, overlap=1, precip_bool=True, sst_bool_input
     if load_library().sml_region_maps(num_regions, region, overlap, int(precip_bool), int(sst_bool_input),
                                       *[_i(a) for a in arrs]):
         raise ValueError("unsupported region count")
+    return dict(zip(("input_map", "input_ms", "output_map", "output_ms", "model_map", "model_ms", "target_map"), arrs))
+
+
+def get_z_res_extent(num_vert_levels, vert_level):
+    """res_domain.f90:143-153 -> (zstart, zend, zchunk)"""
+    v = [C.c_int() for _ in range(3)]
+    if load_library().sml_get_z_res_extent(num_vert_levels, vert_level, *[C.byref(a) for a in v]):
+        raise ValueError("unsupported vertical layout")
+    return tuple(a.value for a in v)
+
+
+def getoverlapindices_vert(num_vert_levels, vert_level, vert_overlap):
+    """res_domain.f90:206-256 -> (input_zstart, input_zend, inputzchunk, top, bottom)"""
+    v = [C.c_int() for _ in range(5)]
+    if load_library().sml_getoverlapindices_vert(num_vert_levels, vert_level, vert_overlap, *[C.byref(a) for a in v]):
+        raise ValueError("unsupported vertical layout")
+    t = tuple(a.value for a in v)
+    return t[:3] + (bool(t[3]), bool(t[4]))
+
+
+def get_trainingdataindices_vert(num_vert_levels, vert_level, vert_overlap):
+    """res_domain.f90:576-600 -> (zstart, zend)"""
+    v = [C.c_int() for _ in range(2)]
+    if load_library().sml_get_trainingdataindices_vert(num_vert_levels, vert_level, vert_overlap, *[C.byref(a) for a in v]):
+        raise ValueError("unsupported vertical layout")
+    return tuple(a.value for a in v)
+
+
+def region_dims_vert(num_regions, region, num_vert_levels, vert_level, vert_overlap, overlap=1, m=6000, deg=6.0,
+                     precip_bool=True, sst_bool=True, sst_bool_input=True, ml_only=False):
+    """allocate_res_new sizes of one vertical slab -> dict(n, k, D, P, S, L)"""
+    v = [C.c_int() for _ in range(6)]
+    if load_library().sml_region_dims_vert(num_regions, region, overlap, num_vert_levels, vert_level, vert_overlap, m,
+                                           float(deg), int(precip_bool), int(sst_bool), int(sst_bool_input), int(ml_only),
+                                           *[C.byref(a) for a in v]):
+        raise ValueError("unsupported layout")
+    return dict(zip(("n", "k", "D", "P", "S", "L"), (a.value for a in v)))
+
+
+def region_maps_vert(num_regions, region, num_vert_levels, vert_level, vert_overlap, overlap=1, precip_bool=True,
+                     sst_bool_input=True):
+    d = region_dims_vert(num_regions, region, num_vert_levels, vert_level, vert_overlap, overlap, precip_bool=precip_bool,
+                         sst_bool_input=sst_bool_input)
+    D, P, S = d["D"], d["P"], d["S"]
+    arrs = [np.zeros(D, np.int32), np.zeros(D, np.int32), np.zeros(P, np.int32), np.zeros(P, np.int32),
+            np.zeros(S, np.int32), np.zeros(S, np.int32), np.zeros(P, np.int32)]
+    if load_library().sml_region_maps_vert(num_regions, region, overlap, num_vert_levels, vert_level, vert_overlap,
+                                           int(precip_bool), int(sst_bool_input), *[_i(a) for a in arrs]):
+        raise ValueError("unsupported layout")
     return dict(zip(("input_map", "input_ms", "output_map", "output_ms", "model_map", "model_ms", "target_map"), arrs))
 
 
