@@ -315,6 +315,9 @@ int sml_ocean_ring_reset(sml_engine *h);
 /* device-only halves of begin/end for callers that keep the grids on the device */
 int sml_step_pack_device(sml_engine *h, int timestep);                 /* gathered -> G (+clamps) */
 int sml_step_unpack_device(sml_engine *h, int timestep);               /* G,F -> feedback, local_model */
+/* the two as ONE cooperative launch (grid barrier between the scatter and the gather): the device-resident step of
+ * ML-only runs.  Bit-identical to sml_step_pack_device + sml_step_unpack_device in the sequential mode. */
+int sml_step_exchange_device(sml_engine *h, int timestep);
 
 /* ---- training: reservoir_layer_chunking_hybrid/_ml + chunking_matmul(_ml)
  *      (src/mod_reservoir.f90:963-1175,1594-1701), fit_chunk_hybrid/_ml (:1177-1334) ---- */

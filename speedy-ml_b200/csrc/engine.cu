@@ -209,6 +209,11 @@ struct sml_engine {
     int run_speedy = 1;                // what the root passed to sml_set_run_speedy (travels with the forecast)
     double *h_pin_flag = nullptr;      // pinned read-back of the run_speedy slot on the other ranks
     double setup_upload_s = 0.0;       // host wall clock spent inside sml_region_upload (bench: setup split)
+    unsigned xch_calls = 0;            // fused exchange launches since the arrival counter was last zeroed
+    // ranks other than the root never wait for the host model; a ring of blocking events keeps them at most a few
+    // steps ahead of the device so that they neither fill the launch queue nor burn a core spinning in it
+    cudaEvent_t ev_ahead[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long consumer_steps = 0;
 };
 
 #define FAIL(h, ...)                                      \
@@ -359,6 +364,8 @@ int sml_destroy(sml_engine *h)
     if (h->ev_pack) cudaEventDestroy(h->ev_pack);
     if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
     if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
+    for (cudaEvent_t e : h->ev_ahead)
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pt_pack.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pt_unpack.ev) cudaEventDestroy(e);
@@ -1655,13 +1662,76 @@ int sml_ocean_ring_reset(sml_engine *h)
     return 0;
 }
 
+static int build_pack_args(sml_engine *h, PackArgs &a);
+
 int sml_step_pack_device(sml_engine *h, int timestep)
 {
     (void)timestep;
     if (check_ready(h, SML_ATMO)) return -1;
     CK(h, cudaSetDevice(h->p.device));
-    KindState &K = h->kinds[SML_ATMO];
     PackArgs a{};
+    if (build_pack_args(h, a)) return -1;
+    const int nsst = (a.sst_mode >= 0) ? (XG * YG + 255) / 256 : 0;
+    cudaEvent_t *pe = phase_events(h, h->pt_pack);
+    if (pe) CK(h, cudaEventRecord(pe[0], h->stream));
+    k_pack_grids<<<a.nsc + nsst, 256, 0, h->stream>>>(a);
+    if (pe) CK(h, cudaEventRecord(pe[1], h->stream));
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+// pack + unpack of the device-resident step as ONE cooperative launch (kernels.cuh k_exchange_fused); equivalent to
+// sml_step_pack_device followed by sml_step_unpack_device(timestep) in the sequential mode, bit for bit
+int sml_step_exchange_device(sml_engine *h, int timestep)
+{
+    if (check_ready(h, SML_ATMO)) return -1;
+    CK(h, cudaSetDevice(h->p.device));
+    if (h->overlap && h->ahead_pending) FAIL(h, "sml_step_exchange_device is the sequential device step; close the overlapped step first");
+    KindState &K = h->kinds[SML_ATMO];
+    static const bool off = getenv("SML_FUSED_EXCHANGE") && atoi(getenv("SML_FUSED_EXCHANGE")) == 0;   // A/B switch
+    if (off) {
+        if (sml_step_pack_device(h, timestep)) return -1;
+        return sml_step_unpack_device(h, timestep);
+    }
+    if (h->n_ocean_fb > 0 && timestep < 1)
+        FAIL(h, "timestep must be the 1-based hybrid step (it selects the ring slot mod(timestep-1,%d)+1)", h->ocean_slots);
+    PackArgs a{};
+    if (build_pack_args(h, a)) return -1;
+    if (h->xch_calls >= (1u << 20)) {   // keep the arrival counter far from wrapping
+        CK(h, cudaMemsetAsync(h->d_done + 3, 0, sizeof(unsigned int), h->stream));
+        h->xch_calls = 0;
+    }
+    const unsigned grid = (unsigned)h->num_sms;
+    unsigned target = grid * (++h->xch_calls);
+    const RegionDev *regs = K.d_regs;
+    int nreg = (int)K.regs.size(), do_model = h->p.ml_only ? 0 : 1;
+    const double *F = h->d_F;
+    double *fb = K.d_fb, *lm = K.d_lm;
+    unsigned *ctr = h->d_done + 3;
+    void *args[] = {&a, &regs, &nreg, &F, &fb, &lm, &do_model, &ctr, &target};
+    cudaEvent_t *pe = phase_events(h, h->pt_pack);
+    cudaEvent_t *ue = phase_events(h, h->pt_unpack);
+    if (pe) CK(h, cudaEventRecord(pe[0], h->stream));
+    CK(h, cudaLaunchCooperativeKernel((const void *)k_exchange_fused, dim3(grid), dim3(512), args, 0, h->stream));
+    if (pe) CK(h, cudaEventRecord(pe[1], h->stream));
+    if (ue) {   // the fused kernel is booked under "pack"; "unpack" reads zero
+        CK(h, cudaEventRecord(ue[0], h->stream));
+        CK(h, cudaEventRecord(ue[1], h->stream));
+    }
+    h->launches++;
+    if (h->n_ocean_fb > 0) {
+        k_build_ocean_inputs<<<h->n_ocean_fb, 128, 0, h->stream>>>(h->d_ocean_fb, h->d_G, K.d_fb, h->kinds[SML_OCEAN].d_fb,
+                                                                   h->d_ocean_ring, (timestep - 1) % h->ocean_slots, h->ocean_slots);
+        h->launches++;
+    }
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+static int build_pack_args(sml_engine *h, PackArgs &a)
+{
+    KindState &K = h->kinds[SML_ATMO];
     a.total = h->p.number_of_regions * K.P;
     a.out_dst = h->d_out_dst;
     a.G = h->d_G;
@@ -1699,13 +1769,6 @@ int sml_step_pack_device(sml_engine *h, int timestep)
                               : h->d_ocean_gathered;
         a.ocean_P = h->P_ocean;
     }
-    const int nsst = (a.sst_mode >= 0) ? (XG * YG + 255) / 256 : 0;
-    cudaEvent_t *pe = phase_events(h, h->pt_pack);
-    if (pe) CK(h, cudaEventRecord(pe[0], h->stream));
-    k_pack_grids<<<a.nsc + nsst, 256, 0, h->stream>>>(a);
-    if (pe) CK(h, cudaEventRecord(pe[1], h->stream));
-    h->launches++;
-    CK(h, cudaGetLastError());
     return 0;
 }
 
@@ -2039,7 +2102,15 @@ int sml_step_exchange_end(sml_engine *h, int timestep, const double *f4d, const 
                                               take_tisr ? h->d_F + FCST_TISR : nullptr, h->d_G + G_TISR, take_tisr ? XG * YG : 0);
         h->launches++;
         CK(h, cudaGetLastError());
-        return sml_step_unpack_device(h, timestep);
+        if (sml_step_unpack_device(h, timestep)) return -1;
+        // bounded run-ahead: sleep (blocking event, no spinning) until the step enqueued two calls ago is done
+        const int slot = (int)(h->consumer_steps & 3);
+        if (!h->ev_ahead[slot]) CK(h, cudaEventCreateWithFlags(&h->ev_ahead[slot], cudaEventDisableTiming | cudaEventBlockingSync));
+        CK(h, cudaEventRecord(h->ev_ahead[slot], h->stream));
+        ++h->consumer_steps;
+        const int old_slot = (int)((h->consumer_steps + 1) & 3);   // recorded three calls ago
+        if (h->consumer_steps >= 3 && h->ev_ahead[old_slot]) CK(h, cudaEventSynchronize(h->ev_ahead[old_slot]));
+        return 0;
     }
     if (!tisr && !ahead) FAIL(h, "tisr_grid is required");
     // the forecast goes up on the copy stream in the overlapped mode (the main stream is busy with the look-ahead

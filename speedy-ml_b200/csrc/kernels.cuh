@@ -1061,6 +1061,94 @@ __global__ void k_build_inputs(const RegionDev *__restrict__ regs, const double 
         }
 }
 
+// k_exchange_fused: k_pack_grids and k_build_inputs as ONE cooperative launch for the device-resident step (ML-only
+// runs, and the `value` leg of bench.py): every CTA scatters its share of the gathered outvecs into G (after the wait
+// for the peers' flags), a grid barrier makes G complete, then the CTAs rebuild the local regions' feedback and
+// local_model.  Saves one launch boundary and one kernel ramp per step -- at 144 regions per GPU the four small kernels
+// and their gaps were a fifth of the step.  Same element-wise arithmetic as the two kernels it replaces: bit-identical.
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32x(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(512)
+k_exchange_fused(PackArgs a, const RegionDev *__restrict__ regs, int nregions, const double *__restrict__ F,
+                 double *__restrict__ fb_pool, double *__restrict__ lm_pool, int do_model, unsigned *__restrict__ ctr,
+                 unsigned target)
+{
+    if (a.world > 1) {
+        if ((int)threadIdx.x < 2 * a.world) {
+            const int kind = threadIdx.x / a.world, r = threadIdx.x % a.world;
+            const unsigned long long want = kind ? a.ocean_seq : a.seq;
+            const unsigned long long *f = a.my_flags + kind * MAX_PEERS + r;
+            const long long t0 = clock64();
+            while (want > 0 && ld_acquire_sys(f) < want) {
+                if (clock64() - t0 > 20000000000LL) {
+                    *a.err = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = gtid; i < a.total; i += nthreads) {
+        const int dst = a.out_dst[i];
+        double v = ld_cg_f64(a.gathered + i);
+        int bad = 0;
+        if (dst < a.w4d_hi) {
+            const int var = dst & 3;
+            if (var == 3 && v < 0.000001) v = 0.000001;
+            if (var == 0) bad = (v < 160.0 || v > 330.0) ? 8 : 0;
+            else if (var == 1) bad = (v < -150.0 || v > 150.0) ? 2 : 0;
+            else if (var == 2) bad = (v < -120.0 || v > 120.0) ? 4 : 0;
+            else bad = (v < -6.0 || v > 30.0) ? 16 : 0;
+        } else if (dst >= a.precip_lo && dst < a.precip_hi) {
+            if (v < 0.00001) v = 0.0;
+        }
+        if (!(fabs(v) <= 1.7976931348623157e308)) bad = 1;
+        if (bad) atomicOr(a.status, bad);
+        a.G[dst] = v;
+    }
+    if (a.sst_mode >= 0)
+        for (int e = gtid; e < 96 * 48; e += nthreads) {
+            double v;
+            if (a.sst_mode == 1) v = a.prescribed[e];
+            else v = ld_cg_f64(a.ocean_out + (size_t)a.cell_region[e] * a.ocean_P + a.cell_slot[e]);
+            if (a.mask[e] > 0.0) v = a.base[e];
+            if (v < 272.0) v = 272.0;
+            a.G[a.sst_off + e] = v;
+        }
+    // ---- grid barrier: G is complete (monotonic arrival counter, release / acquire at gpu scope)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_gpu_u32x(ctr) < target) {
+        }
+    }
+    __syncthreads();
+    // ---- feedback / local_model of the local regions (k_build_inputs)
+    for (int reg = blockIdx.x; reg < nregions; reg += gridDim.x) {
+        const RegionDev R = regs[reg];
+        for (int d = threadIdx.x; d < R.D; d += blockDim.x) {
+            double v = ld_cg_f64(a.G + R.fb_src[d]);
+            const int ms = R.fb_ms[d];
+            if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
+            fb_pool[R.fb_off + d] = v;
+        }
+        if (do_model)
+            for (int sidx = threadIdx.x; sidx < R.S; sidx += blockDim.x) {
+                double v = F[R.lm_src[sidx]];
+                const int ms = R.lm_ms[sidx];
+                if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
+                lm_pool[R.lm_off + sidx] = v;
+            }
+    }
+}
+
 // ocean reservoir feedback (src/mpires.f90:594-600, 776-781; intended semantics):
 //   ring(:, slot) = the atmosphere reservoir's standardised lowest-level + logp feedback
 //   feedback(1:A) = sum(ring, dim=2) / nslots   (slot order, divides by nslots even while slots are zero)

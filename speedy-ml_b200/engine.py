@@ -121,6 +121,7 @@ _SIGNATURES = {
     "sml_peer_check": ([C.c_void_p], C.c_int),
     "sml_step_pack_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_step_unpack_device": ([C.c_void_p, C.c_int], C.c_int),
+    "sml_step_exchange_device": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_begin": ([C.c_void_p, C.c_int, _ip, C.c_int, C.c_int], C.c_int),
     "sml_train_feed": ([C.c_void_p, _dp, _lp, _dp, _lp, C.c_int, C.c_int], C.c_int),
     "sml_train_global_series": ([C.c_void_p, _dp, _dp, C.c_int], C.c_int),
@@ -673,6 +674,10 @@ class Engine:
 
     def step_unpack_device(self, timestep=0):
         self._ck(self.lib.sml_step_unpack_device(self.h, timestep))
+
+    def step_exchange_device(self, timestep=0):
+        """pack + unpack of the device-resident step as one cooperative launch"""
+        self._ck(self.lib.sml_step_exchange_device(self.h, timestep))
 
     def exchange_buffers(self):
         """-> dict of DeviceArray: outvec_slab, gathered, G, F"""

@@ -122,6 +122,9 @@ class EngineShard:
     def unpack(self, t):
         self.eng.step_unpack_device(t)
 
+    def exchange_device(self, t):
+        self.eng.step_exchange_device(t)
+
     def exchange_begin(self, t, copy_out=True):
         if not copy_out:
             return self.eng.step_exchange_begin(t, copy_out=False)   # only enqueues the grid assembly
@@ -268,7 +271,12 @@ class HybridStepper:
     def device_step(self, t: int):
         """everything resident on the device; the forecast buffer F keeps what the last host step left"""
         stepped = self._predict(t)
-        if not getattr(self.s, "comm_ready", False):
+        if self.world > 1 and not getattr(self.s, "comm_ready", False):
             self._gather_outvecs(stepped)
-        self.s.pack(t)
-        self.s.unpack(t)
+            self.s.pack(t)
+            self.s.unpack(t)
+        elif hasattr(self.s, "exchange_device"):
+            self.s.exchange_device(t)        # scatter + gather in one cooperative launch
+        else:
+            self.s.pack(t)
+            self.s.unpack(t)

@@ -495,3 +495,28 @@ def test_zero_copy_staging_views(E, small_model):
     eng.step_exchange_end(1, s4, s2, st)
     for r, (fb, lm) in fb_copy.items():
         assert np.array_equal(eng.feedback_get(r), fb) and np.array_equal(eng.local_model_get(r), lm)
+
+
+def test_fused_exchange_kernel_equals_pack_then_unpack(E, small_model):
+    """sml_step_exchange_device (one cooperative launch: scatter, grid barrier, gather) against the two separate kernels:
+    grids, feedback and local_model bit for bit"""
+    ws, eng, rcs = small_model
+    G = initial_grids()
+    eng.set_sst_static(G["base_sst"], G["sea_mask"])
+    eng.set_sst_prescribed(G["base_sst"])
+    _reset_small_model(ws, eng, rcs, 77)
+    eng.predict()
+    probe = (0, 23, 555, 700, 1128, 1151)
+    eng.step_pack_device(1)
+    eng.step_unpack_device(1)
+    ref_grids = eng.grids_get()
+    ref = {r: (eng.feedback_get(r), eng.local_model_get(r)) for r in probe}
+    for r in probe:                                   # scramble what the exchange rebuilds
+        eng.feedback_set(r, np.zeros(ws[r]["D"]))
+        eng.local_model_set(r, np.zeros(ws[r]["S"]))
+    for _ in range(3):                                # the arrival counter of the grid barrier is monotonic: several calls
+        eng.step_exchange_device(1)
+    for a, b in zip(eng.grids_get(), ref_grids):
+        assert np.array_equal(a, b)
+    for r, (fb, lm) in ref.items():
+        assert np.array_equal(eng.feedback_get(r), fb) and np.array_equal(eng.local_model_get(r), lm)

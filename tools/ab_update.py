@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A/B of the update-only kernels (synchronize path) on one engine: k_update<RPT> (x gathered from L2) against
-k_update_sx<RPT> (x staged in shared memory) at several row splits.  The engine re-reads SML_UPDATE_KERNEL /
+"""A/B of the update-only kernels (synchronize path) on one engine: k_update<RPT> (x gathered from L2), k_update_sx<RPT>
+(x staged in shared memory) at several row splits, and k_update_ring (round 2: the adjacency streamed by a TMA producer warp
+through a shared-memory ring) at several ring depths / tile sizes.  The engine re-reads SML_UPDATE_KERNEL /
 SML_UPDATE_RPT / SML_UPDATE_SPLIT at every launch, so one set-up serves all variants.  One JSON line per variant."""
 import argparse
 import importlib
@@ -40,12 +41,21 @@ def main():
     rng = np.random.default_rng(0)
     inputs = [np.asfortranarray(rng.standard_normal((D, args.steps))) for (_, D) in dims]
     peak, _ = bench.measured_peak()
-    variants = [("global", 4, 0, 0), ("sx", 2, 0, 0), ("sx", 2, 1, 512), ("sx", 2, 1, 480), ("sx", 2, 1, 448), ("sx", 2, 1, 384),
-                ("sx", 2, 2, 0), ("sx", 1, 1, 0), ("sx", 1, 2, 0), ("global", 4, 0, 0)]
+    # (kernel, rows per thread, row splits, threads | ring: stages, tile rows)
+    variants = [("global", 4, 0, 0), ("sx", 2, 0, 0), ("sx", 2, 2, 0), ("ring", 2, 0, 0), ("ring", 3, 0, 0), ("ring", 4, 0, 0),
+                ("ring", 3, 2, 0), ("ring", 4, 0, 320), ("ring", 6, 0, 256), ("global", 4, 0, 0)]
     ref = None
     for kern, rpt, split, threads in variants:
         os.environ["SML_UPDATE_KERNEL"] = kern
         os.environ["SML_UPDATE_RPT"] = str(rpt)
+        os.environ.pop("SML_UPDATE_STAGES", None)
+        os.environ.pop("SML_UPDATE_TILE_ROWS", None)
+        if kern == "ring":
+            os.environ["SML_UPDATE_STAGES"] = str(rpt)
+            os.environ.pop("SML_UPDATE_RPT", None)
+            if threads:
+                os.environ["SML_UPDATE_TILE_ROWS"] = str(threads)
+                threads = 0
         for key, val in (("SML_UPDATE_SPLIT", split), ("SML_UPDATE_THREADS", threads)):
             if val:
                 os.environ[key] = str(val)
