@@ -245,6 +245,25 @@ int dev_upload(sml_engine *h, HostRegion *hr, const T *src, size_t count, const 
     return 0;
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor in the stream is
+// still draining; it calls pdl_wait() before touching dependent memory (kernels.cuh).  SML_PDL=0 launches the ordinary way.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    static const bool pdl = !(getenv("SML_PDL") && atoi(getenv("SML_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 int check_ready(sml_engine *h, int kind)
 {
     if (!h) return -1;
@@ -1397,9 +1416,9 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
     if (K.persist && all) {
         // persistent kernel: one CTA per slot, each with its statically balanced run of items
         const StepSeg *segs = (d_items == K.d_items_split) ? K.d_segs_split : K.d_segs;
-        k_step_persist<<<K.nslots, NTHREADS, K.p_smem_bytes, h->stream>>>(
-            K.d_regs, segs, K.d_slots, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm, K.d_temp, K.d_partials,
-            K.ldw, K.p_stage_cols, K.p_ldp, K.p_xs_cap, K.part_rows, K.p_cpi, K.p_stages);
+        CK(h, launch_pdl(k_step_persist, dim3(K.nslots), dim3(NTHREADS), K.p_smem_bytes, h->stream,
+                         K.d_regs, segs, K.d_slots, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm, K.d_temp, K.d_partials,
+                         K.ldw, K.p_stage_cols, K.p_ldp, K.p_xs_cap, K.part_rows, K.p_cpi, K.p_stages));
         h->launches++;
         CK(h, cudaGetLastError());
         return 0;
@@ -1413,10 +1432,9 @@ static int launch_step(sml_engine *h, KindState &K, const StepItem *d_items, int
     static const bool lpt = getenv("SML_LPT") != nullptr;
     const bool full = (d_items == K.d_items || d_items == K.d_items_split) && nitems == K.nitems;
     const int item_base = full ? 0 : (int)(d_items - K.d_items);
-    k_step<STAGES><<<nitems, NTHREADS, smem, h->stream>>>(K.d_regs, d_items, (full && lpt) ? K.d_order : nullptr, item_base,
-                                                          K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm,
-                                                          K.d_temp, K.d_partials, K.ldw, K.stage_cols, K.stage_bytes,
-                                                          K.xs_cap, do_readout);
+    CK(h, launch_pdl(k_step<STAGES>, dim3(nitems), dim3(NTHREADS), smem, h->stream, K.d_regs, d_items,
+                     (full && lpt) ? K.d_order : nullptr, item_base, K.d_x[K.cur], K.d_x[K.cur ^ 1], u_pool, u_offs, u_t, K.d_lm,
+                     K.d_temp, K.d_partials, K.ldw, K.stage_cols, K.stage_bytes, K.xs_cap, do_readout));
     h->launches++;
     CK(h, cudaGetLastError());
     return 0;
@@ -1452,11 +1470,11 @@ static int launch_finish(sml_engine *h, KindState &K, int model_part)
     // sequential mode: one group of threads sums the partials; overlapped mode: 4 groups share the model columns
     const int threads = model_part ? FIN_GROUPS * FIN_PMAX : FIN_PMAX;
     const size_t fsmem = sizeof(double) * ((K.P + 1) & ~1) * (model_part ? FIN_GROUPS + 1 : 1);
-    k_readout_finish<<<(unsigned)K.regs.size(), threads, fsmem, h->stream>>>(K.d_regs, K.d_partials, K.ldw, K.d_out, 1,
-                                                                         model_part, K.d_lm, pt, seq, peer_off, h->d_done,
-                                                                         (atmo && h->contribs && model_part) ? h->d_vp : nullptr,
-                                                                         (atmo && h->contribs && model_part) ? h->d_vml : nullptr,
-                                                                         K.persist ? 1 : 0, (!atmo && !model_part) ? K.d_lm : nullptr);
+    CK(h, launch_pdl(k_readout_finish, dim3((unsigned)K.regs.size()), dim3(threads), fsmem, h->stream, K.d_regs, K.d_partials, K.ldw,
+                     K.d_out, 1, model_part, K.d_lm, pt, seq, peer_off, h->d_done,
+                     (atmo && h->contribs && model_part) ? h->d_vp : nullptr,
+                     (atmo && h->contribs && model_part) ? h->d_vml : nullptr, K.persist ? 1 : 0,
+                     (!atmo && !model_part) ? K.d_lm : nullptr));
     h->launches++;
     CK(h, cudaGetLastError());
     if (!atmo && h->peers.world > 1) h->ocean_publish_pending = true;   // pushed by the next grid assembly
@@ -1674,7 +1692,7 @@ int sml_step_pack_device(sml_engine *h, int timestep)
     const int nsst = (a.sst_mode >= 0) ? (XG * YG + 255) / 256 : 0;
     cudaEvent_t *pe = phase_events(h, h->pt_pack);
     if (pe) CK(h, cudaEventRecord(pe[0], h->stream));
-    k_pack_grids<<<a.nsc + nsst, 256, 0, h->stream>>>(a);
+    CK(h, launch_pdl(k_pack_grids, dim3(a.nsc + nsst), dim3(256), 0, h->stream, a));
     if (pe) CK(h, cudaEventRecord(pe[1], h->stream));
     h->launches++;
     CK(h, cudaGetLastError());
@@ -1689,8 +1707,10 @@ int sml_step_exchange_device(sml_engine *h, int timestep)
     CK(h, cudaSetDevice(h->p.device));
     if (h->overlap && h->ahead_pending) FAIL(h, "sml_step_exchange_device is the sequential device step; close the overlapped step first");
     KindState &K = h->kinds[SML_ATMO];
-    static const bool off = getenv("SML_FUSED_EXCHANGE") && atoi(getenv("SML_FUSED_EXCHANGE")) == 0;   // A/B switch
-    if (off) {
+    // measured (profiles/round2_summary.md): 18.6 us against 19.7 us for the two kernels at 144 regions per GPU, but 36 us
+    // against 23 us at 1152 (148 CTAs walk 1152 regions) -- so the separate kernels stay the default, this is the A/B switch
+    static const bool fused = getenv("SML_FUSED_EXCHANGE") && atoi(getenv("SML_FUSED_EXCHANGE")) == 1;
+    if (!fused) {
         if (sml_step_pack_device(h, timestep)) return -1;
         return sml_step_unpack_device(h, timestep);
     }
@@ -1893,7 +1913,7 @@ int sml_step_predict_ahead(sml_engine *h, int timestep)
     if (!h->tisr_fresh) FAIL(h, "overlapped step: call sml_set_tisr with the date's TISR field before the exchange begins");
     KindState &K = h->kinds[SML_ATMO];
     if (h->n_ocean_fb > 0 && timestep < 1) FAIL(h, "timestep must be the 1-based hybrid step");
-    k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm, 0, 1);
+    CK(h, launch_pdl(k_build_inputs, dim3((unsigned)K.regs.size()), dim3(256), 0, h->stream, K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm, 0, 1));
     h->launches++;
     if (h->n_ocean_fb > 0) {
         k_build_ocean_inputs<<<h->n_ocean_fb, 128, 0, h->stream>>>(h->d_ocean_fb, h->d_G, K.d_fb,
@@ -2052,8 +2072,8 @@ int sml_step_unpack_device(sml_engine *h, int timestep)
     KindState &K = h->kinds[SML_ATMO];
     if (h->overlap && h->ahead_pending) {
         // the forecast is in F: local_model, then v_p = W_out[:, 0:S]*local_model joins the partials
-        k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
-                                                                       h->p.ml_only ? 0 : 1, 0);
+        CK(h, launch_pdl(k_build_inputs, dim3((unsigned)K.regs.size()), dim3(256), 0, h->stream, K.d_regs, h->d_G, h->d_F, K.d_fb,
+                         K.d_lm, h->p.ml_only ? 0 : 1, 0));
         h->launches++;
         if (launch_finish(h, K, 1)) return -1;
         h->ahead_pending = false;
@@ -2064,8 +2084,8 @@ int sml_step_unpack_device(sml_engine *h, int timestep)
         FAIL(h, "timestep must be the 1-based hybrid step (it selects the ring slot mod(timestep-1,%d)+1)", h->ocean_slots);
     cudaEvent_t *pe = phase_events(h, h->pt_unpack);
     if (pe) CK(h, cudaEventRecord(pe[0], h->stream));
-    k_build_inputs<<<(unsigned)K.regs.size(), 256, 0, h->stream>>>(K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
-                                                                   h->p.ml_only ? 0 : 1, 1);
+    CK(h, launch_pdl(k_build_inputs, dim3((unsigned)K.regs.size()), dim3(256), 0, h->stream, K.d_regs, h->d_G, h->d_F, K.d_fb, K.d_lm,
+                     h->p.ml_only ? 0 : 1, 1));
     if (pe) CK(h, cudaEventRecord(pe[1], h->stream));
     h->launches++;
     if (h->n_ocean_fb > 0) {

@@ -57,6 +57,13 @@ constexpr int NCONS = 544;            // consumer threads (17 warps); 2*NCONS = 
 constexpr int NTHREADS = NCONS + 32;  // + one TMA producer warp
 constexpr int NCONS_WARPS = NCONS / 32;
 
+// Programmatic dependent launch (PDL): the four kernels of a step are launched with programmatic stream serialization, so
+// a kernel's CTAs may be scheduled while its predecessor is still draining.  pdl_launch() lets the successor be staged as
+// early as possible; pdl_wait() -- the first thing every such kernel does before touching memory its predecessor writes or
+// reads -- returns once the predecessor has completed and its writes are visible.  Launched the ordinary way both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -221,6 +228,7 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
     uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * NCONS);
     uint64_t *empty = full + STAGES;
 
+    pdl_launch();
     const int item = order ? order[blockIdx.x] : (int)blockIdx.x;  // optional launch-order permutation
     const StepItem it = items[item];
     const RegionDev R = regs[it.reg];
@@ -240,6 +248,7 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
         }
         __syncthreads();
     }
+    pdl_wait();   // the plan tables and W_out are constants; the state, inputs and partials belong to the predecessors
 
     if (warp == NCONS_WARPS) {
         // ---------------- TMA producer ----------------
@@ -354,6 +363,7 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
     uint64_t *full = reinterpret_cast<uint64_t *>(xs + xs_cap);
     uint64_t *empty = full + nstages;
 
+    pdl_launch();
     const int2 slot = slots[blockIdx.x];   // (first item, item count)
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -369,6 +379,8 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
 
     if (warp == NCONS_WARPS) {
         // ---------------- TMA producer warp: the tile sequence of every item of the slot, back to back ----------------
+        // It does NOT wait for the predecessor kernel (PDL): the plan tables and W_out are constants of the step, so the
+        // ring is already full when the consumers are released
         int s = 0;
         uint32_t par = 1;   // parity to wait for on empty[s]: passes at once on the first lap
         for (int i = 0; i < slot.y; ++i) {
@@ -400,6 +412,7 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
     }
 
     // ---------------- consumers ----------------
+    pdl_wait();   // state, inputs, local_model and the partials belong to the predecessor kernels of the stream
     // lane -> (row pair within the warp, column group): the 8 lanes of one 128-bit load phase are rpw consecutive row
     // pairs (contiguous 16-byte pieces of a column) x 8/rpw column groups, which hit 32 distinct banks when the column
     // stride is 2*ldp = 16 (mod 32) words -- true for the UNPADDED W_out of the standard tiling (ldw = 136)
@@ -819,7 +832,9 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
 {
     extern __shared__ __align__(16) double s_fin[];   // [pstride] outvec staging, then [FIN_GROUPS][pstride] (overlapped mode)
     __shared__ int s_last;
-    const RegionDev R = regs[blockIdx.x];
+    pdl_launch();
+    const RegionDev R = regs[blockIdx.x];   // the region table is constant after sml_finalize
+    pdl_wait();
     const int pstride = (R.P + 1) & ~1;
     double *s_out = s_fin, *s_vp = s_fin + pstride;
     const int grp = threadIdx.x / FIN_PMAX, p0 = threadIdx.x % FIN_PMAX;
@@ -991,6 +1006,8 @@ struct PackArgs {
 
 __global__ void k_pack_grids(PackArgs a)
 {
+    pdl_launch();
+    pdl_wait();
     if (a.world > 1) {
         if ((int)threadIdx.x < 2 * a.world) {
             const int kind = threadIdx.x / a.world, r = threadIdx.x % a.world;
@@ -1044,7 +1061,9 @@ __global__ void k_build_inputs(const RegionDev *__restrict__ regs, const double 
                                const double *__restrict__ F, double *__restrict__ fb_pool,
                                double *__restrict__ lm_pool, int do_model, int do_feedback)
 {
+    pdl_launch();
     const RegionDev R = regs[blockIdx.x];
+    pdl_wait();
     if (do_feedback)
         for (int d = threadIdx.x; d < R.D; d += blockDim.x) {
             double v = G[R.fb_src[d]];
