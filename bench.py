@@ -591,12 +591,15 @@ def run_gpu(args):
     for i in range(args.warmup):
         device_step(i + 1)
     launches0 = eng.kernel_launch_count()
+    dev_ms, dev_wall = timed(device_step, args.steps, 1)       # the headline: nothing but the step's own launches in the stream
+    launches = eng.kernel_launch_count() - launches0
+    # per-kernel times from a SECOND pass of the same steps with the engine's CUDA-event brackets on (seven event records
+    # per step sit between the kernels and cost the step ~3 %, so they stay out of the headline pass)
     eng.profile(True)
-    dev_ms, dev_wall = timed(device_step, args.steps, 1)
+    prof_ms, _ = timed(device_step, args.steps, 1 + args.steps)
     k_step_ms, k_fin_ms, k_cnt = eng.kernel_times()
     pack_ms, unpack_ms, ph_cnt = eng.phase_times()
     eng.profile(False)
-    launches = eng.kernel_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
 
     # sanity: the model state is finite
@@ -658,7 +661,10 @@ def run_gpu(args):
                          "finish_kernel_ms_per_launch": k_fin_ms / max(1, k_cnt), "launches_timed": k_cnt,
                          "pack_kernel_ms_per_launch": pack_ms / max(1, ph_cnt),
                          "unpack_kernel_ms_per_launch": unpack_ms / max(1, ph_cnt),
-                         "other_ms_per_step": ms_per_step - (step_kernel_ms + (k_fin_ms + pack_ms + unpack_ms) / max(1, k_cnt))},
+                         "profiled_pass_ms_per_step": prof_ms / args.steps,
+                         "other_ms_per_step": prof_ms / args.steps - (step_kernel_ms + (k_fin_ms + pack_ms + unpack_ms) / max(1, k_cnt)),
+                         "note": "kernel times come from a second pass with CUDA-event brackets between the kernels; "
+                                 "ms_per_step / value come from the un-instrumented pass"},
             "clocks": clocks,
             "wall_ms_per_step": dev_wall / args.steps,
         }
