@@ -823,7 +823,7 @@ __global__ void k_win_dense(const RegionDev *__restrict__ regs, const int *__res
 constexpr int FIN_GROUPS = 4;     // column groups of the model-part GEMV
 constexpr int FIN_PMAX = 160;     // threads per group (outputs are strided over them: any chunk_size_prediction)
 
-__global__ void __launch_bounds__(FIN_GROUPS *FIN_PMAX)
+__global__ void __launch_bounds__(FIN_GROUPS *FIN_PMAX, 2)
 k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ partials, int ldw_max,
                  double *__restrict__ out_pool, int unstandardize, int model_part,
                  const double *__restrict__ lm_pool, PeerTable pt, unsigned long long seq,
@@ -843,18 +843,23 @@ k_readout_finish(const RegionDev *__restrict__ regs, const double *__restrict__ 
         // v_p = W_out[:, 0:S] * local_model: group g takes columns g, g+4, ...; 4 independent FMA chains per thread
         // keep the loads in flight; the groups are combined in fixed order below (deterministic)
         const double *lm = lm_pool + R.lm_off;
+        // 8 independent FMA chains per thread: eight W_out loads in flight each (ncu, round 2: with four the kernel sat at
+        // 26 % of the DRAM roof, latency-bound on its 197 MB); the chains are combined in fixed order (deterministic)
         for (int p = p0; p < R.P; p += FIN_PMAX) {
             const double *w = R.wout + p;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            double a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = 0.0;
             int j = grp;
-            for (; j + 3 * FIN_GROUPS < R.S; j += 4 * FIN_GROUPS) {
-                a0 = fma(w[(size_t)j * R.ldw], lm[j], a0);
-                a1 = fma(w[(size_t)(j + FIN_GROUPS) * R.ldw], lm[j + FIN_GROUPS], a1);
-                a2 = fma(w[(size_t)(j + 2 * FIN_GROUPS) * R.ldw], lm[j + 2 * FIN_GROUPS], a2);
-                a3 = fma(w[(size_t)(j + 3 * FIN_GROUPS) * R.ldw], lm[j + 3 * FIN_GROUPS], a3);
+            for (; j + 7 * FIN_GROUPS < R.S; j += 8 * FIN_GROUPS) {
+                double wv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(j + u * FIN_GROUPS) * R.ldw);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = fma(wv[u], lm[j + u * FIN_GROUPS], a[u]);
             }
-            for (; j < R.S; j += FIN_GROUPS) a0 = fma(w[(size_t)j * R.ldw], lm[j], a0);
-            s_vp[grp * pstride + p] = (a0 + a1) + (a2 + a3);
+            for (; j < R.S; j += FIN_GROUPS) a[0] = fma(__ldg(w + (size_t)j * R.ldw), lm[j], a[0]);
+            s_vp[grp * pstride + p] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
         }
         __syncthreads();
     }
