@@ -146,7 +146,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.idx), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(self.idx), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -535,6 +535,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks and throttle reasons are sampled from here to the end of the timed regions (a 20-step region lasts ~30 ms,
+    # too short on its own for nvidia-smi's sampling period).  nvidia-smi is started NOW and given time to initialise: its
+    # start-up competes with the root's host thread and stretched a 20-step e2e region by 15 % when it fell inside it
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.6)
+
     # ---- correctness inside the scaling run: 6 sequential hybrid steps from the fixed start, checksum of the grids
     for t in range(1, CHECK_STEPS + 1):
         stepper.step(t, host_model, F["tisr"])
@@ -569,12 +577,6 @@ def run_gpu(args):
         eng.set_overlap(True)
     for i in range(args.warmup):
         e2e_step(CHECK_STEPS + i + 1)
-    # clocks and throttle reasons are sampled across BOTH timed regions (e2e, then device-resident) and the warm-up
-    # between them: a 20-step timed region lasts ~30 ms, too short on its own for nvidia-smi's sampling period
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.05)
     e2e_ms, e2e_wall = timed(e2e_step, args.steps, CHECK_STEPS + args.warmup + 1)
     # where the host side of an e2e step spends its time (a few extra steps after the timed region, clocked per section)
     e2e_sections = {}
