@@ -82,6 +82,14 @@ struct KindState {
     size_t p_smem_bytes = 0;
     int *d_one_region = nullptr;  // region index for one region's synchronize
     int one_region = -1;
+    int *d_sync_list = nullptr;   // regions of one k_sync_persist launch
+    size_t sync_list_cap = 0;
+    // tile-major copy of the adjacency + compact W_in for k_sync_persist (k_sync_pack), built lazily
+    unsigned char *d_sync_pack = nullptr;
+    long long *d_sync_pack_off = nullptr;
+    size_t sync_pack_cap = 0;
+    int pack_tr = 0, pack_w = 0;
+    bool pack_valid = false;
     size_t smem_bytes = 0;
     bool any_dense = false;
     int64_t alg_bytes = 0, alg_bytes_update = 0;
@@ -355,7 +363,7 @@ static void free_kind(KindState &K)
         for (void *p : r.allocs) cudaFree(p);
     cudaFree(K.d_regs); cudaFree(K.d_items); cudaFree(K.d_items_split); cudaFree(K.d_order); cudaFree(K.d_one_region); cudaFree(K.d_x[0]); cudaFree(K.d_x[1]); cudaFree(K.d_fb);
     cudaFree(K.d_lm); cudaFree(K.d_out); cudaFree(K.d_partials); cudaFree(K.d_temp); cudaFree(K.d_fb_offs);
-    cudaFree(K.d_in); cudaFree(K.d_in_offs);
+    cudaFree(K.d_in); cudaFree(K.d_in_offs); cudaFree(K.d_sync_list); cudaFree(K.d_sync_pack); cudaFree(K.d_sync_pack_off);
     cudaFree(K.d_segs); cudaFree(K.d_segs_split); cudaFree(K.d_slots);
     cudaFree(K.d_gen); cudaFree(K.d_gen_of_local);
 }
@@ -1223,6 +1231,7 @@ int sml_finalize(sml_engine *h)
     CK(h, cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
     CK(h, cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
     CK(h, cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) h->kinds[k].pack_valid = false;
     h->finalized = true;
     return 0;
 }
@@ -1537,6 +1546,110 @@ int sml_predict(sml_engine *h, int kind)
     return 0;
 }
 
+// The whole time loop of synchronize in ONE launch (k_sync_persist): a CTA per SM runs all `length` steps of a region
+// before it takes the next one, the state vector stays in shared memory and the adjacency is re-read from L2.
+// Returns 1 when launched, 0 when the shard does not qualify (dense W_in, odd sizes, no room in shared memory, or
+// SML_SYNC_KERNEL=steps) and the caller launches step by step, -1 on error.  The state pool K.d_x[K.cur] is updated in place.
+static int launch_sync_persist(sml_engine *h, KindState &K, int first, int last, bool one_region, int length)
+{
+    const char *sk = getenv("SML_SYNC_KERNEL");
+    if (sk && std::string(sk) == "steps") return 0;
+    if (K.any_dense) return 0;
+    std::vector<int> list;
+    for (int i = first; i < last; ++i) {
+        const HostRegion &hr = K.regs[i];
+        if (!hr.uploaded) continue;
+        const RegionDev &d = hr.dev;
+        if (d.win_mode != 0 || d.n % 4 != 0 || d.D % 2 != 0 || d.n <= 0 || d.D <= 0) return 0;
+        list.push_back(i);
+    }
+    if (list.empty()) return 1;
+    (void)one_region;
+    // the ring geometry follows the whole kind (not the listed regions), so that one pack serves every call
+    int w_max = 1;
+    const int n_max = K.n_max, D_max = K.D_max;
+    for (const HostRegion &hr : K.regs)
+        if (hr.uploaded) w_max = std::max(w_max, hr.dev.ell_w);
+    // plan: ngroups consumer groups of tr threads, nstages ring slots of tr rows (nstages a multiple of ngroups)
+    const int xs_cap = (n_max + 1) & ~1, us_cap = (D_max + 1) & ~1;
+    const size_t fixed = sizeof(double) * 2 * ((size_t)xs_cap + us_cap);
+    if (n_max > 65535 || D_max > 65535) return 0;   // the tile-major pack stores 16-bit column indices
+    const size_t row_bytes = (size_t)sp_row_bytes(w_max);
+    const size_t budget = 227 * 1024 - 128;
+    int ngroups = getenv("SML_SYNC_GROUPS") ? atoi(getenv("SML_SYNC_GROUPS")) : 2;
+    ngroups = std::max(1, std::min(ngroups, 4));
+    int nst = getenv("SML_SYNC_STAGES") ? atoi(getenv("SML_SYNC_STAGES")) : 2 * ngroups;
+    nst = std::max(ngroups, std::min(nst, 12)) / ngroups * ngroups;
+    if (fixed + 4096 > budget) return 0;
+    const size_t bar_bytes = 8 * (2 * (size_t)nst + 5);
+    int tr = (int)((budget - fixed - bar_bytes) / ((size_t)nst * row_bytes));
+    tr = std::min(tr, (SP_MAX_THREADS - 32) / ngroups) / 32 * 32;
+    if (getenv("SML_SYNC_TILE_ROWS")) tr = std::min(tr, std::max(32, atoi(getenv("SML_SYNC_TILE_ROWS")) / 32 * 32));
+    if (tr < 64) return 0;
+    {   // even out the tiles of the largest region: same tile count, no short last tile
+        const int nt = (n_max + tr - 1) / tr;
+        tr = std::min(tr, ((n_max + nt - 1) / nt + 31) / 32 * 32);
+    }
+    const size_t tile_stride = (size_t)tr * row_bytes;
+    const size_t smem = fixed + (size_t)nst * tile_stride + bar_bytes;
+    if (smem > 227 * 1024 || tile_stride >= (1u << 20)) return 0;
+    // the tile-major pack of this geometry (all regions of the kind)
+    if (!K.pack_valid || K.pack_tr != tr || K.pack_w != w_max) {
+        const int nloc = (int)K.regs.size();
+        std::vector<long long> poff(nloc, 0);
+        size_t total = 0;
+        for (int i = 0; i < nloc; ++i) {
+            if (!K.regs[i].uploaded) continue;
+            poff[i] = (long long)total;
+            total += (size_t)((K.regs[i].dev.n + tr - 1) / tr) * tile_stride;
+        }
+        if (total > K.sync_pack_cap) {
+            cudaFree(K.d_sync_pack);
+            K.d_sync_pack = nullptr;
+            K.sync_pack_cap = 0;
+            CK(h, cudaMalloc(&K.d_sync_pack, total));
+            K.sync_pack_cap = total;
+        }
+        if (!K.d_sync_pack_off) CK(h, cudaMalloc(&K.d_sync_pack_off, sizeof(long long) * nloc));
+        CK(h, cudaMemcpyAsync(K.d_sync_pack_off, poff.data(), sizeof(long long) * nloc, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));   // `poff` is a local
+        k_sync_pack<<<dim3((unsigned)((n_max + tr - 1) / tr), (unsigned)nloc), 256, 0, h->stream>>>(K.d_regs, K.d_sync_pack,
+                                                                                                     K.d_sync_pack_off, tr, w_max);
+        h->launches++;
+        CK(h, cudaGetLastError());
+        K.pack_valid = true;
+        K.pack_tr = tr;
+        K.pack_w = w_max;
+    }
+    if (K.sync_list_cap < list.size()) {
+        cudaFree(K.d_sync_list);
+        K.d_sync_list = nullptr;
+        K.sync_list_cap = 0;
+        CK(h, cudaMalloc(&K.d_sync_list, sizeof(int) * K.regs.size()));
+        K.sync_list_cap = K.regs.size();
+    }
+    CK(h, cudaMemcpyAsync(K.d_sync_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));   // `list` is a local
+    int ctas = getenv("SML_SYNC_CTAS") ? atoi(getenv("SML_SYNC_CTAS")) : h->num_sms;
+    ctas = std::max(1, std::min({ctas, (int)list.size(), 4 * h->num_sms}));
+    // compile-time width for the common cases (one column slab, 2 or 3 value pairs), any width otherwise
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<ctas, ngroups * tr + 32, smem, h->stream>>>(K.d_regs, K.d_sync_list, (int)list.size(), K.d_x[K.cur], K.d_in, K.d_in_offs,
+                                                           length, xs_cap, us_cap, w_max, nst, tr, ngroups, K.d_sync_pack,
+                                                           K.d_sync_pack_off);
+        return cudaSuccess;
+    };
+    const bool generic = getenv("SML_SYNC_GENERIC") != nullptr;   // test hook: the any-width instantiation
+    if (w_max <= 4 && !generic) CK(h, launch(k_sync_persist<2>));
+    else if (w_max <= 6 && !generic) CK(h, launch(k_sync_persist<3>));
+    else CK(h, launch(k_sync_persist<0>));
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return 1;
+}
+
 int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, int ld, int length,
                     const int64_t *offsets)
 {
@@ -1593,7 +1706,9 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
         CK(h, cudaEventCreate(&se1));
         CK(h, cudaEventRecord(se0, h->stream));
     }
-    for (int t = 0; t < length; ++t) {
+    int persisted = launch_sync_persist(h, K, first, last, region != SML_ALL_REGIONS, length);
+    if (persisted < 0) return -1;
+    for (int t = 0; t < length && !persisted; ++t) {
         if (region != SML_ALL_REGIONS) {
             // the untouched regions keep their state: only this region's slice of the ping-pong pair alternates, and
             // ONE copy at the end brings it back to the current buffer when the step count is odd
@@ -1603,7 +1718,7 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
             K.cur ^= 1;
         }
     }
-    if (region != SML_ALL_REGIONS && (length & 1)) {
+    if (!persisted && region != SML_ALL_REGIONS && (length & 1)) {
         const RegionDev &d = K.regs[first].dev;
         CK(h, cudaMemcpyAsync(K.d_x[K.cur] + d.x_off, K.d_x[K.cur ^ 1] + d.x_off, (size_t)d.n * 8,
                               cudaMemcpyDeviceToDevice, h->stream));
@@ -2282,6 +2397,7 @@ int sml_adjacency_scale(sml_engine *h, int kind, const double *factor)
     CK(h, cudaMemcpyAsync(df, factor, sizeof(double) * nloc, cudaMemcpyHostToDevice, h->stream));
     k_adj_scale<<<dim3(32, nloc), 256, 0, h->stream>>>(K.d_regs, df);
     h->launches++;
+    K.pack_valid = false;   // the spin-up kernel's tile-major copy holds the old values
     if (K.d_gen) {   // generated regions keep their COO on the device: reservoir%vals is rescaled there as well
         k_coo_scale<<<dim3(32, nloc), 256, 0, h->stream>>>(K.d_gen, K.d_gen_of_local, df);
         h->launches++;

@@ -793,6 +793,233 @@ k_update_ring(const RegionDev *__restrict__ regs, const int *__restrict__ region
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_sync_persist: the WHOLE time loop of synchronize in one launch (src/mod_reservoir.f90:1354-1381, the slab-ocean
+// twin src/mod_slab_ocean_reservoir.f90:1237-1266):   do i = 1, T:  x <- (1-leak) x + leak tanh(A x + W_in u(:, i)).
+// A step-per-launch kernel streams every region's adjacency from HBM once per step (k_update_ring: 0.80 of the HBM roof
+// and no further).  Regions do not interact during the spin-up, so the loop order can be turned inside out: ONE CTA per
+// SM takes a region and runs all T steps of it before the next region.  Then
+//   * the state vector never leaves shared memory (two copies, read one / write the other, one consumer barrier per step);
+//   * the region's adjacency (484 KB at the headline config) is re-read every step by the TMA producer warp, but only
+//     one region per SM is live at any time: 148 x 484 KB = 72 MB stays resident in the 126 MB L2, so steps 2..T stream from
+//     L2, not from HBM -- cache blocking over time, which a launch per step cannot have at 1152 regions (558 MB per step);
+//   * the step's input vector u(:, t) arrives by one bulk copy into a two-deep buffer of its own;
+//   * the tiles come from a TILE-MAJOR copy of the adjacency (k_sync_pack): one bulk copy per tile.  Fed from the
+//     slot-major ELL (2W+2 copies of 1.5-3 KB per tile) the first version ran at exactly the speed of the step launches
+//     -- 17.6 us per region-step, the producer warp's ~140 cycles per copy x 14 copies x 15 tiles.
+// Ring: nstages slots of `tr` rows, `ngroups` consumer groups of `tr` threads (one row per thread); tile g (counted over
+// the whole launch) lives in slot g % nstages and belongs to group g % ngroups; nstages % ngroups == 0, so a slot is
+// always drained by the same group and a parity wait can never alias an older phase.
+// Per-row arithmetic and order are those of update_row: the states are bit-identical to T launches of any of the
+// update kernels above.  The state pool is updated in place.  Needs every listed region in compact-W_in form with
+// n % 4 == 0 and an even D (bulk copies are 16-byte multiples); the host falls back to step launches otherwise.
+// grid min(regions, SMs); block ngroups*tr + 32; dynamic shared memory 2*xs_cap*8 + 2*us_cap*8 + nstages*tile + barriers.
+// ---------------------------------------------------------------------------------------------
+constexpr int SP_MAX_THREADS = 1024;
+// Tile-major copy of every region's adjacency and compact W_in for k_sync_persist.  Tile k of region r is ONE contiguous
+// block of tr rows, laid out for 128-bit shared-memory loads (thread j of the tile's group owns row j):
+//     [VP][tr] double2   values of slots (2p, 2p+1)                         VP = ceil(w_max / 2)
+//     [CP][tr] 8 x u16   column indices of slots 8q .. 8q+7; the LAST u16 of the LAST slab is the row's W_in column
+//                                                                           CP = ceil((w_max + 1) / 8)
+//     [tr]     double    the row's W_in value
+// (rows past n and slots past the region's width are zero).  72 bytes per row at width 6 against 84 in the slot-major
+// ELL: 16-bit indices suffice for n, D <= 65535.  One bulk copy per tile; 5 shared-memory loads per row instead of 14.
+// grid (tiles of the largest region, local regions); rebuilt when the ring geometry or the adjacency changes.
+__host__ __device__ inline int sp_vp(int w_max) { return (w_max + 1) / 2; }
+__host__ __device__ inline int sp_cp(int w_max) { return (w_max + 1 + 7) / 8; }
+__host__ __device__ inline int sp_row_bytes(int w_max) { return 16 * sp_vp(w_max) + 16 * sp_cp(w_max) + 8; }
+
+__global__ void __launch_bounds__(256)
+k_sync_pack(const RegionDev *__restrict__ regs, unsigned char *__restrict__ pack, const long long *__restrict__ pack_off,
+            int tr, int w_max)
+{
+    const RegionDev &R = regs[blockIdx.y];
+    const int n = R.n, W = R.ell_w;
+    const int t0 = blockIdx.x * tr;
+    if (n <= 0 || t0 >= n || R.winc == nullptr) return;
+    const int VP = sp_vp(w_max), CP = sp_cp(w_max);
+    const size_t tile_stride = (size_t)tr * sp_row_bytes(w_max);
+    unsigned char *dst = pack + pack_off[blockIdx.y] + (size_t)blockIdx.x * tile_stride;
+    double *pv = reinterpret_cast<double *>(dst);
+    unsigned short *pc = reinterpret_cast<unsigned short *>(dst + (size_t)VP * tr * 16);
+    double *pw = reinterpret_cast<double *>(dst + (size_t)(VP + CP) * tr * 16);
+    for (int j = threadIdx.x; j < tr; j += blockDim.x) {
+        const int row = t0 + j;
+        const bool ok = row < n;
+        for (int s = 0; s < 2 * VP; ++s) {
+            const bool in = ok && s < W;
+            pv[((size_t)(s >> 1) * tr + j) * 2 + (s & 1)] = in ? R.ell_val[(size_t)s * n + row] : 0.0;
+        }
+        for (int s = 0; s < 8 * CP; ++s) {
+            const bool in = ok && s < W;
+            unsigned short c = in ? (unsigned short)R.ell_col[(size_t)s * n + row] : (unsigned short)0;
+            if (s == 8 * CP - 1) c = ok ? (unsigned short)R.wcol[row] : (unsigned short)0;
+            pc[((size_t)(s >> 3) * tr + j) * 8 + (s & 7)] = c;
+        }
+        pw[j] = ok ? R.winc[row] : 0.0;
+    }
+}
+
+// one row of a packed tile: y = sum over the region's W slots in slot order (FMA chain, as update_row), then the W_in
+// product, tanh and the leak.  VPT > 0: compile-time number of value pairs with ONE column slab (w_max <= min(2 VPT, 7));
+// VPT == 0: any width.
+template <int VPT>
+__device__ __forceinline__ double sp_row(const unsigned char *__restrict__ tile, int gt, int tr, int w_max, int W,
+                                         const double *__restrict__ xr, const double *__restrict__ uu, double x_own, double leak)
+{
+    const int VP = VPT > 0 ? VPT : sp_vp(w_max), CP = VPT > 0 ? 1 : sp_cp(w_max);
+    const double2 *tv = reinterpret_cast<const double2 *>(tile) + gt;
+    const uint4 *tc = reinterpret_cast<const uint4 *>(tile + (size_t)VP * tr * 16) + gt;
+    const double wv = reinterpret_cast<const double *>(tile + (size_t)(VP + CP) * tr * 16)[gt];
+    double acc = 0.0;
+    unsigned wc;
+    if constexpr (VPT > 0) {
+        const uint4 cw = tc[0];
+        const unsigned cwa[4] = {cw.x, cw.y, cw.z, cw.w};
+        double2 v[VPT];
+#pragma unroll
+        for (int p = 0; p < VPT; ++p) v[p] = tv[(size_t)p * tr];
+        double xa[VPT], xb[VPT];
+#pragma unroll
+        for (int p = 0; p < VPT; ++p) {
+            xa[p] = xr[cwa[p] & 0xffffu];
+            xb[p] = xr[cwa[p] >> 16];
+        }
+#pragma unroll
+        for (int p = 0; p < VPT; ++p) {
+            if (2 * p < W) acc = fma(v[p].x, xa[p], acc);
+            if (2 * p + 1 < W) acc = fma(v[p].y, xb[p], acc);
+        }
+        wc = cw.w >> 16;
+    } else {
+        uint4 cw = tc[0];
+        for (int p = 0; p < VP; ++p) {
+            if ((p & 3) == 0 && p) cw = tc[(size_t)(p >> 2) * tr];
+            const unsigned pair = (p & 3) == 0 ? cw.x : (p & 3) == 1 ? cw.y : (p & 3) == 2 ? cw.z : cw.w;
+            const double2 v = tv[(size_t)p * tr];
+            if (2 * p < W) acc = fma(v.x, xr[pair & 0xffffu], acc);
+            if (2 * p + 1 < W) acc = fma(v.y, xr[pair >> 16], acc);
+        }
+        wc = tc[(size_t)(CP - 1) * tr].w >> 16;
+    }
+    const double xt = tanh(__dadd_rn(acc, __dmul_rn(wv, uu[wc])));
+    return __dadd_rn(__dmul_rn(1.0 - leak, x_own), __dmul_rn(leak, xt));
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(SP_MAX_THREADS, 1)
+k_sync_persist(const RegionDev *__restrict__ regs, const int *__restrict__ region_list, int nreg, double *__restrict__ x_pool,
+               const double *__restrict__ u_pool, const long long *__restrict__ u_offs, int T, int xs_cap, int us_cap,
+               int w_max, int nstages, int tr, int ngroups, const unsigned char *__restrict__ pack,
+               const long long *__restrict__ pack_off)
+{
+    extern __shared__ __align__(128) unsigned char sp_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncons = ngroups * tr;           // consumer threads; the last warp of the block is the producer
+    double *xs = reinterpret_cast<double *>(sp_smem), *us = xs + 2 * (size_t)xs_cap;
+    unsigned char *ring = reinterpret_cast<unsigned char *>(us + 2 * (size_t)us_cap);
+    const int tile_stride = tr * sp_row_bytes(w_max);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)nstages * tile_stride);
+    uint64_t *empty = full + nstages, *ufull = empty + nstages, *uempty = ufull + 2, *xbar = uempty + 2;
+    if (tid == 0) {
+        for (int s = 0; s < nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], tr / 32);     // the warps of the one group that drains the slot
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&ufull[b], 1);
+            mbar_init(&uempty[b], ncons / 32); // every consumer warp, once per step
+        }
+        mbar_init(xbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == ncons / 32) {
+        // ---------------- producer: for every region of this CTA, T passes over its row tiles ----------------
+        int s = 0;
+        uint32_t par = 1;
+        unsigned ug = 0;
+        for (int ri = blockIdx.x; ri < nreg; ri += gridDim.x) {
+            const int reg = region_list ? region_list[ri] : ri;
+            const RegionDev &R = regs[reg];
+            const int n = R.n, D = R.D;
+            const int ntiles = (n + tr - 1) / tr;
+            const double *__restrict__ u0 = u_pool + u_offs[reg];
+            const unsigned char *__restrict__ tiles = pack + pack_off[reg];
+            for (int t = 0; t < T; ++t) {
+                const unsigned b = ug & 1u;
+                mbar_wait(&uempty[b], ((ug >> 1) & 1u) ^ 1u);   // the consumers are done with step t-2
+                if (lane == 0) {
+                    mbar_expect_tx(&ufull[b], (uint32_t)D * 8u);
+                    tma_load_1d(us + (size_t)b * us_cap, u0 + (long long)t * D, (uint32_t)D * 8u, &ufull[b]);
+                }
+                ++ug;
+                for (int k = 0; k < ntiles; ++k) {
+                    mbar_wait(&empty[s], par);
+                    if (lane == 0) {
+                        // ONE bulk copy per tile: issuing a copy costs the warp ~140 cycles whatever its size, and the
+                        // 2W+2 slot-major pieces per tile of the first version made that issue rate the bound
+                        mbar_expect_tx(&full[s], (uint32_t)tile_stride);
+                        tma_load_1d(ring + (size_t)s * tile_stride, tiles + (size_t)k * tile_stride, (uint32_t)tile_stride, &full[s]);
+                    }
+                    if (++s == nstages) { s = 0; par ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: group gi takes every ngroups-th tile of the launch, one row per thread ----------------
+    const int gi = tid / tr, gt = tid - gi * tr;
+    int s = gi;              // slot of this group's next tile; it advances by ngroups per tile (nstages % ngroups == 0)
+    uint32_t par = 0;
+    int k = gi;              // index of that tile inside its step; carried over step and region boundaries
+    unsigned ug = 0, rg = 0;
+    for (int ri = blockIdx.x; ri < nreg; ri += gridDim.x, ++rg) {
+        const RegionDev &R = regs[region_list ? region_list[ri] : ri];
+        const int n = R.n, W = R.ell_w;
+        const int ntiles = (n + tr - 1) / tr;
+        const double leak = R.leak;
+        double *__restrict__ xg = x_pool + R.x_off;
+        if (tid == 0) {
+            // the previous region's write-back read xs through the generic proxy; order it before the bulk copy
+            asm volatile("fence.proxy.async;" ::: "memory");
+            const uint32_t bytes = (uint32_t)((n + 1) & ~1) * 8u;   // inside the region's padded slot of the x pool
+            mbar_expect_tx(xbar, bytes);
+            tma_load_1d(xs, xg, bytes, xbar);
+        }
+        mbar_wait(xbar, rg & 1u);
+        for (int t = 0; t < T; ++t) {
+            const double *__restrict__ xr = xs + (size_t)(t & 1) * xs_cap;
+            double *__restrict__ xw = xs + (size_t)((t + 1) & 1) * xs_cap;
+            const unsigned b = ug & 1u;
+            mbar_wait(&ufull[b], (ug >> 1) & 1u);
+            const double *__restrict__ uu = us + (size_t)b * us_cap;
+            for (; k < ntiles; k += ngroups) {
+                mbar_wait(&full[s], par);
+                const unsigned char *tile = ring + (size_t)s * tile_stride;
+                const int row = k * tr + gt;
+                if (row < n) xw[row] = sp_row<VPT>(tile, gt, tr, w_max, W, xr, uu, xr[row], leak);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                s += ngroups;
+                if (s >= nstages) { s -= nstages; par ^= 1u; }
+            }
+            k -= ntiles;     // the group's first tile of the next step (of this or the next region)
+            ++ug;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&uempty[b]);
+            // every row of x(t+1) is written and every read of x(t) is over before the buffers swap roles
+            asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+        }
+        const double *__restrict__ xf = xs + (size_t)(T & 1) * xs_cap;
+        for (int i = tid; i < n; i += ncons) xg[i] = xf[i];
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");   // xs[0] is free for the next region's bulk copy
+    }
+}
+
 // dense W_in fallback: temp = matmul(win, u) for regions with win_mode == 1 (src/mod_reservoir.f90:1445).
 // grid: (ceil(n_max/256), nregions)
 __global__ void k_win_dense(const RegionDev *__restrict__ regs, const int *__restrict__ region_list,
