@@ -1644,6 +1644,7 @@ static int launch_sync_persist(sml_engine *h, KindState &K, int first, int last,
     const bool generic = getenv("SML_SYNC_GENERIC") != nullptr;   // test hook: the any-width instantiation
     if (w_max <= 4 && !generic) CK(h, launch(k_sync_persist<2>));
     else if (w_max <= 6 && !generic) CK(h, launch(k_sync_persist<3>));
+    else if (w_max <= 7 && !generic) CK(h, launch(k_sync_persist<4>));
     else CK(h, launch(k_sync_persist<0>));
     h->launches++;
     CK(h, cudaGetLastError());

@@ -860,6 +860,22 @@ k_sync_pack(const RegionDev *__restrict__ regs, unsigned char *__restrict__ pack
     }
 }
 
+// 128-bit shared-memory loads, spelled out: left to the compiler, a double2 / uint4 access whose halves are used under
+// different predicates is split into 64- or 32-bit loads, and with a 16-byte lane stride those are 2- and 4-way bank
+// conflicts (ncu: 43 excess wavefronts per warp-row instead of 25).  volatile: never hoisted above the mbarrier wait.
+__device__ __forceinline__ double2 lds128_f64(const void *p)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128_u32(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
 // one row of a packed tile: y = sum over the region's W slots in slot order (FMA chain, as update_row), then the W_in
 // product, tanh and the leak.  VPT > 0: compile-time number of value pairs with ONE column slab (w_max <= min(2 VPT, 7));
 // VPT == 0: any width.
@@ -874,16 +890,16 @@ __device__ __forceinline__ double sp_row(const unsigned char *__restrict__ tile,
     double acc = 0.0;
     unsigned wc;
     if constexpr (VPT > 0) {
-        const uint4 cw = tc[0];
+        const uint4 cw = lds128_u32(tc);
         const unsigned cwa[4] = {cw.x, cw.y, cw.z, cw.w};
         double2 v[VPT];
 #pragma unroll
-        for (int p = 0; p < VPT; ++p) v[p] = tv[(size_t)p * tr];
+        for (int p = 0; p < VPT; ++p) v[p] = lds128_f64(tv + (size_t)p * tr);
         double xa[VPT], xb[VPT];
 #pragma unroll
         for (int p = 0; p < VPT; ++p) {
             xa[p] = xr[cwa[p] & 0xffffu];
-            xb[p] = xr[cwa[p] >> 16];
+            xb[p] = xr[p == 3 ? 0u : cwa[p] >> 16];   // pair 3's upper half is the W_in column, never a slot
         }
 #pragma unroll
         for (int p = 0; p < VPT; ++p) {
@@ -892,15 +908,16 @@ __device__ __forceinline__ double sp_row(const unsigned char *__restrict__ tile,
         }
         wc = cw.w >> 16;
     } else {
-        uint4 cw = tc[0];
+        uint4 cw = lds128_u32(tc);
         for (int p = 0; p < VP; ++p) {
-            if ((p & 3) == 0 && p) cw = tc[(size_t)(p >> 2) * tr];
+            if ((p & 3) == 0 && p) cw = lds128_u32(tc + (size_t)(p >> 2) * tr);
             const unsigned pair = (p & 3) == 0 ? cw.x : (p & 3) == 1 ? cw.y : (p & 3) == 2 ? cw.z : cw.w;
-            const double2 v = tv[(size_t)p * tr];
+            const double2 v = lds128_f64(tv + (size_t)p * tr);
             if (2 * p < W) acc = fma(v.x, xr[pair & 0xffffu], acc);
             if (2 * p + 1 < W) acc = fma(v.y, xr[pair >> 16], acc);
         }
-        wc = tc[(size_t)(CP - 1) * tr].w >> 16;
+        if (((VP - 1) >> 2) != CP - 1) cw = lds128_u32(tc + (size_t)(CP - 1) * tr);   // the last slab was not the last one read
+        wc = cw.w >> 16;
     }
     const double xt = tanh(__dadd_rn(acc, __dmul_rn(wv, uu[wc])));
     return __dadd_rn(__dmul_rn(1.0 - leak, x_own), __dmul_rn(leak, xt));
