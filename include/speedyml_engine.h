@@ -382,6 +382,9 @@ int sml_train_set_overlap(sml_engine *h, int on);
 int sml_train_trim(sml_engine *h);
 /* measurement: useful Gram flops N(N+1)K + 2PNK accumulated by sml_train_feed and the CUDA-event time (ms) of
  * the Gram kernels, the state generation and the solves of the current wave */
+/* how the last training phase generated its states: 0 one launch per time step (k_train_update), 1 the time loop inside
+ * k_train_stategen, 2 the same loop on the TMA ring (k_train_stategen_ring, the default for waves of >= 24 regions); -1 none yet */
+int sml_train_stategen_route(const sml_engine *h);
 int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms,
                     double *solve_ms);
 /* the roof the Gram figure is reported against: FP64 tensor-core (DMMA m8n8k4) issue peak of this GPU in TFLOP/s,

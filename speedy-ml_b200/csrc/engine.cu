@@ -90,6 +90,7 @@ struct KindState {
     size_t sync_pack_cap = 0;
     int pack_tr = 0, pack_w = 0;
     bool pack_valid = false;
+    std::vector<long long> sync_pack_off;   // host copy of d_sync_pack_off
     size_t smem_bytes = 0;
     bool any_dense = false;
     int64_t alg_bytes = 0, alg_bytes_update = 0;
@@ -179,6 +180,7 @@ struct sml_engine {
     double sync_ms_sum = 0.0;   // update-only launches of sml_synchronize while profiling (tools/sweep.py)
     long long sync_steps = 0;
     int64_t launches = 0;
+    int train_last_route = -1;   // state-generation route of the last training phase: 0 steps, 1 kernel, 2 ring
     TrainState train;
     TrainGlobal train_global;
     TrainPool train_pool;
@@ -1546,26 +1548,15 @@ int sml_predict(sml_engine *h, int kind)
     return 0;
 }
 
-// The whole time loop of synchronize in ONE launch (k_sync_persist): a CTA per SM runs all `length` steps of a region
-// before it takes the next one, the state vector stays in shared memory and the adjacency is re-read from L2.
-// Returns 1 when launched, 0 when the shard does not qualify (dense W_in, odd sizes, no room in shared memory, or
-// SML_SYNC_KERNEL=steps) and the caller launches step by step, -1 on error.  The state pool K.d_x[K.cur] is updated in place.
-static int launch_sync_persist(sml_engine *h, KindState &K, int first, int last, bool one_region, int length)
+// Ring geometry of the time-loop kernels (k_sync_persist, k_train_stategen_ring) and the tile-major pack they stream.
+// The geometry follows the whole kind (not the regions of one call), so that one pack serves every call.
+struct SyncPlan {
+    int ngroups = 0, nst = 0, tr = 0, w_max = 1, xs_cap = 0, us_cap = 0;
+    size_t tile_stride = 0, smem = 0;
+};
+// -> 1: plan made and the pack is current; 0: the kind does not qualify (too large for shared memory, > 16-bit indices); -1: error
+static int sync_plan_and_pack(sml_engine *h, KindState &K, SyncPlan &P)
 {
-    const char *sk = getenv("SML_SYNC_KERNEL");
-    if (sk && std::string(sk) == "steps") return 0;
-    if (K.any_dense) return 0;
-    std::vector<int> list;
-    for (int i = first; i < last; ++i) {
-        const HostRegion &hr = K.regs[i];
-        if (!hr.uploaded) continue;
-        const RegionDev &d = hr.dev;
-        if (d.win_mode != 0 || d.n % 4 != 0 || d.D % 2 != 0 || d.n <= 0 || d.D <= 0) return 0;
-        list.push_back(i);
-    }
-    if (list.empty()) return 1;
-    (void)one_region;
-    // the ring geometry follows the whole kind (not the listed regions), so that one pack serves every call
     int w_max = 1;
     const int n_max = K.n_max, D_max = K.D_max;
     for (const HostRegion &hr : K.regs)
@@ -1593,14 +1584,16 @@ static int launch_sync_persist(sml_engine *h, KindState &K, int first, int last,
     const size_t tile_stride = (size_t)tr * row_bytes;
     const size_t smem = fixed + (size_t)nst * tile_stride + bar_bytes;
     if (smem > 227 * 1024 || tile_stride >= (1u << 20)) return 0;
+    P.ngroups = ngroups; P.nst = nst; P.tr = tr; P.w_max = w_max; P.xs_cap = xs_cap; P.us_cap = us_cap;
+    P.tile_stride = tile_stride; P.smem = smem;
     // the tile-major pack of this geometry (all regions of the kind)
     if (!K.pack_valid || K.pack_tr != tr || K.pack_w != w_max) {
         const int nloc = (int)K.regs.size();
-        std::vector<long long> poff(nloc, 0);
+        K.sync_pack_off.assign(nloc, 0);
         size_t total = 0;
         for (int i = 0; i < nloc; ++i) {
             if (!K.regs[i].uploaded) continue;
-            poff[i] = (long long)total;
+            K.sync_pack_off[i] = (long long)total;
             total += (size_t)((K.regs[i].dev.n + tr - 1) / tr) * tile_stride;
         }
         if (total > K.sync_pack_cap) {
@@ -1611,16 +1604,44 @@ static int launch_sync_persist(sml_engine *h, KindState &K, int first, int last,
             K.sync_pack_cap = total;
         }
         if (!K.d_sync_pack_off) CK(h, cudaMalloc(&K.d_sync_pack_off, sizeof(long long) * nloc));
-        CK(h, cudaMemcpyAsync(K.d_sync_pack_off, poff.data(), sizeof(long long) * nloc, cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));   // `poff` is a local
+        CK(h, cudaMemcpyAsync(K.d_sync_pack_off, K.sync_pack_off.data(), sizeof(long long) * nloc, cudaMemcpyHostToDevice, h->stream));
         k_sync_pack<<<dim3((unsigned)((n_max + tr - 1) / tr), (unsigned)nloc), 256, 0, h->stream>>>(K.d_regs, K.d_sync_pack,
                                                                                                      K.d_sync_pack_off, tr, w_max);
         h->launches++;
         CK(h, cudaGetLastError());
+        CK(h, cudaStreamSynchronize(h->stream));
         K.pack_valid = true;
         K.pack_tr = tr;
         K.pack_w = w_max;
     }
+    return 1;
+}
+static bool sync_region_ok(const RegionDev &d)
+{
+    // compact W_in, bulk copies in 16-byte multiples
+    return d.win_mode == 0 && d.n % 4 == 0 && d.D % 2 == 0 && d.n > 0 && d.D > 0;
+}
+
+// The whole time loop of synchronize in ONE launch (k_sync_persist): a CTA per SM runs all `length` steps of a region
+// before it takes the next one, the state vector stays in shared memory and the adjacency is re-read from L2.
+// Returns 1 when launched, 0 when the shard does not qualify (dense W_in, odd sizes, no room in shared memory, or
+// SML_SYNC_KERNEL=steps) and the caller launches step by step, -1 on error.  The state pool K.d_x[K.cur] is updated in place.
+static int launch_sync_persist(sml_engine *h, KindState &K, int first, int last, int length)
+{
+    const char *sk = getenv("SML_SYNC_KERNEL");
+    if (sk && std::string(sk) == "steps") return 0;
+    if (K.any_dense) return 0;
+    std::vector<int> list;
+    for (int i = first; i < last; ++i) {
+        const HostRegion &hr = K.regs[i];
+        if (!hr.uploaded) continue;
+        if (!sync_region_ok(hr.dev)) return 0;
+        list.push_back(i);
+    }
+    if (list.empty()) return 1;
+    SyncPlan P;
+    const int ok = sync_plan_and_pack(h, K, P);
+    if (ok <= 0) return ok;
     if (K.sync_list_cap < list.size()) {
         cudaFree(K.d_sync_list);
         K.d_sync_list = nullptr;
@@ -1632,19 +1653,19 @@ static int launch_sync_persist(sml_engine *h, KindState &K, int first, int last,
     CK(h, cudaStreamSynchronize(h->stream));   // `list` is a local
     int ctas = getenv("SML_SYNC_CTAS") ? atoi(getenv("SML_SYNC_CTAS")) : h->num_sms;
     ctas = std::max(1, std::min({ctas, (int)list.size(), 4 * h->num_sms}));
-    // compile-time width for the common cases (one column slab, 2 or 3 value pairs), any width otherwise
+    // compile-time width for the common cases (one column slab, 2 to 4 value pairs), any width otherwise
     auto launch = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
         if (e != cudaSuccess) return e;
-        kern<<<ctas, ngroups * tr + 32, smem, h->stream>>>(K.d_regs, K.d_sync_list, (int)list.size(), K.d_x[K.cur], K.d_in, K.d_in_offs,
-                                                           length, xs_cap, us_cap, w_max, nst, tr, ngroups, K.d_sync_pack,
-                                                           K.d_sync_pack_off);
+        kern<<<ctas, P.ngroups * P.tr + 32, P.smem, h->stream>>>(K.d_regs, K.d_sync_list, (int)list.size(), K.d_x[K.cur], K.d_in,
+                                                                 K.d_in_offs, length, P.xs_cap, P.us_cap, P.w_max, P.nst, P.tr,
+                                                                 P.ngroups, K.d_sync_pack, K.d_sync_pack_off);
         return cudaSuccess;
     };
     const bool generic = getenv("SML_SYNC_GENERIC") != nullptr;   // test hook: the any-width instantiation
-    if (w_max <= 4 && !generic) CK(h, launch(k_sync_persist<2>));
-    else if (w_max <= 6 && !generic) CK(h, launch(k_sync_persist<3>));
-    else if (w_max <= 7 && !generic) CK(h, launch(k_sync_persist<4>));
+    if (P.w_max <= 4 && !generic) CK(h, launch(k_sync_persist<2>));
+    else if (P.w_max <= 6 && !generic) CK(h, launch(k_sync_persist<3>));
+    else if (P.w_max <= 7 && !generic) CK(h, launch(k_sync_persist<4>));
     else CK(h, launch(k_sync_persist<0>));
     h->launches++;
     CK(h, cudaGetLastError());
@@ -1707,7 +1728,7 @@ int sml_synchronize(sml_engine *h, int kind, int region, const double *inputs, i
         CK(h, cudaEventCreate(&se1));
         CK(h, cudaEventRecord(se0, h->stream));
     }
-    int persisted = launch_sync_persist(h, K, first, last, region != SML_ALL_REGIONS, length);
+    int persisted = launch_sync_persist(h, K, first, last, length);
     if (persisted < 0) return -1;
     for (int t = 0; t < length && !persisted; ++t) {
         if (region != SML_ALL_REGIONS) {

@@ -878,8 +878,9 @@ __device__ __forceinline__ uint4 lds128_u32(const void *p)
 
 // one row of a packed tile: y = sum over the region's W slots in slot order (FMA chain, as update_row), then the W_in
 // product, tanh and the leak.  VPT > 0: compile-time number of value pairs with ONE column slab (w_max <= min(2 VPT, 7));
-// VPT == 0: any width.
-template <int VPT>
+// VPT == 0: any width.  RS: the ML-only restart of training (src/mod_reservoir.f90:1034) -- the SpMV operand is the
+// squared copy of the state, i.e. gathered values of odd 0-based columns are squared first.
+template <int VPT, bool RS = false>
 __device__ __forceinline__ double sp_row(const unsigned char *__restrict__ tile, int gt, int tr, int w_max, int W,
                                          const double *__restrict__ xr, const double *__restrict__ uu, double x_own, double leak)
 {
@@ -898,8 +899,13 @@ __device__ __forceinline__ double sp_row(const unsigned char *__restrict__ tile,
         double xa[VPT], xb[VPT];
 #pragma unroll
         for (int p = 0; p < VPT; ++p) {
-            xa[p] = xr[cwa[p] & 0xffffu];
-            xb[p] = xr[p == 3 ? 0u : cwa[p] >> 16];   // pair 3's upper half is the W_in column, never a slot
+            const unsigned ca = cwa[p] & 0xffffu, cb = p == 3 ? 0u : cwa[p] >> 16;   // pair 3's upper half is the W_in column
+            xa[p] = xr[ca];
+            xb[p] = xr[cb];
+            if (RS) {
+                if (ca & 1u) xa[p] = __dmul_rn(xa[p], xa[p]);
+                if (cb & 1u) xb[p] = __dmul_rn(xb[p], xb[p]);
+            }
         }
 #pragma unroll
         for (int p = 0; p < VPT; ++p) {
@@ -913,8 +919,14 @@ __device__ __forceinline__ double sp_row(const unsigned char *__restrict__ tile,
             if ((p & 3) == 0 && p) cw = lds128_u32(tc + (size_t)(p >> 2) * tr);
             const unsigned pair = (p & 3) == 0 ? cw.x : (p & 3) == 1 ? cw.y : (p & 3) == 2 ? cw.z : cw.w;
             const double2 v = lds128_f64(tv + (size_t)p * tr);
-            if (2 * p < W) acc = fma(v.x, xr[pair & 0xffffu], acc);
-            if (2 * p + 1 < W) acc = fma(v.y, xr[pair >> 16], acc);
+            const unsigned ca = pair & 0xffffu, cb = pair >> 16;
+            double ga = xr[ca], gb = xr[cb];
+            if (RS) {
+                if (ca & 1u) ga = __dmul_rn(ga, ga);
+                if (cb & 1u) gb = __dmul_rn(gb, gb);
+            }
+            if (2 * p < W) acc = fma(v.x, ga, acc);
+            if (2 * p + 1 < W) acc = fma(v.y, gb, acc);
         }
         if (((VP - 1) >> 2) != CP - 1) cw = lds128_u32(tc + (size_t)(CP - 1) * tr);   // the last slab was not the last one read
         wc = cw.w >> 16;

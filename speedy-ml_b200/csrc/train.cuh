@@ -31,6 +31,7 @@ struct TrainRegionDev {
     int *chol_info;           // 0: on the Cholesky path; > 0: non-positive pivot at that column; < 0: not eligible
     int region;               // reservoir%assigned_region (keys the input-noise generator)
     int precip_off, precip_len;  // rows of the input vector that hold precip (noised in linear space), -1 / 0 if none
+    long long pack_off;       // the region's tiles in the kind's tile-major adjacency pack (k_sync_pack), k_train_stategen_ring
 };
 
 // Device-resident global training series (sml_train_global_series): column t is the conditioned global state at time
@@ -266,6 +267,139 @@ k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, 
     }
     __syncthreads();
     for (int i = tid; i < n; i += nt) xa[i] = xs[i];
+}
+
+// the two halves of train_input for a kernel that wants the load in flight early: the raw series value, and
+// standardisation + noise applied to it later.  finish(raw(...)) == train_input(...) bit for bit.
+__device__ __forceinline__ double train_input_raw(const GlobalSeries &gs, const TrainRegionDev &t, int col, int c)
+{
+    if (gs.G) return gs.G[(size_t)(gs.first + gs.stride * col) * gs.g_len + t.R.fb_src[c]];
+    return t.td[(size_t)t.R.D * col + c];
+}
+__device__ __forceinline__ double train_input_finish(const GlobalSeries &gs, const TrainRegionDev &t, int col, int c, double v)
+{
+    if (!gs.G) return v;
+    const int ms = t.R.fb_ms[c];
+    if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, t.R.mean[ms]), t.R.std[ms]);
+    if (gs.noisemag != 0.0) {
+        const double g = counter_gauss(gs.seed, t.region, gs.first + gs.stride * col, c);
+        v = noised_value(gs, t.R, t.region, t.precip_off, t.precip_len, col, c, v, g);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_train_stategen_ring: the same time loop on the ring of k_sync_persist (kernels.cuh).  k_train_stategen fetches the
+// ELL slots with ordinary loads -- a thread issues a group, waits an L2 round trip, gathers, issues the next: 26 us per
+// step for a wave of 144 (2.9 TB/s although the adjacency is L2-resident).  Here ONE CTA per region and per SM keeps the
+// state in shared memory (two copies, one consumer barrier per step), a TMA producer warp streams the region's
+// tile-major adjacency pack (one bulk copy per tile) through the ring, and the consumers take one row per thread from
+// shared memory only; the step's input vector is evaluated once per element by the first D consumer threads -- its
+// raw loads are issued before the step's tiles and finished (standardise + noise) after them, so their latency hides
+// behind the step.  x~ goes to the slab column as before.  Per-row arithmetic and order are those of k_train_update:
+// bit-identical accumulators.  Needs compact W_in, n % 4 == 0, D <= 2 * consumer threads.
+// grid (nwave): one wave region per CTA; waves larger than the SM count run in rounds.
+// ---------------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(SP_MAX_THREADS, 1)
+k_train_stategen_ring(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, int out_col0, int store_first, int s_first,
+                      int restart_period, int xs_cap, int us_cap, int w_max, int nstages, int tr, int ngroups,
+                      const unsigned char *__restrict__ pack, GlobalSeries gs)
+{
+    extern __shared__ __align__(128) unsigned char sr_smem[];
+    const TrainRegionDev &t = T[blockIdx.x];
+    const RegionDev &R = t.R;
+    const int n = R.n, D = R.D, W = R.ell_w, S = R.S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncons = ngroups * tr;
+    double *xs = reinterpret_cast<double *>(sr_smem), *us = xs + 2 * (size_t)xs_cap;
+    unsigned char *ring = reinterpret_cast<unsigned char *>(us + 2 * (size_t)us_cap);
+    const int tile_stride = tr * sp_row_bytes(w_max);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)nstages * tile_stride);
+    uint64_t *empty = full + nstages;
+    const int ntiles = (n + tr - 1) / tr;
+    if (tid == 0) {
+        for (int s = 0; s < nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], tr / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == ncons / 32) {
+        // ---------------- producer: nsteps passes over the region's tiles ----------------
+        const unsigned char *__restrict__ tiles = pack + t.pack_off;
+        int s = 0;
+        uint32_t par = 1;
+        for (int k = 0; k < nsteps; ++k)
+            for (int j = 0; j < ntiles; ++j) {
+                mbar_wait(&empty[s], par);
+                if (lane == 0) {
+                    mbar_expect_tx(&full[s], (uint32_t)tile_stride);
+                    tma_load_1d(ring + (size_t)s * tile_stride, tiles + (size_t)j * tile_stride, (uint32_t)tile_stride, &full[s]);
+                }
+                if (++s == nstages) { s = 0; par ^= 1u; }
+            }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int gi = tid / tr, gt = tid - gi * tr;
+    const double leak = R.leak;
+    double *__restrict__ xa = t.xa;
+    for (int i = tid; i < n; i += ncons) xs[i] = xa[i];
+    for (int i = tid; i < D && nsteps > 0; i += ncons) us[i] = train_input_finish(gs, t, in_col0, i, train_input_raw(gs, t, in_col0, i));
+    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    if (store_first) {   // states(:,1) = x after the discard loop: no update, only the x~ copy
+        double *col = t.slab + (size_t)t.ld * (out_col0 - 1) + S;
+        for (int i = tid; i < n; i += ncons) {
+            const double xv = xs[i];
+            col[i] = (i & 1) ? __dmul_rn(xv, xv) : xv;
+        }
+    }
+    int s = gi, j = gi;
+    uint32_t par = 0;
+    const int i0 = tid, i1 = tid + ncons;   // the input elements this thread evaluates for the next step
+    for (int k = 0; k < nsteps; ++k) {
+        const double *__restrict__ xr = xs + (size_t)(k & 1) * xs_cap;
+        double *__restrict__ xw = xs + (size_t)((k + 1) & 1) * xs_cap;
+        const double *__restrict__ uu = us + (size_t)(k & 1) * us_cap;
+        double *__restrict__ un = us + (size_t)((k + 1) & 1) * us_cap;
+        const bool more = k + 1 < nsteps;
+        const int ncol = in_col0 + k + 1;
+        double raw0 = 0.0, raw1 = 0.0;
+        if (more) {
+            if (i0 < D) raw0 = train_input_raw(gs, t, ncol, i0);
+            if (i1 < D) raw1 = train_input_raw(gs, t, ncol, i1);
+        }
+        const bool restart = restart_period > 0 && ((s_first + k) % restart_period) == 0;
+        double *slabcol = (out_col0 >= 0) ? t.slab + (size_t)t.ld * (out_col0 + k) + S : nullptr;
+        for (; j < ntiles; j += ngroups) {
+            mbar_wait(&full[s], par);
+            const unsigned char *tile = ring + (size_t)s * tile_stride;
+            const int row = j * tr + gt;
+            if (row < n) {
+                const double xv = restart ? sp_row<VPT, true>(tile, gt, tr, w_max, W, xr, uu, xr[row], leak)
+                                          : sp_row<VPT, false>(tile, gt, tr, w_max, W, xr, uu, xr[row], leak);
+                xw[row] = xv;
+                if (slabcol) slabcol[row] = (row & 1) ? __dmul_rn(xv, xv) : xv;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            s += ngroups;
+            if (s >= nstages) { s -= nstages; par ^= 1u; }
+        }
+        j -= ntiles;
+        if (more) {
+            if (i0 < D) un[i0] = train_input_finish(gs, t, ncol, i0, raw0);
+            if (i1 < D) un[i1] = train_input_finish(gs, t, ncol, i1, raw1);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    }
+    const double *__restrict__ xf = xs + (size_t)(nsteps & 1) * xs_cap;
+    for (int i = tid; i < n; i += ncons) xa[i] = xf[i];
 }
 
 // copy the current state (no update) into slab column out_col: states(:,1) = x after the discard loop

@@ -13,6 +13,7 @@ namespace {
 // state generation alone on the SMs (serial schedule): whether the <6, 384> instantiation of k_train_stategen is used
 constexpr bool SG_WIDE_DEFAULT = false;   // measured slower (0.91 vs 0.76 s for 384 regions)
 constexpr int SG_MIN_WAVE = 64;   // smallest wave for which the in-kernel time loop is the default route
+constexpr int SG_RING_MIN_WAVE = 24;   // smallest wave for which the ring kernel (one CTA per region and per SM) is the default
 
 // device buffer freed on every exit path of its scope
 struct ScopedDev {
@@ -199,7 +200,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         }
         T.overlap = ov != 0;
         const char *sg = getenv("SML_TRAIN_STATEGEN");
-        T.stategen_route = !sg ? 0 : (std::string(sg) == "steps" ? 1 : (std::string(sg) == "kernel" ? 2 : 0));
+        T.stategen_route = !sg ? 0 : (std::string(sg) == "steps" ? 1 : (std::string(sg) == "kernel" ? 2 : (std::string(sg) == "ring" ? 3 : 0)));
         if (T.overlap && !h->train_gram_stream) {
             int lo = 0, hi = 0;   // lowest priority: the small state-generation launches must not queue behind Gram CTAs
             CK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -387,13 +388,58 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
     const size_t sg_smem = sizeof(double) * ((size_t)sg_xs_cap + ((T.D_max + 1) & ~1));
     // one CTA per region: pays once the wave fills the machine (32 us per step at 192 regions against 42-48 us for the
     // per-step launches; 18 us against 7.5 us at 16 regions, where the per-step launches spread the rows over all SMs)
-    const bool persistent = sg_smem <= 90 * 1024 && (T.stategen_route == 2 || (T.stategen_route == 0 && nw >= SG_MIN_WAVE));
+    bool persistent = sg_smem <= 90 * 1024 && (T.stategen_route == 2 || (T.stategen_route == 0 && nw >= SG_MIN_WAVE));
     // serial schedule, A/B: SML_TRAIN_SG_GROUP=6 -> 6 ELL slots per group and 384 threads (more loads in flight per thread)
     const bool sg_wide = !T.overlap && (getenv("SML_TRAIN_SG_GROUP") ? atoi(getenv("SML_TRAIN_SG_GROUP")) == 6 : SG_WIDE_DEFAULT);
     const int sg_cap = sg_wide ? 384 : SG_MAX_THREADS;
     const int sg_threads = getenv("SML_TRAIN_SG_THREADS") ? std::max(64, std::min(sg_cap, atoi(getenv("SML_TRAIN_SG_THREADS")) / 32 * 32))
                                                            : (T.overlap ? 256 : sg_cap);
+    // k_train_stategen_ring: the time loop on the TMA ring of k_sync_persist, fed by the kind's tile-major adjacency pack.
+    // Needs the whole SM (serial schedule only), compact W_in and 16-byte-multiple sizes in every region of the wave.
+    SyncPlan ring_plan;
+    bool ring = false;
+    if (!T.overlap && (T.stategen_route == 3 || (T.stategen_route == 0 && nw >= SG_RING_MIN_WAVE))) {
+        KindState &K = h->kinds[T.kind];
+        ring = !K.any_dense;
+        for (auto &r : T.regs) ring = ring && sync_region_ok(r.dev.R);
+        if (ring) {
+            const int ok = sync_plan_and_pack(h, K, ring_plan);
+            if (ok < 0) return -1;
+            ring = ok == 1 && T.D_max <= 2 * ring_plan.ngroups * ring_plan.tr;
+        }
+        if (ring) {
+            bool changed = false;
+            for (int i = 0; i < nw; ++i) {
+                const long long off = K.sync_pack_off[T.regs[i].local];
+                if (T.regs[i].dev.pack_off != off) { T.regs[i].dev.pack_off = off; changed = true; }
+            }
+            if (changed) {
+                if (train_sync(h)) return -1;
+                for (int i = 0; i < nw; ++i) devs[i] = T.regs[i].dev;
+                CK(h, cudaMemcpyAsync(T.d_regs, devs.data(), sizeof(TrainRegionDev) * nw, cudaMemcpyHostToDevice, h->stream));
+                CK(h, cudaStreamSynchronize(h->stream));
+                T.uploaded = devs;
+            }
+        }
+    }
+    const unsigned char *ring_pack = ring ? h->kinds[T.kind].d_sync_pack : nullptr;
+    auto launch_ring = [&](auto kern, int in_col0, int nsteps, int out_col0, int store_first, int s_first, int restart_period) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_plan.smem);
+        kern<<<nw, ring_plan.ngroups * ring_plan.tr + 32, ring_plan.smem, S>>>(T.d_regs, in_col0, nsteps, out_col0, store_first, s_first,
+                                                                              restart_period, ring_plan.xs_cap, ring_plan.us_cap,
+                                                                              ring_plan.w_max, ring_plan.nst, ring_plan.tr,
+                                                                              ring_plan.ngroups, ring_pack, gs);
+    };
     auto launch_stategen = [&](int in_col0, int nsteps, int out_col0, int store_first, int s_first, int restart_period) {
+        if (ring) {
+            const bool generic = getenv("SML_SYNC_GENERIC") != nullptr;
+            if (ring_plan.w_max <= 4 && !generic) launch_ring(k_train_stategen_ring<2>, in_col0, nsteps, out_col0, store_first, s_first, restart_period);
+            else if (ring_plan.w_max <= 6 && !generic) launch_ring(k_train_stategen_ring<3>, in_col0, nsteps, out_col0, store_first, s_first, restart_period);
+            else if (ring_plan.w_max <= 7 && !generic) launch_ring(k_train_stategen_ring<4>, in_col0, nsteps, out_col0, store_first, s_first, restart_period);
+            else launch_ring(k_train_stategen_ring<0>, in_col0, nsteps, out_col0, store_first, s_first, restart_period);
+            h->launches++;
+            return;
+        }
         if (sg_wide)
             k_train_stategen<6, 384><<<nw, sg_threads, sg_smem, S>>>(T.d_regs, in_col0, nsteps, out_col0, store_first, s_first,
                                                                       restart_period, sg_xs_cap, gs);
@@ -402,7 +448,9 @@ static int train_run_phase(sml_engine *h, int ncols, int discard_cols, const Glo
                                                                                  restart_period, sg_xs_cap, gs);
         h->launches++;
     };
-    if (persistent) {
+    if (ring) persistent = true;   // same launch structure: one launch per discard loop / slab
+    h->train_last_route = ring ? 2 : persistent ? 1 : 0;
+    if (persistent && !ring) {
         CK(h, cudaFuncSetAttribute(k_train_stategen<3, SG_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
         CK(h, cudaFuncSetAttribute(k_train_stategen<6, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sg_smem));
     }
@@ -910,6 +958,8 @@ int sml_train_gram_get(sml_engine *h, int region, double *sxs, double *sxt)
     }
     FAIL(h, "region %d is not in the training wave", region);
 }
+
+int sml_train_stategen_route(const sml_engine *h) { return h ? h->train_last_route : -1; }
 
 int sml_train_stats(sml_engine *h, double *gram_flops_useful, double *gram_ms, double *stategen_ms, double *solve_ms)
 {

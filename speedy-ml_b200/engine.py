@@ -138,6 +138,7 @@ _SIGNATURES = {
     "sml_train_trim": ([C.c_void_p], C.c_int),
     "sml_train_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_stats": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
+    "sml_train_stategen_route": ([C.c_void_p], C.c_int),
     "sml_dmma_probe": ([C.c_void_p, _dp], C.c_int),
     "sml_rolling_average_2d": ([C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
@@ -863,6 +864,10 @@ class Engine:
         v = [C.c_double() for _ in range(4)]
         self._ck(self.lib.sml_train_stats(self.h, *[C.byref(a) for a in v]))
         return dict(zip(("gram_flops_useful", "gram_ms", "stategen_ms", "solve_ms"), (a.value for a in v)))
+
+    def train_stategen_route(self) -> str:
+        """state-generation route of the last training phase"""
+        return {0: "steps", 1: "kernel", 2: "ring"}.get(int(self.lib.sml_train_stategen_route(self.h)), "none")
 
     def dmma_probe(self) -> float:
         """FP64 tensor-core issue peak of this GPU, TFLOP/s, measured now"""

@@ -209,10 +209,11 @@ def test_device_input_noise_for_global_feed(monkeypatch):
     assert np.array_equal(eng.train_gram_get(1)[0], noisy_gram)
     eng.train_end()
     # the per-time-step launches (k_train_update) and the in-kernel time loop (k_train_stategen) see the same noised inputs
-    for route in ("steps", "kernel"):
+    for route in ("steps", "kernel", "ring"):
         monkeypatch.setenv("SML_TRAIN_STATEGEN", route)
         eng.train_begin(regions, bs)
         eng.train_feed_global(1, 2, 20, 2)
+        assert eng.train_stategen_route() == route
         assert np.array_equal(eng.train_gram_get(1)[0], noisy_gram)
         eng.train_end()
     monkeypatch.delenv("SML_TRAIN_STATEGEN", raising=False)

@@ -291,8 +291,9 @@ def test_overlapped_schedule_is_bit_identical(E, monkeypatch, ml_only):
     # (overlap, state generation): the time loop inside one kernel per slab (k_train_stategen: the default for waves of
     # 64 regions and more, SML_TRAIN_STATEGEN=kernel forces it) or one launch per time step (k_train_update, =steps);
     # SML_TRAIN_SG_GROUP=6 selects the wide instantiation of the in-kernel loop
+    # =ring: the same loop on the TMA ring of the spin-up kernel (k_train_stategen_ring, the default for waves >= 24)
     for on, stategen, group in ((True, "kernel", None), (False, "kernel", None), (False, "kernel", "6"), (True, "steps", None),
-                                (False, "steps", None), (False, None, None)):
+                                (False, "steps", None), (False, None, None), (False, "ring", None)):
         if group:
             monkeypatch.setenv("SML_TRAIN_SG_GROUP", group)
         else:
@@ -308,6 +309,8 @@ def test_overlapped_schedule_is_bit_identical(E, monkeypatch, ml_only):
             eng.train_feed([td], [im] if im is not None else None, discard)
         grams.append(eng.train_gram_get(region))
         st = eng.train_stats()
+        if stategen and not on:
+            assert eng.train_stategen_route() == stategen
         assert st["gram_ms"] > 0.0 and st["stategen_ms"] > 0.0
         assert eng.train_solve(1e-2, 1.0, True, 0.0)[0] == 0 if not ml_only else eng.train_solve(1e-2)[0] == 0
         eng.train_end()
