@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "speedy-ml_b200", "lib", "libspeedyml_b200.so")
-KERNELS = ["k_step_persist", "k_stepILi4", "k_update_ring", "k_update_sx", "k_readout_finish", "k_peer_push", "k_wait_flag",
+KERNELS = ["k_step_persist", "k_stepILi4", "k_sync_persistILi4", "k_train_stategen_ringILi4", "k_sync_pack", "k_update_ring", "k_update_sx", "k_readout_finish", "k_peer_push", "k_wait_flag",
            "k_pack_grids", "k_syrk_dmma", "k_chol_gemm", "k_lu_gemm", "k_makesparse_shuffle", "k_dmma_probe"]
 PATTERNS = ["UBLKCP", "SYNCS", "DMMA", "SHFL", "MEMBAR", r"ST\.E\.\S*SYS", r"LD\.E\.\S*SYS", "BAR.SYNC", "RED", "ATOM", "MUFU", "LDS", "LDG"]
 
