@@ -17,14 +17,16 @@ namespace sml {
 
 struct TrainRegionDev {
     RegionDev R;              // the reservoir's weights (ELL adjacency, W_in, ...)
-    double *slab;             // [ld][KS] column-major ([ld][2*KS], two buffers, in overlap mode)
+    double *slab;             // augmented state slab, ROW-BLOCK-major and padded (slab_at): block b = rows 128b..128b+127,
+                              // inside a block column k is a run of 132 doubles (128 rows + 4 pad) -- exactly the padded
+                              // shared-memory operand layout of k_syrk_dmma, so a K-chunk of a tile operand is ONE bulk copy
     double *gram;             // [ld][ld] column-major, lower triangle accumulated
     double *xa, *xb;          // training state ping-pong [n]
     const double *td;         // [D][ncols] this phase's (pre-noised) input series
     const double *im;         // [S][ncols] imperfect-model series (hybrid) or null
     const int *target_map;    // [P] rows of the input vector that form the target
     int ld;                   // padded N+P (multiple of 16)
-    int pad0;
+    int ks_total;             // slab columns per row block (KS, or 2*KS with two buffers in overlap mode)
     // ridge solve (chol.cuh)
     double *linv;             // [ceil(N/128)][2][128*128]: inverse of every diagonal block of L, and its transpose
     double *dsave;            // [ld] diagonal of the regularised A (restored if the region falls back to LU)
@@ -33,6 +35,17 @@ struct TrainRegionDev {
     int precip_off, precip_len;  // rows of the input vector that hold precip (noised in linear space), -1 / 0 if none
     long long pack_off;       // the region's tiles in the kind's tile-major adjacency pack (k_sync_pack), k_train_stategen_ring
 };
+
+// element (row i, column k) of a region's slab; SLAB_LD == SY_LDS (static_assert below)
+constexpr int SLAB_RB = 128, SLAB_LD = 132;
+__host__ __device__ __forceinline__ size_t slab_at(int ks_total, int i, int k)
+{
+    return ((size_t)(i >> 7) * ks_total + k) * SLAB_LD + (i & 127);
+}
+__host__ __device__ __forceinline__ size_t slab_doubles(int ld, int ks_total)
+{
+    return (size_t)((ld + SLAB_RB - 1) / SLAB_RB) * ks_total * SLAB_LD;
+}
 
 // Device-resident global training series (sml_train_global_series): column t is the conditioned global state at time
 // t in the layout of the exchange buffers, G = [w4d | w2d | precip | sst | tisr] and F = [f4d | f2d].  With it the
@@ -132,13 +145,16 @@ __global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity,
     if (row >= R.n) return;
     const double *xo = parity ? t.xb : t.xa;
     double *xn = parity ? t.xa : t.xb;
-    const double *gsrc = (gather_col >= 0) ? t.slab + (size_t)t.ld * gather_col + R.S : xo;
+    const bool from_slab = gather_col >= 0;   // ML-only restart: the SpMV operand is x~ of the previous column
     const double *u = gs.G ? nullptr : t.td + (size_t)R.D * in_col;
     const int n = R.n;
     const int *__restrict__ ec = R.ell_col + row;
     const double *__restrict__ ev = R.ell_val + row;
     double acc = 0.0;
-    for (int s = 0; s < R.ell_w; ++s) acc = fma(__ldg(ev + (size_t)s * n), gsrc[__ldg(ec + (size_t)s * n)], acc);
+    for (int s = 0; s < R.ell_w; ++s) {
+        const int c = __ldg(ec + (size_t)s * n);
+        acc = fma(__ldg(ev + (size_t)s * n), from_slab ? t.slab[slab_at(t.ks_total, R.S + c, gather_col)] : xo[c], acc);
+    }
     double tw;
     if (R.win_mode == 0) {
         const int wc = __ldg(R.wcol + row);
@@ -151,7 +167,7 @@ __global__ void k_train_update(const TrainRegionDev *__restrict__ T, int parity,
     const double xt = tanh(__dadd_rn(acc, tw));
     const double xv = __dadd_rn(__dmul_rn(1.0 - R.leak, xo[row]), __dmul_rn(R.leak, xt));
     xn[row] = xv;
-    if (out_col >= 0) t.slab[(size_t)t.ld * out_col + R.S + row] = (row & 1) ? __dmul_rn(xv, xv) : xv;
+    if (out_col >= 0) t.slab[slab_at(t.ks_total, R.S + row, out_col)] = (row & 1) ? __dmul_rn(xv, xv) : xv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -188,10 +204,9 @@ k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, 
     for (int i = tid; i < n; i += nt) xs[i] = xa[i];
     __syncthreads();
     if (store_first) {   // states(:,1) = x after the discard loop: no update, only the x~ copy
-        double *col = t.slab + (size_t)t.ld * (out_col0 - 1) + S;
         for (int i = tid; i < n; i += nt) {
             const double xv = xs[i];
-            col[i] = (i & 1) ? __dmul_rn(xv, xv) : xv;
+            t.slab[slab_at(t.ks_total, S + i, out_col0 - 1)] = (i & 1) ? __dmul_rn(xv, xv) : xv;
         }
     }
     const int *__restrict__ ecol = R.ell_col;
@@ -210,7 +225,8 @@ k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, 
         __syncthreads();
         // (b) rows of this thread
         const bool restart = restart_period > 0 && ((s_first + k) % restart_period) == 0;
-        double *slabcol = (out_col0 >= 0) ? t.slab + (size_t)t.ld * (out_col0 + k) + S : nullptr;
+        const bool keep = out_col0 >= 0;
+        const int ocol = out_col0 + k;
         for (int base = tid; base < n; base += 2 * nt) {
             const int r0 = base, r1 = base + nt;
             const bool ok1 = r1 < n;
@@ -254,10 +270,10 @@ k_train_stategen(const TrainRegionDev *__restrict__ T, int in_col0, int nsteps, 
             const double xv0 = __dadd_rn(__dmul_rn(1.0 - leak, xs[r0]), __dmul_rn(leak, tanh(__dadd_rn(acc0, tw0))));
             const double xv1 = __dadd_rn(__dmul_rn(1.0 - leak, xs[q1]), __dmul_rn(leak, tanh(__dadd_rn(acc1, tw1))));
             xb[r0] = xv0;
-            if (slabcol) slabcol[r0] = (r0 & 1) ? __dmul_rn(xv0, xv0) : xv0;
+            if (keep) t.slab[slab_at(t.ks_total, S + r0, ocol)] = (r0 & 1) ? __dmul_rn(xv0, xv0) : xv0;
             if (ok1) {
                 xb[r1] = xv1;
-                if (slabcol) slabcol[r1] = (r1 & 1) ? __dmul_rn(xv1, xv1) : xv1;
+                if (keep) t.slab[slab_at(t.ks_total, S + r1, ocol)] = (r1 & 1) ? __dmul_rn(xv1, xv1) : xv1;
             }
         }
         __syncthreads();   // every gather of the old state is done
@@ -353,10 +369,9 @@ k_train_stategen_ring(const TrainRegionDev *__restrict__ T, int in_col0, int nst
     for (int i = tid; i < D && nsteps > 0; i += ncons) us[i] = train_input_finish(gs, t, in_col0, i, train_input_raw(gs, t, in_col0, i));
     asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
     if (store_first) {   // states(:,1) = x after the discard loop: no update, only the x~ copy
-        double *col = t.slab + (size_t)t.ld * (out_col0 - 1) + S;
         for (int i = tid; i < n; i += ncons) {
             const double xv = xs[i];
-            col[i] = (i & 1) ? __dmul_rn(xv, xv) : xv;
+            t.slab[slab_at(t.ks_total, S + i, out_col0 - 1)] = (i & 1) ? __dmul_rn(xv, xv) : xv;
         }
     }
     int s = gi, j = gi;
@@ -375,7 +390,8 @@ k_train_stategen_ring(const TrainRegionDev *__restrict__ T, int in_col0, int nst
             if (i1 < D) raw1 = train_input_raw(gs, t, ncol, i1);
         }
         const bool restart = restart_period > 0 && ((s_first + k) % restart_period) == 0;
-        double *slabcol = (out_col0 >= 0) ? t.slab + (size_t)t.ld * (out_col0 + k) + S : nullptr;
+        const bool keep = out_col0 >= 0;
+        const int ocol = out_col0 + k;
         for (; j < ntiles; j += ngroups) {
             mbar_wait(&full[s], par);
             const unsigned char *tile = ring + (size_t)s * tile_stride;
@@ -384,7 +400,7 @@ k_train_stategen_ring(const TrainRegionDev *__restrict__ T, int in_col0, int nst
                 const double xv = restart ? sp_row<VPT, true>(tile, gt, tr, w_max, W, xr, uu, xr[row], leak)
                                           : sp_row<VPT, false>(tile, gt, tr, w_max, W, xr, uu, xr[row], leak);
                 xw[row] = xv;
-                if (slabcol) slabcol[row] = (row & 1) ? __dmul_rn(xv, xv) : xv;
+                if (keep) t.slab[slab_at(t.ks_total, S + row, ocol)] = (row & 1) ? __dmul_rn(xv, xv) : xv;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -409,7 +425,7 @@ __global__ void k_train_store_state(const TrainRegionDev *__restrict__ T, int pa
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= t.R.n) return;
     const double xv = (parity ? t.xb : t.xa)[row];
-    t.slab[(size_t)t.ld * out_col + t.R.S + row] = (row & 1) ? __dmul_rn(xv, xv) : xv;
+    t.slab[slab_at(t.ks_total, t.R.S + row, out_col)] = (row & 1) ? __dmul_rn(xv, xv) : xv;
 }
 
 // imperfect-model rows and target rows of slab columns [0, ncols): series column = first_series_col + c.
@@ -422,10 +438,11 @@ __global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_ser
     const TrainRegionDev &t = T[blockIdx.y];
     const RegionDev &R = t.R;
     const int c = blockIdx.x;
-    double *col = t.slab + (size_t)t.ld * (col_base + c);
+    const int kst = t.ks_total, kc = col_base + c;
+    auto at = [&](int i) -> double & { return t.slab[slab_at(kst, i, kc)]; };
     const int N = R.S + R.n;
     if (c >= ncols) {
-        for (int i = threadIdx.x; i < t.ld; i += blockDim.x) col[i] = 0.0;
+        for (int i = threadIdx.x; i < t.ld; i += blockDim.x) at(i) = 0.0;
         return;
     }
     const int sc = first_series_col + c;
@@ -436,14 +453,14 @@ __global__ void k_train_fill(const TrainRegionDev *__restrict__ T, int first_ser
             double v = Fc[R.lm_src[i]];
             const int ms = R.lm_ms[i];
             if (ms >= 0) v = __ddiv_rn(__dsub_rn(v, R.mean[ms]), R.std[ms]);
-            col[i] = v;
+            at(i) = v;
         }
-        for (int p = threadIdx.x; p < R.P; p += blockDim.x) col[N + p] = series_input(gs, R, sc, t.target_map[p]);
+        for (int p = threadIdx.x; p < R.P; p += blockDim.x) at(N + p) = series_input(gs, R, sc, t.target_map[p]);
     } else {
-        for (int i = threadIdx.x; i < R.S; i += blockDim.x) col[i] = t.im[(size_t)R.S * sc + i];
-        for (int p = threadIdx.x; p < R.P; p += blockDim.x) col[N + p] = t.td[(size_t)R.D * sc + t.target_map[p]];
+        for (int i = threadIdx.x; i < R.S; i += blockDim.x) at(i) = t.im[(size_t)R.S * sc + i];
+        for (int p = threadIdx.x; p < R.P; p += blockDim.x) at(N + p) = t.td[(size_t)R.D * sc + t.target_map[p]];
     }
-    for (int i = N + R.P + threadIdx.x; i < t.ld; i += blockDim.x) col[i] = 0.0;
+    for (int i = N + R.P + threadIdx.x; i < t.ld; i += blockDim.x) at(i) = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -457,6 +474,7 @@ constexpr int SY_BM = 128, SY_BK = 16, SY_LDS = 132, SY_STAGES = 4;
 constexpr int SY_CONS_WARPS = 8;
 constexpr int SY_THREADS = (SY_CONS_WARPS + 1) * 32;
 constexpr int SY_STAGE_DOUBLES = 2 * SY_BK * SY_LDS;
+static_assert(SY_LDS == SLAB_LD && SY_BM == SLAB_RB, "the slab is stored in the Gram kernel's padded operand layout");
 constexpr size_t SY_SMEM = (size_t)SY_STAGES * SY_STAGE_DOUBLES * 8 + 2 * SY_STAGES * 8;
 constexpr int SY_STAGES_DEEP = 6;   // A/B: SML_SYRK_STAGES=6 (203 KB of shared memory)
 constexpr size_t SY_SMEM_DEEP = (size_t)SY_STAGES_DEEP * SY_STAGE_DOUBLES * 8 + 2 * SY_STAGES_DEEP * 8;
@@ -511,18 +529,22 @@ k_syrk_dmma(const TrainRegionDev *__restrict__ T, const int2 *__restrict__ tiles
 
     if (warp == NCW) {
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)SY_BK * (rowsA + (diag ? 0 : rowsB)) * 8u;
+            // the slab is stored row-block-major with 132-double padded columns (slab_at): the K-chunk of a tile operand
+            // is ONE contiguous run that lands in the padded shared-memory layout as it is.  (Column-major, a chunk was
+            // 16 + 16 copies of 1 KB; at ~140 cycles of issue each the producer lane needed longer than the 4096 cycles
+            // the tensor pipe takes for the chunk.)
+            constexpr uint32_t OPB = (uint32_t)SY_BK * SY_LDS * 8u;   // bytes of one operand chunk
+            const uint32_t bytes = diag ? OPB : 2u * OPB;
+            const int kst = t.ks_total;
             for (int kc = 0; kc < nchunks; ++kc) {
                 const int s = kc % ST;
                 mbar_wait(&empty[s], ((kc / ST) & 1) ^ 1);
                 mbar_expect_tx(&full[s], bytes);
                 double *sA = stage0 + (size_t)s * SY_STAGE_DOUBLES;
                 double *sB = sA + SY_BK * SY_LDS;
-                const double *src = t.slab + (size_t)ld * (col_base + kc * SY_BK);
-                for (int kk = 0; kk < SY_BK; ++kk) {
-                    tma_load_1d(sA + kk * SY_LDS, src + (size_t)ld * kk + i0, rowsA * 8u, &full[s]);
-                    if (!diag) tma_load_1d(sB + kk * SY_LDS, src + (size_t)ld * kk + j0, rowsB * 8u, &full[s]);
-                }
+                const int k0 = col_base + kc * SY_BK;
+                tma_load_1d(sA, t.slab + ((size_t)tile.x * kst + k0) * SLAB_LD, OPB, &full[s]);
+                if (!diag) tma_load_1d(sB, t.slab + ((size_t)tile.y * kst + k0) * SLAB_LD, OPB, &full[s]);
             }
         }
         return;
@@ -694,7 +716,7 @@ struct TrainState {
     TrainRegionDev *d_regs = nullptr;
     int2 *d_tiles = nullptr;
     int ntiles = 0;
-    int ld_max = 0, n_max = 0, D_max = 0, ks = 1024;
+    int ld_max = 0, n_max = 0, D_max = 0, ks = 2048;
     double *d_series_td = nullptr, *d_series_im = nullptr;
     size_t series_td_cap = 0, series_im_cap = 0;
     double gram_flops_useful = 0.0;   // N(N+1)K + 2PNK summed over feeds

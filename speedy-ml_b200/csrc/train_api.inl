@@ -222,7 +222,7 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         if (local_of(h, kind, regions[i], &li)) return -1;
         const RegionDev &R = K.regs[li].dev;
         const size_t N = (size_t)R.n + R.S, ld = (N + R.P + 15) / 16 * 16;
-        arena_need += al256(ld * ld * 8) + al256(ld * T.ks * 8 * (T.overlap ? 2 : 1)) + 2 * al256((size_t)R.n * 8) +
+        arena_need += al256(ld * ld * 8) + al256(slab_doubles((int)ld, T.ks * (T.overlap ? 2 : 1)) * 8) + 2 * al256((size_t)R.n * 8) +
                       al256(((N + CH_NB - 1) / CH_NB) * CH_LINV * 8) + al256(ld * 8) + al256(sizeof(int)) + al256(sizeof(int) * R.P);
     }
     {
@@ -283,7 +283,8 @@ int sml_train_begin(sml_engine *h, int kind, const int32_t *regions, int nregion
         t_alloc += now() - tq; tq = now();
         if (!bad) CK(h, cudaMemsetAsync(d.gram, 0, (size_t)d.ld * d.ld * 8, h->stream));
         t_memset += now() - tq; tq = now();
-        bad = bad || alloc((size_t)d.ld * T.ks * 8 * (T.overlap ? 2 : 1), &p); d.slab = (double *)p;
+        d.ks_total = T.ks * (T.overlap ? 2 : 1);
+        bad = bad || alloc(slab_doubles(d.ld, d.ks_total) * 8, &p); d.slab = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xa = (double *)p;
         bad = bad || alloc((size_t)d.R.n * 8, &p); d.xb = (double *)p;
         bad = bad || alloc((size_t)((N + CH_NB - 1) / CH_NB) * CH_LINV * 8, &p); d.linv = (double *)p;
