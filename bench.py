@@ -480,6 +480,52 @@ def train_leg(eng, E, torch, dist, world, regions, ws_dims, cols=2000, discard=4
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+class OracleCheck:
+    """Per-step parity inside the bench run: before every correctness step the CPU oracle (oracle/, the checker) takes
+    the engine's state, feedback and local_model of a few local regions, after the step its own predict must reproduce the
+    engine's new state and outvec (<= 1e-12 relative, the tolerance of tests/test_fullsize_gpu.py).  Runs on every rank."""
+    TOL = 1e-12
+
+    def __init__(self, weights):
+        self.regs, self.worst, self.err = {}, 0.0, None
+        try:
+            from oracle import oracle_c as oc
+            for r, w in weights.items():
+                rc = oc.Region(R_TOTAL, r, m=M_RES, precip_bool=True, sst_bool=True, sst_bool_input=w["sst_bool_input"])
+                rc.set_weights(w["rows"], w["cols"], w["vals"], None, w["wout"], w["mean"], w["std"])
+                rc.set_win_compact(w["winc"], w["wcol"])
+                self.regs[r] = rc
+        except Exception as e:   # the oracle library is test infrastructure: its absence must not break the measurement
+            self.err = f"{type(e).__name__}: {e}"
+
+    def before(self, eng):
+        for r, rc in self.regs.items():
+            rc.x[:] = eng.state_get(r)
+            rc.feedback[:] = eng.feedback_get(r)
+            rc.local_model[:] = eng.local_model_get(r)
+
+    def after(self, eng):
+        def rel(a, b):
+            return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+        for r, rc in self.regs.items():
+            rc.predict()
+            self.worst = max(self.worst, rel(eng.state_get(r), rc.x), rel(eng.outvec_get(r), rc.outvec))
+
+    def result(self, torch, dist, world):
+        worst, n = self.worst, len(self.regs)
+        if world > 1:
+            t = torch.tensor([worst, float(n)], dtype=torch.float64, device="cuda")
+            tmax, tsum = t.clone(), t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            worst, n = float(tmax[0]), int(tsum[1])
+        if n == 0:
+            return {"ok": None, "unavailable": self.err or "no regions"}
+        return {"ok": bool(worst <= self.TOL), "max_rel_err": worst, "tol": self.TOL, "regions_checked": n, "steps": CHECK_STEPS,
+                "what": "CPU oracle predict (state + outvec) from the engine's own state / feedback / local_model of the first, "
+                        "middle and last region of every rank, every correctness step"}
+
+
 def grid_checksum(eng, torch, dist, world):
     """FP64 sum + XOR of the bit patterns of the grids THIS rank assembled; all ranks must agree"""
     g = np.concatenate([a.ravel(order="F") for a in eng.grids_get()])
@@ -526,6 +572,9 @@ def run_gpu(args):
 
     t_setup = time.perf_counter()
     ws_dims = {}
+    # regions of this rank that are also stepped by the CPU oracle during the correctness steps (first / middle / last)
+    check_ids = sorted({my_regions[0], my_regions[len(my_regions) // 2], my_regions[-1]})
+    check_w = {}
     workers = max(1, min(16, (os.cpu_count() or 2) // max(1, world)))
     with ThreadPoolExecutor(max_workers=workers) as ex:
         batch = 4 * workers
@@ -535,6 +584,8 @@ def run_gpu(args):
                                   win_compact=w["winc"], win_col=w["wcol"], D=w["D"],
                                   sst_bool_input=w["sst_bool_input"])
                 ws_dims[w["region"]] = {k: w[k] for k in ("n", "k", "D", "P", "S", "L")}
+                if w["region"] in check_ids:
+                    check_w[w["region"]] = w
     eng.finalize()
     t_setup = time.perf_counter() - t_setup
     setup = eng.setup_stats()
@@ -578,10 +629,16 @@ def run_gpu(args):
         time.sleep(0.6)
 
     # ---- correctness inside the scaling run: 6 sequential hybrid steps from the fixed start, checksum of the grids
+    #      and, on EVERY rank, the CPU oracle stepping three of the rank's regions from the engine's own state and inputs
+    #      (checker only, outside every timed region; the exchange itself is covered by the checksum all ranks must share)
+    ocheck = OracleCheck(check_w)
     for t in range(1, CHECK_STEPS + 1):
+        ocheck.before(eng)
         stepper.step(t, host_model, F["tisr"])
+        ocheck.after(eng)
     barrier()
     checksum = grid_checksum(eng, torch, dist, world)
+    oracle_check = ocheck.result(torch, dist, world)
 
     device_step = stepper.device_step
 
@@ -685,6 +742,7 @@ def run_gpu(args):
                        **({"emulate_world": eng_world, "note": "DIAGNOSTIC: one rank's shard of an emulated "
                            f"{eng_world}-rank run, not a whole-model number"} if eng_world != world else {})},
             "grid_checksum": checksum,
+            "oracle_check": oracle_check,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((lay["f_total"] + 96 * 48) * 8),
                     "d2h_bytes_per_step": int(lay["tisr"] * 8), "ms_per_step": e2e_wall / args.steps,
                     "ms_per_step_device_events": e2e_ms / args.steps,

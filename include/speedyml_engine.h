@@ -413,6 +413,9 @@ int sml_step_chunk_rows(const sml_engine *h, int kind); /* rows per CTA the step
 /* the step plan in use: kernel 0 = k_step (one CTA per item), 1 = k_step_persist; slots = persistent CTAs,
  * part_rows = rows per fixed row block, parts = partial outvecs per launch */
 int sml_step_plan(const sml_engine *h, int kind, int *kernel, int *slots, int *part_rows, int *parts);
+/* 1 when the persistent step kernel keeps the shard's adjacency, W_in and state vectors L2-resident across steps (evict-last
+ * loads, W_out streamed evict-first): chosen at sml_finalize when they fit (SML_L2_KEEP=0/1 forces it) */
+int sml_step_l2_keep(const sml_engine *h, int kind);
 /* set-up cost: host seconds spent inside sml_region_upload so far, bytes of the weight arena, device allocations made for it */
 int sml_setup_stats(const sml_engine *h, double *upload_seconds, int64_t *arena_bytes, int *arena_chunks);
 int64_t sml_kernel_launch_count(const sml_engine *h);

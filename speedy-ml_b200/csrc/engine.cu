@@ -76,6 +76,7 @@ struct KindState {
     // persistent step kernel (k_step_persist): fixed row blocks ("parts") per region, items = runs of whole blocks,
     // slots = statically balanced contiguous runs of items, one CTA each
     bool persist = false;
+    bool l2_keep = false;   // evict-last adjacency / evict-first W_out in the persistent step kernel
     StepSeg *d_segs = nullptr, *d_segs_split = nullptr;
     int2 *d_slots = nullptr;
     int nslots = 0, nparts = 0, part_rows = 0, p_stage_cols = 0, p_ldp = 0, p_xs_cap = 0, p_cpi = 0, p_stages = 0;
@@ -1056,6 +1057,27 @@ static int finalize_kind(sml_engine *h, int kind)
     if (K.smem_bytes > 227 * 1024) FAIL(h, "step kernel needs %zu B of shared memory", K.smem_bytes);
 
     if (build_persistent_plan(h, K, S_max)) return -1;   // fills part0 / nparts of every RegionDev
+    {
+        // L2 residency (kernels.cuh, l2_policy_*): when the shard's adjacency, W_in and state vectors fit in L2 beside the
+        // W_out stream, the persistent step kernel loads them evict-last and streams W_out evict-first.
+        // SML_L2_KEEP=0/1 forces it off/on; default: always on with the persistent kernel (measured: -4.9 % at 144 regions
+        // per GPU, -2.8 % at 288, -2.7 % at 1152, where only the state vectors and the partials can stay); SML_L2_KEEP_MB caps it
+        size_t keep_bytes = 0;
+        for (int i = 0; i < nloc; ++i)
+            if (K.regs[i].uploaded) {
+                const RegionDev &d = K.regs[i].dev;
+                keep_bytes += (size_t)d.n * (12 * (size_t)d.ell_w + 12 + 16) + 8 * (size_t)d.D;
+            }
+        const char *lk = getenv("SML_L2_KEEP");
+        const size_t cap_mb = getenv("SML_L2_KEEP_MB") ? (size_t)atoi(getenv("SML_L2_KEEP_MB")) : ((size_t)1 << 30);
+        const bool keep = K.persist && (lk ? atoi(lk) != 0 : keep_bytes <= cap_mb * 1024 * 1024);
+        K.l2_keep = keep;
+        // (a persisting carve-out of L2 -- cudaLimitPersistingL2CacheSize -- for the evict-last lines was measured too and
+        //  is WORSE: 0.1672 -> 0.1760 ms at 144 regions, 1.2548 -> 1.2987 ms at 1152; the policies alone are the default)
+        if (keep)
+            for (int i = 0; i < nloc; ++i)
+                if (K.regs[i].uploaded && getenv("SML_ELL_STREAM") == nullptr) K.regs[i].dev.ell_stream = 2;
+    }
     std::vector<RegionDev> regs(nloc);
     for (int i = 0; i < nloc; ++i) regs[i] = K.regs[i].dev;
     CK(h, cudaMalloc(&K.d_regs, sizeof(RegionDev) * nloc));
@@ -2535,6 +2557,7 @@ int sml_step_plan(const sml_engine *h, int kind, int *kernel, int *slots, int *p
     if (parts) *parts = K.persist ? K.nparts : K.nitems;
     return 0;
 }
+int sml_step_l2_keep(const sml_engine *h, int kind) { return (h && kind >= 0 && kind < 2 && h->kinds[kind].l2_keep) ? 1 : 0; }
 int sml_setup_stats(const sml_engine *h, double *upload_seconds, int64_t *arena_bytes, int *arena_chunks)
 {
     if (!h) return -1;

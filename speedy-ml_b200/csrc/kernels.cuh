@@ -159,15 +159,70 @@ __device__ __forceinline__ double ld_cg_f64(const double *p)
 // temp = W_in u (one product), x <- (1-leak) x + leak tanh(y + temp)
 // src/mod_reservoir.f90:1444-1448 (predict), :1373-1377 (synchronize)
 // ---------------------------------------------------------------------------------------------
-template <bool EF, typename T>
-__device__ __forceinline__ T ld_stream(const T *p)
+// L2 residency control (round 2).  At small shards (N = 8: 144 regions per GPU) the adjacency, W_in and state vectors of
+// the whole shard are 90 MB -- they would live in the 126 MB L2 from one step to the next if the 920 MB W_out stream
+// did not flush them every step.  So the W_out bulk copies carry an evict-first policy and the ELL / W_in loads an
+// evict-last one (createpolicy + .L2::cache_hint); RegionDev::ell_stream == 2 selects it (sml_finalize decides by size).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
-    return EF ? __ldcs(p) : __ldg(p);
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+// MODE 0: ld.global.nc, 1: evict-first streaming load (ld.global.cs), 2: L2 evict-last through a cache-hint policy
+template <int MODE>
+__device__ __forceinline__ int ld_stream(const int *p, uint64_t pol)
+{
+    if (MODE == 2) {
+        int v;
+        asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+        return v;
+    }
+    return MODE == 1 ? __ldcs(p) : __ldg(p);
+}
+template <int MODE>
+__device__ __forceinline__ double ld_stream(const double *p, uint64_t pol)
+{
+    if (MODE == 2) {
+        double v;
+        asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+        return v;
+    }
+    return MODE == 1 ? __ldcs(p) : __ldg(p);
 }
 
-template <bool EF>
+// state-vector gathers / stores with the evict-last policy (MODE 2): x is re-read by the next step's gathers
+template <int MODE>
+__device__ __forceinline__ double ld_state(const double *p, uint64_t pol)
+{
+    if (MODE == 2) {
+        double v;
+        asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+        return v;
+    }
+    return *p;
+}
+__device__ __forceinline__ void st_keep_f64(double *p, double v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
+template <int MODE>
 __device__ __forceinline__ double update_row_t(const RegionDev &R, int row, const double *__restrict__ xo,
-                                               const double *__restrict__ u, const double *__restrict__ temp_pool)
+                                               const double *__restrict__ u, const double *__restrict__ temp_pool, uint64_t pol)
 {
     const int n = R.n;
     const int *__restrict__ ec = R.ell_col + row;
@@ -180,30 +235,31 @@ __device__ __forceinline__ double update_row_t(const RegionDev &R, int row, cons
         double v[6], xv[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            c[i] = ld_stream<EF>(ec + (size_t)(s + i) * n);
-            v[i] = ld_stream<EF>(ev + (size_t)(s + i) * n);
+            c[i] = ld_stream<MODE>(ec + (size_t)(s + i) * n, pol);
+            v[i] = ld_stream<MODE>(ev + (size_t)(s + i) * n, pol);
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) xv[i] = xo[c[i]];
+        for (int i = 0; i < 6; ++i) xv[i] = ld_state<MODE>(xo + c[i], pol);
 #pragma unroll
         for (int i = 0; i < 6; ++i) acc = fma(v[i], xv[i], acc);
     }
     for (; s < W; ++s) {
-        const int c = ld_stream<EF>(ec + (size_t)s * n);
-        const double v = ld_stream<EF>(ev + (size_t)s * n);
-        acc = fma(v, xo[c], acc);
+        const int c = ld_stream<MODE>(ec + (size_t)s * n, pol);
+        const double v = ld_stream<MODE>(ev + (size_t)s * n, pol);
+        acc = fma(v, ld_state<MODE>(xo + c, pol), acc);
     }
     double t;
-    if (R.win_mode == 0) t = __dmul_rn(ld_stream<EF>(R.winc + row), u[ld_stream<EF>(R.wcol + row)]);
+    if (R.win_mode == 0) t = __dmul_rn(ld_stream<MODE>(R.winc + row, pol), u[ld_stream<MODE>(R.wcol + row, pol)]);
     else t = temp_pool[R.x_off + row];
     const double xt = tanh(__dadd_rn(acc, t));
     return __dadd_rn(__dmul_rn(1.0 - R.leak, xo[row]), __dmul_rn(R.leak, xt));
 }
 
 __device__ __forceinline__ double update_row(const RegionDev &R, int row, const double *__restrict__ xo,
-                                             const double *__restrict__ u, const double *__restrict__ temp_pool)
+                                             const double *__restrict__ u, const double *__restrict__ temp_pool, uint64_t pol)
 {
-    return R.ell_stream ? update_row_t<true>(R, row, xo, u, temp_pool) : update_row_t<false>(R, row, xo, u, temp_pool);
+    if (R.ell_stream == 2) return update_row_t<2>(R, row, xo, u, temp_pool, pol);
+    return R.ell_stream ? update_row_t<1>(R, row, xo, u, temp_pool, pol) : update_row_t<0>(R, row, xo, u, temp_pool, pol);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -275,9 +331,10 @@ k_step(const RegionDev *__restrict__ regs, const StepItem *__restrict__ items, c
         const double *lm = lm_pool + R.lm_off;
         for (int i = tid; i < it.xs_off; i += NCONS) xs[i] = lm[i];
     }
+    const uint64_t pol_last = l2_policy_evict_last();   // only read when RegionDev::ell_stream == 2
     for (int j = tid; j < it.nrows; j += NCONS) {
         const int row = it.row0 + j;
-        const double xv = update_row(R, row, xo, u, temp_pool);
+        const double xv = update_row(R, row, xo, u, temp_pool, pol_last);
         xn[row] = xv;
         if (do_readout) xs[it.xs_off + j] = (row & 1) ? __dmul_rn(xv, xv) : xv;  // even 1-based index squared
     }
@@ -383,9 +440,11 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
         // ring is already full when the consumers are released
         int s = 0;
         uint32_t par = 1;   // parity to wait for on empty[s]: passes at once on the first lap
+        const uint64_t pol_first = l2_policy_evict_first();
         for (int i = 0; i < slot.y; ++i) {
             const StepSeg sg = segs[slot.x + i];
             const int ldw = regs[sg.reg].ldw, S = regs[sg.reg].S;
+            const bool keep_l2 = regs[sg.reg].ell_stream == 2;   // W_out must not flush the L2-resident adjacency
             const double *wout = regs[sg.reg].wout;
             const uint32_t colbytes = (uint32_t)ldw * 8u;
             // segment A: the S local_model columns (fused order only); segment B: the item's state rows
@@ -399,7 +458,10 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
                     __syncwarp();
                     unsigned char *dst = smem_raw + (size_t)s * stage_bytes;
                     if (ldp == ldw) {   // unpadded tile: the nc columns are one contiguous block -- ONE bulk copy
-                        if (lane == 0) tma_load_1d(dst, src + (size_t)c0 * ldw, (uint32_t)nc * colbytes, &full[s]);
+                        if (lane == 0) {
+                            if (keep_l2) tma_load_1d_hint(dst, src + (size_t)c0 * ldw, (uint32_t)nc * colbytes, &full[s], pol_first);
+                            else tma_load_1d(dst, src + (size_t)c0 * ldw, (uint32_t)nc * colbytes, &full[s]);
+                        }
                     } else {
                         for (int c = lane; c < nc; c += 32)
                             tma_load_1d(dst + (size_t)c * ldp * 8, src + (size_t)(c0 + c) * ldw, colbytes, &full[s]);
@@ -421,6 +483,7 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
     const int rp = warp * rpw + (lane % rpw);
     int s = 0;
     uint32_t par = 0;
+    const uint64_t pol_last = l2_policy_evict_last();
     for (int i = 0; i < slot.y; ++i) {
         const StepSeg sg = segs[slot.x + i];
         const RegionDev R = regs[sg.reg];
@@ -437,8 +500,9 @@ k_step_persist(const RegionDev *__restrict__ regs, const StepSeg *__restrict__ s
             }
             for (int j = tid; j < sg.nrows; j += NCONS) {
                 const int row = sg.row0 + j;
-                const double xv = update_row(R, row, xo, u, temp_pool);
-                xn[row] = xv;
+                const double xv = update_row(R, row, xo, u, temp_pool, pol_last);
+                if (R.ell_stream == 2) st_keep_f64(xn + row, xv, pol_last);
+                else xn[row] = xv;
                 xs[xs_off + j] = (row & 1) ? __dmul_rn(xv, xv) : xv;  // even 1-based index squared
             }
         }

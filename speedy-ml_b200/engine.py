@@ -139,6 +139,7 @@ _SIGNATURES = {
     "sml_train_set_overlap": ([C.c_void_p, C.c_int], C.c_int),
     "sml_train_stats": ([C.c_void_p, _dp, _dp, _dp, _dp], C.c_int),
     "sml_train_stategen_route": ([C.c_void_p], C.c_int),
+    "sml_step_l2_keep": ([C.c_void_p, C.c_int], C.c_int),
     "sml_dmma_probe": ([C.c_void_p, _dp], C.c_int),
     "sml_rolling_average_2d": ([C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int], C.c_int),
     "sml_mldivide": ([C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int], C.c_int),
@@ -744,7 +745,7 @@ class Engine:
         v = [C.c_int() for _ in range(4)]
         self._ck(self.lib.sml_step_plan(self.h, kind, *[C.byref(a) for a in v]))
         return dict(kernel="k_step_persist" if v[0].value else "k_step", slots=v[1].value, part_rows=v[2].value,
-                    parts=v[3].value)
+                    parts=v[3].value, l2_keep=bool(self.lib.sml_step_l2_keep(self.h, kind)))
 
     def setup_stats(self):
         a, b, c = C.c_double(), C.c_int64(), C.c_int()
