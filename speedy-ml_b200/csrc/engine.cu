@@ -1606,6 +1606,10 @@ static int sync_plan_and_pack(sml_engine *h, KindState &K, SyncPlan &P)
     const size_t tile_stride = (size_t)tr * row_bytes;
     const size_t smem = fixed + (size_t)nst * tile_stride + bar_bytes;
     if (smem > 227 * 1024 || tile_stride >= (1u << 20)) return 0;
+    // large reservoirs (m = 12000: two state vectors take 190 KB) leave room for a ring of ~100-row tiles only, i.e. ~200
+    // consumer threads: below ~400 threads the time loop is slower than the step launches (measured: 576 threads 36 ms,
+    // 768+ threads 24 ms, step launches 49 ms at m = 6000), so such shards keep the step-per-launch kernels
+    if (!getenv("SML_SYNC_TILE_ROWS") && n_max >= 4096 && ngroups * tr < 384) return 0;
     P.ngroups = ngroups; P.nst = nst; P.tr = tr; P.w_max = w_max; P.xs_cap = xs_cap; P.us_cap = us_cap;
     P.tile_stride = tile_stride; P.smem = smem;
     // the tile-major pack of this geometry (all regions of the kind)

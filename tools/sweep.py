@@ -57,12 +57,26 @@ def point(m, deg, nregions, steps):
     assert eng.predict_algorithmic_bytes() == upd_bytes + rd_bytes
     rng = np.random.default_rng(0)
     inputs = [np.asfortranarray(rng.standard_normal((D, steps))) for (_, D) in dims]
+    os.environ["SML_SYNC_KERNEL"] = "steps"
     eng.synchronize_all(inputs, 3)               # warm-up
     eng.profile(True)
     eng.synchronize_all(inputs, steps)           # update-only launches, bracketed by CUDA events in the engine
     upd_ms, nsteps = eng.sync_times()
     eng.profile(False)
     upd_ms /= nsteps
+    os.environ.pop("SML_SYNC_KERNEL")
+    # the default synchronize: the whole time loop in one launch (k_sync_persist), `spin_steps` steps
+    spin_steps = 100
+    spin_in = [np.asfortranarray(np.tile(a, (1, (spin_steps + steps - 1) // steps))[:, :spin_steps]) for a in inputs]
+    n0 = eng.kernel_launch_count()
+    eng.synchronize_all(spin_in, 4)
+    one_launch = eng.kernel_launch_count() - n0 <= 2
+    eng.profile(True)
+    eng.synchronize_all(spin_in, spin_steps)
+    spin_ms, nspin = eng.sync_times()
+    eng.profile(False)
+    spin_ms /= nspin
+    del spin_in
     for _ in range(3):
         eng.predict()
     eng.profile(True)
@@ -76,6 +90,7 @@ def point(m, deg, nregions, steps):
     rd_ms = max(step_ms - upd_ms, 1e-9)
     return {"m": m, "degree": deg, "regions": nregions, "n_typ": dims[len(dims) // 2][0],
             "update_ms": upd_ms, "update_GBs": upd_bytes / upd_ms / 1e6, "update_frac": upd_bytes / upd_ms / 1e6 / peak,
+            "spin_ms_per_step": spin_ms, "spin_one_launch": one_launch, "spin_vs_roof": upd_bytes / spin_ms / 1e6 / peak,
             "step_ms": step_ms, "step_GBs": (upd_bytes + rd_bytes) / step_ms / 1e6,
             "step_frac": (upd_bytes + rd_bytes) / step_ms / 1e6 / peak,
             "readout_ms": rd_ms, "readout_GBs": rd_bytes / rd_ms / 1e6, "readout_frac": rd_bytes / rd_ms / 1e6 / peak,
@@ -100,11 +115,11 @@ def main():
             print(json.dumps(r), flush=True)
     if args.md:
         with open(args.md, "w") as f:
-            f.write("| m | degree | update MB | update ms | update GB/s | frac | readout MB | readout ms | readout GB/s | frac "
-                    "| fused step ms | step GB/s | frac |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+            f.write("| m | degree | update MB | update ms (step launches) | update GB/s | frac | spin-up ms per step (one launch, 100 steps) | x HBM roof "
+                    "| readout MB | readout ms | readout GB/s | frac | fused step ms | step GB/s | frac |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
             for r in rows:
                 f.write(f"| {r['m']} | {r['degree']} | {r['update_MB']:.0f} | {r['update_ms']:.3f} | {r['update_GBs']:.0f} | "
-                        f"{r['update_frac']:.2f} | {r['readout_MB']:.0f} | {r['readout_ms']:.3f} | {r['readout_GBs']:.0f} | "
+                        f"{r['update_frac']:.2f} | {r['spin_ms_per_step']:.3f}{'' if r['spin_one_launch'] else ' (step launches)'} | {r['spin_vs_roof']:.2f} | {r['readout_MB']:.0f} | {r['readout_ms']:.3f} | {r['readout_GBs']:.0f} | "
                         f"{r['readout_frac']:.2f} | {r['step_ms']:.3f} | {r['step_GBs']:.0f} | {r['step_frac']:.2f} |\n")
 
 
