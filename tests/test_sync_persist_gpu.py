@@ -178,6 +178,24 @@ def test_wide_and_narrow_rows_bitwise(E, deg):
     assert rel_inf(got[None], rc.x) < TOL_STEP * 10
 
 
+def test_large_reservoir_keeps_the_step_launches(E):
+    """m = 12000: two state vectors take 190 KB of shared memory, the ring that is left would feed ~200 consumer threads --
+    slower than one launch per step -- so the engine falls back (and still matches the oracle)"""
+    region = 555
+    w = region_weights(R, region, m=12000, with_dense_win=False)
+    rng = np.random.default_rng(12)
+    T = 4
+    series = syn.ar1_series(w["D"], T, rng)
+    rc = c_region(w)
+    rc.synchronize(series, T)
+    eng = one_region_engine(E, w)
+    n0 = eng.kernel_launch_count()
+    eng.synchronize(region, series)
+    assert eng.kernel_launch_count() - n0 >= T
+    assert rel_inf(eng.state_get(region), rc.x) < TOL_STEP * 10
+    eng.close()
+
+
 def test_ocean_spin_up_bitwise(E):
     """the slab-ocean reservoirs' synchronize goes through the same kernel (kind = OCEAN)"""
     region = 700
