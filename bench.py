@@ -14,6 +14,8 @@ rebuild of every region's feedback / local_model.  1 step = 0.25 sim-day.
            wholegrid copy-out (D2H), the host model stub, forecast + TISR copy-in (H2D), every step.  At N > 1
            every exchange -- outvec all-gather, forecast distribution -- runs inside the engine
            (sml_comm_bootstrap); this file issues no collective inside a step
+  oracle_check  : the CPU oracle (checker only, outside the timed regions) reproduces the engine's state and outvec of three
+                  regions per rank at every one of the 6 correctness steps (<= 1e-12)
   grid_checksum : FP64 sum and XOR of the bit patterns of the global grids after 6 sequential hybrid steps from a
            fixed start, on every rank: sharding does not change any region's arithmetic, so the value is the same
            for N = 1, 2, 4, 8 (and all ranks of a run must agree)
